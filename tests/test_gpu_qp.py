@@ -1,0 +1,76 @@
+"""-m gpu: K1 (batched node QP, through the C ABI) against the CPU oracle and against
+solver-independent certificates (oracle/certify.py = the reference fixture's plug-in checkers)."""
+import numpy as np
+import pytest
+
+from oracle.models import load_model
+from oracle.qp_c import CoreC
+from oracle.condense import Condensed
+from oracle import certify as cert
+from tests.util import make_controller, random_nodes, families_from_records
+
+pytestmark = pytest.mark.gpu
+
+# relative cost tolerance of north_star ("optimal cost ... within 1e-6 relative")
+COST_RTOL = 1e-6
+
+
+def _check_batch(model, N, seed, n_slots):
+    ctl = make_controller(model)
+    x0, lb, ub = random_nodes(model, N, seed=seed)
+    h = ctl.handle(n_slots=n_slots)
+    out = h.solve_nodes(x0, lb, ub)
+    st = out['status'].cpu().numpy(); cost = out['cost'].cpu().numpy(); dobj = out['dobj'].cpu().numpy()
+    P = out['primal'].cpu().numpy(); D = out['dual'].cpu().numpy()
+    oracle = CoreC(model)
+    cond = Condensed(model)
+    arow = np.linalg.norm(cond.Aall, axis=1)
+    n_inf = 0
+    for i in range(N):
+        ref = oracle.solve(x0[i], lb[i], ub[i])
+        assert st[i] == ref['status'], (i, st[i], ref['status'])
+        fam = families_from_records(ctl.problem, h.layout, st[i], P[i], D[i])
+        ds, neg = cert.dual_residuals(model, cond, fam)
+        assert neg >= 0.
+        dob = cert.dual_objective(model, cond, x0[i], lb[i], ub[i], fam)
+        if st[i] == 2:
+            assert abs(cost[i] - ref['cost']) <= COST_RTOL * abs(ref['cost']), (i, cost[i], ref['cost'])
+            pe, pv = cert.primal_residuals(model, cond, x0[i], lb[i], ub[i], fam)
+            assert pe <= 1e-9 and pv <= 2e-4, (i, pe, pv)
+            assert ds <= 1e-7, (i, ds)
+            assert abs(cost[i] - dob) <= 1e-6 * abs(cost[i]), (i, cost[i], dob)       # duality gap
+            assert dobj[i] == cost[i]
+        else:
+            n_inf += 1
+            assert np.isinf(cost[i])
+            y = np.concatenate(fam['mu'] + fam['nu_lb'] + fam['nu_ub'])
+            scale = np.sum(np.concatenate(fam['mu']) * arow[:cond.mc]) + np.sum(np.concatenate(fam['nu_lb'] + fam['nu_ub']))
+            assert ds <= 1e-9 * scale, (i, ds, scale)            # A'y = 0
+            assert dob > 1e-9 * scale, (i, dob, scale)           # positive cost: a Farkas proof
+            assert abs(dobj[i] - dob) <= 1e-9 * max(1., abs(dob))
+            assert y.min() >= 0.
+    return n_inf
+
+
+def test_cp20_random_nodes_match_oracle():
+    n_inf = _check_batch(load_model('cp20'), 96, seed=0, n_slots=32)
+    assert n_inf > 0          # the sample must exercise the Farkas path too
+
+
+def test_cp20_hot_start_equals_cold_cost():
+    """A node solved hot (from another node's working set) must reach the same optimum."""
+    model = load_model('cp20')
+    ctl = make_controller(model)
+    x0, lb, ub = random_nodes(model, 24, seed=3)
+    h = ctl.handle(n_slots=24)
+    cold = h.solve_nodes(x0, lb, ub)
+    hot = h.solve_nodes(x0, lb, ub, slot=np.zeros(24, np.int32), hot=np.ones(24, np.int32))
+    sc, sh = cold['status'].cpu().numpy(), hot['status'].cpu().numpy()
+    assert np.array_equal(sc, sh)
+    cc, ch = cold['cost'].cpu().numpy(), hot['cost'].cpu().numpy()
+    ok = sc == 2
+    assert np.all(np.abs(cc[ok] - ch[ok]) <= COST_RTOL * np.abs(cc[ok]))
+
+
+def test_syn30_random_nodes_match_oracle():
+    _check_batch(load_model('syn30'), 16, seed=1, n_slots=16)

@@ -1,0 +1,44 @@
+"""Shared helpers of the test-suite (test infrastructure: may import oracle/)."""
+import numpy as np
+
+
+def make_controller(model, **kw):
+    import warm_start_hmpc_b200 as ws
+    mld = ws.MLDSystem([model['A'], model['B']], [model['F'], model['G'], model['h']], int(model['nub']))
+    return ws.HybridModelPredictiveController(mld, int(model['T']), [model['Q'], model['R'], model['Q_T']],
+                                              [model['F_T'], model['h_T']], **kw)
+
+
+def random_nodes(model, N, seed=0, pin_prob=0.15):
+    """Seeded random (x0, partial identifier) pairs: prefix-in-time identifiers like the B&B produces."""
+    rng = np.random.default_rng(seed)
+    nx = model['A'].shape[0]
+    T, nub = int(model['T']), int(model['nub'])
+    nb = T * nub
+    xm = model['x_max'] * (np.array([0.7, 0.64, 1.0, 0.6]) if nx == 4 else 0.5)
+    x0 = rng.uniform(-1, 1, (N, nx)) * xm
+    lb = np.zeros((N, nb)); ub = np.ones((N, nb))
+    for k in range(N):
+        d = int(rng.integers(0, nb // 2))
+        vals = (rng.random(d) < pin_prob).astype(float)
+        lb[k, :d] = vals; ub[k, :d] = vals
+    return x0, lb, ub
+
+
+def families_from_records(pd, layout, status, primal, dual):
+    """GPU records -> the dict oracle/certify.py works on."""
+    T, nx, nu, nub, nh, nh1, nq, nqT, nr = pd.T, pd.nx, pd.nu, pd.nub, pd.nh, pd.nh1, pd.nq, pd.nqT, pd.nr
+    fam = {}
+    lam = dual[layout.off_lam:layout.off_mu].reshape(T + 1, nx)
+    mu = dual[layout.off_mu:layout.off_nu_lb]
+    fam['lam'] = [lam[t] for t in range(T + 1)]
+    fam['mu'] = [mu[t * nh:(t + 1) * nh] for t in range(T - 1)] + [mu[(T - 1) * nh:]]
+    fam['nu_lb'] = list(dual[layout.off_nu_lb:layout.off_nu_ub].reshape(T, nub))
+    fam['nu_ub'] = list(dual[layout.off_nu_ub:layout.off_rho].reshape(T, nub))
+    rho = dual[layout.off_rho:layout.off_sigma]
+    fam['rho'] = [rho[t * nq:(t + 1) * nq] for t in range(T)] + [rho[T * nq:]]
+    fam['sigma'] = list(dual[layout.off_sigma:layout.dual].reshape(T, nr))
+    if status == 2:
+        fam['x'] = primal[:(T + 1) * nx].reshape(T + 1, nx)
+        fam['u'] = primal[(T + 1) * nx:].reshape(T, nu)
+    return fam

@@ -1,0 +1,111 @@
+// records.cuh -- per-node outputs in the reference's layout (K1 epilogue).
+//
+// Replaces PrimalSolution.from_controller / DualSolution.from_controller
+// (subproblem_solution.py:68-99, 119-168) and BoundedQP.primal_objective / dual_objective
+// (bounded_qp.py:292-332):  primal record  x_0..x_T | u_0..u_{T-1},
+// dual record  lam_0..lam_T | mu_0..mu_{T-1} | nu_lb | nu_ub | rho_0..rho_T | sigma_0..sigma_{T-1}.
+#pragma once
+#include "qp_device.cuh"
+
+// yc: solution in orthonormal coordinates (shared memory), y: signed row multipliers (global, m).
+// scratch: >= n doubles of shared memory.  Returns cost (inf if infeasible) and dual objective.
+__device__ inline void build_records(const DevProblem &P, int status, const double *yc, const double *y,
+                                     const double *x0, const double *lb, const double *ub,
+                                     double *primal, double *dual, double *cost_out, double *dobj_out,
+                                     double *scratch, double *red)
+{
+    const int n = P.n, nx = P.nx, nu = P.nu, nub = P.nub, nuc = P.nuc, T = P.T, mc = P.mc, nb = P.nb;
+    double *X = primal, *U = primal + (size_t)(T + 1) * nx;
+    double *lam = dual + P.off_lam, *mu = dual + P.off_mu, *nulb = dual + P.off_nulb,
+           *nuub = dual + P.off_nuub, *rho = dual + P.off_rho, *sigma = dual + P.off_sigma;
+    const bool opt = status == WS_OPTIMAL;
+    double cost = INFINITY;
+    if (opt) {
+        // z = Zmap yc ; pinned binaries hold exactly (rows lb <= z_i <= ub with lb == ub)
+        for (int c = threadIdx.x; c < n; c += WS_NT) {
+            double s = 0.;
+            for (int j = 0; j < n; ++j) s += P.ZmapT[(size_t)j * n + c] * yc[j];
+            U[c] = s;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < nb; i += WS_NT) if (lb[i] == ub[i]) U[P.bin_idx[i]] = lb[i];
+        for (int j = threadIdx.x; j < nx; j += WS_NT) X[j] = x0[j];
+        __syncthreads();
+        for (int t = 0; t < T; ++t) {
+            for (int j = threadIdx.x; j < nx; j += WS_NT) {
+                double s = 0.;
+                for (int c = 0; c < nx; ++c) s += P.A[j * nx + c] * X[(size_t)t * nx + c];
+                for (int c = 0; c < nu; ++c) s += P.B[j * nu + c] * U[(size_t)t * nu + c];
+                X[(size_t)(t + 1) * nx + j] = s;
+            }
+            __syncthreads();
+        }
+        // rho_t = 2 Q x_t, rho_T = 2 Q_T x_T, sigma_t = 2 R u_t ; cost = 1/4 (|rho|^2 + |sigma|^2)
+        double part = 0.;
+        for (int e = threadIdx.x; e < T * P.nq; e += WS_NT) {
+            const int t = e / P.nq, i = e % P.nq;
+            double s = 0.;
+            for (int c = 0; c < nx; ++c) s += P.Q[i * nx + c] * X[(size_t)t * nx + c];
+            rho[e] = 2. * s; part += s * s;
+        }
+        for (int i = threadIdx.x; i < P.nqT; i += WS_NT) {
+            double s = 0.;
+            for (int c = 0; c < nx; ++c) s += P.QT[i * nx + c] * X[(size_t)T * nx + c];
+            rho[T * P.nq + i] = 2. * s; part += s * s;
+        }
+        for (int e = threadIdx.x; e < T * P.nr; e += WS_NT) {
+            const int t = e / P.nr, i = e % P.nr;
+            double s = 0.;
+            for (int c = 0; c < nu; ++c) s += P.R[i * nu + c] * U[(size_t)t * nu + c];
+            sigma[e] = 2. * s; part += s * s;
+        }
+        cost = block_sum(part, red);
+    } else {
+        for (int e = threadIdx.x; e < T * P.nq + P.nqT; e += WS_NT) rho[e] = 0.;
+        for (int e = threadIdx.x; e < T * P.nr; e += WS_NT) sigma[e] = 0.;
+    }
+    // multipliers of the inequality rows
+    for (int r = threadIdx.x; r < mc; r += WS_NT) mu[r] = y[r] > 0. ? y[r] : 0.;
+    for (int i = threadIdx.x; i < nb; i += WS_NT) {
+        const double yy = y[mc + i];
+        nuub[i] = yy > 0. ? yy : 0.;
+        nulb[i] = yy < 0. ? -yy : 0.;
+    }
+    __syncthreads();
+    // lam_T = -Q_T' rho_T ; lam_t = A' lam_{t+1} - Q' rho_t - F_t' mu_t
+    for (int j = threadIdx.x; j < nx; j += WS_NT) {
+        double s = 0.;
+        for (int i = 0; i < P.nqT; ++i) s += P.QT[i * nx + j] * rho[T * P.nq + i];
+        lam[(size_t)T * nx + j] = -s;
+    }
+    __syncthreads();
+    for (int t = T - 1; t >= 0; --t) {
+        const double *Ft = t < T - 1 ? P.F : P.F1;
+        const int k = t < T - 1 ? P.nh : P.nh1;
+        const double *mut = mu + (size_t)t * P.nh;
+        for (int j = threadIdx.x; j < nx; j += WS_NT) {
+            double s = 0.;
+            for (int c = 0; c < nx; ++c) s += P.A[c * nx + j] * lam[(size_t)(t + 1) * nx + c];
+            for (int i = 0; i < P.nq; ++i) s -= P.Q[i * nx + j] * rho[(size_t)t * P.nq + i];
+            for (int i = 0; i < k; ++i) s -= Ft[i * nx + j] * mut[i];
+            lam[(size_t)t * nx + j] = s;
+        }
+        __syncthreads();
+    }
+    double dobj = cost;
+    if (!opt) {
+        // cost of the Farkas proof: -(sum rhs_r y_r)  (bounded_qp.py:328-332)
+        double part = 0.;
+        for (int j = threadIdx.x; j < nx; j += WS_NT) part -= lam[j] * x0[j];
+        for (int r = threadIdx.x; r < mc; r += WS_NT) {
+            const int t = r / P.nh < T - 1 ? r / P.nh : T - 1;
+            const double hr = t < T - 1 ? P.h[r - t * P.nh] : P.h1[r - (T - 1) * P.nh];
+            part -= hr * mu[r];
+        }
+        for (int i = threadIdx.x; i < nb; i += WS_NT) part += lb[i] * nulb[i] - ub[i] * nuub[i];
+        dobj = block_sum(part, red);
+    }
+    if (threadIdx.x == 0) { *cost_out = cost; *dobj_out = dobj; }
+    __syncthreads();
+    (void)nub; (void)nuc; (void)scratch;
+}

@@ -1,0 +1,175 @@
+// wshmpc.cu -- kernels + C ABI (include/wshmpc.h) of the B200-native hybrid-MPC B&B hot path.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include "../../include/wshmpc.h"
+#include "qp_device.cuh"
+#include "records.cuh"
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+static thread_local std::string g_err;
+#define WS_FAIL(code, ...) do { char _b[512]; snprintf(_b, sizeof(_b), __VA_ARGS__); g_err = _b; return code; } while (0)
+#define WS_CUDA(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) WS_FAIL(-2, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(_e), __FILE__, __LINE__); } while (0)
+
+struct wshmpc_handle {
+    DevProblem P;
+    int device, n_slots;
+    cudaStream_t stream;
+    std::vector<void *> allocs;
+    double *slot_d;
+    int *slot_i;
+    double *ybuf;            // n_slots x m : signed row multipliers of the node being solved
+    size_t smem;
+    wshmpc_layout layout;
+};
+
+extern "C" const char *wshmpc_last_error(void) { return g_err.c_str(); }
+
+// ---------------------------------------------------------------------------------------------
+// K1: one CTA per solver slot; the CTA solves, in index order, every node assigned to its slot
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(WS_NT, 2)
+solve_nodes_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, int n_nodes,
+                   const double *__restrict__ x0, const double *__restrict__ lb, const double *__restrict__ ub,
+                   const int *__restrict__ slot_of, const int *__restrict__ hot,
+                   int *status, double *cost, double *dobj, int *iters, double *primal, double *dual)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int slot = blockIdx.x;
+    SlotPtrs sp = slot_ptrs(slot_d, slot_i, slot, P.n);
+    Smem sm = carve_smem(smem_raw, P.n, P.m, P.nb, P.r_in_smem, sp.Rg);
+    double *y = ybuf + (size_t)slot * P.m;
+    int k = 0;
+    bool loaded = false;
+    for (int i = 0; i < n_nodes; ++i) {
+        if (slot_of[i] != slot) continue;
+        const bool reset = hot[i] == 0;
+        if (!loaded || reset) { load_slot(P, sp, sm, k, reset); loaded = true; }
+        else begin_node(P, sm);
+        const double *xi = x0 + (size_t)i * P.nx, *lbi = lb + (size_t)i * P.nb, *ubi = ub + (size_t)i * P.nb;
+        const int st = qp_solve(P, sp, sm, k, xi, lbi, ubi, y, iters + i);
+        build_records(P, st, sm.yc, y, xi, lbi, ubi, primal + (size_t)i * P.n_primal,
+                      dual + (size_t)i * P.n_dual, cost + i, dobj + i, sm.c, sm.red);
+        if (threadIdx.x == 0) status[i] = st;
+        __syncthreads();
+    }
+    if (loaded) store_slot(P, sp, sm, k);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+template <class Tv>
+static int upload(wshmpc_handle *h, const Tv *src, size_t count, const Tv **dst) {
+    void *d = nullptr;
+    if (count == 0) count = 1;
+    WS_CUDA(cudaMalloc(&d, count * sizeof(Tv)));
+    h->allocs.push_back(d);
+    if (src) WS_CUDA(cudaMemcpy(d, src, count * sizeof(Tv), cudaMemcpyHostToDevice));
+    *dst = (const Tv *)d;
+    return 0;
+}
+
+static std::vector<double> transpose(const double *a, int rows, int cols) {
+    std::vector<double> t((size_t)rows * cols);
+    for (int i = 0; i < rows; ++i) for (int j = 0; j < cols; ++j) t[(size_t)j * rows + i] = a[(size_t)i * cols + j];
+    return t;
+}
+
+extern "C" int wshmpc_create(const wshmpc_problem *p, int device, int n_slots, void *stream, wshmpc_handle **out)
+{
+    if (!p || !out) WS_FAIL(-1, "null argument");
+    if (n_slots <= 0) WS_FAIL(-1, "n_slots must be positive");
+    if (p->n != p->T * p->nu || p->nb != p->T * p->nub || p->m != p->mc + p->nb ||
+        p->mc != (p->T - 1) * p->nh + p->nh1)
+        WS_FAIL(-1, "inconsistent sizes: n=%d m=%d mc=%d nb=%d", p->n, p->m, p->mc, p->nb);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) WS_FAIL(-3, "no CUDA device: the hot path has no CPU fallback");
+    WS_CUDA(cudaSetDevice(device));
+    wshmpc_handle *h = new wshmpc_handle();
+    h->device = device; h->n_slots = n_slots; h->stream = (cudaStream_t)stream;
+    DevProblem &P = h->P;
+    memset(&P, 0, sizeof(P));
+    P.nx = p->nx; P.nu = p->nu; P.nub = p->nub; P.nuc = p->nu - p->nub; P.T = p->T; P.nh = p->nh; P.nh1 = p->nh1;
+    P.nq = p->nq; P.nqT = p->nqT; P.nr = p->nr; P.n = p->n; P.m = p->m; P.mc = p->mc; P.nb = p->nb;
+    P.eps = p->eps; P.tol_p = p->tol_p; P.tol_d = p->tol_d; P.tol_sing = p->tol_sing; P.tol_ray = p->tol_ray;
+    P.prox_tol = p->prox_tol; P.max_iter = p->max_iter; P.max_prox = p->max_prox;
+    P.tri = (p->n + 1) * (p->n + 2) / 2;
+    const int nx = p->nx, nu = p->nu, n = p->n, m = p->m;
+    int rc = 0;
+#define UP(field, src, cnt) if ((rc = upload(h, src, (size_t)(cnt), &P.field))) { wshmpc_destroy(h); return rc; }
+    UP(A, p->A, nx * nx) UP(B, p->B, nx * nu) UP(F, p->F, p->nh * nx) UP(G, p->G, p->nh * nu) UP(h, p->h, p->nh)
+    UP(F1, p->F_Tm1, p->nh1 * nx) UP(G1, p->G_Tm1, p->nh1 * nu) UP(h1, p->h_Tm1, p->nh1)
+    UP(Q, p->Q, p->nq * nx) UP(R, p->R, p->nr * nu) UP(QT, p->Q_T, p->nqT * nx)
+    UP(Mmu, p->M_mu, p->nh * p->nh1) UP(Mrho, p->M_rho, p->nq * p->nqT)
+    UP(Mh, p->Mh, (size_t)m * n) UP(nrm, p->nrm, m) UP(vscale, p->vscale, m) UP(Eh, p->Eh, (size_t)p->mc * nx)
+    UP(hh, p->hh, p->mc) UP(Rinv, p->Rinv, (size_t)n * n) UP(Kx, p->Kx, (size_t)n * nx)
+    UP(bin_idx, p->bin_idx, p->nb)
+    {
+        std::vector<double> t = transpose(p->Mh, m, n); UP(MhT, t.data(), (size_t)m * n)
+        std::vector<double> r = transpose(p->Rinv, n, n); UP(RinvT, r.data(), (size_t)n * n)
+        std::vector<double> z = transpose(p->Zmap, n, n); UP(ZmapT, z.data(), (size_t)n * n)
+    }
+#undef UP
+    // record layout (subproblem_solution.py:86-91, 137-166)
+    wshmpc_layout &L = h->layout;
+    L.primal = (p->T + 1) * nx + p->T * nu;
+    L.off_lam = 0;
+    L.off_mu = (p->T + 1) * nx;
+    L.off_nu_lb = L.off_mu + p->mc;
+    L.off_nu_ub = L.off_nu_lb + p->nb;
+    L.off_rho = L.off_nu_ub + p->nb;
+    L.off_sigma = L.off_rho + p->T * p->nq + p->nqT;
+    L.dual = L.off_sigma + p->T * p->nr;
+    P.n_primal = L.primal; P.n_dual = L.dual; P.off_lam = L.off_lam; P.off_mu = L.off_mu; P.off_nulb = L.off_nu_lb;
+    P.off_nuub = L.off_nu_ub; P.off_rho = L.off_rho; P.off_sigma = L.off_sigma;
+    // shared memory budget: keep R in shared memory when two CTAs per SM still fit
+    cudaDeviceProp prop;
+    WS_CUDA(cudaGetDeviceProperties(&prop, device));
+    const size_t optin = prop.sharedMemPerBlockOptin;
+    P.r_in_smem = smem_bytes(n, m, p->nb, 1) <= optin ? 1 : 0;
+    h->smem = smem_bytes(n, m, p->nb, P.r_in_smem);
+    if (h->smem > optin) { wshmpc_destroy(h); WS_FAIL(-4, "problem too large: %zu bytes of shared memory needed, %zu available", h->smem, optin); }
+    WS_CUDA(cudaFuncSetAttribute(solve_nodes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+    // slot memory
+    void *d = nullptr;
+    WS_CUDA(cudaMalloc(&d, (size_t)n_slots * slot_doubles(n) * sizeof(double))); h->allocs.push_back(d); h->slot_d = (double *)d;
+    WS_CUDA(cudaMalloc(&d, (size_t)n_slots * slot_ints(n) * sizeof(int))); h->allocs.push_back(d); h->slot_i = (int *)d;
+    WS_CUDA(cudaMemset(h->slot_i, 0, (size_t)n_slots * slot_ints(n) * sizeof(int)));
+    WS_CUDA(cudaMalloc(&d, (size_t)n_slots * m * sizeof(double))); h->allocs.push_back(d); h->ybuf = (double *)d;
+    *out = h;
+    return 0;
+}
+
+extern "C" int wshmpc_destroy(wshmpc_handle *h)
+{
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    for (void *p : h->allocs) cudaFree(p);
+    delete h;
+    return 0;
+}
+
+extern "C" int wshmpc_get_layout(const wshmpc_handle *h, wshmpc_layout *out)
+{
+    if (!h || !out) WS_FAIL(-1, "null argument");
+    *out = h->layout;
+    return 0;
+}
+
+extern "C" int wshmpc_solve_nodes(wshmpc_handle *h, int n_nodes, const double *d_x0, const double *d_lb,
+                                  const double *d_ub, const int *d_slot, const int *d_hot,
+                                  int *d_status, double *d_cost, double *d_dobj, int *d_iters,
+                                  double *d_primal, double *d_dual)
+{
+    if (!h) WS_FAIL(-1, "null handle");
+    if (n_nodes <= 0) return 0;
+    WS_CUDA(cudaSetDevice(h->device));
+    solve_nodes_kernel<<<h->n_slots, WS_NT, h->smem, h->stream>>>(
+        h->P, h->slot_d, h->slot_i, h->ybuf, n_nodes, d_x0, d_lb, d_ub, d_slot, d_hot,
+        d_status, d_cost, d_dobj, d_iters, d_primal, d_dual);
+    WS_CUDA(cudaGetLastError());
+    return 0;
+}
