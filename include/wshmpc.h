@@ -83,6 +83,65 @@ int wshmpc_solve_nodes(wshmpc_handle *h, int n_nodes, const double *d_x0, const 
                        int *d_status, double *d_cost, double *d_dobj, int *d_iters,
                        double *d_primal, double *d_dual);
 
+/* ---------------------------------------------------------------------------------------------
+ * Branch-and-bound trees of a batch of independent MPC instances (device memory, caller-owned:
+ * torch tensors).  Replaces the Python `leaves` list of branch_and_bound.py:432 and the Node objects
+ * (branch_and_bound.py:7-55): instance k owns nodes [k][0 .. n_nodes[k]) in CREATION order, which is
+ * the order of the reference's list (children are appended, branch_and_bound.py:488-489; a branched
+ * node is removed = alive 0).  With the reference's default `branch_in_time` rule (controller.py:13-44)
+ * every identifier is a prefix of the chronological order (0,0),(0,1),...,(T-1,nub-1), so a node is
+ * (depth, value bits); time shifting keeps it a prefix (controller.py:476).
+ * Dual records follow wshmpc_layout.dual; children alias the parent's record (controller.py:426).
+ */
+typedef struct {
+    int cap_nodes, cap_recs, words;   /* words = ceil(T*nub / 32) uint32 per identifier */
+    int *n_nodes;                     /* [n_inst] */
+    int *n_recs;                      /* [n_inst] */
+    int *depth;                       /* [n_inst][cap_nodes]  number of pinned binaries */
+    int *alive;                       /* [n_inst][cap_nodes]  1 = leaf, 0 = branched (removed from `leaves`) */
+    int *rec;                         /* [n_inst][cap_nodes]  dual record of the node, -1 = None */
+    unsigned int *bits;               /* [n_inst][cap_nodes][words]  bit j = value of binary j = t*nub+i, j < depth */
+    double *lb;                       /* [n_inst][cap_nodes]  Node.lb */
+    double *rec_dobj;                 /* [n_inst][cap_recs]   DualSolution.objective */
+    double *rec_dual;                 /* [n_inst][cap_recs][layout.dual]  DualSolution.variables */
+} wshmpc_tree;
+
+/* K3 -- device-side branch and bound, one CTA per instance, no host round trip per node.
+ * Replaces branch_and_bound(solver, best_first, brancher, tol, warm_start) (branch_and_bound.py:408-499)
+ * with the controller's closures (controller.py:365-380): select = best_first (first minimum wins,
+ * branch_and_bound.py:541-563), solve = K1 (hot-started from the node solved before it), prune /
+ * incumbent / branch with child bounds from the parent's multipliers (controller.py:395-429).
+ * `tree` holds the initial leaves on entry (root node or warm start) and the final leaves on exit.
+ *   d_active    [n_inst] or NULL  instances with 0 are skipped
+ *   d_inc_cost  [n_inst]          optimal cost, +inf if the MIQP is infeasible
+ *   d_inc_node  [n_inst]          node index of the incumbent, -1 if none
+ *   d_inc_primal[n_inst][layout.primal]
+ *   d_n_solves  [n_inst]          number of QP relaxations solved
+ *   d_status    [n_inst]          0 optimal, 1 infeasible MIQP, 2 capacity reached, 3 QP iteration limit
+ *   d_trace     [n_inst][2*max_solves] or NULL : (node index, active-set iterations) of every solve, in order
+ */
+int wshmpc_bnb_solve(wshmpc_handle *h, int n_inst, const double *d_x0, const int *d_active,
+                     const wshmpc_tree *tree, double tol, int max_solves,
+                     double *d_inc_cost, int *d_inc_node, double *d_inc_primal, int *d_n_solves,
+                     int *d_status, int *d_trace);
+
+/* cold start: every instance gets the single root node Node({}) with lb = -inf (branch_and_bound.py:432) */
+int wshmpc_tree_init_root(wshmpc_handle *h, int n_inst, const wshmpc_tree *tree);
+
+/* K2 + K4 -- warm start for the next time step, one CTA per instance, one warp per leaf.
+ * Replaces construct_warm_start (controller.py:431-564) = _retain_leaf (:615-633) + identifier shift
+ * (:476) + _shift_dual_variables (:635-666) + _pi_sum (:668-721) + the runtime pi3 / lb rules
+ * (:541-558), and the plant update x <- x_1|t + e_t of the closed loop
+ * (notebooks/cart_pole_with_walls/statistical_analysis.py:194).
+ *   d_x0 [n_inst][nx] state the old tree was solved at; d_e0 [n_inst][nx] model error (NULL = 0)
+ *   d_inc_cost / d_inc_primal : incumbents of the old tree (u_0 = applied input)
+ *   d_active [n_inst] in/out or NULL : instances without incumbent are switched off
+ *   d_x_next [n_inst][nx] = x_1 + e0 ; d_u0 [n_inst][nu] applied input (either may be NULL)
+ */
+int wshmpc_shift_tree(wshmpc_handle *h, int n_inst, const double *d_x0, const double *d_e0,
+                      const wshmpc_tree *old_tree, const double *d_inc_cost, const double *d_inc_primal,
+                      int *d_active, const wshmpc_tree *new_tree, double *d_x_next, double *d_u0);
+
 #ifdef __cplusplus
 }
 #endif

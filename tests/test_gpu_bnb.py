@@ -1,0 +1,188 @@
+"""-m gpu: device-side branch and bound (K3) and warm-start construction (K2 + K4) through the C ABI.
+
+* K3 against the reference's host loop (branch_and_bound.py:408-499 restated in
+  warm_start_hmpc_b200.branch_and_bound) driven by the same K1 solves: identical explored node
+  sequence, identical leaves, bit-identical cost.
+* K3 against the golden run of the reference's own code + oracle QP core (tests/golden, made by
+  oracle/make_golden.py): identical mode sequence, cost and first input within 1e-6 relative.
+* K2/K4 against the output of the reference's construct_warm_start frozen in tests/golden.
+"""
+import os
+import numpy as np
+import pytest
+import torch
+
+from oracle.models import load_model, GOLDEN
+from tests.util import make_controller
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-6          # north_star: optimal cost and first control input within 1e-6 relative
+
+
+@pytest.fixture(scope='module')
+def cp20():
+    model = load_model('cp20')
+    return model, make_controller(model)
+
+
+def _ident_key(identifier):
+    return tuple(sorted(identifier.items()))
+
+
+def test_device_bnb_equals_host_bnb(cp20):
+    model, ctl = cp20
+    x0 = model['x0_nominal']
+    ctl.device_search = False
+    order = []
+    orig = ctl._solve_subproblem
+
+    def spy(identifier, x0_, active_set=None, hot=True):
+        order.append(_ident_key(identifier))
+        return orig(identifier, x0_, active_set, hot)
+    ctl._solve_subproblem = spy
+    try:
+        sol_h, leaves_h, n_h, _ = ctl.feedforward(x0, printing_period=None)
+    finally:
+        ctl._solve_subproblem = orig
+        ctl.device_search = True
+    res, tree = ctl.feedforward_batch(x0[None], trace=True, n_slots=1)
+    assert int(res['status'][0]) == 0
+    n_d = int(res['n_solves'][0])
+    assert n_d == n_h
+    assert float(res['cost'][0]) == sol_h.objective                       # bit-identical
+    # explored sequence
+    tr = res['trace'][0].cpu().numpy().reshape(-1, 2)[:n_d]
+    depth = tree.depth[0].cpu().numpy(); bits = tree.bits[0].cpu().numpy().view(np.uint32)
+    nub = ctl.mld.nub
+    dev_order = [tuple(sorted({(q // nub, q % nub): float((bits[j, q >> 5] >> (q & 31)) & 1) for q in range(depth[j])}.items()))
+                 for j in tr[:, 0]]
+    assert dev_order == order
+    # leaves: same identifiers in the same order, same bounds
+    leaves_d = ctl.tree_to_leaves(tree, 0)
+    assert [_ident_key(l.identifier) for l in leaves_d] == [_ident_key(l.identifier) for l in leaves_h]
+    assert np.array_equal(np.array([l.lb for l in leaves_d]), np.array([l.lb for l in leaves_h]))
+    # drop-in call returns the same thing
+    sol_d, leaves_dd, n_dd, _ = ctl.feedforward(x0, printing_period=None)
+    assert n_dd == n_h and sol_d.objective == sol_h.objective
+    for t in range(ctl.T):
+        assert np.array_equal(sol_d.variables['ub'][t], sol_h.variables['ub'][t])
+        assert np.array_equal(sol_d.variables['uc'][t], sol_h.variables['uc'][t])
+
+
+def test_device_bnb_matches_reference_golden(cp20):
+    model, ctl = cp20
+    g = np.load(os.path.join(GOLDEN, 'cp20_nodes.npz'))
+    sol, leaves, n_qp, _ = ctl.feedforward(g['x0'], printing_period=None)
+    assert abs(sol.objective - float(g['opt_cost'])) <= RTOL * abs(float(g['opt_cost']))
+    ub = np.array(sol.variables['ub'])
+    assert np.array_equal(ub, g['opt_ub'])                                # identical binary mode sequence
+    u0 = np.concatenate((sol.variables['uc'][0], sol.variables['ub'][0]))
+    assert np.allclose(u0[:1], g['opt_u0'][:1], rtol=RTOL, atol=1e-9)     # the force actually applied (fc)
+    assert n_qp == len(g['status'])                                       # 160 = published Gurobi count too
+
+
+def test_k1_on_golden_bnb_nodes(cp20):
+    """The 160 node QPs the reference B&B visited (oracle results frozen): status and cost parity."""
+    model, ctl = cp20
+    g = np.load(os.path.join(GOLDEN, 'cp20_nodes.npz'))
+    N = len(g['status'])
+    x0 = np.repeat(g['x0'][None], N, 0)
+    out = ctl.handle(n_slots=64).solve_nodes(x0, g['lb'], g['ub'])
+    st = out['status'].cpu().numpy(); cost = out['cost'].cpu().numpy()
+    assert np.array_equal(st, g['status'])
+    ok = st == 2
+    assert np.all(np.abs(cost[ok] - g['cost'][ok]) <= RTOL * np.abs(g['cost'][ok]))
+    assert np.all(np.isinf(cost[~ok]))
+    assert np.all(out['dobj'].cpu().numpy()[~ok] > 0.)
+
+
+def _upload_golden_tree(ctl, g):
+    h = ctl.handle()
+    n0 = len(g['lb'])
+    tree = ctl.new_tree(1, n0, 64)
+    dev = tree.lb.device
+    tree.n_nodes[0] = n0; tree.n_recs[0] = len(g['dobj'])
+    tree.depth[0, :n0] = torch.as_tensor(g['depth'], device=dev); tree.alive[0, :n0] = 1
+    tree.rec[0, :n0] = torch.as_tensor(g['rec'], device=dev); tree.lb[0, :n0] = torch.as_tensor(g['lb'], device=dev)
+    tree.bits[0, :n0] = torch.as_tensor(g['bits'].view(np.int32), device=dev)
+    tree.rec_dual[0, :len(g['dobj'])] = torch.as_tensor(g['recs'], device=dev)
+    tree.rec_dobj[0, :len(g['dobj'])] = torch.as_tensor(g['dobj'], device=dev)
+    return tree
+
+
+@pytest.mark.parametrize('tag', ['zero', 'rand'])
+def test_shift_tree_matches_reference_golden(cp20, tag):
+    """K2 + K4 on the reference's own leaves vs the reference's construct_warm_start output."""
+    model, ctl = cp20
+    g = np.load(os.path.join(GOLDEN, 'cp20_warmstart.npz'))
+    h = ctl.handle()
+    assert h.layout.dual == g['recs'].shape[1] == ctl.problem.layout.dual
+    tree = _upload_golden_tree(ctl, g)
+    dev = tree.lb.device
+    T, nx, nu = ctl.T, ctl.mld.nx, ctl.mld.nu
+    primal = torch.zeros((1, h.layout.primal), dtype=torch.float64, device=dev)
+    primal[0, nx:2 * nx] = torch.as_tensor(g['x1'], device=dev)
+    primal[0, (T + 1) * nx:(T + 1) * nx + nu] = torch.as_tensor(np.concatenate((g['uc0'], g['ub0'])), device=dev)
+    res = dict(x0=torch.as_tensor(g['x0'][None], device=dev).contiguous(), primal=primal,
+               cost=torch.zeros(1, dtype=torch.float64, device=dev))
+    e0 = np.zeros(nx) if tag == 'zero' else g['e_rand']
+    new, x_next, u0 = ctl.construct_warm_start_batch(res, tree, e0=e0[None])
+    n = int(new.n_nodes[0])
+    assert n == len(g['ws_%s_lb' % tag])                                 # cover size (77)
+    assert np.array_equal(new.depth[0, :n].cpu().numpy(), g['ws_%s_depth' % tag])
+    assert np.array_equal(new.bits[0, :n].cpu().numpy().view(np.uint32), g['ws_%s_bits' % tag])
+    lb = new.lb[0, :n].cpu().numpy(); ref = g['ws_%s_lb' % tag]
+    assert np.array_equal(np.isinf(lb), np.isinf(ref))
+    fin = np.isfinite(ref)
+    scale = max(1., np.abs(g['dobj']).max())
+    assert np.all(np.abs(lb[fin] - ref[fin]) <= 1e-11 * scale)
+    none = new.rec[0, :n].cpu().numpy() < 0
+    assert np.array_equal(none, g['ws_%s_none' % tag])
+    dobj = new.rec_dobj[0, :n].cpu().numpy()
+    assert np.all(np.abs(dobj[~none] - g['ws_%s_dobj' % tag][~none]) <= 1e-11 * scale)
+    assert np.allclose(x_next[0].cpu().numpy(), g['x1'] + e0, rtol=0, atol=0)
+    if tag == 'rand':
+        j = int(g['ws_rand_sample'])
+        rec = new.rec_dual[0, int(new.rec[0, j])].cpu().numpy()
+        assert np.allclose(rec, g['ws_rand_sample_rec'], rtol=1e-13, atol=1e-13)
+
+
+def test_closed_loop_warm_equals_cold_and_golden(cp20):
+    """Nominal closed loop: warm-started cost == cold-started cost every step (test_controller.py:165-170),
+    trajectory equals the golden run of the reference code, warm start needs far fewer QPs."""
+    model, ctl = cp20
+    from warm_start_hmpc_b200.closed_loop import ClosedLoop
+    g = np.load(os.path.join(GOLDEN, 'cp20_closed_loop.npz'))
+    n_steps = len(g['nom_cost'])
+    loops = {w: ClosedLoop(ctl, 1, warm=w, max_solves=1024, max_roots=512, n_slots=1) for w in (True, False)}
+    cost = {True: [], False: []}; nq = {True: [], False: []}; ub0 = []
+    for w, L in loops.items():
+        L.reset(model['x0_nominal'][None])
+        for t in range(n_steps):
+            out = L.step()
+            assert int(out['status'][0]) == 0
+            cost[w].append(float(out['cost'][0])); nq[w].append(int(out['n_solves'][0]))
+            if w:
+                T, nx, nu, nub = ctl.T, ctl.mld.nx, ctl.mld.nu, ctl.mld.nub
+                ub0.append(out['primal'][0, (T + 1) * nx:].reshape(T, nu)[:, nu - nub:].cpu().numpy().copy())
+    cw, cc = np.array(cost[True]), np.array(cost[False])
+    assert np.all(np.abs(cw - cc) <= 1e-9 * np.abs(cc))
+    assert np.all(np.abs(cc - g['nom_cost']) <= RTOL * np.abs(g['nom_cost']))
+    assert all(np.array_equal(ub0[t], g['nom_ub'][t]) for t in range(n_steps))
+    assert nq[False][0] == nq[True][0] == int(g['nom_n_cold'][0])
+    assert sum(nq[True][1:]) * 5 < sum(nq[False][1:])                     # published: 12.6x fewer QPs
+
+
+def test_batch_equals_single(cp20):
+    """Instances are independent: a batch over many slots gives bit-identical results to solving alone."""
+    model, ctl = cp20
+    rng = np.random.default_rng(7)
+    N = 24
+    x0 = model['x0_nominal'][None] + rng.uniform(-1, 1, (N, 4)) * np.array([0.05, 0.02, 0.2, 0.1])
+    res, tree = ctl.feedforward_batch(x0, n_slots=8)
+    c = res['cost'].cpu().numpy(); ns = res['n_solves'].cpu().numpy(); st = res['status'].cpu().numpy()
+    assert np.all(st <= 1)
+    for k in (0, 5, 23):
+        r1, _ = ctl.feedforward_batch(x0[k:k + 1], n_slots=1)
+        assert float(r1['cost'][0]) == c[k] or (np.isinf(c[k]) and np.isinf(float(r1['cost'][0])))
+        assert int(r1['n_solves'][0]) == ns[k]

@@ -9,6 +9,14 @@ def make_controller(model, **kw):
                                               [model['F_T'], model['h_T']], **kw)
 
 
+def make_problem(model, **kw):
+    """Host-side problem compiler only (no GPU, no library)."""
+    from warm_start_hmpc_b200.problem import ProblemData
+    return ProblemData(model['A'], model['B'], model['F'], model['G'], model['h'], int(model['nub']), int(model['T']),
+                       model['Q'], model['R'], model['Q_T'], model['F_Tm1'], model['G_Tm1'], model['h_Tm1'],
+                       model['M_mu'], model['M_rho'], **kw)
+
+
 def random_nodes(model, N, seed=0, pin_prob=0.15):
     """Seeded random (x0, partial identifier) pairs: prefix-in-time identifiers like the B&B produces."""
     rng = np.random.default_rng(seed)

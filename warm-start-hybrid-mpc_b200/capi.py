@@ -41,7 +41,44 @@ def load_library():
     return _lib
 
 
-EXPORTS = ('wshmpc_last_error', 'wshmpc_create', 'wshmpc_destroy', 'wshmpc_get_layout', 'wshmpc_solve_nodes')
+EXPORTS = ('wshmpc_last_error', 'wshmpc_create', 'wshmpc_destroy', 'wshmpc_get_layout', 'wshmpc_solve_nodes',
+           'wshmpc_tree_init_root', 'wshmpc_bnb_solve', 'wshmpc_shift_tree')
+
+
+class _Tree(C.Structure):
+    _fields_ = ([(k, C.c_int) for k in ('cap_nodes', 'cap_recs', 'words')]
+                + [(k, C.c_void_p) for k in ('n_nodes', 'n_recs', 'depth', 'alive', 'rec', 'bits', 'lb', 'rec_dobj',
+                                             'rec_dual')])
+
+
+class Tree(object):
+    """Device-resident B&B trees of `n_inst` independent MPC instances (wshmpc_tree in include/wshmpc.h).
+    torch owns the memory; the kernels read and write it in place."""
+
+    def __init__(self, n_inst, nb, n_dual, cap_nodes, cap_recs, device):
+        import torch
+        self.n_inst, self.nb, self.n_dual = n_inst, nb, n_dual
+        self.cap_nodes, self.cap_recs, self.words = cap_nodes, cap_recs, (nb + 31) // 32
+        i32 = dict(dtype=torch.int32, device=device)
+        f64 = dict(dtype=torch.float64, device=device)
+        self.n_nodes = torch.zeros(n_inst, **i32)
+        self.n_recs = torch.zeros(n_inst, **i32)
+        self.depth = torch.zeros((n_inst, cap_nodes), **i32)
+        self.alive = torch.zeros((n_inst, cap_nodes), **i32)
+        self.rec = torch.zeros((n_inst, cap_nodes), **i32)
+        self.bits = torch.zeros((n_inst, cap_nodes, self.words), **i32)     # uint32 payload
+        self.lb = torch.zeros((n_inst, cap_nodes), **f64)
+        self.rec_dobj = torch.zeros((n_inst, cap_recs), **f64)
+        self.rec_dual = torch.empty((n_inst, cap_recs, n_dual), **f64)
+        c = _Tree()
+        c.cap_nodes, c.cap_recs, c.words = cap_nodes, cap_recs, self.words
+        for k in ('n_nodes', 'n_recs', 'depth', 'alive', 'rec', 'bits', 'lb', 'rec_dobj', 'rec_dual'):
+            setattr(c, k, getattr(self, k).data_ptr())
+        self.c = c
+
+    def nbytes(self):
+        return sum(getattr(self, k).numel() * getattr(self, k).element_size()
+                   for k in ('n_nodes', 'n_recs', 'depth', 'alive', 'rec', 'bits', 'lb', 'rec_dobj', 'rec_dual'))
 
 
 def _check(rc):
@@ -112,3 +149,37 @@ class Handle(object):
                                            P(out['cost']), P(out['dobj']), P(out['iters']), P(out['primal']),
                                            P(out['dual'])))
         return out
+
+    # -- trees / K3 / K2+K4 ---------------------------------------------------------------------
+    def new_tree(self, n_inst, cap_nodes, cap_recs):
+        return Tree(n_inst, self.pd.nb, self.layout.dual, cap_nodes, cap_recs, self.torch_device)
+
+    def tree_init_root(self, tree):
+        _check(self.lib.wshmpc_tree_init_root(self._h, tree.n_inst, C.byref(tree.c)))
+
+    def bnb_solve(self, x0, tree, tol=0., max_solves=1024, active=None, out=None, trace=False):
+        """K3: branch and bound of every instance of `tree` at states x0 [n_inst, nx] (CUDA fp64 tensor).
+        Asynchronous on the handle's stream; returns a dict of CUDA tensors."""
+        import torch
+        dev = self.torch_device
+        N = tree.n_inst
+        assert x0.is_cuda and x0.dtype == torch.float64 and x0.is_contiguous() and x0.shape == (N, self.pd.nx)
+        if out is None:
+            out = dict(cost=torch.empty(N, dtype=torch.float64, device=dev),
+                       node=torch.empty(N, dtype=torch.int32, device=dev),
+                       primal=torch.zeros((N, self.layout.primal), dtype=torch.float64, device=dev),
+                       n_solves=torch.empty(N, dtype=torch.int32, device=dev),
+                       status=torch.empty(N, dtype=torch.int32, device=dev))
+        if trace:
+            out['trace'] = torch.full((N, 2 * max_solves), -1, dtype=torch.int32, device=dev)
+        P = lambda a: C.c_void_p(a.data_ptr()) if a is not None else None
+        _check(self.lib.wshmpc_bnb_solve(self._h, N, P(x0), P(active), C.byref(tree.c), C.c_double(tol), int(max_solves),
+                                         P(out['cost']), P(out['node']), P(out['primal']), P(out['n_solves']),
+                                         P(out['status']), P(out.get('trace'))))
+        return out
+
+    def shift_tree(self, x0, e0, old_tree, inc_cost, inc_primal, new_tree, active=None, x_next=None, u0=None):
+        """K2 + K4: warm start for the next step + plant update.  Asynchronous."""
+        P = lambda a: C.c_void_p(a.data_ptr()) if a is not None else None
+        _check(self.lib.wshmpc_shift_tree(self._h, old_tree.n_inst, P(x0), P(e0), C.byref(old_tree.c), P(inc_cost),
+                                          P(inc_primal), P(active), C.byref(new_tree.c), P(x_next), P(u0)))

@@ -1,0 +1,77 @@
+"""Batched closed loop of independent MPC instances, entirely on the device.
+
+Restates the experiment loop of notebooks/cart_pole_with_walls/statistical_analysis.py:93-196
+(without its Gurobi legs) for `n_inst` instances at once: per step  branch and bound (K3, warm- or
+cold-started)  ->  construct_warm_start + plant update x <- x_1|t + e_t (K2 + K4).  Two device trees
+are used alternately (the shift reads one and writes the other); nothing synchronises with the host
+unless the caller reads a result.  Instances are independent: under torch.distributed each rank owns
+a contiguous block of instances (`shard`) and no collective is on the data path.
+"""
+import numpy as np
+
+
+def shard(n_total, rank, world):
+    """Contiguous block [lo, hi) of the instances owned by `rank`."""
+    base, rem = divmod(n_total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class ClosedLoop(object):
+
+    def __init__(self, controller, n_inst, warm=True, tol=0., max_solves=1024, max_roots=512, n_slots=None):
+        import torch
+        self.ctl, self.n_inst, self.warm, self.tol = controller, n_inst, warm, tol
+        self.max_solves, self.max_roots = max_solves, max_roots
+        slots = n_slots if n_slots is not None else min(n_inst, controller.default_slots())
+        self.h = h = controller.handle(slots)
+        dev = h.torch_device
+        cap_nodes, cap_recs = max_roots + 2 * max_solves + 2, max_roots + max_solves + 1
+        self.trees = [h.new_tree(n_inst, cap_nodes, cap_recs) for _ in range(2)]
+        self.cur = 0
+        nx, nu = controller.mld.nx, controller.mld.nu
+        f64 = dict(dtype=torch.float64, device=dev)
+        self.x = torch.zeros((n_inst, nx), **f64)
+        self.x_next = torch.zeros((n_inst, nx), **f64)
+        self.u0 = torch.zeros((n_inst, nu), **f64)
+        self.active = torch.ones(n_inst, dtype=torch.int32, device=dev)
+        self.out = dict(cost=torch.zeros(n_inst, **f64), node=torch.zeros(n_inst, dtype=torch.int32, device=dev),
+                        primal=torch.zeros((n_inst, h.layout.primal), **f64),
+                        n_solves=torch.zeros(n_inst, dtype=torch.int32, device=dev),
+                        status=torch.zeros(n_inst, dtype=torch.int32, device=dev))
+        self.total_solves = torch.zeros((), dtype=torch.int64, device=dev)
+        self.fresh = True
+        self.launches = 0
+
+    def nbytes(self):
+        return sum(t.nbytes() for t in self.trees)
+
+    def reset(self, x0):
+        """New initial states [n_inst, nx]; the next step starts from the root node."""
+        import torch
+        self.x.copy_(torch.as_tensor(np.asarray(x0, dtype=float) if not torch.is_tensor(x0) else x0))
+        self.active.fill_(1)
+        self.total_solves.zero_()
+        self.fresh = True
+
+    def step(self, e=None, x=None):
+        """One receding-horizon step of every instance.  `x` (optional, [n_inst, nx] CUDA tensor)
+        overrides the state (measured state fed back from the host); `e` is the model error e_t."""
+        h = self.h
+        if x is not None:
+            self.x.copy_(x)
+        tree = self.trees[self.cur]
+        if self.fresh or not self.warm:
+            h.tree_init_root(tree); self.launches += 1
+            self.fresh = False
+        h.bnb_solve(self.x, tree, tol=self.tol, max_solves=self.max_solves, active=self.active, out=self.out)
+        self.launches += 1
+        self.total_solves += self.out['n_solves'].sum()
+        # K2 + K4 (in cold mode only its plant update matters: the next step re-initialises the root)
+        new = self.trees[1 - self.cur]
+        h.shift_tree(self.x, e, tree, self.out['cost'], self.out['primal'], new, active=self.active,
+                     x_next=self.x_next, u0=self.u0)
+        self.cur = 1 - self.cur
+        self.launches += 1
+        self.x, self.x_next = self.x_next, self.x
+        return self.out

@@ -22,6 +22,11 @@ from .subproblem_solution import SubproblemSolution, PrimalSolution, DualSolutio
 from .problem import ProblemData
 
 
+def _is_prefix(identifier, nub):
+    """True iff the identifier pins exactly the first len(identifier) binaries in chronological order."""
+    return all((q // nub, q % nub) in identifier for q in range(len(identifier)))
+
+
 def branch_in_time(identifier, nub):
     """controller.py:13-44: fix the binaries in chronological order, children [value 0, value 1]."""
     t = max([k[0] for k in identifier.keys()] + [0])
@@ -53,6 +58,8 @@ class HybridModelPredictiveController(object):
         self.device = device
         self._handle = None
         self._n_slots = 1
+        self.device_search = True
+        self.max_solves = 4096
 
     # -- construction ---------------------------------------------------------------------------
     def _check_input_sizes(self):
@@ -146,7 +153,14 @@ class HybridModelPredictiveController(object):
     # -- per-solve seam -------------------------------------------------------------------------
     def feedforward(self, x0, gurobi_params={}, search_rule=best_first, branch_rule=branch_in_time, **kwargs):
         """controller.py:329-393.  `gurobi_params` is accepted for signature compatibility and ignored
-        (there is no Gurobi underneath)."""
+        (there is no Gurobi underneath).  With the reference's default rules (best_first, branch_in_time)
+        and `device_search=True` the whole search runs in the device-side B&B kernel (K3); any other
+        rule, or `device_search=False`, runs the reference's host loop with one K1 launch per node --
+        both visit the same nodes in the same order and return bit-identical results."""
+        if self.device_search and search_rule is best_first and branch_rule is branch_in_time:
+            ws = kwargs.get('warm_start')
+            if ws is None or all(_is_prefix(l.identifier, self.mld.nub) for l in ws):
+                return self._feedforward_device(x0, kwargs.get('tol', 0.), ws)
         first = [True]
 
         def solver(identifier, cutoff, extra):
@@ -247,6 +261,149 @@ class HybridModelPredictiveController(object):
         pi_sum += .25 * squared(variables['rho'][self.T]) - .25 * squared(shifted_variables['rho'][self.T - 1])
         pi_sum += self.h_Tm1.dot(variables['mu'][self.T - 1]) - self.mld.h.dot(shifted_variables['mu'][self.T - 2])
         return pi_sum
+
+    # -- device-resident batch path (K3, K2 + K4) ----------------------------------------------------
+    def _as_device(self, a, shape):
+        import torch
+        t = torch.as_tensor(np.asarray(a, dtype=float) if not torch.is_tensor(a) else a, dtype=torch.float64,
+                            device=torch.device('cuda', self.device)).contiguous()
+        assert tuple(t.shape) == tuple(shape), (tuple(t.shape), tuple(shape))
+        return t
+
+    def new_tree(self, n_inst, n_roots=1, max_solves=None):
+        """Device tree with room for `n_roots` initial leaves and `max_solves` QP solves per instance."""
+        ms = self.max_solves if max_solves is None else max_solves
+        return self.handle().new_tree(n_inst, n_roots + 2 * ms + 2, n_roots + ms + 1)
+
+    def feedforward_batch(self, x0, warm_start=None, tol=0., max_solves=None, n_slots=None, active=None, trace=False,
+                          out=None):
+        """Batched feedforward (controller.py:329-393 for many independent initial states at once).
+        x0 [N, nx] (numpy or CUDA tensor); warm_start: a device `Tree` (from construct_warm_start_batch)
+        or None for the cold root.  Returns (result dict of CUDA tensors, tree); nothing is synchronised."""
+        ms = self.max_solves if max_solves is None else max_solves
+        N = x0.shape[0]
+        h = self.handle(n_slots if n_slots is not None else max(self._n_slots, min(N, self.default_slots())))
+        x0 = self._as_device(x0, (N, self.mld.nx))
+        tree = warm_start
+        if tree is None:
+            tree = self.new_tree(N, 1, ms)
+            h.tree_init_root(tree)
+        res = h.bnb_solve(x0, tree, tol=tol, max_solves=ms, active=active, out=out, trace=trace)
+        res['x0'] = x0
+        return res, tree
+
+    def construct_warm_start_batch(self, res, tree, e0=None, new_tree=None, active=None, x_next=None, u0=None,
+                                   max_solves=None):
+        """Batched construct_warm_start (controller.py:503-564) + plant update x <- x_1 + e0.
+        Returns (new_tree, x_next [N, nx], u0 [N, nu])."""
+        import torch
+        h = self.handle()
+        N = tree.n_inst
+        dev = torch.device('cuda', self.device)
+        if new_tree is None:
+            ms = self.max_solves if max_solves is None else max_solves
+            new_tree = h.new_tree(N, tree.cap_nodes + 2 * ms + 2, tree.cap_nodes + ms + 1)
+        if e0 is not None:
+            e0 = self._as_device(e0, (N, self.mld.nx))
+        if x_next is None:
+            x_next = torch.empty((N, self.mld.nx), dtype=torch.float64, device=dev)
+        if u0 is None:
+            u0 = torch.empty((N, self.mld.nu), dtype=torch.float64, device=dev)
+        h.shift_tree(res['x0'], e0, tree, res['cost'], res['primal'], new_tree, active=active, x_next=x_next, u0=u0)
+        return new_tree, x_next, u0
+
+    @staticmethod
+    def default_slots():
+        """Solver states resident at once: 2 CTAs per SM on the 148 SMs of a B200."""
+        import torch
+        return 2 * torch.cuda.get_device_properties(0).multi_processor_count
+
+    # -- tree <-> reference Node lists ---------------------------------------------------------------
+    def tree_to_leaves(self, tree, inst=0):
+        """The reference's `leaves` list (branch_and_bound.py:497) of one instance of a device tree."""
+        h = self.handle()
+        T, nub = self.T, self.mld.nub
+        nn = int(tree.n_nodes[inst])
+        depth = tree.depth[inst, :nn].cpu().numpy(); alive = tree.alive[inst, :nn].cpu().numpy()
+        rec = tree.rec[inst, :nn].cpu().numpy(); lb = tree.lb[inst, :nn].cpu().numpy()
+        bits = tree.bits[inst, :nn].cpu().numpy().view(np.uint32)
+        nr = int(tree.n_recs[inst])
+        duals = tree.rec_dual[inst, :nr].cpu().numpy(); dobj = tree.rec_dobj[inst, :nr].cpu().numpy()
+        cache = {}
+        leaves = []
+        for j in range(nn):
+            if not alive[j]:
+                continue
+            ident = {(q // nub, q % nub): float((bits[j, q >> 5] >> (q & 31)) & 1) for q in range(depth[j])}
+            r = int(rec[j])
+            if r < 0:
+                extra = SubproblemSolution(None, None) if depth[j] or np.isfinite(lb[j]) else None
+            else:
+                if r not in cache:          # children alias the parent's dual object (controller.py:426)
+                    cache[r] = DualSolution.from_record(self.problem, h.layout, duals[r], dobj[r])
+                extra = SubproblemSolution(None, cache[r])
+            node = Node(ident, float(lb[j]), extra)
+            node.index = j
+            leaves.append(node)
+        return leaves
+
+    def leaves_to_tree(self, leaves, max_solves=None):
+        """Uploads a reference-style warm start (list of Node with prefix identifiers) as a device tree."""
+        import torch
+        h = self.handle()
+        ms = self.max_solves if max_solves is None else max_solves
+        n0 = len(leaves)
+        tree = self.new_tree(1, n0, ms)
+        nub = self.mld.nub
+        depth = np.zeros(n0, np.int32); rec = np.full(n0, -1, np.int32); lb = np.zeros(n0)
+        bits = np.zeros((n0, tree.words), np.uint32)
+        recs, dobj, seen = [], [], {}
+        for j, l in enumerate(leaves):
+            depth[j] = len(l.identifier)
+            for (t, i), v in l.identifier.items():
+                if v:
+                    q = t * nub + i
+                    bits[j, q >> 5] |= np.uint32(1 << (q & 31))
+            lb[j] = l.lb
+            dual = None if l.extra is None else l.extra.dual
+            if dual is not None:
+                if id(dual) not in seen:
+                    seen[id(dual)] = len(recs)
+                    recs.append(DualSolution.to_record(self.problem, h.layout, dual.variables))
+                    dobj.append(dual.objective)
+                rec[j] = seen[id(dual)]
+        dev = tree.lb.device
+        tree.n_nodes[0] = n0; tree.n_recs[0] = len(recs)
+        tree.depth[0, :n0] = torch.as_tensor(depth, device=dev); tree.alive[0, :n0] = 1
+        tree.rec[0, :n0] = torch.as_tensor(rec, device=dev); tree.lb[0, :n0] = torch.as_tensor(lb, device=dev)
+        tree.bits[0, :n0] = torch.as_tensor(bits.view(np.int32), device=dev)
+        if recs:
+            tree.rec_dual[0, :len(recs)] = torch.as_tensor(np.vstack(recs), device=dev)
+            tree.rec_dobj[0, :len(recs)] = torch.as_tensor(np.array(dobj), device=dev)
+        return tree
+
+    def _feedforward_device(self, x0, tol, warm_start):
+        import torch
+        tree = None if warm_start is None else self.leaves_to_tree(warm_start)
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        res, tree = self.feedforward_batch(np.asarray(x0, dtype=float)[None], warm_start=tree, tol=tol, n_slots=1)
+        end.record()
+        end.synchronize()
+        solver_time = start.elapsed_time(end) * 1e-3
+        status = int(res['status'][0])
+        if status >= 2:
+            raise RuntimeError('device branch and bound failed with status %d (2 = capacity, 3 = QP iteration limit)' % status)
+        leaves = self.tree_to_leaves(tree, 0)
+        if warm_start is not None:          # the reference mutates the list it is given (branch_and_bound.py:432)
+            warm_start[:] = leaves
+            leaves = warm_start
+        self.last_batch = (res, tree)
+        n_qp = int(res['n_solves'][0])
+        if status == 1:
+            return None, leaves, n_qp, solver_time
+        primal = PrimalSolution.from_record(self.problem, res['primal'][0].cpu().numpy(), float(res['cost'][0]), True, True)
+        return primal, leaves, n_qp, solver_time
 
     def shift_binary_solution(self, ub):
         """controller.py:811-812."""

@@ -3,6 +3,7 @@
 #include "../../include/wshmpc.h"
 #include "qp_device.cuh"
 #include "records.cuh"
+#include "bnb.cuh"
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -21,6 +22,9 @@ struct wshmpc_handle {
     double *slot_d;
     int *slot_i;
     double *ybuf;            // n_slots x m : signed row multipliers of the node being solved
+    double *scratch;         // n_slots x bnb_scratch_doubles : node bounds, primal record of the node being solved
+    int *work_counter;       // instance hand-out of the B&B kernel
+    size_t shift_smem;
     size_t smem;
     wshmpc_layout layout;
 };
@@ -139,6 +143,12 @@ extern "C" int wshmpc_create(const wshmpc_problem *p, int device, int n_slots, v
     WS_CUDA(cudaMalloc(&d, (size_t)n_slots * slot_ints(n) * sizeof(int))); h->allocs.push_back(d); h->slot_i = (int *)d;
     WS_CUDA(cudaMemset(h->slot_i, 0, (size_t)n_slots * slot_ints(n) * sizeof(int)));
     WS_CUDA(cudaMalloc(&d, (size_t)n_slots * m * sizeof(double))); h->allocs.push_back(d); h->ybuf = (double *)d;
+    WS_CUDA(cudaFuncSetAttribute(bnb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+    WS_CUDA(cudaMalloc(&d, (size_t)n_slots * bnb_scratch_doubles(p->nb, L.primal) * sizeof(double))); h->allocs.push_back(d); h->scratch = (double *)d;
+    WS_CUDA(cudaMalloc(&d, 64)); h->allocs.push_back(d); h->work_counter = (int *)d;
+    h->shift_smem = shift_smem_bytes(P);
+    if (h->shift_smem > 48 * 1024)
+        WS_CUDA(cudaFuncSetAttribute(shift_tree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->shift_smem));
     *out = h;
     return 0;
 }
@@ -170,6 +180,72 @@ extern "C" int wshmpc_solve_nodes(wshmpc_handle *h, int n_nodes, const double *d
     solve_nodes_kernel<<<h->n_slots, WS_NT, h->smem, h->stream>>>(
         h->P, h->slot_d, h->slot_i, h->ybuf, n_nodes, d_x0, d_lb, d_ub, d_slot, d_hot,
         d_status, d_cost, d_dobj, d_iters, d_primal, d_dual);
+    WS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// trees, K3, K2 + K4
+// ---------------------------------------------------------------------------------------------
+static int tree_view(const wshmpc_handle *h, const wshmpc_tree *t, TreeView *v)
+{
+    if (!t) WS_FAIL(-1, "null tree");
+    if (t->words != (h->P.nb + 31) / 32) WS_FAIL(-1, "tree.words = %d, expected %d", t->words, (h->P.nb + 31) / 32);
+    if (t->cap_nodes < 3 || t->cap_recs < 1) WS_FAIL(-1, "tree capacity too small");
+    if (!t->n_nodes || !t->n_recs || !t->depth || !t->alive || !t->rec || !t->bits || !t->lb || !t->rec_dobj || !t->rec_dual)
+        WS_FAIL(-1, "null pointer in tree");
+    v->cap_nodes = t->cap_nodes; v->cap_recs = t->cap_recs; v->words = t->words;
+    v->n_nodes = t->n_nodes; v->n_recs = t->n_recs; v->depth = t->depth; v->alive = t->alive; v->rec = t->rec;
+    v->bits = t->bits; v->lb = t->lb; v->rec_dobj = t->rec_dobj; v->rec_dual = t->rec_dual;
+    return 0;
+}
+
+extern "C" int wshmpc_tree_init_root(wshmpc_handle *h, int n_inst, const wshmpc_tree *tree)
+{
+    if (!h) WS_FAIL(-1, "null handle");
+    if (n_inst <= 0) return 0;
+    TreeView tv; int rc = tree_view(h, tree, &tv); if (rc) return rc;
+    WS_CUDA(cudaSetDevice(h->device));
+    init_root_kernel<<<(n_inst + 127) / 128, 128, 0, h->stream>>>(n_inst, tv);
+    WS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int wshmpc_bnb_solve(wshmpc_handle *h, int n_inst, const double *d_x0, const int *d_active,
+                                const wshmpc_tree *tree, double tol, int max_solves,
+                                double *d_inc_cost, int *d_inc_node, double *d_inc_primal, int *d_n_solves,
+                                int *d_status, int *d_trace)
+{
+    if (!h) WS_FAIL(-1, "null handle");
+    if (n_inst <= 0) return 0;
+    if (max_solves <= 0) WS_FAIL(-1, "max_solves must be positive");
+    if (!d_x0 || !d_inc_cost || !d_inc_node || !d_inc_primal || !d_n_solves || !d_status) WS_FAIL(-1, "null argument");
+    TreeView tv; int rc = tree_view(h, tree, &tv); if (rc) return rc;
+    WS_CUDA(cudaSetDevice(h->device));
+    WS_CUDA(cudaMemsetAsync(h->work_counter, 0, sizeof(int), h->stream));
+    const int grid = n_inst < h->n_slots ? n_inst : h->n_slots;
+    bnb_kernel<<<grid, WS_NT, h->smem, h->stream>>>(
+        h->P, h->slot_d, h->slot_i, h->ybuf, h->scratch, h->work_counter, n_inst, d_x0, d_active, tv, tol, max_solves,
+        d_inc_cost, d_inc_node, d_inc_primal, d_n_solves, d_status, d_trace);
+    WS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int wshmpc_shift_tree(wshmpc_handle *h, int n_inst, const double *d_x0, const double *d_e0,
+                                 const wshmpc_tree *old_tree, const double *d_inc_cost, const double *d_inc_primal,
+                                 int *d_active, const wshmpc_tree *new_tree, double *d_x_next, double *d_u0)
+{
+    if (!h) WS_FAIL(-1, "null handle");
+    if (n_inst <= 0) return 0;
+    if (!d_x0 || !d_inc_cost || !d_inc_primal) WS_FAIL(-1, "null argument");
+    if (h->P.T < 2) WS_FAIL(-1, "tree shifting needs T >= 2");
+    if (h->P.nub > 32) WS_FAIL(-1, "tree shifting supports nub <= 32");
+    TreeView ov, nv; int rc = tree_view(h, old_tree, &ov); if (rc) return rc;
+    rc = tree_view(h, new_tree, &nv); if (rc) return rc;
+    if (ov.rec_dual == nv.rec_dual || ov.lb == nv.lb) WS_FAIL(-1, "old and new tree must be distinct buffers");
+    WS_CUDA(cudaSetDevice(h->device));
+    shift_tree_kernel<<<n_inst, SH_NT, h->shift_smem, h->stream>>>(
+        h->P, n_inst, d_x0, d_e0, ov, d_inc_cost, d_inc_primal, d_active, nv, d_x_next, d_u0);
     WS_CUDA(cudaGetLastError());
     return 0;
 }

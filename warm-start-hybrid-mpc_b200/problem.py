@@ -17,6 +17,21 @@ the curved directions are scaled column by column) and v = Rinv^-1 y + Rinv' f,
 import numpy as np
 
 
+class RecordLayout(object):
+    """Offsets (in doubles) of the per-node records, identical to wshmpc_layout (include/wshmpc.h):
+    primal  x_0..x_T | u_0..u_{T-1} ;  dual  lam | mu | nu_lb | nu_ub | rho | sigma."""
+
+    def __init__(self, T, nx, nu, nub, mc, nq, nqT, nr):
+        self.primal = (T + 1) * nx + T * nu
+        self.off_lam = 0
+        self.off_mu = (T + 1) * nx
+        self.off_nu_lb = self.off_mu + mc
+        self.off_nu_ub = self.off_nu_lb + T * nub
+        self.off_rho = self.off_nu_ub + T * nub
+        self.off_sigma = self.off_rho + T * nq + nqT
+        self.dual = self.off_sigma + T * nr
+
+
 class ProblemData(object):
     """All arrays the C ABI needs (contiguous fp64 / int32), plus sizes."""
 
@@ -38,6 +53,7 @@ class ProblemData(object):
         self.m = self.mc + self.nb
         self.tol_p, self.tol_d, self.tol_sing, self.tol_ray = tol_p, tol_d, tol_sing, tol_ray
         self.prox_tol, self.max_iter, self.max_prox = prox_tol, max_iter, max_prox
+        self.layout = RecordLayout(self.T, nx, nu, self.nub, self.mc, self.nq, self.nqT, self.nr)
         self._build(eps)
 
     def _build(self, eps):
