@@ -119,11 +119,12 @@ typedef struct {
  *   d_n_solves  [n_inst]          number of QP relaxations solved
  *   d_status    [n_inst]          0 optimal, 1 infeasible MIQP, 2 capacity reached, 3 QP iteration limit
  *   d_trace     [n_inst][2*max_solves] or NULL : (node index, active-set iterations) of every solve, in order
+ *   d_totals    [2] or NULL : running 64-bit counters, += QP relaxations solved, += active-set iterations
  */
 int wshmpc_bnb_solve(wshmpc_handle *h, int n_inst, const double *d_x0, const int *d_active,
                      const wshmpc_tree *tree, double tol, int max_solves,
                      double *d_inc_cost, int *d_inc_node, double *d_inc_primal, int *d_n_solves,
-                     int *d_status, int *d_trace);
+                     int *d_status, int *d_trace, unsigned long long *d_totals);
 
 /* cold start: every instance gets the single root node Node({}) with lb = -inf (branch_and_bound.py:432) */
 int wshmpc_tree_init_root(wshmpc_handle *h, int n_inst, const wshmpc_tree *tree);

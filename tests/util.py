@@ -50,3 +50,19 @@ def families_from_records(pd, layout, status, primal, dual):
         fam['x'] = primal[:(T + 1) * nx].reshape(T + 1, nx)
         fam['u'] = primal[(T + 1) * nx:].reshape(T, nu)
     return fam
+
+
+def leaves_from_golden(pd, g):
+    """tests/golden/cp20_warmstart.npz -> [(identifier, lb, DualSolution or None)] in leaf order."""
+    from warm_start_hmpc_b200.subproblem_solution import DualSolution
+    nub = pd.nub
+    cache = {}
+    out = []
+    for j in range(len(g['lb'])):
+        ident = {(q // nub, q % nub): float((g['bits'][j, q >> 5] >> np.uint32(q & 31)) & np.uint32(1))
+                 for q in range(int(g['depth'][j]))}
+        r = int(g['rec'][j])
+        if r >= 0 and r not in cache:
+            cache[r] = DualSolution.from_record(pd, pd.layout, g['recs'][r], float(g['dobj'][r]))
+        out.append((ident, float(g['lb'][j]), cache.get(r)))
+    return out

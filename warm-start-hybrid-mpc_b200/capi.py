@@ -157,7 +157,7 @@ class Handle(object):
     def tree_init_root(self, tree):
         _check(self.lib.wshmpc_tree_init_root(self._h, tree.n_inst, C.byref(tree.c)))
 
-    def bnb_solve(self, x0, tree, tol=0., max_solves=1024, active=None, out=None, trace=False):
+    def bnb_solve(self, x0, tree, tol=0., max_solves=1024, active=None, out=None, trace=False, totals=None):
         """K3: branch and bound of every instance of `tree` at states x0 [n_inst, nx] (CUDA fp64 tensor).
         Asynchronous on the handle's stream; returns a dict of CUDA tensors."""
         import torch
@@ -175,7 +175,7 @@ class Handle(object):
         P = lambda a: C.c_void_p(a.data_ptr()) if a is not None else None
         _check(self.lib.wshmpc_bnb_solve(self._h, N, P(x0), P(active), C.byref(tree.c), C.c_double(tol), int(max_solves),
                                          P(out['cost']), P(out['node']), P(out['primal']), P(out['n_solves']),
-                                         P(out['status']), P(out.get('trace'))))
+                                         P(out['status']), P(out.get('trace')), P(totals)))
         return out
 
     def shift_tree(self, x0, e0, old_tree, inc_cost, inc_primal, new_tree, active=None, x_next=None, u0=None):

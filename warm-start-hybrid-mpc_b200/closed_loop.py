@@ -39,7 +39,7 @@ class ClosedLoop(object):
                         primal=torch.zeros((n_inst, h.layout.primal), **f64),
                         n_solves=torch.zeros(n_inst, dtype=torch.int32, device=dev),
                         status=torch.zeros(n_inst, dtype=torch.int32, device=dev))
-        self.total_solves = torch.zeros((), dtype=torch.int64, device=dev)
+        self.totals = torch.zeros(2, dtype=torch.int64, device=dev)     # QP solves, active-set iterations
         self.fresh = True
         self.launches = 0
 
@@ -51,7 +51,7 @@ class ClosedLoop(object):
         import torch
         self.x.copy_(torch.as_tensor(np.asarray(x0, dtype=float) if not torch.is_tensor(x0) else x0))
         self.active.fill_(1)
-        self.total_solves.zero_()
+        self.totals.zero_()
         self.fresh = True
 
     def step(self, e=None, x=None):
@@ -64,9 +64,9 @@ class ClosedLoop(object):
         if self.fresh or not self.warm:
             h.tree_init_root(tree); self.launches += 1
             self.fresh = False
-        h.bnb_solve(self.x, tree, tol=self.tol, max_solves=self.max_solves, active=self.active, out=self.out)
+        h.bnb_solve(self.x, tree, tol=self.tol, max_solves=self.max_solves, active=self.active, out=self.out,
+                    totals=self.totals)
         self.launches += 1
-        self.total_solves += self.out['n_solves'].sum()
         # K2 + K4 (in cold mode only its plant update matters: the next step re-initialises the root)
         new = self.trees[1 - self.cur]
         h.shift_tree(self.x, e, tree, self.out['cost'], self.out['primal'], new, active=self.active,
@@ -75,3 +75,19 @@ class ClosedLoop(object):
         self.launches += 1
         self.x, self.x_next = self.x_next, self.x
         return self.out
+
+
+def reduce_stats(n_units, elapsed_ms, device=None):
+    """Whole-job aggregate under torch.distributed (one process per GPU, no data-path collective):
+    units are summed over ranks, time is the MAX over ranks.  Works with NCCL (CUDA tensors) and gloo
+    (CPU tensors); without an initialised process group it returns the inputs."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return int(n_units), float(elapsed_ms)
+    dev = device if device is not None else ('cuda' if dist.get_backend() == 'nccl' else 'cpu')
+    u = torch.tensor([int(n_units)], dtype=torch.int64, device=dev)
+    t = torch.tensor([float(elapsed_ms)], dtype=torch.float64, device=dev)
+    dist.all_reduce(u, op=dist.ReduceOp.SUM)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return int(u.item()), float(t.item())

@@ -104,8 +104,15 @@ class HybridModelPredictiveController(object):
         return np.vstack(cols).T if cols else np.zeros((n, 0))
 
     # -- device handle --------------------------------------------------------------------------
+    @staticmethod
+    def _require_gpu():
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError('no CUDA device: the B&B hot path has no CPU fallback')
+
     def handle(self, n_slots=None):
         from .capi import Handle
+        self._require_gpu()
         if n_slots is not None and (self._handle is None or n_slots > self._handle.n_slots):
             if self._handle is not None:
                 self._handle.close()
@@ -280,6 +287,7 @@ class HybridModelPredictiveController(object):
         """Batched feedforward (controller.py:329-393 for many independent initial states at once).
         x0 [N, nx] (numpy or CUDA tensor); warm_start: a device `Tree` (from construct_warm_start_batch)
         or None for the cold root.  Returns (result dict of CUDA tensors, tree); nothing is synchronised."""
+        self._require_gpu()
         ms = self.max_solves if max_solves is None else max_solves
         N = x0.shape[0]
         h = self.handle(n_slots if n_slots is not None else max(self._n_slots, min(N, self.default_slots())))
@@ -384,6 +392,7 @@ class HybridModelPredictiveController(object):
 
     def _feedforward_device(self, x0, tol, warm_start):
         import torch
+        self._require_gpu()
         tree = None if warm_start is None else self.leaves_to_tree(warm_start)
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         start.record()

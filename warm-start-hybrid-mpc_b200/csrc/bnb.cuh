@@ -40,7 +40,8 @@ __global__ void __launch_bounds__(WS_NT, 2)
 bnb_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, double *scratch, int *work_counter,
            int n_inst, const double *__restrict__ x0, const int *__restrict__ active, TreeView tr,
            double tol, int max_solves,
-           double *inc_cost, int *inc_node, double *inc_primal, int *n_solves, int *status_out, int *trace)
+           double *inc_cost, int *inc_node, double *inc_primal, int *n_solves, int *status_out, int *trace,
+           unsigned long long *totals)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_inst;
@@ -76,6 +77,7 @@ bnb_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, double *scra
         int nn = tr.n_nodes[inst], nr = tr.n_recs[inst];
         double ub = INFINITY;
         int inc = -1, solves = 0, st = -1, k = 0;
+        long long iters = 0;
         bool first = true;
 
         while (st < 0) {
@@ -112,6 +114,7 @@ bnb_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, double *scra
                 if (tr_i) { tr_i[2 * solves] = bi; tr_i[2 * solves + 1] = *iters_s; }
             }
             const int myrec = nr;
+            iters += *iters_s;
             ++nr; ++solves;
             // ---- prune / incumbent / branch (branch_and_bound.py:476-489)
             if (cost >= cutoff) {
@@ -141,6 +144,7 @@ bnb_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, double *scra
         if (threadIdx.x == 0) {
             tr.n_nodes[inst] = nn; tr.n_recs[inst] = nr;
             inc_cost[inst] = ub; inc_node[inst] = inc; n_solves[inst] = solves; status_out[inst] = st;
+            if (totals) { atomicAdd(totals, (unsigned long long)solves); atomicAdd(totals + 1, (unsigned long long)iters); }
         }
     }
 }

@@ -214,7 +214,7 @@ extern "C" int wshmpc_tree_init_root(wshmpc_handle *h, int n_inst, const wshmpc_
 extern "C" int wshmpc_bnb_solve(wshmpc_handle *h, int n_inst, const double *d_x0, const int *d_active,
                                 const wshmpc_tree *tree, double tol, int max_solves,
                                 double *d_inc_cost, int *d_inc_node, double *d_inc_primal, int *d_n_solves,
-                                int *d_status, int *d_trace)
+                                int *d_status, int *d_trace, unsigned long long *d_totals)
 {
     if (!h) WS_FAIL(-1, "null handle");
     if (n_inst <= 0) return 0;
@@ -226,7 +226,7 @@ extern "C" int wshmpc_bnb_solve(wshmpc_handle *h, int n_inst, const double *d_x0
     const int grid = n_inst < h->n_slots ? n_inst : h->n_slots;
     bnb_kernel<<<grid, WS_NT, h->smem, h->stream>>>(
         h->P, h->slot_d, h->slot_i, h->ybuf, h->scratch, h->work_counter, n_inst, d_x0, d_active, tv, tol, max_solves,
-        d_inc_cost, d_inc_node, d_inc_primal, d_n_solves, d_status, d_trace);
+        d_inc_cost, d_inc_node, d_inc_primal, d_n_solves, d_status, d_trace, d_totals);
     WS_CUDA(cudaGetLastError());
     return 0;
 }
