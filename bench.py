@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py -- B&B QP relaxations/s (and ms per MPC step, warm vs cold) of the hybrid-MPC hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1] per instance, configs[2] = 4096 instances over 8 GPUs as the batch):
+closed loop of the notebook two-wall cart-pole (T = 20), `--instances` independent initial states per GPU
+(tests/golden/cp20_instances.npy), model error e_t = sigma * randn * x_max, warm-started branch and bound
+with tree shifting.  One "step" = one receding-horizon step of the whole batch = K3 (device B&B, K1
+inside) + K2/K4 (tree shift + plant update).  Instances are independent: ranks own contiguous blocks
+of instances, there is no collective on the data path (weak scaling).
+
+Prints ONE JSON line (rank 0).  `value` = QP relaxations solved by all ranks / max-over-ranks device time,
+states resident in HBM; `e2e` = the same loop driven from HOST buffers through the public Python API
+(pinned H2D of the measured state and model error, D2H of input, cost and next state, every step).
+`--impl reference` times the CPU path (oracle/bnb_ref.py + oracle/qp_core.c, the restatement of the
+reference's Python B&B pinned bit-exactly against it -- Gurobi is not available offline) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'bnb_qp_relaxations_per_s'
+UNIT = 'QP/s'
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--instances', type=int, default=512, help='independent MPC instances per GPU')
+    ap.add_argument('--sigma', type=float, default=0.003, help='model error std (fraction of x_max)')
+    ap.add_argument('--max-solves', type=int, default=1024)
+    ap.add_argument('--max-roots', type=int, default=512)
+    ap.add_argument('--no-extras', action='store_true', help='skip cold / single-instance / cpu legs')
+    ap.add_argument('--cpu-seconds', type=float, default=15., help='budget of the cpu_baseline sample')
+    return ap.parse_args()
+
+
+def workload_config(args, world):
+    return {'workload': 'cp20_closed_loop_warm_start (two-wall cart-pole, T=20, nx=4, nu=7, 4 binaries/step; '
+                        'BASELINE configs[1] per instance, batched as configs[2])',
+            'instances_per_gpu': args.instances, 'instances_total': args.instances * world,
+            'horizon': 20, 'sigma': args.sigma, 'tol': 0.,
+            'step': 'one receding-horizon step of every instance: device B&B (K3+K1) + tree shift/plant update (K2+K4)',
+            'search': 'best_first / branch_in_time, reference order, no speculative solves',
+            'parallelism': 'instances sharded over %d GPU(s), no data-path collective' % world}
+
+
+def load_instances(lo, hi):
+    x = np.load(os.path.join(ROOT, 'tests', 'golden', 'cp20_instances.npy'))
+    idx = np.arange(lo, hi) % len(x)
+    return np.ascontiguousarray(x[idx])
+
+
+def noise(model, n_steps, n_inst, sigma, seed):
+    rng = np.random.default_rng(seed)
+    return sigma * rng.standard_normal((n_steps, n_inst, model['A'].shape[0])) * model['x_max']
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.samples.append(line.strip())
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        self.join(timeout=2.)
+        sm, mx, reasons = [], [], set()
+        for s in self.samples:
+            f = [v.strip() for v in s.split(',')]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except Exception:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU path (oracle restatement of the reference; the only place bench.py touches oracle/)
+# ---------------------------------------------------------------------------------------------------
+def _cpu_worker(job):
+    """Closed loop of one instance on one host core.  Returns per-step (t_start, t_end, solves)."""
+    k, x0, e, n_steps, budget = job
+    from oracle.models import load_model
+    from oracle.qp_c import CoreC
+    from oracle.bnb_ref import OracleController
+    model = load_model('cp20')
+    ctl = OracleController(model, CoreC(model), hot_start=True)
+    x = x0.copy(); ws = None; rows = []
+    t_begin = time.perf_counter()
+    for t in range(n_steps):
+        t0 = time.perf_counter()
+        inc, leaves, solves = ctl.feedforward(x, warm_start=ws)
+        if inc is None:
+            rows.append((t0, time.perf_counter(), solves)); break
+        u0 = inc.primal['u'][0]
+        ws = ctl.construct_warm_start(leaves, x, u0[:ctl.nuc], u0[ctl.nuc:], e[t])
+        x = inc.primal['x'][1] + e[t]
+        rows.append((t0, time.perf_counter(), solves))
+        if budget is not None and time.perf_counter() - t_begin > budget:
+            break
+    return rows, ctl.qp_time
+
+
+def cpu_baseline_sample(args, model, x0, e, seconds):
+    """rank 0, N = 1: instance 0 of the workload on ONE host core (the reference loop is single-threaded)."""
+    from oracle import qp_c
+    qp_c.build()
+    t0 = time.perf_counter()
+    rows, qp_time = _cpu_worker((0, x0[0], e[:, 0], e.shape[0], seconds))
+    wall = time.perf_counter() - t0
+    solves = sum(r[2] for r in rows)
+    return {'value': solves / wall, 'unit': UNIT, 'cores': 1, 'kind': 'port',
+            'sample': 'instance 0 of the workload, %d closed-loop steps (1 cold + %d warm), %d QPs in %.1f s; '
+                      'oracle/bnb_ref.py + oracle/qp_core.c (hot-started dual active-set), Python overhead included'
+                      % (len(rows), len(rows) - 1, solves, wall),
+            'qp_only_value': solves / max(qp_time, 1e-9), 'ms_per_qp': 1e3 * wall / max(solves, 1),
+            'host_cores_available': os.cpu_count()}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    world = args.gpus
+    import multiprocessing as mp
+    from oracle import qp_c
+    from oracle.models import load_model
+    qp_c.build()
+    model = load_model('cp20')
+    cores = max(1, os.cpu_count() or 1)
+    n_steps = args.warmup + args.steps
+    x0 = load_instances(0, cores)
+    e = noise(model, n_steps, cores, args.sigma, 1000)
+    jobs = [(k, x0[k], e[:, k], n_steps, None) for k in range(cores)]
+    with mp.get_context('fork').Pool(cores) as pool:
+        res = pool.map(_cpu_worker, jobs)
+    solves, t_lo, t_hi = 0, [], []
+    for rows, _ in res:
+        timed = rows[args.warmup:]
+        if not timed:
+            continue
+        solves += sum(r[2] for r in timed)
+        t_lo.append(timed[0][0]); t_hi.append(timed[-1][1])
+    # each worker has its own clock origin (perf_counter is monotonic system-wide on Linux): whole-job time
+    elapsed = max(hi - lo for lo, hi in zip(t_lo, t_hi)) if t_lo else float('nan')
+    value = solves / elapsed
+    cfg = workload_config(args, world)
+    sample = ('%d instances (one per host core) x %d timed closed-loop steps after %d warm-up steps (step 0 = cold solve); '
+              '%d QPs' % (cores, args.steps, args.warmup, solves))
+    line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': 1e3 * elapsed / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': cfg,
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample,
+                             'note': 'Gurobi (the reference QP back end) is not installable offline; the reference B&B / '
+                                     'warm-start logic is restated in oracle/bnb_ref.py (pinned bit-exactly against the '
+                                     'reference code) on the oracle C QP core'},
+            'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# B200 path
+# ---------------------------------------------------------------------------------------------------
+def fp64_peak_probe(torch, dev):
+    """cuBLAS DGEMM 4096^3, best of 5 (MEASURED_PEAKS.json has no fp64 entry)."""
+    n = 4096
+    a = torch.randn((n, n), dtype=torch.float64, device=dev); b = torch.randn((n, n), dtype=torch.float64, device=dev)
+    torch.matmul(a, b); torch.cuda.synchronize()
+    best = float('inf')
+    for _ in range(5):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); torch.matmul(a, b); e.record(); e.synchronize()
+        best = min(best, s.elapsed_time(e))
+    del a, b
+    return 2. * n ** 3 / (best * 1e-3) / 1e12
+
+
+def timed_loop(torch, dist, loop, e_dev, steps, world, e2e=None):
+    """Times `steps` steps bracketed by barrier + synchronize; returns (elapsed ms max over ranks, QPs, iterations)."""
+    from warm_start_hmpc_b200.closed_loop import reduce_stats
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    before = loop.totals.clone()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for t in range(steps):
+        if e2e is None:
+            loop.step(e=e_dev[t])
+        else:
+            e2e(t)
+    e.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = s.elapsed_time(e)
+    d = (loop.totals - before).cpu().numpy()
+    qps, ms_max = reduce_stats(int(d[0]), ms)
+    iters, _ = reduce_stats(int(d[1]), ms)
+    return ms_max, qps, iters, int(d[0])
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    rank = int(os.environ.get('RANK', '0')); world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py --impl b200 needs a GPU (there is no CPU fallback)')
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    if not os.path.exists(g.LIB):
+        if rank == 0:
+            g.build()
+        if world > 1:
+            dist.barrier()
+    from warm_start_hmpc_b200.instances import load_model, controller_from_model
+    from warm_start_hmpc_b200.closed_loop import ClosedLoop, shard
+    model = load_model('cp20')
+    ctl = controller_from_model(model, device=local)
+    dev = torch.device('cuda', local)
+    n_inst = args.instances
+    lo, hi = shard(n_inst * world, rank, world)
+    x0 = load_instances(lo, hi)
+    n_steps = args.warmup + args.steps
+    e_host = noise(model, 2 * n_steps + 8, n_inst, args.sigma, 1000 + rank)
+    e_dev = torch.as_tensor(e_host, device=dev)
+
+    loop = ClosedLoop(ctl, n_inst, warm=True, max_solves=args.max_solves, max_roots=args.max_roots)
+    tree_bytes = loop.nbytes()
+    loop.reset(x0)
+    for t in range(args.warmup):
+        loop.step(e=e_dev[t])
+    torch.cuda.synchronize()
+
+    # ---- device-resident timed region
+    sampler = ClockSampler(local); sampler.start(); time.sleep(0.3)
+    loop.events = []
+    l0 = loop.launches
+    ms, qps, iters, my_qps = timed_loop(torch, dist, loop, e_dev[args.warmup:], args.steps, world)
+    launches = loop.launches - l0
+    ev = loop.events; loop.events = None
+    clocks = sampler.stop()
+    bnb_ms = [a.elapsed_time(b) for a, b, c in ev]; shift_ms = [b.elapsed_time(c) for a, b, c in ev]
+    n_active = int(loop.active.sum())
+    status = loop.out['status'].cpu().numpy()
+    value = qps / (ms * 1e-3)
+
+    # ---- end-to-end through the public API with HOST buffers
+    nx, nu = ctl.mld.nx, ctl.mld.nu
+    pin = lambda *shape: torch.empty(shape, dtype=torch.float64).pin_memory()
+    xh, eh, uh, ch, xnh = pin(n_inst, nx), pin(n_inst, nx), pin(n_inst, nu), pin(n_inst), pin(n_inst, nx)
+    xd, ed = torch.empty((n_inst, nx), dtype=torch.float64, device=dev), torch.empty((n_inst, nx), dtype=torch.float64, device=dev)
+    xh.copy_(loop.x); torch.cuda.synchronize()
+    e_host_t = torch.as_tensor(e_host)
+
+    def e2e_step(t):
+        eh.copy_(e_host_t[n_steps + t])
+        xd.copy_(xh, non_blocking=True); ed.copy_(eh, non_blocking=True)          # measured state, model error
+        out = loop.step(e=ed, x=xd)
+        uh.copy_(loop.u0, non_blocking=True); ch.copy_(out['cost'], non_blocking=True); xnh.copy_(loop.x, non_blocking=True)
+        torch.cuda.synchronize()                                                    # the host needs u0 now
+        xh.copy_(xnh)
+    ms_e, qps_e, _, _ = timed_loop(torch, dist, loop, None, args.steps, world, e2e=e2e_step)
+    e2e = {'value': qps_e / (ms_e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': 2 * n_inst * nx * 8,
+           'd2h_bytes_per_step': n_inst * (nu + 1 + nx) * 8, 'ms_per_step': ms_e / args.steps,
+           'api': 'ClosedLoop.step(e, x) of warm_start_hmpc_b200 (ctypes -> C ABI wshmpc_bnb_solve + wshmpc_shift_tree)'}
+
+    # ---- roofline of the dominant kernel (bnb_kernel = K3 with K1 inside)
+    F_iter = 2. * ctl.problem.n ** 2 + 4. * ctl.problem.mc * ctl.problem.n      # flops / iteration
+    flops_per_launch = F_iter * iters / world / max(len(bnb_ms), 1)
+    bnb_avg_ms = float(np.mean(bnb_ms))
+    achieved = flops_per_launch / (bnb_avg_ms * 1e-3) / 1e12
+    peak = fp64_peak_probe(torch, dev)
+    roofline = {'bound': 'tensor', 'kernel': 'bnb_kernel', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
+                'frac': achieved / peak, 'traffic': None,
+                'peak_source': 'measured in this run: cuBLAS DGEMM 4096^3 best of 5 (fp64 pipe; MEASURED_PEAKS.json has no fp64 entry)',
+                'algorithmic': 'F_iter = 2 n^2 + 4 m_c n = %.0f flop per active-set iteration (SURVEY 8d), %.1f iterations/QP, '
+                               '%.0f QPs/launch' % (F_iter, iters / max(qps, 1), qps / world / max(len(bnb_ms), 1)),
+                'kernel_ms_avg': bnb_avg_ms, 'kernel_share_of_step': float(np.sum(bnb_ms) / ms),
+                'shift_kernel_ms_avg': float(np.mean(shift_ms))}
+    peaks_file = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(peaks_file):
+        roofline['hbm_peak_gbs_measured'] = json.load(open(peaks_file)).get('hbm_gbs')
+
+    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(args, world),
+            'roofline': roofline, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks,
+            'qp_per_step_per_instance': qps / args.steps / (n_inst * world),
+            'active_instances_rank0': n_active, 'bnb_status_counts_rank0': {int(k): int((status == k).sum()) for k in np.unique(status)}}
+    line['config']['l2'] = 'inputs larger than L2: two device trees of %.1f GB per rank, leaf records touched per step >> 126 MB' % (tree_bytes / 2 / 1e9)
+
+    # ---- extras (outside the timed region): cold start, single instance latency, CPU baseline
+    if not args.no_extras:
+        del loop
+        torch.cuda.empty_cache()
+        cold = ClosedLoop(ctl, n_inst, warm=False, max_solves=args.max_solves, max_roots=args.max_roots)
+        cold.reset(x0)
+        cold.step(e=e_dev[0])
+        ms_c, qps_c, _, _ = timed_loop(torch, dist, cold, e_dev[1:], 2, world)
+        line['cold_start'] = {'value': qps_c / (ms_c * 1e-3), 'unit': UNIT, 'ms_per_step': ms_c / 2,
+                              'qp_per_step_per_instance': qps_c / 2 / (n_inst * world)}
+        line['warm_start'] = {'value': value, 'unit': UNIT, 'ms_per_step': ms / args.steps,
+                              'qp_per_step_per_instance': line['qp_per_step_per_instance']}
+        del cold
+        torch.cuda.empty_cache()
+        if rank == 0:
+            single = {}
+            for warm in (True, False):
+                L = ClosedLoop(ctl, 1, warm=warm, max_solves=4096, max_roots=512, n_slots=1)
+                L.reset(model['x0_nominal'][None])
+                L.step(); torch.cuda.synchronize()
+                before = L.totals.clone()
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                k = 5
+                s.record()
+                for _ in range(k):
+                    L.step()
+                e.record(); torch.cuda.synchronize()
+                d = (L.totals - before).cpu().numpy()
+                single['warm' if warm else 'cold'] = {'ms_per_mpc_step': s.elapsed_time(e) / k, 'qp_per_step': float(d[0]) / k,
+                                                      'qp_per_s': float(d[0]) / (s.elapsed_time(e) * 1e-3)}
+            single['reference_published'] = {'cold_ms_per_mpc_step': 530., 'warm_ms_per_mpc_step': 37.4, 'qp_per_s': 300.,
+                                             'source': 'BASELINE.md (Gurobi, unknown CPU)'}
+            line['single_instance_nominal'] = single
+    if rank == 0 and world == 1 and not args.no_extras:
+        line['cpu_baseline'] = cpu_baseline_sample(args, model, x0, e_host, args.cpu_seconds)
+    elif rank == 0:
+        line['cpu_baseline'] = None
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    a = parse_args()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -42,6 +42,7 @@ class ClosedLoop(object):
         self.totals = torch.zeros(2, dtype=torch.int64, device=dev)     # QP solves, active-set iterations
         self.fresh = True
         self.launches = 0
+        self.events = None          # list -> (start, after K3, after K2+K4) CUDA events of every step
 
     def nbytes(self):
         return sum(t.nbytes() for t in self.trees)
@@ -64,15 +65,24 @@ class ClosedLoop(object):
         if self.fresh or not self.warm:
             h.tree_init_root(tree); self.launches += 1
             self.fresh = False
+        if self.events is not None:
+            import torch
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev[0].record()
         h.bnb_solve(self.x, tree, tol=self.tol, max_solves=self.max_solves, active=self.active, out=self.out,
                     totals=self.totals)
         self.launches += 1
+        if self.events is not None:
+            ev[1].record()
         # K2 + K4 (in cold mode only its plant update matters: the next step re-initialises the root)
         new = self.trees[1 - self.cur]
         h.shift_tree(self.x, e, tree, self.out['cost'], self.out['primal'], new, active=self.active,
                      x_next=self.x_next, u0=self.u0)
         self.cur = 1 - self.cur
         self.launches += 1
+        if self.events is not None:
+            ev[2].record()
+            self.events.append(tuple(ev))
         self.x, self.x_next = self.x_next, self.x
         return self.out
 
