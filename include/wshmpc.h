@@ -25,12 +25,14 @@ typedef struct {
     int nh, nh1;                 /* rows of F (stage) and of F_Tm1 (last stage, controller.py:85-87) */
     int nq, nqT, nr;             /* rows of Q, Q_T, R (controller.py:79) */
     int n, m, mc, nb;            /* n = T*nu condensed inputs, m = mc + nb rows, nb = T*nub */
+    int ns;                      /* n + T*nx : inputs and states of the sparse form */
     /* stage data (host pointers, row-major) */
     const double *A, *B, *F, *G, *h, *F_Tm1, *G_Tm1, *h_Tm1, *Q, *R, *Q_T;
     const double *M_mu;          /* nh x nh1, controller.py:186-227 */
     const double *M_rho;         /* nq x nqT, controller.py:96 */
     /* shared least-distance operator (host pointers) */
     const double *Mh;            /* m x n, unit rows */
+    const double *Wf;            /* ns x n : N Rinv, maps v to (inputs, states) for factored row pricing */
     const double *nrm;           /* m */
     const double *vscale;        /* m */
     const double *Eh;            /* mc x nx */

@@ -322,9 +322,9 @@ class HybridModelPredictiveController(object):
 
     @staticmethod
     def default_slots():
-        """Solver states resident at once: 2 CTAs per SM on the 148 SMs of a B200."""
+        """Solver states resident at once: one 512-thread CTA per SM (148 on a B200)."""
         import torch
-        return 2 * torch.cuda.get_device_properties(0).multi_processor_count
+        return torch.cuda.get_device_properties(0).multi_processor_count
 
     # -- tree <-> reference Node lists ---------------------------------------------------------------
     def tree_to_leaves(self, tree, inst=0):

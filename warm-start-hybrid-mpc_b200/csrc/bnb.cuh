@@ -36,7 +36,7 @@ __global__ void init_root_kernel(int n_inst, TreeView tr)
 // ---------------------------------------------------------------------------------------------
 // K3
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(WS_NT, 2)
+__global__ void __launch_bounds__(WS_NT, 1)
 bnb_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, double *scratch, int *work_counter,
            int n_inst, const double *__restrict__ x0, const int *__restrict__ active, TreeView tr,
            double tol, int max_solves,
@@ -48,7 +48,7 @@ bnb_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, double *scra
     const int slot = blockIdx.x;
     const int nb = P.nb;
     SlotPtrs sp = slot_ptrs(slot_d, slot_i, slot, P.n);
-    Smem sm = carve_smem(smem_raw, P.n, P.m, P.nb, P.r_in_smem, sp.Rg);
+    Smem sm = carve_smem(smem_raw, P.n, P.m, P.nb, P.ns, P.q_in_smem, sp.Q);
     double *y = ybuf + (size_t)slot * P.m;
     double *sc = scratch + (size_t)slot * bnb_scratch_doubles(nb, P.n_primal);
     double *lbv = sc, *ubv = sc + nb, *prim = sc + 2 * nb, *cost_s = prim + P.n_primal, *dobj_s = cost_s + 1;
@@ -107,7 +107,7 @@ bnb_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, double *scra
             const int qs = qp_solve(P, sp, sm, k, xi, lbv, ubv, y, iters_s);
             if (qs == WS_ITER_LIMIT) { st = BNB_QP_LIMIT; break; }
             double *dual = rdual + (size_t)nr * P.n_dual;
-            build_records(P, qs, sm.yc, y, xi, lbv, ubv, prim, dual, cost_s, dobj_s, sm.c, sm.red);
+            build_records(P, qs, sm.yc, y, xi, lbv, ubv, prim, dual, cost_s, dobj_s, sm.part, sm.red);
             const double cost = *cost_s;
             if (threadIdx.x == 0) {
                 lb[bi] = cost; rec[bi] = nr; rdobj[nr] = *dobj_s;

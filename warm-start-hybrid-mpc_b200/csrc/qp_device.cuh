@@ -4,11 +4,16 @@
 // relaxation of one node.  All nodes of all instances share the least-distance operator
 //     min_v 1/2 |v|^2   s.t.   bl_r <= mh_r . v <= bu_r        (unit rows mh_r, r < m)
 // and differ only in the bounds (x0 and the bounds on the relaxed binaries), see DESIGN.md.
-// One CTA (NT threads) owns one solver state ("slot"):
+// One CTA (WS_NT threads, one CTA per SM) owns one solver state ("slot"):
 //     working set W (rows, sides, multipliers lam >= 0 of the sign-normalised rows),
-//     Mw' = Q[:, :k] R   (Q n x n orthogonal, column major, global/L2;  R upper triangular, packed by
-//     columns, in SHARED memory when it fits),  Ri = R^-1 (packed, global) so that every solve with R
-//     is a parallel mat-vec instead of a sequential substitution,  yc = proximal centre.
+//     Mw' = Q[:, :k] R   Q n x n orthogonal, column major, in SHARED memory when it fits (157 KB for the
+//                        T=20 cart-pole), else in global memory / L2;
+//                        R upper triangular, packed by columns, global memory / L2;
+//     Ri = R^-1 (packed) so that every solve with R is a parallel mat-vec instead of a substitution,
+//     yc = proximal centre.
+// Rows are priced in FACTORED form: mh_r . x = a_r . (Wf x) / nrm_r with Wf = N Rinv (ns x n, shared by
+// every CTA, L2 resident) and a_r the sparse stage row [F_t G_t] of the MLD system, instead of streaming
+// the dense m x n operator (6x less L2 traffic on the cart-pole).
 // The state survives between nodes: any lam >= 0 is dual feasible for every node, so each node is
 // hot-started from whatever node the slot solved last.
 #pragma once
@@ -16,20 +21,20 @@
 #include <math.h>
 #include <stdint.h>
 
-#define WS_NT 256
+#define WS_NT 512
 #define WS_NW (WS_NT / 32)
 #define WS_OPTIMAL 2
 #define WS_INFEASIBLE 3
 #define WS_ITER_LIMIT 9
 
 struct DevProblem {
-    int nx, nu, nub, nuc, T, nh, nh1, nq, nqT, nr, n, m, mc, nb;
+    int nx, nu, nub, nuc, T, nh, nh1, nq, nqT, nr, n, m, mc, nb, ns;
     const double *A, *B, *F, *G, *h, *F1, *G1, *h1, *Q, *R, *QT, *Mmu, *Mrho;
-    const double *Mh, *MhT, *nrm, *vscale, *Eh, *hh, *Rinv, *RinvT, *Kx, *ZmapT;
+    const double *Mh, *Wf, *nrm, *inr, *vscale, *Eh, *hh, *Rinv, *RinvT, *Kx, *ZmapT;
     const int *bin_idx;
     double eps, tol_p, tol_d, tol_sing, tol_ray, prox_tol;
     int max_iter, max_prox;
-    int r_in_smem;           // 1: R lives in shared memory while a CTA works on the slot
+    int q_in_smem;           // 1: Q lives in shared memory while a CTA works on the slot
     int tri;                 // (n+1)(n+2)/2 packed triangle size
     // record layout
     int n_primal, n_dual, off_lam, off_mu, off_nulb, off_nuub, off_rho, off_sigma;
@@ -37,10 +42,11 @@ struct DevProblem {
 
 // per-slot persistent state in global memory
 struct SlotPtrs {
-    double *Q;      // n*n
+    double *Q;      // n*n   (home of Q; working copy when it does not fit in shared memory)
+    double *R;      // tri
     double *Ri;     // tri
-    double *Rg;     // tri (home of R)
-    double *tmp;    // tri (scratch for the Ri down-date)
+    double *tmp;    // tri (scratch: R down-date)
+    double *tmp2;   // tri (scratch: Ri down-date)
     double *lam;    // n+1
     double *yc;     // n
     int *row;       // n+1
@@ -50,7 +56,7 @@ struct SlotPtrs {
 
 __host__ __device__ inline size_t slot_doubles(int n) {
     size_t tri = (size_t)(n + 1) * (n + 2) / 2;
-    return (size_t)n * n + 3 * tri + (n + 1) + n;
+    return (size_t)n * n + 4 * tri + (n + 1) + n;
 }
 __host__ __device__ inline size_t slot_ints(int n) { return 2 * (size_t)(n + 1) + 4; }
 
@@ -60,9 +66,10 @@ __device__ inline SlotPtrs slot_ptrs(double *dbase, int *ibase, int slot, int n)
     double *d = dbase + (size_t)slot * slot_doubles(n);
     int *i = ibase + (size_t)slot * slot_ints(n);
     s.Q = d; d += (size_t)n * n;
+    s.R = d; d += tri;
     s.Ri = d; d += tri;
-    s.Rg = d; d += tri;
     s.tmp = d; d += tri;
+    s.tmp2 = d; d += tri;
     s.lam = d; d += n + 1;
     s.yc = d;
     s.row = i; i += n + 1;
@@ -73,30 +80,36 @@ __device__ inline SlotPtrs slot_ptrs(double *dbase, int *ibase, int slot, int n)
 
 // shared-memory working vectors of one CTA
 struct Smem {
-    double *v, *wv, *c, *hv, *t, *ls, *u, *yc, *lam, *bu, *blb, *gc, *gs, *red;
-    double *R;          // packed triangle (smem or global)
+    double *v, *wv, *c, *hv, *t, *ls, *u, *yc, *lam, *bu, *blb, *gc, *gs, *red, *xi, *mj, *part, *stage;
+    double *Q;          // n x n column major (smem or global)
     int *row, *side, *ired;
     signed char *inW;
     unsigned char *ign, *nadd;
 };
 
-__host__ __device__ inline size_t smem_bytes(int n, int m, int nb, int r_in_smem) {
-    size_t d = 9 * (size_t)(n + 1) + m + nb + 2 * (size_t)(n + 1) + 4 * WS_NW + 8;
-    if (r_in_smem) d += (size_t)(n + 1) * (n + 2) / 2;
+__host__ __device__ inline size_t smem_doubles(int n, int m, int nb, int ns) {
+    const size_t part = (size_t)(n > WS_NT ? n : WS_NT);
+    return 12 * (size_t)(n + 1) + m + nb + ns + part + 32 * 33 + 4 * WS_NW + 8;
+}
+__host__ __device__ inline size_t smem_bytes(int n, int m, int nb, int ns, int q_in_smem) {
+    size_t d = smem_doubles(n, m, nb, ns);
+    if (q_in_smem) d += (size_t)n * n;
     size_t b = d * 8 + (2 * (size_t)(n + 1) + 2 * WS_NW + 8) * 4 + 3 * (size_t)m + 16;
     return (b + 15) & ~(size_t)15;
 }
 
-__device__ inline Smem carve_smem(unsigned char *base, int n, int m, int nb, int r_in_smem, double *Rglobal) {
+__device__ inline Smem carve_smem(unsigned char *base, int n, int m, int nb, int ns, int q_in_smem, double *Qglobal) {
     Smem s;
     double *d = reinterpret_cast<double *>(base);
+    if (q_in_smem) { s.Q = d; d += (size_t)n * n; } else s.Q = Qglobal;
     s.v = d; d += n + 1;  s.wv = d; d += n + 1;  s.c = d; d += n + 1;  s.hv = d; d += n + 1;
     s.t = d; d += n + 1;  s.ls = d; d += n + 1;  s.u = d; d += n + 1;  s.yc = d; d += n + 1;
-    s.lam = d; d += n + 1;
-    s.bu = d; d += m;  s.blb = d; d += nb;
+    s.lam = d; d += n + 1;  s.mj = d; d += n + 1;
     s.gc = d; d += n + 1;  s.gs = d; d += n + 1;
+    s.bu = d; d += m;  s.blb = d; d += nb;  s.xi = d; d += ns;
+    s.part = d; d += (n > WS_NT ? n : WS_NT);
+    s.stage = d; d += 32 * 33;
     s.red = d; d += 4 * WS_NW + 8;
-    if (r_in_smem) { s.R = d; d += (size_t)(n + 1) * (n + 2) / 2; } else s.R = Rglobal;
     int *i = reinterpret_cast<int *>(d);
     s.row = i; i += n + 1;  s.side = i; i += n + 1;  s.ired = i; i += 2 * WS_NW + 8;
     signed char *b = reinterpret_cast<signed char *>(i);
@@ -155,50 +168,113 @@ __device__ inline void block_argmin(double &val, int &idx, double *red, int *ire
 }
 
 // ---------------------------------------------------------------------------------------------
-// factor updates
+// grouped mat-vec:  out(i, sum_{j0 <= j < j1} M[j * ld + i] * x[j])  for i < rows.
+// Adjacent threads take adjacent i (coalesced / conflict free); when rows <= WS_NT the threads form
+// G = WS_NT / rows groups that split the j range and combine through `part` (>= max(WS_NT, rows) doubles).
+// Ends with a barrier-protected combine; `out` is called once per row.  Contains __syncthreads.
 // ---------------------------------------------------------------------------------------------
-
-// t = Ri * c[:k]   (thread per row; Ri packed by columns -> coalesced over rows)
-__device__ inline void ri_matvec(const double *Ri, int k, const double *c, double *t) {
-    for (int i = threadIdx.x; i < k; i += WS_NT) {
-        double s = 0.;
-        for (int j = i; j < k; ++j) s += Ri[tri_off(j) + i] * c[j];
-        t[i] = s;
+template <class Out>
+__device__ inline void grouped_matvec(const double *__restrict__ M, int ld, int rows, int j0, int j1,
+                                      const double *x, double *part, Out out) {
+    if (rows <= WS_NT) {
+        const int G = WS_NT / rows;
+        const int g = threadIdx.x / rows, i = threadIdx.x - g * rows;
+        if (g < G) {
+            double s0 = 0., s1 = 0.;
+            int j = j0 + g;
+            for (; j + G < j1; j += 2 * G) {
+                s0 += M[(size_t)j * ld + i] * x[j];
+                s1 += M[(size_t)(j + G) * ld + i] * x[j + G];
+            }
+            if (j < j1) s0 += M[(size_t)j * ld + i] * x[j];
+            part[g * rows + i] = s0 + s1;
+        }
+        __syncthreads();
+        if (threadIdx.x < rows) {
+            double s = part[threadIdx.x];
+            for (int q = 1; q < G; ++q) s += part[q * rows + threadIdx.x];
+            out(threadIdx.x, s);
+        }
+        __syncthreads();
+    } else {
+        for (int i = threadIdx.x; i < rows; i += WS_NT) {
+            double s0 = 0., s1 = 0.;
+            int j = j0;
+            for (; j + 1 < j1; j += 2) { s0 += M[(size_t)j * ld + i] * x[j]; s1 += M[(size_t)(j + 1) * ld + i] * x[j + 1]; }
+            if (j < j1) s0 += M[(size_t)j * ld + i] * x[j];
+            out(i, s0 + s1);
+        }
+        __syncthreads();
     }
 }
 
-// u = Ri' * d[:k]  (thread per column: u_j = sum_{i<=j} Ri[i][j] d_i)
-__device__ inline void rit_matvec(const double *Ri, int k, const double *d, double *u) {
-    for (int j = threadIdx.x; j < k; j += WS_NT) {
+// ---------------------------------------------------------------------------------------------
+// factor updates
+// ---------------------------------------------------------------------------------------------
+
+// t = Ri * c[:k]   (t_i = sum_{j >= i} Ri[tri_off(j) + i] c_j ; adjacent threads -> adjacent i, coalesced)
+__device__ inline void ri_matvec(const double *__restrict__ Ri, int k, const double *c, double *t, double *part) {
+    if (k <= 0) { __syncthreads(); return; }
+    if (k <= WS_NT) {
+        const int G = WS_NT / k;
+        const int g = threadIdx.x / k, i = threadIdx.x - g * k;
+        if (g < G) {
+            double s = 0.;
+            for (int j = i + g; j < k; j += G) s += Ri[tri_off(j) + i] * c[j];
+            part[g * k + i] = s;
+        }
+        __syncthreads();
+        if (threadIdx.x < k) {
+            double s = part[threadIdx.x];
+            for (int q = 1; q < G; ++q) s += part[q * k + threadIdx.x];
+            t[threadIdx.x] = s;
+        }
+    } else {
+        for (int i = threadIdx.x; i < k; i += WS_NT) {
+            double s = 0.;
+            for (int j = i; j < k; ++j) s += Ri[tri_off(j) + i] * c[j];
+            t[i] = s;
+        }
+    }
+    __syncthreads();
+}
+
+// u = Ri' * d[:k]  (u_j = sum_{i <= j} Ri[tri_off(j) + i] d_i ; warp per column, lanes over rows)
+__device__ inline void rit_matvec(const double *__restrict__ Ri, int k, const double *d, double *u) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int j = w; j < k; j += WS_NW) {
         const double *col = Ri + tri_off(j);
         double s = 0.;
-        for (int i = 0; i <= j; ++i) s += col[i] * d[i];
-        u[j] = s;
+        for (int i = lane; i <= j; i += 32) s += col[i] * d[i];
+        s = warp_sum(s);
+        if (lane == 0) u[j] = s;
     }
+    __syncthreads();
 }
 
 // Try to append the sign-normalised row (r, sgn).  Returns 1 if appended (lam = 0), 0 if the row is
 // numerically in the span of the working rows; in that case sm.t = R^-1 c[:k]  (mj = Mw' t).
 __device__ inline int qr_append(const DevProblem &P, const SlotPtrs &sp, Smem &sm, int &k, int r, int sgn) {
     const int n = P.n, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const double *mj = P.Mh + (size_t)r * n;
-    // c = sgn * Q' mj   (warp per column)
-    for (int col = w; col < n; col += WS_NW) {
-        const double *q = sp.Q + (size_t)col * n;
-        double s = 0.;
-        for (int i = lane; i < n; i += 32) s += q[i] * mj[i];
-        s = warp_sum(s);
-        if (lane == 0) sm.c[col] = (double)sgn * s;
+    const double *Q = sm.Q;
+    for (int i = threadIdx.x; i < n; i += WS_NT) sm.mj[i] = P.Mh[(size_t)r * n + i];
+    __syncthreads();
+    // c = sgn * Q' mj   (warp per column, two columns in flight)
+    for (int col = w; col < n; col += 2 * WS_NW) {
+        const int col2 = col + WS_NW;
+        const double *q0 = Q + (size_t)col * n, *q1 = Q + (size_t)(col2 < n ? col2 : col) * n;
+        double s0 = 0., s1 = 0.;
+        for (int i = lane; i < n; i += 32) { const double x = sm.mj[i]; s0 += q0[i] * x; s1 += q1[i] * x; }
+        s0 = warp_sum(s0); s1 = warp_sum(s1);
+        if (lane == 0) { sm.c[col] = (double)sgn * s0; if (col2 < n) sm.c[col2] = (double)sgn * s1; }
     }
     __syncthreads();
     double part = 0.;
     for (int j = k + threadIdx.x; j < n; j += WS_NT) part += sm.c[j] * sm.c[j];
     const double rho2 = block_sum(part, sm.red);
-    if (k >= n || rho2 <= P.tol_sing * P.tol_sing) {
-        ri_matvec(sp.Ri, k, sm.c, sm.t);
-        __syncthreads();
-        return 0;
-    }
+    // t = Ri c1: the dual ray of a dependent row / the new column of Ri (before R, Ri are touched)
+    ri_matvec(sp.Ri, k, sm.c, sm.t, sm.part);
+    if (k >= n || rho2 <= P.tol_sing * P.tol_sing) return 0;
     const double rho = sqrt(rho2);
     const double ck = sm.c[k];
     const double sg = ck >= 0. ? 1. : -1.;
@@ -207,18 +283,36 @@ __device__ inline int qr_append(const DevProblem &P, const SlotPtrs &sp, Smem &s
     const double beta = 2. / hh;
     __syncthreads();
     for (int j = k + threadIdx.x; j < n; j += WS_NT) sm.hv[j] = (j == k) ? hk : sm.c[j];
-    // t = Ri c1 for the new column of Ri (before R / Ri are touched)
-    ri_matvec(sp.Ri, k, sm.c, sm.t);
     __syncthreads();
-    // Q2 <- Q2 - beta (Q2 hv) hv'   (thread per row, coalesced in the column-major Q)
-    for (int i = threadIdx.x; i < n; i += WS_NT) {
-        double a = 0.;
-        for (int j = k; j < n; ++j) a += sp.Q[(size_t)j * n + i] * sm.hv[j];
-        a *= beta;
-        for (int j = k; j < n; ++j) sp.Q[(size_t)j * n + i] -= a * sm.hv[j];
+    // Q2 <- Q2 - beta (Q2 hv) hv'   (adjacent threads -> adjacent rows of the column-major Q)
+    {
+        double *Qw = sm.Q;
+        if (n <= WS_NT) {
+            const int G = WS_NT / n;
+            const int g = threadIdx.x / n, i = threadIdx.x - g * n;
+            if (g < G) {
+                double a = 0.;
+                for (int j = k + g; j < n; j += G) a += Qw[(size_t)j * n + i] * sm.hv[j];
+                sm.part[g * n + i] = a;
+            }
+            __syncthreads();
+            if (g < G) {
+                double a = sm.part[i];
+                for (int q = 1; q < G; ++q) a += sm.part[q * n + i];
+                a *= beta;
+                for (int j = k + g; j < n; j += G) Qw[(size_t)j * n + i] -= a * sm.hv[j];
+            }
+        } else {
+            for (int i = threadIdx.x; i < n; i += WS_NT) {
+                double a = 0.;
+                for (int j = k; j < n; ++j) a += Qw[(size_t)j * n + i] * sm.hv[j];
+                a *= beta;
+                for (int j = k; j < n; ++j) Qw[(size_t)j * n + i] -= a * sm.hv[j];
+            }
+        }
     }
     const double rkk = -sg * rho, irkk = 1. / rkk;
-    double *Rc = sm.R + tri_off(k), *Ric = sp.Ri + tri_off(k);
+    double *Rc = sp.R + tri_off(k), *Ric = sp.Ri + tri_off(k);
     for (int i = threadIdx.x; i < k; i += WS_NT) { Rc[i] = sm.c[i]; Ric[i] = -sm.t[i] * irkk; }
     if (threadIdx.x == 0) {
         Rc[k] = rkk; Ric[k] = irkk;
@@ -233,79 +327,93 @@ __device__ inline int qr_append(const DevProblem &P, const SlotPtrs &sp, Smem &s
 // rotations of rows (i, i+1), i = kp..k-2; the same rotations act on the columns of Q and of R^-1.
 __device__ inline void qr_remove(const DevProblem &P, const SlotPtrs &sp, Smem &sm, int &k, int kp) {
     const int n = P.n, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int nrot = k - 1 - kp;          // rotations i = kp .. k-2
-    double *R = sm.R;
-    // ---- 1. Givens chain on the Hessenberg part of R, one warp, columns distributed over lanes.
-    // Old column j (> kp) keeps its storage while it is rotated; it becomes new column j-1.
-    if (w == 0 && nrot > 0) {
-        for (int i = kp; i < k - 1; ++i) {
-            const int jown = i + 1;                       // old column that defines rotation i
-            double cs = 1., sn = 0.;
-            {
-                // every lane reads the two defining entries (broadcast read, already up to date
-                // because the owner lane finished rotation i-1 on this column in the last step)
-                const double a = R[tri_off(jown) + i], b = R[tri_off(jown) + i + 1];
-                const double hyp = sqrt(a * a + b * b);
-                if (hyp > 0.) { const double ih = 1. / hyp; cs = a * ih; sn = b * ih; }
+    const double *R = sp.R;
+    double *Rn = sp.tmp;                  // new R (columns kp .. k-2), built out of place
+    // ---- 1. warp 0: Givens chain.  Old column j (> kp) becomes new column j-1.  A lane owns one
+    // column of a block of 32 and carries its running entry in a register: entries of R are read once
+    // (no read-after-write through L2).  The other warps copy the untouched rows < kp meanwhile.
+    if (w == 0) {
+        for (int j0 = kp + 1; j0 < k; j0 += 32) {
+            const int j = j0 + lane;
+            const bool has = j < k;
+            const double *col = R + tri_off(has ? j : kp);
+            double *out = Rn + tri_off(has ? j - 1 : kp);
+            double carry = has ? col[kp] : 0.;
+            // rotations defined by earlier blocks: i = kp .. j0-2
+#pragma unroll 4
+            for (int i = kp; i < j0 - 1; ++i) {
+                const double b = has ? col[i + 1] : 0.;
+                const double cs = sm.gc[i], sn = sm.gs[i];
+                if (has) out[i] = cs * carry + sn * b;
+                carry = -sn * carry + cs * b;
             }
-            if (lane == 0) { sm.gc[i] = cs; sm.gs[i] = sn; }
-            for (int j = jown + lane; j < k; j += 32) {
-                double *col = R + tri_off(j);
-                const double x = col[i], y = col[i + 1];
-                col[i] = cs * x + sn * y;
-                col[i + 1] = -sn * x + cs * y;
+            // stage rows j0 .. j of the own column (the triangular part of the block)
+            for (int q = 0; q < 32; ++q) sm.stage[q * 33 + lane] = (has && j0 + q <= j) ? col[j0 + q] : 0.;
+            __syncwarp();
+            const int iend = (j0 + 32 < k ? j0 + 32 : k) - 1;          // rotations i = j0-1 .. iend-1
+            for (int i = j0 - 1; i < iend; ++i) {
+                const int q = i + 1 - j0;                               // defining column = lane q, its row i+1
+                const double b = sm.stage[q * 33 + lane];
+                const double a_d = __shfl_sync(0xffffffffu, carry, q), b_d = __shfl_sync(0xffffffffu, b, q);
+                double cs = 1., sn = 0.;
+                const double hyp = sqrt(a_d * a_d + b_d * b_d);
+                if (hyp > 0.) { const double ih = 1. / hyp; cs = a_d * ih; sn = b_d * ih; }
+                if (lane == 0) { sm.gc[i] = cs; sm.gs[i] = sn; }
+                if (has && j >= i + 1) {
+                    out[i] = cs * carry + sn * b;
+                    carry = -sn * carry + cs * b;
+                }
             }
             __syncwarp();
         }
+    } else {
+        // rows < kp of the shifted columns are unchanged
+        for (int j = kp + 1 + (w - 1); j < k; j += WS_NW - 1) {
+            const double *col = R + tri_off(j);
+            double *out = Rn + tri_off(j - 1);
+            for (int i = lane; i < kp; i += 32) out[i] = col[i];
+        }
     }
     __syncthreads();
-    // ---- 2. compact R: new column j-1 <- old column j (rows 0..j-1), ascending chunks (src > dst)
+    // ---- 2. copy the new columns back
     {
-        const int dst0 = tri_off(kp), dst1 = tri_off(k - 1);       // [dst0, dst1) in new indexing
-        for (int base = dst0; base < dst1; base += WS_NT) {
-            const int a = base + threadIdx.x;
-            double val = 0.;
-            if (a < dst1) {
-                // column jn of address a: largest jn with tri_off(jn) <= a
-                int jn = (int)((sqrt(8. * (double)a + 1.) - 1.) * .5);
-                while (tri_off(jn + 1) <= a) ++jn;
-                while (tri_off(jn) > a) --jn;
-                const int i = a - tri_off(jn);
-                val = R[tri_off(jn + 1) + i];
-            }
-            __syncthreads();
-            if (a < dst1) R[a] = val;
-            __syncthreads();
-        }
+        const int a0 = tri_off(kp), a1 = tri_off(k - 1);
+        for (int a = a0 + threadIdx.x; a < a1; a += WS_NT) sp.R[a] = Rn[a];
     }
     // ---- 3. Q columns: q_i <- c q_i + s q_{i+1} ; carry the other combination (thread per row)
-    for (int r = threadIdx.x; r < n; r += WS_NT) {
-        double carry = sp.Q[(size_t)kp * n + r];
-        for (int i = kp; i < k - 1; ++i) {
-            const double b = sp.Q[(size_t)(i + 1) * n + r];
-            const double cs = sm.gc[i], sn = sm.gs[i];
-            sp.Q[(size_t)i * n + r] = cs * carry + sn * b;
-            carry = -sn * carry + cs * b;
+    {
+        double *Qw = sm.Q;
+        for (int r = threadIdx.x; r < n; r += WS_NT) {
+            double carry = Qw[(size_t)kp * n + r];
+#pragma unroll 4
+            for (int i = kp; i < k - 1; ++i) {
+                const double b = Qw[(size_t)(i + 1) * n + r];
+                const double cs = sm.gc[i], sn = sm.gs[i];
+                Qw[(size_t)i * n + r] = cs * carry + sn * b;
+                carry = -sn * carry + cs * b;
+            }
+            Qw[(size_t)(k - 1) * n + r] = carry;
         }
-        sp.Q[(size_t)(k - 1) * n + r] = carry;
     }
     // ---- 4. Ri: delete row kp, rotate columns, drop the last column.  new row rr <- old row
-    // (rr < kp ? rr : rr+1).  Written to tmp then copied back (threads own rows, columns interleave).
+    // (rr < kp ? rr : rr+1).  Written to tmp2 then copied back (threads own rows, columns interleave).
+    // Threads WS_NT/2.. take the rows from the top so that both halves of the CTA have work.
     for (int rr = threadIdx.x; rr < k - 1; rr += WS_NT) {
         const int ro = rr < kp ? rr : rr + 1;
         // X[rr][j] = old Ri[ro][j] if ro <= j else 0
         double carry = (ro <= kp) ? sp.Ri[tri_off(kp) + ro] : 0.;
+#pragma unroll 4
         for (int i = kp; i < k - 1; ++i) {
             const double b = (ro <= i + 1) ? sp.Ri[tri_off(i + 1) + ro] : 0.;
             const double cs = sm.gc[i], sn = sm.gs[i];
-            if (rr <= i) sp.tmp[tri_off(i) + rr] = cs * carry + sn * b;
+            if (rr <= i) sp.tmp2[tri_off(i) + rr] = cs * carry + sn * b;
             carry = -sn * carry + cs * b;
         }
     }
     __syncthreads();
     {
         const int a0 = tri_off(kp), a1 = tri_off(k - 1);
-        for (int a = a0 + threadIdx.x; a < a1; a += WS_NT) sp.Ri[a] = sp.tmp[a];
+        for (int a = a0 + threadIdx.x; a < a1; a += WS_NT) sp.Ri[a] = sp.tmp2[a];
     }
     // ---- 5. shift the bookkeeping (chunked: k may exceed the block size)
     __syncthreads();
@@ -329,7 +437,7 @@ __device__ inline void ws_remove(const DevProblem &P, const SlotPtrs &sp, Smem &
     for (;;) {
         double val = 0.; int bad = -1;
         for (int i = kp + threadIdx.x; i < k; i += WS_NT)
-            if (fabs(sm.R[tri_off(i) + i]) <= P.tol_sing && (bad < 0 || i < bad)) bad = i;
+            if (fabs(sp.R[tri_off(i) + i]) <= P.tol_sing && (bad < 0 || i < bad)) bad = i;
         // smallest index wins: encode as arg-max of -index
         val = bad >= 0 ? -(double)bad : 0.;
         block_argmax(val, bad, sm.red, sm.ired);
@@ -341,22 +449,42 @@ __device__ inline void ws_remove(const DevProblem &P, const SlotPtrs &sp, Smem &
     }
 }
 
-// sv_r = mh_r . x for all rows, thread per row through the transposed operator (coalesced);
-// calls f(r, sv) for every row.
+// sv_r = mh_r . x for all rows in factored form; calls f(r, sv) once per row.
+//   xi = Wf x  (ns = n + T nx entries: inputs zeta_t, then states xi_1 .. xi_T of the homogeneous dynamics)
+//   row (t, i):  sv = (F_t[i] . xi_t + G_t[i] . zeta_t) / nrm_r   (xi_0 = 0: the x0 part is in the bounds)
+//   binary (t, i): sv = zeta_t[nuc + i] / nrm_r
 template <class Fn>
-__device__ inline void price_rows(const DevProblem &P, const double *x, Fn f) {
-    const int n = P.n, m = P.m;
-    for (int r0 = threadIdx.x; r0 < m; r0 += 2 * WS_NT) {
-        const int r1 = r0 + WS_NT;
+__device__ inline void price_rows(const DevProblem &P, Smem &sm, const double *x, Fn f) {
+    const int n = P.n, m = P.m, mc = P.mc, nx = P.nx, nu = P.nu, ns = P.ns;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    // xi = Wf x : warp per row of Wf (row major, coalesced over lanes), two rows in flight
+    for (int r = w; r < ns; r += 2 * WS_NW) {
+        const int r2 = r + WS_NW;
+        const double *w0 = P.Wf + (size_t)r * n, *w1 = P.Wf + (size_t)(r2 < ns ? r2 : r) * n;
         double s0 = 0., s1 = 0.;
-        const double *p0 = P.MhT + r0;
-        if (r1 < m) {
-            for (int c = 0; c < n; ++c) { const double xc = x[c]; s0 += p0[(size_t)c * m] * xc; s1 += p0[(size_t)c * m + WS_NT] * xc; }
-            f(r0, s0); f(r1, s1);
+        for (int c = lane; c < n; c += 32) { const double xc = x[c]; s0 += w0[c] * xc; s1 += w1[c] * xc; }
+        s0 = warp_sum(s0); s1 = warp_sum(s1);
+        if (lane == 0) { sm.xi[r] = s0; if (r2 < ns) sm.xi[r2] = s1; }
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < m; r += WS_NT) {
+        double s;
+        if (r < mc) {
+            int t = r / P.nh; if (t > P.T - 1) t = P.T - 1;
+            const int i = r - t * P.nh;
+            const double *Fr = (t < P.T - 1 ? P.F : P.F1) + (size_t)i * nx;
+            const double *Gr = (t < P.T - 1 ? P.G : P.G1) + (size_t)i * nu;
+            const double *zt = sm.xi + (size_t)t * nu;
+            s = 0.;
+            for (int c = 0; c < nu; ++c) s += Gr[c] * zt[c];
+            if (t > 0) {
+                const double *xt = sm.xi + n + (size_t)(t - 1) * nx;
+                for (int c = 0; c < nx; ++c) s += Fr[c] * xt[c];
+            }
         } else {
-            for (int c = 0; c < n; ++c) s0 += p0[(size_t)c * m] * x[c];
-            f(r0, s0);
+            s = sm.xi[P.bin_idx[r - mc]];
         }
+        f(r, s * P.inr[r]);
     }
 }
 
@@ -368,15 +496,15 @@ __device__ inline void price_rows(const DevProblem &P, const double *x, Fn f) {
 __device__ inline void load_slot(const DevProblem &P, const SlotPtrs &sp, Smem &sm, int &k, bool reset) {
     const int n = P.n;
     if (reset) {
-        for (size_t a = threadIdx.x; a < (size_t)n * n; a += WS_NT) sp.Q[a] = 0.;
+        for (size_t a = threadIdx.x; a < (size_t)n * n; a += WS_NT) sm.Q[a] = 0.;
         __syncthreads();
-        for (int i = threadIdx.x; i < n; i += WS_NT) { sp.Q[(size_t)i * n + i] = 1.; sm.yc[i] = 0.; }
+        for (int i = threadIdx.x; i < n; i += WS_NT) { sm.Q[(size_t)i * n + i] = 1.; sm.yc[i] = 0.; }
         k = 0;
     } else {
         k = *sp.nW;
         for (int i = threadIdx.x; i < n; i += WS_NT) sm.yc[i] = sp.yc[i];
         for (int i = threadIdx.x; i < k; i += WS_NT) { sm.row[i] = sp.row[i]; sm.side[i] = sp.side[i]; sm.lam[i] = sp.lam[i]; }
-        if (P.r_in_smem) for (int a = threadIdx.x; a < tri_off(k); a += WS_NT) sm.R[a] = sp.Rg[a];
+        if (P.q_in_smem) for (size_t a = threadIdx.x; a < (size_t)n * n; a += WS_NT) sm.Q[a] = sp.Q[a];
     }
     for (int r = threadIdx.x; r < P.m; r += WS_NT) { sm.inW[r] = 0; sm.ign[r] = 0; sm.nadd[r] = 0; }
     __syncthreads();
@@ -388,7 +516,7 @@ __device__ inline void store_slot(const DevProblem &P, const SlotPtrs &sp, Smem 
     const int n = P.n;
     for (int i = threadIdx.x; i < n; i += WS_NT) sp.yc[i] = sm.yc[i];
     for (int i = threadIdx.x; i < k; i += WS_NT) { sp.row[i] = sm.row[i]; sp.side[i] = sm.side[i]; sp.lam[i] = sm.lam[i]; }
-    if (P.r_in_smem) for (int a = threadIdx.x; a < tri_off(k); a += WS_NT) sp.Rg[a] = sm.R[a];
+    if (P.q_in_smem) for (size_t a = threadIdx.x; a < (size_t)n * n; a += WS_NT) sp.Q[a] = sm.Q[a];
     if (threadIdx.x == 0) *sp.nW = k;
     __syncthreads();
 }
@@ -403,31 +531,27 @@ __device__ inline int qp_solve(const DevProblem &P, const SlotPtrs &sp, Smem &sm
                                const double *x0, const double *lb, const double *ub,
                                double *y_out, int *iters_out)
 {
-    const int n = P.n, m = P.m, mc = P.mc, nb = P.nb, nx = P.nx;
+    const int n = P.n, m = P.m, mc = P.mc, nx = P.nx;
     int it = 0, status = WS_ITER_LIMIT;
     int pending = -1, pside = 0, just_added = -1;
     double plam = 0.;
 
     for (int pk = 0; pk < P.max_prox; ++pk) {
-        // wv = Kx x0 - eps Rinv' yc
-        for (int c = threadIdx.x; c < n; c += WS_NT) {
+        // wv = Kx x0 - eps Rinv' yc     ((Rinv' yc)_c = sum_r Rinv[r][c] yc[r], coalesced over c)
+        grouped_matvec(P.Rinv, n, n, 0, n, sm.yc, sm.part, [&](int c, double a) {
             double s = 0.;
             for (int j = 0; j < nx; ++j) s += P.Kx[(size_t)c * nx + j] * x0[j];
-            double a = 0.;
-            const double *rt = P.RinvT + (size_t)c * n;          // row c of Rinv' = column c of Rinv
-            for (int rr = 0; rr < n; ++rr) a += rt[rr] * sm.yc[rr];
             sm.wv[c] = s - P.eps * a;
-        }
-        __syncthreads();
+        });
         // bounds of this proximal sub-problem: g = Mh wv
-        price_rows(P, sm.wv, [&](int r, double g) {
+        price_rows(P, sm, sm.wv, [&](int r, double g) {
             if (r < mc) {
                 double e = 0.;
                 for (int j = 0; j < nx; ++j) e += P.Eh[(size_t)r * nx + j] * x0[j];
                 sm.bu[r] = P.hh[r] - e + g;
             } else {
                 const int i = r - mc;
-                const double inr = 1. / P.nrm[r];
+                const double inr = P.inr[r];
                 sm.bu[r] = ub[i] * inr + g;
                 sm.blb[i] = lb[i] * inr + g;
             }
@@ -445,9 +569,7 @@ __device__ inline int qp_solve(const DevProblem &P, const SlotPtrs &sp, Smem &sm
                 }
                 __syncthreads();
                 rit_matvec(sp.Ri, k, sm.c, sm.u);
-                __syncthreads();
-                ri_matvec(sp.Ri, k, sm.u, sm.ls);
-                __syncthreads();
+                ri_matvec(sp.Ri, k, sm.u, sm.ls, sm.part);
                 double amin = INFINITY; int kmin = -1;
                 for (int i = threadIdx.x; i < k; i += WS_NT) if (sm.ls[i] < -P.tol_d) {
                     const double a = sm.lam[i] / (sm.lam[i] - sm.ls[i]);
@@ -467,18 +589,14 @@ __device__ inline int qp_solve(const DevProblem &P, const SlotPtrs &sp, Smem &sm
                     continue;
                 }
                 for (int i = threadIdx.x; i < k; i += WS_NT) sm.lam[i] = sm.ls[i] > 0. ? sm.ls[i] : 0.;
-                // v = -Q1 u   (thread per row)
-                for (int i = threadIdx.x; i < n; i += WS_NT) {
-                    double s = 0.;
-                    for (int j = 0; j < k; ++j) s += sp.Q[(size_t)j * n + i] * sm.u[j];
-                    sm.v[i] = -s;
-                }
+                // v = -Q1 u
+                grouped_matvec(sm.Q, n, n, 0, k, sm.u, sm.part, [&](int i, double s) { sm.v[i] = -s; });
                 double lpart = 0.;
                 for (int i = threadIdx.x; i < k; i += WS_NT) lpart += sm.ls[i] > 0. ? sm.ls[i] : 0.;
-                const double lsum = block_sum(lpart, sm.red);      // (also the barrier after v)
+                const double lsum = block_sum(lpart, sm.red);
                 const double vnoise = 1e-14 * lsum, vcap = 100. * P.tol_p;
                 double vbest = 0.; int ibest = -1;                 // ibest = 2 r + (lower side)
-                price_rows(P, sm.v, [&](int r, double sv) {
+                price_rows(P, sm, sm.v, [&](int r, double sv) {
                     if (sm.inW[r]) return;
                     const int na = sm.nadd[r];
                     double tolr = P.tol_p * (na == 0 ? 1. : (na == 1 ? 10. : 100.));
@@ -531,9 +649,9 @@ __device__ inline int qp_solve(const DevProblem &P, const SlotPtrs &sp, Smem &sm
                         for (int i = threadIdx.x; i < k; i += WS_NT) {
                             const double pi = sm.t[i] < 0. ? -sm.t[i] : 0.;
                             const int r = sm.row[i];
-                            y_out[r] = (double)sm.side[i] * pi / P.nrm[r];
+                            y_out[r] = (double)sm.side[i] * pi * P.inr[r];
                         }
-                        if (threadIdx.x == 0) y_out[pending] = (double)pside / P.nrm[pending];
+                        if (threadIdx.x == 0) y_out[pending] = (double)pside * P.inr[pending];
                         __syncthreads();
                         status = WS_INFEASIBLE;
                         break;
@@ -557,17 +675,14 @@ __device__ inline int qp_solve(const DevProblem &P, const SlotPtrs &sp, Smem &sm
         }
         if (status != WS_OPTIMAL) break;
         // yc <- Rinv (v - wv) ; proximal convergence
-        double dz = 0.;
         __syncthreads();
         for (int r = threadIdx.x; r < n; r += WS_NT) sm.c[r] = sm.v[r] - sm.wv[r];
         __syncthreads();
-        for (int r = threadIdx.x; r < n; r += WS_NT) {
-            double s = 0.;
-            const double *ri = P.Rinv + (size_t)r * n;
-            for (int c = 0; c < n; ++c) s += ri[c] * sm.c[c];
+        double dz = 0.;
+        grouped_matvec(P.RinvT, n, n, 0, n, sm.c, sm.part, [&](int r, double s) {
             dz = fmax(dz, fabs(s - sm.yc[r]));
             sm.hv[r] = s;
-        }
+        });
         { int dummy = 0; block_argmax(dz, dummy, sm.red, sm.ired); }
         for (int r = threadIdx.x; r < n; r += WS_NT) sm.yc[r] = sm.hv[r];
         __syncthreads();
@@ -578,7 +693,7 @@ __device__ inline int qp_solve(const DevProblem &P, const SlotPtrs &sp, Smem &sm
         __syncthreads();
         for (int i = threadIdx.x; i < k; i += WS_NT) {
             const int r = sm.row[i];
-            y_out[r] = (double)sm.side[i] * sm.lam[i] / P.nrm[r];
+            y_out[r] = (double)sm.side[i] * sm.lam[i] * P.inr[r];
         }
         __syncthreads();
     }

@@ -8,7 +8,7 @@
 #include "qp_device.cuh"
 
 // yc: solution in orthonormal coordinates (shared memory), y: signed row multipliers (global, m).
-// scratch: >= n doubles of shared memory.  Returns cost (inf if infeasible) and dual objective.
+// scratch: >= max(WS_NT, n) doubles of shared memory (Smem::part).  Returns cost (inf if infeasible) and dual objective.
 __device__ inline void build_records(const DevProblem &P, int status, const double *yc, const double *y,
                                      const double *x0, const double *lb, const double *ub,
                                      double *primal, double *dual, double *cost_out, double *dobj_out,
@@ -22,12 +22,7 @@ __device__ inline void build_records(const DevProblem &P, int status, const doub
     double cost = INFINITY;
     if (opt) {
         // z = Zmap yc ; pinned binaries hold exactly (rows lb <= z_i <= ub with lb == ub)
-        for (int c = threadIdx.x; c < n; c += WS_NT) {
-            double s = 0.;
-            for (int j = 0; j < n; ++j) s += P.ZmapT[(size_t)j * n + c] * yc[j];
-            U[c] = s;
-        }
-        __syncthreads();
+        grouped_matvec(P.ZmapT, n, n, 0, n, yc, scratch, [&](int c, double s) { U[c] = s; });
         for (int i = threadIdx.x; i < nb; i += WS_NT) if (lb[i] == ub[i]) U[P.bin_idx[i]] = lb[i];
         for (int j = threadIdx.x; j < nx; j += WS_NT) X[j] = x0[j];
         __syncthreads();

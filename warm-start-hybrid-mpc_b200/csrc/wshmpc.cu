@@ -34,7 +34,7 @@ extern "C" const char *wshmpc_last_error(void) { return g_err.c_str(); }
 // ---------------------------------------------------------------------------------------------
 // K1: one CTA per solver slot; the CTA solves, in index order, every node assigned to its slot
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(WS_NT, 2)
+__global__ void __launch_bounds__(WS_NT, 1)
 solve_nodes_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, int n_nodes,
                    const double *__restrict__ x0, const double *__restrict__ lb, const double *__restrict__ ub,
                    const int *__restrict__ slot_of, const int *__restrict__ hot,
@@ -43,7 +43,7 @@ solve_nodes_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, int 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int slot = blockIdx.x;
     SlotPtrs sp = slot_ptrs(slot_d, slot_i, slot, P.n);
-    Smem sm = carve_smem(smem_raw, P.n, P.m, P.nb, P.r_in_smem, sp.Rg);
+    Smem sm = carve_smem(smem_raw, P.n, P.m, P.nb, P.ns, P.q_in_smem, sp.Q);
     double *y = ybuf + (size_t)slot * P.m;
     int k = 0;
     bool loaded = false;
@@ -55,7 +55,7 @@ solve_nodes_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, int 
         const double *xi = x0 + (size_t)i * P.nx, *lbi = lb + (size_t)i * P.nb, *ubi = ub + (size_t)i * P.nb;
         const int st = qp_solve(P, sp, sm, k, xi, lbi, ubi, y, iters + i);
         build_records(P, st, sm.yc, y, xi, lbi, ubi, primal + (size_t)i * P.n_primal,
-                      dual + (size_t)i * P.n_dual, cost + i, dobj + i, sm.c, sm.red);
+                      dual + (size_t)i * P.n_dual, cost + i, dobj + i, sm.part, sm.red);
         if (threadIdx.x == 0) status[i] = st;
         __syncthreads();
     }
@@ -87,7 +87,7 @@ extern "C" int wshmpc_create(const wshmpc_problem *p, int device, int n_slots, v
     if (!p || !out) WS_FAIL(-1, "null argument");
     if (n_slots <= 0) WS_FAIL(-1, "n_slots must be positive");
     if (p->n != p->T * p->nu || p->nb != p->T * p->nub || p->m != p->mc + p->nb ||
-        p->mc != (p->T - 1) * p->nh + p->nh1)
+        p->mc != (p->T - 1) * p->nh + p->nh1 || p->ns != p->n + p->T * p->nx)
         WS_FAIL(-1, "inconsistent sizes: n=%d m=%d mc=%d nb=%d", p->n, p->m, p->mc, p->nb);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) WS_FAIL(-3, "no CUDA device: the hot path has no CPU fallback");
@@ -97,7 +97,7 @@ extern "C" int wshmpc_create(const wshmpc_problem *p, int device, int n_slots, v
     DevProblem &P = h->P;
     memset(&P, 0, sizeof(P));
     P.nx = p->nx; P.nu = p->nu; P.nub = p->nub; P.nuc = p->nu - p->nub; P.T = p->T; P.nh = p->nh; P.nh1 = p->nh1;
-    P.nq = p->nq; P.nqT = p->nqT; P.nr = p->nr; P.n = p->n; P.m = p->m; P.mc = p->mc; P.nb = p->nb;
+    P.nq = p->nq; P.nqT = p->nqT; P.nr = p->nr; P.n = p->n; P.m = p->m; P.mc = p->mc; P.nb = p->nb; P.ns = p->ns;
     P.eps = p->eps; P.tol_p = p->tol_p; P.tol_d = p->tol_d; P.tol_sing = p->tol_sing; P.tol_ray = p->tol_ray;
     P.prox_tol = p->prox_tol; P.max_iter = p->max_iter; P.max_prox = p->max_prox;
     P.tri = (p->n + 1) * (p->n + 2) / 2;
@@ -108,11 +108,11 @@ extern "C" int wshmpc_create(const wshmpc_problem *p, int device, int n_slots, v
     UP(F1, p->F_Tm1, p->nh1 * nx) UP(G1, p->G_Tm1, p->nh1 * nu) UP(h1, p->h_Tm1, p->nh1)
     UP(Q, p->Q, p->nq * nx) UP(R, p->R, p->nr * nu) UP(QT, p->Q_T, p->nqT * nx)
     UP(Mmu, p->M_mu, p->nh * p->nh1) UP(Mrho, p->M_rho, p->nq * p->nqT)
-    UP(Mh, p->Mh, (size_t)m * n) UP(nrm, p->nrm, m) UP(vscale, p->vscale, m) UP(Eh, p->Eh, (size_t)p->mc * nx)
+    UP(Mh, p->Mh, (size_t)m * n) UP(Wf, p->Wf, (size_t)p->ns * n) UP(nrm, p->nrm, m) UP(vscale, p->vscale, m) UP(Eh, p->Eh, (size_t)p->mc * nx)
     UP(hh, p->hh, p->mc) UP(Rinv, p->Rinv, (size_t)n * n) UP(Kx, p->Kx, (size_t)n * nx)
     UP(bin_idx, p->bin_idx, p->nb)
     {
-        std::vector<double> t = transpose(p->Mh, m, n); UP(MhT, t.data(), (size_t)m * n)
+        std::vector<double> ir(m); for (int r = 0; r < m; ++r) ir[r] = 1. / p->nrm[r]; UP(inr, ir.data(), m)
         std::vector<double> r = transpose(p->Rinv, n, n); UP(RinvT, r.data(), (size_t)n * n)
         std::vector<double> z = transpose(p->Zmap, n, n); UP(ZmapT, z.data(), (size_t)n * n)
     }
@@ -129,12 +129,12 @@ extern "C" int wshmpc_create(const wshmpc_problem *p, int device, int n_slots, v
     L.dual = L.off_sigma + p->T * p->nr;
     P.n_primal = L.primal; P.n_dual = L.dual; P.off_lam = L.off_lam; P.off_mu = L.off_mu; P.off_nulb = L.off_nu_lb;
     P.off_nuub = L.off_nu_ub; P.off_rho = L.off_rho; P.off_sigma = L.off_sigma;
-    // shared memory budget: keep R in shared memory when two CTAs per SM still fit
+    // shared memory budget: one CTA per SM; Q lives in shared memory when it fits
     cudaDeviceProp prop;
     WS_CUDA(cudaGetDeviceProperties(&prop, device));
     const size_t optin = prop.sharedMemPerBlockOptin;
-    P.r_in_smem = smem_bytes(n, m, p->nb, 1) <= optin ? 1 : 0;
-    h->smem = smem_bytes(n, m, p->nb, P.r_in_smem);
+    P.q_in_smem = smem_bytes(n, m, p->nb, p->ns, 1) <= optin ? 1 : 0;
+    h->smem = smem_bytes(n, m, p->nb, p->ns, P.q_in_smem);
     if (h->smem > optin) { wshmpc_destroy(h); WS_FAIL(-4, "problem too large: %zu bytes of shared memory needed, %zu available", h->smem, optin); }
     WS_CUDA(cudaFuncSetAttribute(solve_nodes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
     // slot memory

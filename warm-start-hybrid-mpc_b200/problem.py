@@ -109,6 +109,7 @@ class ProblemData(object):
         self.Mh = c(M / nrm[:, None]); self.nrm = c(nrm); self.vscale = c(nrm / np.maximum(1., arow))
         self.Eh = c(Ey / nrm[:self.mc, None]); self.hh = c(hbar / nrm[:self.mc])
         self.Rinv = c(Rinv); self.Kx = c(Rinv.T.dot(Fy)); self.Zmap = c(N[:n])
+        self.Wf = c(N.dot(Rinv)); self.ns = ns
 
     @staticmethod
     def from_controller_data(mld, T, objective, F_Tm1, G_Tm1, h_Tm1, M_mu, M_rho, **kw):
