@@ -71,10 +71,12 @@ def branch_and_bound(solve, branch, tol=0., warm_start=None, on_solve=None):
 
 class OracleController(object):
 
-    def __init__(self, model, core, hot_start=True):
+    def __init__(self, model, core, hot_start=True, persistent=False):
         """model: dict of oracle/models.py; core: oracle.qp_c.CoreC (or any object with
         solve(x0, lb, ub, warm=None)).  `hot_start`: each node starts from the working set of the node
-        solved before it (what the CUDA path does); False = every node from scratch."""
+        solved before it (what the CUDA path does); False = every node from scratch.
+        `persistent`: the factorisation itself survives between the nodes of one feedforward call (exactly
+        what a CUDA solver slot does) instead of being rebuilt from the inherited working set."""
         self.m = model
         self.core = core
         self.hot_start = hot_start
@@ -85,6 +87,8 @@ class OracleController(object):
         self.V = np.hstack((np.zeros((self.nub, self.nuc)), np.eye(self.nub)))
         self.qp_time = 0.
         self._warm = None
+        self._state = core.new_state() if persistent else None
+        self._reset = True
 
     # -- controller.py:300-327
     def bounds(self, identifier):
@@ -98,7 +102,11 @@ class OracleController(object):
         m, c, T = self.m, self.c, self.T
         lb, ub = self.bounds(node.identifier)
         tic = time.perf_counter()
-        out = self.core.solve(x0, lb.ravel(), ub.ravel(), warm=self._warm if self.hot_start else None)
+        if self._state is not None:
+            out = self.core.solve(x0, lb.ravel(), ub.ravel(), state=self._state, reset=self._reset)
+            self._reset = False
+        else:
+            out = self.core.solve(x0, lb.ravel(), ub.ravel(), warm=self._warm if self.hot_start else None)
         self.qp_time += time.perf_counter() - tic
         if out['status'] not in (2, 3):
             raise RuntimeError('oracle QP core failed with status %r' % out['status'])
@@ -143,6 +151,7 @@ class OracleController(object):
     # -- controller.py:329-393
     def feedforward(self, x0, warm_start=None, tol=0., on_solve=None):
         self._warm = None
+        self._reset = True
         inc, leaves, solves = branch_and_bound(lambda n: self.solve_node(n, x0), self.branch, tol, warm_start, on_solve)
         return inc, leaves, solves
 

@@ -28,7 +28,8 @@ class _Shared(C.Structure):
                 ('Mh', C.c_void_p), ('nrm', C.c_void_p), ('vscale', C.c_void_p), ('Eh', C.c_void_p),
                 ('hh', C.c_void_p), ('Rinv', C.c_void_p), ('Kx', C.c_void_p), ('Zmap', C.c_void_p), ('bin_idx', C.c_void_p),
                 ('eps', C.c_double), ('tol_p', C.c_double), ('tol_d', C.c_double), ('tol_sing', C.c_double),
-                ('tol_ray', C.c_double), ('prox_tol', C.c_double), ('max_iter', C.c_int), ('max_prox', C.c_int)]
+                ('tol_ray', C.c_double), ('prox_tol', C.c_double), ('max_iter', C.c_int), ('max_prox', C.c_int),
+                ('variant', C.c_int)]
 
 
 def pack_shared(of, eps):
@@ -61,10 +62,21 @@ def default_eps(Hy):
     return 1e-2 * float(pos.min())
 
 
+class _State(object):
+    def __init__(self, lib, ptr):
+        self.lib, self.ptr = lib, ptr
+
+    def __del__(self):
+        try:
+            self.lib.qp_state_free(C.c_void_p(self.ptr))
+        except Exception:
+            pass
+
+
 class CoreC(object):
 
     def __init__(self, model, eps=None, tol_p=1e-7, tol_d=1e-12, tol_sing=1e-7, tol_ray=1e-9,
-                 prox_tol=1e-11, max_iter=5000, max_prox=50):
+                 prox_tol=1e-11, max_iter=5000, max_prox=50, variant=0):
         self.lib = C.CDLL(build())
         self.lib.qp_solve.restype = C.c_int
         self.cond = c = Condensed(model)
@@ -80,9 +92,15 @@ class CoreC(object):
             setattr(S, k, v.ctypes.data)
         S.eps, S.tol_p, S.tol_d, S.tol_sing, S.tol_ray, S.prox_tol = eps, tol_p, tol_d, tol_sing, tol_ray, prox_tol
         S.max_iter, S.max_prox = max_iter, max_prox
+        S.variant = variant
         self.S = S
 
-    def solve(self, x0, lb, ub, warm=None):
+    def new_state(self):
+        """A persistent solver state (one CUDA slot): pass it as `state=` to solve()."""
+        self.lib.qp_state_new.restype = C.c_void_p
+        return _State(self.lib, self.lib.qp_state_new(self.cond.n, self.cond.m))
+
+    def solve(self, x0, lb, ub, warm=None, state=None, reset=False):
         c = self.cond
         n, m = c.n, c.m
         x0 = np.ascontiguousarray(x0, dtype=float); lb = np.ascontiguousarray(lb, dtype=float)
@@ -98,9 +116,14 @@ class CoreC(object):
             l0 = np.ascontiguousarray(warm['lam'], float)
             z0 = None if warm.get('z') is None else np.ascontiguousarray(warm['z'], float)
             nW0, a0, a1, a2, a3 = r0.size, P(r0), P(s0), P(l0), (None if z0 is None else P(z0))
-        st = self.lib.qp_solve(C.byref(self.S), P(x0), P(lb), P(ub), nW0, a0, a1, a2, a3,
-                               P(z), P(yc), P(y), C.byref(fark), C.byref(nW), P(Wr), P(Ws), P(Wl),
-                               C.byref(it), C.byref(px))
+        if state is not None:
+            st = self.lib.qp_solve_state(C.byref(self.S), C.c_void_p(state.ptr), int(bool(reset)), P(x0), P(lb), P(ub),
+                                         P(z), P(yc), P(y), C.byref(fark), C.byref(nW), P(Wr), P(Ws), P(Wl),
+                                         C.byref(it), C.byref(px))
+        else:
+            st = self.lib.qp_solve(C.byref(self.S), P(x0), P(lb), P(ub), nW0, a0, a1, a2, a3,
+                                   P(z), P(yc), P(y), C.byref(fark), C.byref(nW), P(Wr), P(Ws), P(Wl),
+                                   C.byref(it), C.byref(px))
         k = nW.value
         out = dict(status=st, iters=it.value, prox=px.value,
                    warm=dict(rows=Wr[:k].copy(), sides=Ws[:k].copy(), lam=Wl[:k].copy(), z=yc if st == 2 else None))

@@ -44,6 +44,7 @@ typedef struct {
     const int *bin_idx;    /* nb : position of binary (t,i) in z */
     double eps, tol_p, tol_d, tol_sing, tol_ray, prox_tol;
     int max_iter, max_prox;
+    int variant;           /* 0: full Q (Householder) + R ; 1: thin Q1 (Gram-Schmidt, re-orthogonalised) + R^-1 only */
 } qp_shared;
 
 typedef struct {
@@ -156,13 +157,122 @@ static void ws_remove(const qp_shared *S, qp_ws *w, int k, int *inW) {
     }
 }
 
+
+/* ------------------------------------------------------------------------------------------------
+ * variant 1: THIN factorisation  Mw' = Q1 R  kept as  Q1 (n x k, the first k columns of w->Q) and
+ * Ri = R^-1 (packed by columns: column j at Ri + j(j+1)/2), no R and no null-space basis.  This is the
+ * layout the CUDA kernel uses (csrc/qp_device.cuh): appends are classical Gram-Schmidt with one
+ * re-orthogonalisation pass (Daniel, Gragg, Kaufman & Stewart 1976), removals rotate the columns of
+ * Q1 and Ri with the Givens sequence that carries row kp of Ri into its last entry -- every rotation
+ * is known up front from prefix sums of squares of that row, so nothing is a sequential chain of
+ * square roots.  Same pivoting rules as variant 0; the two variants must agree (tests/).
+ * ---------------------------------------------------------------------------------------------- */
+#define TRI(j) ((size_t)(j) * ((size_t)(j) + 1) / 2)
+
+/* t = Ri c  (leading k x k) */
+static void thin_ri_mul(const double *Ri, int k, const double *c, double *t) {
+    for (int i = 0; i < k; ++i) {
+        double s = 0.;
+        for (int j = i; j < k; ++j) s += Ri[TRI(j) + i] * c[j];
+        t[i] = s;
+    }
+}
+
+/* u = Ri' c */
+static void thin_rit_mul(const double *Ri, int k, const double *c, double *u) {
+    for (int j = 0; j < k; ++j) {
+        double s = 0.;
+        for (int i = 0; i <= j; ++i) s += Ri[TRI(j) + i] * c[i];
+        u[j] = s;
+    }
+}
+
+static int thin_append(const qp_shared *S, qp_ws *w, double *Ri, int r, int s, double *t, double *c1, double *z, double *c2) {
+    const int n = S->n, k = w->nW;
+    const double *mj = S->Mh + (size_t)r * n;
+    for (int i = 0; i < n; ++i) z[i] = (double)s * mj[i];
+    for (int j = 0; j < k; ++j) c1[j] = dot(w->Q + (size_t)j * n, z, n);
+    for (int j = 0; j < k; ++j) { const double cj = c1[j]; const double *q = w->Q + (size_t)j * n; for (int i = 0; i < n; ++i) z[i] -= cj * q[i]; }
+    double rho2 = dot(z, z, n);
+    if (rho2 < 1e-2) {          /* lost more than one digit: project once more ("twice is enough") */
+        for (int j = 0; j < k; ++j) c2[j] = dot(w->Q + (size_t)j * n, z, n);
+        for (int j = 0; j < k; ++j) { const double cj = c2[j]; const double *q = w->Q + (size_t)j * n; for (int i = 0; i < n; ++i) z[i] -= cj * q[i]; c1[j] += cj; }
+        rho2 = dot(z, z, n);
+    }
+    thin_ri_mul(Ri, k, c1, t);
+    if (k >= n || rho2 <= S->tol_sing * S->tol_sing) return 0;
+    const double rho = sqrt(rho2), ir = 1. / rho;
+    double *qk = w->Q + (size_t)k * n, *rk = Ri + TRI(k);
+    for (int i = 0; i < n; ++i) qk[i] = z[i] * ir;
+    for (int i = 0; i < k; ++i) rk[i] = -t[i] * ir;
+    rk[k] = ir;
+    w->row[k] = r; w->side[k] = s; w->lam[k] = 0.;
+    w->nW = k + 1;
+    return 1;
+}
+
+/* remove position kp; returns the smallest position >= kp whose diagonal of R collapsed (|Ri_ii| >= 1/tol), or -1 */
+static int thin_remove(const qp_shared *S, qp_ws *w, double *Ri, int kp, double *gc, double *gs, double *rowbuf) {
+    const int n = w->n, k = w->nW;
+    /* rotations i = kp .. k-2 on the column pairs (i, i+1): they carry row kp of Ri into its last entry */
+    double run = Ri[TRI(kp) + kp] * Ri[TRI(kp) + kp];
+    double tau = Ri[TRI(kp) + kp];
+    for (int i = kp; i < k - 1; ++i) {
+        const double wj = Ri[TRI(i + 1) + kp];
+        run += wj * wj;
+        const double sj = sqrt(run);
+        gc[i] = wj / sj; gs[i] = -tau / sj;
+        tau = sj;
+    }
+    for (int r = 0; r < n; ++r) {
+        double carry = w->Q[(size_t)kp * n + r];
+        for (int i = kp; i < k - 1; ++i) {
+            const double b = w->Q[(size_t)(i + 1) * n + r];
+            w->Q[(size_t)i * n + r] = gc[i] * carry + gs[i] * b;
+            carry = -gs[i] * carry + gc[i] * b;
+        }
+    }
+    int bad = -1;
+    /* Ri: delete row kp, rotate the columns, drop the last column.  Rows are processed top-down so that
+     * new row rr (= old row rr or rr+1) can be written in place once old row ro has been buffered. */
+    for (int rr = 0; rr < k - 1; ++rr) {
+        const int ro = rr < kp ? rr : rr + 1;
+        for (int j = kp; j < k; ++j) rowbuf[j] = ro <= j ? Ri[TRI(j) + ro] : 0.;
+        double carry = rowbuf[kp];
+        for (int i = kp; i < k - 1; ++i) {
+            const double b = rowbuf[i + 1];
+            const double out = gc[i] * carry + gs[i] * b;
+            if (rr <= i) Ri[TRI(i) + rr] = out;
+            carry = -gs[i] * carry + gc[i] * b;
+            if (rr == i && bad < 0 && fabs(out) * S->tol_sing >= 1.) bad = rr;
+        }
+    }
+    for (int j = kp + 1; j < k; ++j) { w->row[j - 1] = w->row[j]; w->side[j - 1] = w->side[j]; w->lam[j - 1] = w->lam[j]; }
+    w->nW = k - 1;
+    return bad;
+}
+
+static void thin_ws_remove(const qp_shared *S, qp_ws *w, double *Ri, int kp, int *inW, double *gc, double *gs, double *rowbuf) {
+    inW[w->row[kp]] = 0;
+    int bad = thin_remove(S, w, Ri, kp, gc, gs, rowbuf);
+    while (bad >= 0) {
+        inW[w->row[bad]] = 0;
+        bad = thin_remove(S, w, Ri, bad, gc, gs, rowbuf);
+    }
+}
+
 size_t qp_work_doubles(int n, int m) {
-    return (size_t)(n + 1) * (n + 1) + (size_t)n * n + 14 * (size_t)(n + 1) + 4 * (size_t)m + 64;
+    return (size_t)(n + 1) * (n + 1) + (size_t)n * n + 20 * (size_t)(n + 1) + 4 * (size_t)m + 64;
 }
 
 /* returns status.  Outputs: z (n), ycoord (n, the same point in orthonormal coordinates), y (m, signed multipliers of the ORIGINAL rows: > 0 upper side,
- * < 0 lower side; Farkas ray if infeasible), farkas (cost of the ray), final working set. */
-int qp_solve(const qp_shared *S, const double *x0, const double *lb, const double *ub,
+ * < 0 lower side; Farkas ray if infeasible), farkas (cost of the ray), final working set.
+ * buf / ibuf: workspace (qp_work_doubles / qp_work_ints); keep != 0: the workspace holds the state left by the
+ * previous solve (factor, working set, multipliers, proximal centre) and the solve continues from it -- this is
+ * what a CUDA solver slot does between the nodes of one instance. */
+size_t qp_work_ints(int n, int m) { return 2 * (size_t)(n + 1) + 3 * (size_t)m + 4; }
+
+static int qp_solve_impl(const qp_shared *S, double *buf, int *ibuf, int keep, const double *x0, const double *lb, const double *ub,
              int nW0, const int *W0row, const int *W0side, const double *lam0, const double *z0,
              double *z, double *ycoord, double *y, double *farkas,
              int *nWout, int *Wrow, int *Wside, double *Wlam, int *iters, int *prox_iters)
@@ -170,15 +280,15 @@ int qp_solve(const qp_shared *S, const double *x0, const double *lb, const doubl
     const int n = S->n, m = S->m, mc = S->mc, nb = S->nb, nx = S->nx;
     qp_ws w;
     w.ld = n + 1;
-    double *buf = (double *)malloc(sizeof(double) * qp_work_doubles(n, m));
-    int *ibuf = (int *)malloc(sizeof(int) * (2 * (size_t)(n + 1) + 3 * (size_t)m));
     static const double tenpow[3] = {1., 10., 100.};
     double *p = buf;
     w.R = p; p += (size_t)(n + 1) * (n + 1);
     w.Q = p; p += (size_t)n * n;
     w.n = n;
-    memset(w.Q, 0, sizeof(double) * (size_t)n * n);
-    for (int i = 0; i < n; ++i) w.Q[(size_t)i * n + i] = 1.;
+    if (!keep) {
+        memset(w.Q, 0, sizeof(double) * (size_t)n * n);
+        for (int i = 0; i < n; ++i) w.Q[(size_t)i * n + i] = 1.;
+    }
     double *hv = p; p += n + 1;
     w.lam = p; p += n + 1;
     double *lstar = p; p += n + 1;
@@ -192,20 +302,36 @@ int qp_solve(const qp_shared *S, const double *x0, const double *lb, const doubl
     double *bl = p; p += m;
     double *bu = p; p += m;
     double *g = p; p += m;
+    /* variant 1 (thin factor): Ri aliases the storage of R */
+    double *Ri = w.R;
+    double *gc = p; p += n + 1;
+    double *gs = p; p += n + 1;
+    double *rowbuf = p; p += n + 1;
+    double *zt = p; p += n + 1;
+    double *c2 = p; p += n + 1;
+    const int thin = S->variant == 1;
+#define APPEND(r_, s_) (thin ? thin_append(S, &w, Ri, (r_), (s_), t, tmp, zt, c2) : qr_append(S, &w, (r_), (s_), t, tmp, hv))
+#define REMOVE(k_) do { if (thin) thin_ws_remove(S, &w, Ri, (k_), inW, gc, gs, rowbuf); else ws_remove(S, &w, (k_), inW); } while (0)
     w.row = ibuf; w.side = ibuf + (n + 1);
     int *inW = ibuf + 2 * (n + 1);        /* +1 upper, -1 lower, 0 not in W */
     int *ign = inW + m;                   /* bit0: upper side ignored, bit1: lower */
     int *nadd = ign + m;                  /* times a row left the working set on a zero step */
-    memset(inW, 0, sizeof(int) * m); memset(ign, 0, sizeof(int) * m); memset(nadd, 0, sizeof(int) * m);
-    w.nW = 0;
+    int *nWkeep = nadd + m;
+    memset(ign, 0, sizeof(int) * m); memset(nadd, 0, sizeof(int) * m);
     int it = 0, status = QP_ITER_LIMIT, pk = 0;
-    for (int c = 0; c < n; ++c) zc[c] = z0 ? z0[c] : 0.;
+    if (keep) {
+        w.nW = *nWkeep; nW0 = 0;
+    } else {
+        memset(inW, 0, sizeof(int) * m);
+        w.nW = 0;
+        for (int c = 0; c < n; ++c) zc[c] = z0 ? z0[c] : 0.;
+    }
 
     /* warm start: rebuild the factor of the inherited working set, dropping dependent rows */
     for (int i = 0; i < nW0; ++i) {
         const int r = W0row[i], s = W0side[i];
         if (inW[r]) continue;
-        if (qr_append(S, &w, r, s, t, tmp, hv)) { w.lam[w.nW - 1] = lam0[i] * S->nrm[r]; inW[r] = s; }
+        if (APPEND(r, s)) { w.lam[w.nW - 1] = lam0[i] * S->nrm[r]; inW[r] = s; }
     }
 
     int pending = -1, pside = 0;          /* entering row that is dependent on W (singular case) */
@@ -228,8 +354,11 @@ int qp_solve(const qp_shared *S, const double *x0, const double *lb, const doubl
             const int k = w.nW;
             if (pending < 0) {
                 for (int i = 0; i < k; ++i) dW[i] = -(w.side[i] > 0 ? bu[w.row[i]] : -bl[w.row[i]]);
-                rt_forwardsolve(&w, k, dW, res);          /* u = R^-T (-d) ; lam* = R^-1 u ; v = -Q1 u */
-                r_backsolve(&w, k, res, lstar);
+                if (thin) { thin_rit_mul(Ri, k, dW, res); thin_ri_mul(Ri, k, res, lstar); }
+                else {
+                    rt_forwardsolve(&w, k, dW, res);      /* u = R^-T (-d) ; lam* = R^-1 u ; v = -Q1 u */
+                    r_backsolve(&w, k, res, lstar);
+                }
                 int kmin = -1; double amin = INFINITY;
                 for (int i = 0; i < k; ++i) if (lstar[i] < -S->tol_d) {
                     const double a = w.lam[i] / (w.lam[i] - lstar[i]);
@@ -241,7 +370,7 @@ int qp_solve(const qp_shared *S, const double *x0, const double *lb, const doubl
                     just_added = -1;
                     for (int i = 0; i < k; ++i) w.lam[i] += amin * (lstar[i] - w.lam[i]);
                     if (amin <= 1e-9) ++nadd[w.row[kmin]];
-                    ws_remove(S, &w, kmin, inW);
+                    REMOVE(kmin);
                     continue;
                 }
                 for (int i = 0; i < k; ++i) w.lam[i] = lstar[i] > 0. ? lstar[i] : 0.;
@@ -277,7 +406,7 @@ int qp_solve(const qp_shared *S, const double *x0, const double *lb, const doubl
                     }
                 }
                 if (jbest < 0) { status = QP_OPTIMAL; break; }
-                if (qr_append(S, &w, jbest, sbest, t, tmp, hv)) { inW[jbest] = sbest; just_added = jbest; }
+                if (APPEND(jbest, sbest)) { inW[jbest] = sbest; just_added = jbest; }
                 else { pending = jbest; pside = sbest; plam = 0.; }
             } else {
                 /* singular case: dual ray (p_W, 1) with p_W = -t  (t from the failed append) */
@@ -314,8 +443,8 @@ int qp_solve(const qp_shared *S, const double *x0, const double *lb, const doubl
                 for (int i = 0; i < k; ++i) w.lam[i] -= amin * t[i];
                 plam += amin;
                 if (amin <= 1e-9 * (1. + plam)) ++nadd[w.row[kmin]];
-                ws_remove(S, &w, kmin, inW);
-                if (qr_append(S, &w, pending, pside, t, tmp, hv)) {
+                REMOVE(kmin);
+                if (APPEND(pending, pside)) {
                     w.lam[w.nW - 1] = plam; inW[pending] = pside; pending = -1;
                 }
             }
@@ -349,6 +478,78 @@ int qp_solve(const qp_shared *S, const double *x0, const double *lb, const doubl
     }
     *nWout = w.nW;
     for (int i = 0; i < w.nW; ++i) { Wrow[i] = w.row[i]; Wside[i] = w.side[i]; Wlam[i] = w.lam[i] / S->nrm[w.row[i]]; }
-    free(buf); free(ibuf);
+    *nWkeep = w.nW;
     return status;
+}
+
+int qp_solve(const qp_shared *S, const double *x0, const double *lb, const double *ub,
+             int nW0, const int *W0row, const int *W0side, const double *lam0, const double *z0,
+             double *z, double *ycoord, double *y, double *farkas,
+             int *nWout, int *Wrow, int *Wside, double *Wlam, int *iters, int *prox_iters)
+{
+    double *buf = (double *)malloc(sizeof(double) * qp_work_doubles(S->n, S->m));
+    int *ibuf = (int *)malloc(sizeof(int) * qp_work_ints(S->n, S->m));
+    const int st = qp_solve_impl(S, buf, ibuf, 0, x0, lb, ub, nW0, W0row, W0side, lam0, z0, z, ycoord, y, farkas,
+                                 nWout, Wrow, Wside, Wlam, iters, prox_iters);
+    free(buf); free(ibuf);
+    return st;
+}
+
+/* persistent solver state = one CUDA "slot": the factor survives between solves */
+typedef struct { double *buf; int *ibuf; int used; } qp_state;
+
+void *qp_state_new(int n, int m) {
+    qp_state *st = (qp_state *)malloc(sizeof(qp_state));
+    st->buf = (double *)malloc(sizeof(double) * qp_work_doubles(n, m));
+    st->ibuf = (int *)malloc(sizeof(int) * qp_work_ints(n, m));
+    st->used = 0;
+    return st;
+}
+
+void qp_state_free(void *p) { qp_state *st = (qp_state *)p; if (st) { free(st->buf); free(st->ibuf); free(st); } }
+
+/* reset != 0: start from the empty working set (first node of an instance) */
+int qp_solve_state(const qp_shared *S, void *state, int reset, const double *x0, const double *lb, const double *ub,
+                   double *z, double *ycoord, double *y, double *farkas,
+                   int *nWout, int *Wrow, int *Wside, double *Wlam, int *iters, int *prox_iters)
+{
+    qp_state *st = (qp_state *)state;
+    const int keep = st->used && !reset;
+    st->used = 1;
+    return qp_solve_impl(S, st->buf, st->ibuf, keep, x0, lb, ub, 0, NULL, NULL, NULL, NULL, z, ycoord, y, farkas,
+                         nWout, Wrow, Wside, Wlam, iters, prox_iters);
+}
+
+
+/* diagnostics of a persistent state: out[0] = max |Mw' - Q1 R| (variant 0) or max |Mw' Ri - Q1| (variant 1),
+ * out[1] = max |Q1'Q1 - I|, out[2] = nW, out[3] = max |diag| of Ri resp. 1/min |diag R| */
+void qp_state_diag(const qp_shared *S, void *state, double *out)
+{
+    qp_state *st = (qp_state *)state;
+    const int n = S->n, m = S->m;
+    double *R = st->buf, *Q = st->buf + (size_t)(n + 1) * (n + 1);
+    int *row = st->ibuf, *side = st->ibuf + (n + 1);
+    const int k = *(st->ibuf + 2 * (n + 1) + 3 * m);
+    double e0 = 0., e1 = 0., dmax = 0.;
+    for (int j = 0; j < k; ++j) {
+        for (int i = 0; i < n; ++i) {
+            double a = 0.;
+            if (S->variant == 1) {
+                /* (Mw' Ri)[i][j] = sum_{l<=j} s_l Mh[row_l][i] Ri[l][j] */
+                for (int l = 0; l <= j; ++l) a += (double)side[l] * S->Mh[(size_t)row[l] * n + i] * R[TRI(j) + l];
+                a -= Q[(size_t)j * n + i];
+            } else {
+                for (int l = 0; l <= j; ++l) a += Q[(size_t)l * n + i] * R[l * (n + 1) + j];
+                a -= (double)side[j] * S->Mh[(size_t)row[j] * n + i];
+            }
+            if (fabs(a) > e0) e0 = fabs(a);
+        }
+        const double d = S->variant == 1 ? fabs(R[TRI(j) + j]) : 1. / fabs(R[j * (n + 1) + j]);
+        if (d > dmax) dmax = d;
+        for (int l = 0; l <= j; ++l) {
+            double a = dot(Q + (size_t)j * n, Q + (size_t)l * n, n) - (l == j ? 1. : 0.);
+            if (fabs(a) > e1) e1 = fabs(a);
+        }
+    }
+    out[0] = e0; out[1] = e1; out[2] = k; out[3] = dmax;
 }

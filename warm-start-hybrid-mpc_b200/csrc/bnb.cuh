@@ -47,8 +47,9 @@ bnb_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, double *scra
     __shared__ int s_inst;
     const int slot = blockIdx.x;
     const int nb = P.nb;
-    SlotPtrs sp = slot_ptrs(slot_d, slot_i, slot, P.n);
-    Smem sm = carve_smem(smem_raw, P.n, P.m, P.nb, P.ns, P.q_in_smem, sp.Q);
+    SlotPtrs sp = slot_ptrs(slot_d, slot_i, slot, P.n, P.ld);
+    const Ctx cx = make_ctx(P, smem_raw, sp);
+    init_shared_tables(P, cx);
     double *y = ybuf + (size_t)slot * P.m;
     double *sc = scratch + (size_t)slot * bnb_scratch_doubles(nb, P.n_primal);
     double *lbv = sc, *ubv = sc + nb, *prim = sc + 2 * nb, *cost_s = prim + P.n_primal, *dobj_s = cost_s + 1;
@@ -89,7 +90,7 @@ bnb_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, double *scra
                     const double l = lb[j];
                     if (l < cutoff && (bi < 0 || l < best)) { best = l; bi = j; }
                 }
-            block_argmin(best, bi, sm.red, sm.ired);
+            block_argmin(best, bi, SMV(red), SMI(ired));
             if (bi < 0) { st = inc >= 0 ? BNB_OK : BNB_INFEASIBLE; break; }
             if (solves >= max_solves || nn + 2 > tr.cap_nodes || nr + 1 > tr.cap_recs) { st = BNB_CAPACITY; break; }
             // ---- bounds of the node (controller.py:273-298)
@@ -102,12 +103,11 @@ bnb_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, double *scra
             }
             __syncthreads();
             // ---- solve (K1), hot-started from the node solved before it
-            if (first) { load_slot(P, sp, sm, k, true); first = false; }
-            else begin_node(P, sm);
-            const int qs = qp_solve(P, sp, sm, k, xi, lbv, ubv, y, iters_s);
+            if (first) { load_slot(P, cx, sp, k, true); first = false; }
+            const int qs = qp_solve(P, cx, k, xi, lbv, ubv, y, iters_s);
             if (qs == WS_ITER_LIMIT) { st = BNB_QP_LIMIT; break; }
             double *dual = rdual + (size_t)nr * P.n_dual;
-            build_records(P, qs, sm.yc, y, xi, lbv, ubv, prim, dual, cost_s, dobj_s, sm.part, sm.red);
+            build_records(P, qs, SMV(yc), y, xi, lbv, ubv, prim, dual, cost_s, dobj_s, SMV(part), SMV(red));
             const double cost = *cost_s;
             if (threadIdx.x == 0) {
                 lb[bi] = cost; rec[bi] = nr; rdobj[nr] = *dobj_s;

@@ -6,16 +6,29 @@
 // and differ only in the bounds (x0 and the bounds on the relaxed binaries), see DESIGN.md.
 // One CTA (WS_NT threads, one CTA per SM) owns one solver state ("slot"):
 //     working set W (rows, sides, multipliers lam >= 0 of the sign-normalised rows),
-//     Mw' = Q[:, :k] R   Q n x n orthogonal, column major, in SHARED memory when it fits (157 KB for the
-//                        T=20 cart-pole), else in global memory / L2;
-//                        R upper triangular, packed by columns, global memory / L2;
-//     Ri = R^-1 (packed) so that every solve with R is a parallel mat-vec instead of a substitution,
+//     THIN factorisation  Mw' = Q1 R  kept as
+//         Q1  n x k  orthonormal columns, column major (leading dimension ld),
+//         Ri  = R^-1 upper triangular, packed by columns (column j at j (j + 1) / 2),
+//     (no R, no null-space basis); the first `ks` columns of both live in SHARED memory (all of them on the
+//     T = 20 cart-pole), later columns in the slot's global home / L2;
+//     u = R^-T (-d_W), ls = R^-1 u (the multipliers of the equality-constrained sub-problem) and
+//     v = -Q1 u (its primal point) are kept up to date INCREMENTALLY: O(n + k) per append / removal
+//     instead of two triangular solves and an n x k product per iteration;
 //     yc = proximal centre.
+// Appending a row is classical Gram-Schmidt against Q1 with one re-orthogonalisation pass when more than
+// a digit was lost (Daniel, Gragg, Kaufman & Stewart 1976); removing position kp rotates the columns of
+// Q1 and Ri with the Givens sequence that carries row kp of Ri into its last entry: every rotation is
+// known up front from prefix sums of squares of that row, so the removal has no chain of dependent
+// square roots and all matrix work is parallel over rows.  Every solve with R is a mat-vec with Ri.
 // Rows are priced in FACTORED form: mh_r . x = a_r . (Wf x) / nrm_r with Wf = N Rinv (ns x n, shared by
-// every CTA, L2 resident) and a_r the sparse stage row [F_t G_t] of the MLD system, instead of streaming
+// every CTA, L2 resident, stored transposed so that a thread owns two output rows and streams 16-byte
+// words) and a_r the sparse stage row [F_t G_t] of the MLD system (shared memory), instead of streaming
 // the dense m x n operator (6x less L2 traffic on the cart-pole).
-// The state survives between nodes: any lam >= 0 is dual feasible for every node, so each node is
-// hot-started from whatever node the slot solved last.
+// Between the nodes of an instance the WORKING SET survives (any lam >= 0 is dual feasible for every
+// node) and its factor is rebuilt at the start of the node, so rounding never accumulates across nodes;
+// a hot-started solve that degenerates (iteration cap, exploding multipliers) is restarted once from the
+// empty working set.
+// The sequential twin of this file (same pivoting rules, same factorisation) is oracle/qp_core.c variant 1.
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
@@ -23,30 +36,50 @@
 
 #define WS_NT 512
 #define WS_NW (WS_NT / 32)
+#define WS_JW 128               // lanes of the k-indexed phases (columns of Q1 / rows of Ri)
+#define WS_NG (WS_NT / WS_JW)   // groups splitting the long dimension of those phases
+#define WS_CH 8                 // columns per chunk of the removal sweep
 #define WS_OPTIMAL 2
 #define WS_INFEASIBLE 3
 #define WS_ITER_LIMIT 9
+#define WS_REORTH 1e-2          // re-orthogonalise when |z|^2 < WS_REORTH |m_j|^2  (|m_j| = 1)
+#define WS_LAM_MAX 1e13         // sum of multipliers beyond which a hot-started solve is declared degenerate
+
+// offsets (in doubles unless noted) of the shared-memory arrays, resolved on the host (wshmpc_create)
+struct SmemOff {
+    int Q, Ri, z, c1, c2, t, u, ls, lam, cw, yc, wv, v, gc, gs, bu, blb, inr, vsc, xi, part, red, sF, sG, sF1, sG1;
+    int irow, iside, ired, iscr, rinfo;   // int offsets (from the start of the int area)
+    int ints;                             // start of the int area, in doubles
+    int binW, bign, bnadd;                // byte offsets from the start of the byte area
+    int bytes;                            // start of the byte area, in doubles
+    int total_bytes;
+};
 
 struct DevProblem {
     int nx, nu, nub, nuc, T, nh, nh1, nq, nqT, nr, n, m, mc, nb, ns;
     const double *A, *B, *F, *G, *h, *F1, *G1, *h1, *Q, *R, *QT, *Mmu, *Mrho;
-    const double *Mh, *Wf, *nrm, *inr, *vscale, *Eh, *hh, *Rinv, *RinvT, *Kx, *ZmapT;
+    const double *Mh, *WfT, *nrm, *inr, *vscale, *Eh, *hh, *Rinv, *RinvT, *Kx, *ZmapT;
     const int *bin_idx;
     double eps, tol_p, tol_d, tol_sing, tol_ray, prox_tol;
     int max_iter, max_prox;
-    int q_in_smem;           // 1: Q lives in shared memory while a CTA works on the slot
-    int tri;                 // (n+1)(n+2)/2 packed triangle size
+    int ks;                  // columns of Q1 and of Ri held in shared memory
+    int ld;                  // leading dimension of Q1 (even, ld / 2 odd: conflict-free 16-byte column reads)
+    int np;                  // n rounded up to even
+    int ns2;                 // ns rounded up to even
+    int kp_;                 // stride of the k-indexed partial sums (>= n)
+    int gb, gp;              // groups of the n-pair-indexed / ns-pair-indexed phases
+    int hot_cap;             // iteration cap of a hot-started solve before it is restarted cold
+    SmemOff so;
     // record layout
     int n_primal, n_dual, off_lam, off_mu, off_nulb, off_nuub, off_rho, off_sigma;
 };
 
+__host__ __device__ __forceinline__ int tri_off(int j) { return j * (j + 1) / 2; }
+
 // per-slot persistent state in global memory
 struct SlotPtrs {
-    double *Q;      // n*n   (home of Q; working copy when it does not fit in shared memory)
-    double *R;      // tri
-    double *Ri;     // tri
-    double *tmp;    // tri (scratch: R down-date)
-    double *tmp2;   // tri (scratch: Ri down-date)
+    double *Q;      // n*ld  (home of the columns >= ks of Q1)
+    double *Ri;     // n(n+1)/2
     double *lam;    // n+1
     double *yc;     // n
     int *row;       // n+1
@@ -54,22 +87,15 @@ struct SlotPtrs {
     int *nW;        // 1
 };
 
-__host__ __device__ inline size_t slot_doubles(int n) {
-    size_t tri = (size_t)(n + 1) * (n + 2) / 2;
-    return (size_t)n * n + 4 * tri + (n + 1) + n;
-}
+__host__ __device__ inline size_t slot_doubles(int n, int ld) { return (((size_t)n * ld + (size_t)tri_off(n) + (n + 1) + n + 4) + 1) & ~(size_t)1; }   // even: 16-byte aligned slots
 __host__ __device__ inline size_t slot_ints(int n) { return 2 * (size_t)(n + 1) + 4; }
 
-__device__ inline SlotPtrs slot_ptrs(double *dbase, int *ibase, int slot, int n) {
+__device__ inline SlotPtrs slot_ptrs(double *dbase, int *ibase, int slot, int n, int ld) {
     SlotPtrs s;
-    const size_t tri = (size_t)(n + 1) * (n + 2) / 2;
-    double *d = dbase + (size_t)slot * slot_doubles(n);
+    double *d = dbase + (size_t)slot * slot_doubles(n, ld);
     int *i = ibase + (size_t)slot * slot_ints(n);
-    s.Q = d; d += (size_t)n * n;
-    s.R = d; d += tri;
-    s.Ri = d; d += tri;
-    s.tmp = d; d += tri;
-    s.tmp2 = d; d += tri;
+    s.Q = d; d += (size_t)n * ld;
+    s.Ri = d; d += tri_off(n);
     s.lam = d; d += n + 1;
     s.yc = d;
     s.row = i; i += n + 1;
@@ -78,48 +104,27 @@ __device__ inline SlotPtrs slot_ptrs(double *dbase, int *ibase, int slot, int n)
     return s;
 }
 
-// shared-memory working vectors of one CTA
-struct Smem {
-    double *v, *wv, *c, *hv, *t, *ls, *u, *yc, *lam, *bu, *blb, *gc, *gs, *red, *xi, *mj, *part, *stage;
-    double *Q;          // n x n column major (smem or global)
-    int *row, *side, *ired;
-    signed char *inW;
-    unsigned char *ign, *nadd;
+// what a thread keeps in registers
+struct Ctx {
+    double *smd;             // shared memory base
+    double *gQ, *gRi;        // global homes of the columns >= ks
+    int bg, bip;             // (group, pair) of the n-pair-indexed phases
+    int pg, prp;             // (group, pair) of the ns-pair-indexed phases
 };
 
-__host__ __device__ inline size_t smem_doubles(int n, int m, int nb, int ns) {
-    const size_t part = (size_t)(n > WS_NT ? n : WS_NT);
-    return 12 * (size_t)(n + 1) + m + nb + ns + part + 32 * 33 + 4 * WS_NW + 8;
-}
-__host__ __device__ inline size_t smem_bytes(int n, int m, int nb, int ns, int q_in_smem) {
-    size_t d = smem_doubles(n, m, nb, ns);
-    if (q_in_smem) d += (size_t)n * n;
-    size_t b = d * 8 + (2 * (size_t)(n + 1) + 2 * WS_NW + 8) * 4 + 3 * (size_t)m + 16;
-    return (b + 15) & ~(size_t)15;
-}
+#define SMV(name) (cx.smd + P.so.name)
+#define SMI(name) (reinterpret_cast<int *>(cx.smd + P.so.ints) + P.so.name)
+#define SMB(name) (reinterpret_cast<unsigned char *>(cx.smd + P.so.bytes) + P.so.name)
 
-__device__ inline Smem carve_smem(unsigned char *base, int n, int m, int nb, int ns, int q_in_smem, double *Qglobal) {
-    Smem s;
-    double *d = reinterpret_cast<double *>(base);
-    if (q_in_smem) { s.Q = d; d += (size_t)n * n; } else s.Q = Qglobal;
-    s.v = d; d += n + 1;  s.wv = d; d += n + 1;  s.c = d; d += n + 1;  s.hv = d; d += n + 1;
-    s.t = d; d += n + 1;  s.ls = d; d += n + 1;  s.u = d; d += n + 1;  s.yc = d; d += n + 1;
-    s.lam = d; d += n + 1;  s.mj = d; d += n + 1;
-    s.gc = d; d += n + 1;  s.gs = d; d += n + 1;
-    s.bu = d; d += m;  s.blb = d; d += nb;  s.xi = d; d += ns;
-    s.part = d; d += (n > WS_NT ? n : WS_NT);
-    s.stage = d; d += 32 * 33;
-    s.red = d; d += 4 * WS_NW + 8;
-    int *i = reinterpret_cast<int *>(d);
-    s.row = i; i += n + 1;  s.side = i; i += n + 1;  s.ired = i; i += 2 * WS_NW + 8;
-    signed char *b = reinterpret_cast<signed char *>(i);
-    s.inW = b; b += m;
-    s.ign = reinterpret_cast<unsigned char *>(b); b += m;
-    s.nadd = reinterpret_cast<unsigned char *>(b);
-    return s;
+__device__ inline Ctx make_ctx(const DevProblem &P, unsigned char *smem_raw, const SlotPtrs &sp) {
+    Ctx cx;
+    cx.smd = reinterpret_cast<double *>(smem_raw);
+    cx.gQ = sp.Q; cx.gRi = sp.Ri;
+    const int h = P.np >> 1, hs = P.ns2 >> 1;
+    cx.bg = threadIdx.x / h; cx.bip = threadIdx.x - cx.bg * h;
+    cx.pg = threadIdx.x / hs; cx.prp = threadIdx.x - cx.pg * hs;
+    return cx;
 }
-
-__device__ __forceinline__ int tri_off(int j) { return j * (j + 1) / 2; }
 
 __device__ __forceinline__ double warp_sum(double x) {
 #pragma unroll
@@ -138,6 +143,19 @@ __device__ inline double block_sum(double x, double *red) {
 #pragma unroll
     for (int i = 0; i < WS_NW; ++i) s += red[i];
     return s;
+}
+
+// two block-wide sums at once
+__device__ inline void block_sum2(double &x, double &y, double *red) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    x = warp_sum(x); y = warp_sum(y);
+    __syncthreads();
+    if (lane == 0) { red[w] = x; red[WS_NW + w] = y; }
+    __syncthreads();
+    double s = 0., q = 0.;
+#pragma unroll
+    for (int i = 0; i < WS_NW; ++i) { s += red[i]; q += red[WS_NW + i]; }
+    x = s; y = q;
 }
 
 // block-wide arg-max of (val, idx): larger val wins, ties -> smaller idx.  idx < 0 = no candidate.
@@ -167,11 +185,34 @@ __device__ inline void block_argmin(double &val, int &idx, double *red, int *ire
     val = -nv;
 }
 
+// arg-min and a sum in one pass (ratio test + sum of the positive multipliers)
+__device__ inline void block_argmin_sum(double &val, int &idx, double &sum, double *red, int *ired) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, val, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (oi >= 0 && (idx < 0 || ov < val || (ov == val && oi < idx))) { val = ov; idx = oi; }
+    }
+    __syncthreads();
+    if (lane == 0) { red[w] = val; ired[w] = idx; red[WS_NW + w] = sum; }
+    __syncthreads();
+    val = red[0]; idx = ired[0]; sum = red[WS_NW];
+#pragma unroll
+    for (int i = 1; i < WS_NW; ++i) {
+        const double ov = red[i]; const int oi = ired[i];
+        sum += red[WS_NW + i];
+        if (oi >= 0 && (idx < 0 || ov < val || (ov == val && oi < idx))) { val = ov; idx = oi; }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
-// grouped mat-vec:  out(i, sum_{j0 <= j < j1} M[j * ld + i] * x[j])  for i < rows.
-// Adjacent threads take adjacent i (coalesced / conflict free); when rows <= WS_NT the threads form
-// G = WS_NT / rows groups that split the j range and combine through `part` (>= max(WS_NT, rows) doubles).
+// grouped mat-vec with a shared operator:  out(i, sum_{j0 <= j < j1} M[j * ld + i] * x[j])  for i < rows.
+// Adjacent threads take adjacent i (coalesced); when rows <= WS_NT the threads form G = WS_NT / rows
+// groups that split the j range and combine through `part` (>= max(WS_NT, rows) doubles).
 // Ends with a barrier-protected combine; `out` is called once per row.  Contains __syncthreads.
+// (refresh / record paths only: once per proximal pass, not per iteration)
 // ---------------------------------------------------------------------------------------------
 template <class Out>
 __device__ inline void grouped_matvec(const double *__restrict__ M, int ld, int rows, int j0, int j1,
@@ -180,14 +221,16 @@ __device__ inline void grouped_matvec(const double *__restrict__ M, int ld, int 
         const int G = WS_NT / rows;
         const int g = threadIdx.x / rows, i = threadIdx.x - g * rows;
         if (g < G) {
-            double s0 = 0., s1 = 0.;
+            double s0 = 0., s1 = 0., s2 = 0., s3 = 0.;
             int j = j0 + g;
-            for (; j + G < j1; j += 2 * G) {
+            for (; j + 3 * G < j1; j += 4 * G) {
                 s0 += M[(size_t)j * ld + i] * x[j];
                 s1 += M[(size_t)(j + G) * ld + i] * x[j + G];
+                s2 += M[(size_t)(j + 2 * G) * ld + i] * x[j + 2 * G];
+                s3 += M[(size_t)(j + 3 * G) * ld + i] * x[j + 3 * G];
             }
-            if (j < j1) s0 += M[(size_t)j * ld + i] * x[j];
-            part[g * rows + i] = s0 + s1;
+            for (; j < j1; j += G) s0 += M[(size_t)j * ld + i] * x[j];
+            part[g * rows + i] = (s0 + s1) + (s2 + s3);
         }
         __syncthreads();
         if (threadIdx.x < rows) {
@@ -209,243 +252,303 @@ __device__ inline void grouped_matvec(const double *__restrict__ M, int ld, int 
 }
 
 // ---------------------------------------------------------------------------------------------
-// factor updates
+// thin factor: products with Q1 and Ri.  Columns < ks in shared memory, the rest in the global home.
 // ---------------------------------------------------------------------------------------------
 
-// t = Ri * c[:k]   (t_i = sum_{j >= i} Ri[tri_off(j) + i] c_j ; adjacent threads -> adjacent i, coalesced)
-__device__ inline void ri_matvec(const double *__restrict__ Ri, int k, const double *c, double *t, double *part) {
-    if (k <= 0) { __syncthreads(); return; }
-    if (k <= WS_NT) {
-        const int G = WS_NT / k;
-        const int g = threadIdx.x / k, i = threadIdx.x - g * k;
-        if (g < G) {
-            double s = 0.;
-            for (int j = i + g; j < k; j += G) s += Ri[tri_off(j) + i] * c[j];
-            part[g * k + i] = s;
-        }
-        __syncthreads();
-        if (threadIdx.x < k) {
-            double s = part[threadIdx.x];
-            for (int q = 1; q < G; ++q) s += part[q * k + threadIdx.x];
-            t[threadIdx.x] = s;
-        }
-    } else {
-        for (int i = threadIdx.x; i < k; i += WS_NT) {
-            double s = 0.;
-            for (int j = i; j < k; ++j) s += Ri[tri_off(j) + i] * c[j];
-            t[i] = s;
-        }
+// out[j] = q_j . x  for j < k.  Thread (g, jl): column j = jl (+ WS_JW ...), rows of group g; partial sums
+// through `part` (stride kp_).  Ends with a barrier.
+__device__ inline void qt_dots(const DevProblem &P, const Ctx &cx, int k, const double *x, double *out) {
+    double *part = SMV(part);
+    const int g = threadIdx.x >> 7, jl = threadIdx.x & (WS_JW - 1);
+    const int h = P.np >> 1, cp = (h + WS_NG - 1) / WS_NG;
+    const int p0 = g * cp, p1 = min(p0 + cp, h);
+    const double2 *x2 = reinterpret_cast<const double2 *>(x);
+    int j = jl;
+    const int ke = min(k, P.ks);
+    for (; j < ke; j += WS_JW) {
+        const double2 *q2 = reinterpret_cast<const double2 *>(SMV(Q) + j * P.ld);
+        double s0 = 0., s1 = 0.;
+#pragma unroll 4
+        for (int p = p0; p < p1; ++p) { const double2 a = q2[p], b = x2[p]; s0 += a.x * b.x; s1 += a.y * b.y; }
+        part[g * P.kp_ + j] = s0 + s1;
+    }
+    for (; j < k; j += WS_JW) {
+        const double2 *q2 = reinterpret_cast<const double2 *>(cx.gQ + (size_t)j * P.ld);
+        double s0 = 0., s1 = 0.;
+        for (int p = p0; p < p1; ++p) { const double2 a = q2[p], b = x2[p]; s0 += a.x * b.x; s1 += a.y * b.y; }
+        part[g * P.kp_ + j] = s0 + s1;
+    }
+    __syncthreads();
+    for (int jj = threadIdx.x; jj < k; jj += WS_NT) {
+        double s = part[jj];
+#pragma unroll
+        for (int q = 1; q < WS_NG; ++q) s += part[q * P.kp_ + jj];
+        out[jj] = s;
     }
     __syncthreads();
 }
 
-// u = Ri' * d[:k]  (u_j = sum_{i <= j} Ri[tri_off(j) + i] d_i ; warp per column, lanes over rows)
-__device__ inline void rit_matvec(const double *__restrict__ Ri, int k, const double *d, double *u) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int j = w; j < k; j += WS_NW) {
-        const double *col = Ri + tri_off(j);
-        double s = 0.;
-        for (int i = lane; i <= j; i += 32) s += col[i] * d[i];
-        s = warp_sum(s);
-        if (lane == 0) u[j] = s;
+// z[i] -= sum_{j < k} q_j[i] c[j] ; returns this thread's share of |z|^2 (threads < np).  Ends with a barrier.
+__device__ inline double q_apply(const DevProblem &P, const Ctx &cx, int k, const double *c, double *z) {
+    double2 *part2 = reinterpret_cast<double2 *>(SMV(part));
+    const int h = P.np >> 1;
+    if (cx.bg < P.gb) {
+        double ax = 0., ay = 0., bx = 0., by = 0.;
+        int j = cx.bg;
+        const int ke = min(k, P.ks);
+        const double2 *q2 = reinterpret_cast<const double2 *>(SMV(Q)) + cx.bip;
+        const int ldh = P.ld >> 1, G = P.gb;
+        for (; j + G < ke; j += 2 * G) {
+            const double2 a = q2[j * ldh], b = q2[(j + G) * ldh];
+            const double ca = c[j], cb = c[j + G];
+            ax += a.x * ca; ay += a.y * ca; bx += b.x * cb; by += b.y * cb;
+        }
+        for (; j < ke; j += G) { const double2 a = q2[j * ldh]; const double ca = c[j]; ax += a.x * ca; ay += a.y * ca; }
+        const double2 *g2 = reinterpret_cast<const double2 *>(cx.gQ) + cx.bip;
+        for (; j < k; j += G) { const double2 a = g2[(size_t)j * ldh]; const double ca = c[j]; ax += a.x * ca; ay += a.y * ca; }
+        part2[cx.bg * h + cx.bip] = make_double2(ax + bx, ay + by);
     }
     __syncthreads();
+    double zz = 0.;
+    if (threadIdx.x < P.np) {
+        const double *part = SMV(part);
+        double s = part[threadIdx.x];
+        for (int q = 1; q < P.gb; ++q) s += part[q * P.np + threadIdx.x];
+        const double zi = z[threadIdx.x] - s;
+        z[threadIdx.x] = zi; zz = zi * zi;
+    }
+    __syncthreads();
+    return zz;
+}
+
+// t = Ri * c[:k]   (t_i = sum_{j >= i} Ri[tri_off(j) + i] c_j).  Thread (g, il): row i = il (+ WS_JW ...),
+// columns j = i + g, i + g + WS_NG, ...  Ends with a barrier.
+__device__ inline void ri_matvec(const DevProblem &P, const Ctx &cx, int k, const double *c, double *t) {
+    double *part = SMV(part);
+    const int g = threadIdx.x >> 7, il = threadIdx.x & (WS_JW - 1);
+    const int ke = min(k, P.ks);
+    for (int i = il; i < k; i += WS_JW) {
+        double s0 = 0., s1 = 0.;
+        int j = i + g;
+        const double *Ri = SMV(Ri);
+        for (; j + WS_NG < ke; j += 2 * WS_NG) { s0 += Ri[tri_off(j) + i] * c[j]; s1 += Ri[tri_off(j + WS_NG) + i] * c[j + WS_NG]; }
+        for (; j < ke; j += WS_NG) s0 += Ri[tri_off(j) + i] * c[j];
+        for (; j < k; j += WS_NG) s0 += cx.gRi[tri_off(j) + i] * c[j];
+        part[g * P.kp_ + i] = s0 + s1;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < k; i += WS_NT) {
+        double s = part[i];
+#pragma unroll
+        for (int q = 1; q < WS_NG; ++q) s += part[q * P.kp_ + i];
+        t[i] = s;
+    }
+    __syncthreads();
+}
+
+// u = Ri' * d[:k]  (u_j = sum_{i <= j} Ri[tri_off(j) + i] d_i).  Refresh path only.  Ends with a barrier.
+__device__ inline void rit_matvec(const DevProblem &P, const Ctx &cx, int k, const double *d, double *u) {
+    double *part = SMV(part);
+    const int g = threadIdx.x >> 7, jl = threadIdx.x & (WS_JW - 1);
+    for (int j = jl; j < k; j += WS_JW) {
+        const double *col = (j < P.ks ? SMV(Ri) : cx.gRi) + tri_off(j);
+        double s = 0.;
+        for (int i = g; i <= j; i += WS_NG) s += col[i] * d[i];
+        part[g * P.kp_ + j] = s;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < k; j += WS_NT) {
+        double s = part[j];
+#pragma unroll
+        for (int q = 1; q < WS_NG; ++q) s += part[q * P.kp_ + j];
+        u[j] = s;
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ double *qcol_w(const DevProblem &P, const Ctx &cx, int j) { return j < P.ks ? SMV(Q) + j * P.ld : cx.gQ + (size_t)j * P.ld; }
+__device__ __forceinline__ double *ricol_w(const DevProblem &P, const Ctx &cx, int j) { return (j < P.ks ? SMV(Ri) : cx.gRi) + tri_off(j); }
+
+// -(signed bound of row r on side s): the entry of c = -d_W
+__device__ __forceinline__ double neg_bound(const DevProblem &P, const Ctx &cx, int r, int s) {
+    return -(s > 0 ? SMV(bu)[r] : -SMV(blb)[r - P.mc]);
+}
+
+// u = R^-T (-d_W), ls = R^-1 u, v = -Q1 u from scratch (new bounds: node start, proximal pass)
+__device__ inline void refresh_uv(const DevProblem &P, const Ctx &cx, int k) {
+    const int *row = SMI(irow), *side = SMI(iside);
+    for (int i = threadIdx.x; i < k; i += WS_NT) SMV(cw)[i] = neg_bound(P, cx, row[i], side[i]);
+    for (int i = threadIdx.x; i < P.np; i += WS_NT) SMV(v)[i] = 0.;
+    __syncthreads();
+    rit_matvec(P, cx, k, SMV(cw), SMV(u));
+    ri_matvec(P, cx, k, SMV(u), SMV(ls));
+    q_apply(P, cx, k, SMV(u), SMV(v));
 }
 
 // Try to append the sign-normalised row (r, sgn).  Returns 1 if appended (lam = 0), 0 if the row is
-// numerically in the span of the working rows; in that case sm.t = R^-1 c[:k]  (mj = Mw' t).
-__device__ inline int qr_append(const DevProblem &P, const SlotPtrs &sp, Smem &sm, int &k, int r, int sgn) {
-    const int n = P.n, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const double *Q = sm.Q;
-    for (int i = threadIdx.x; i < n; i += WS_NT) sm.mj[i] = P.Mh[(size_t)r * n + i];
+// numerically in the span of the working rows; either way t = R^-1 Q1' mj  (mj = Mw' t if dependent).
+// `track`: also bring u, ls, v up to date (false while the factor of an inherited working set is rebuilt).
+__device__ inline int thin_append(const DevProblem &P, const Ctx &cx, int &k, int r, int sgn, bool track) {
+    const int n = P.n;
+    double *z = SMV(z), *c1 = SMV(c1), *t = SMV(t);
+    for (int i = threadIdx.x; i < P.np; i += WS_NT) z[i] = i < n ? (double)sgn * __ldg(P.Mh + (size_t)r * n + i) : 0.;
     __syncthreads();
-    // c = sgn * Q' mj   (warp per column, two columns in flight)
-    for (int col = w; col < n; col += 2 * WS_NW) {
-        const int col2 = col + WS_NW;
-        const double *q0 = Q + (size_t)col * n, *q1 = Q + (size_t)(col2 < n ? col2 : col) * n;
-        double s0 = 0., s1 = 0.;
-        for (int i = lane; i < n; i += 32) { const double x = sm.mj[i]; s0 += q0[i] * x; s1 += q1[i] * x; }
-        s0 = warp_sum(s0); s1 = warp_sum(s1);
-        if (lane == 0) { sm.c[col] = (double)sgn * s0; if (col2 < n) sm.c[col2] = (double)sgn * s1; }
+    qt_dots(P, cx, k, z, c1);
+    double zz = q_apply(P, cx, k, c1, z);
+    double cu = 0.;
+    if (track) for (int j = threadIdx.x; j < k; j += WS_NT) cu += c1[j] * SMV(u)[j];
+    block_sum2(zz, cu, SMV(red));
+    double rho2 = zz;
+    if (k > 0 && rho2 < WS_REORTH) {
+        double *c2 = SMV(c2);
+        qt_dots(P, cx, k, z, c2);
+        zz = q_apply(P, cx, k, c2, z);
+        double cu2 = 0.;
+        for (int j = threadIdx.x; j < k; j += WS_NT) { const double d = c2[j]; c1[j] += d; if (track) cu2 += d * SMV(u)[j]; }
+        block_sum2(zz, cu2, SMV(red));
+        rho2 = zz; cu += cu2;
     }
-    __syncthreads();
-    double part = 0.;
-    for (int j = k + threadIdx.x; j < n; j += WS_NT) part += sm.c[j] * sm.c[j];
-    const double rho2 = block_sum(part, sm.red);
-    // t = Ri c1: the dual ray of a dependent row / the new column of Ri (before R, Ri are touched)
-    ri_matvec(sp.Ri, k, sm.c, sm.t, sm.part);
+    ri_matvec(P, cx, k, c1, t);
     if (k >= n || rho2 <= P.tol_sing * P.tol_sing) return 0;
-    const double rho = sqrt(rho2);
-    const double ck = sm.c[k];
-    const double sg = ck >= 0. ? 1. : -1.;
-    const double hk = ck + sg * rho;
-    const double hh = rho2 - ck * ck + hk * hk;
-    const double beta = 2. / hh;
-    __syncthreads();
-    for (int j = k + threadIdx.x; j < n; j += WS_NT) sm.hv[j] = (j == k) ? hk : sm.c[j];
-    __syncthreads();
-    // Q2 <- Q2 - beta (Q2 hv) hv'   (adjacent threads -> adjacent rows of the column-major Q)
-    {
-        double *Qw = sm.Q;
-        if (n <= WS_NT) {
-            const int G = WS_NT / n;
-            const int g = threadIdx.x / n, i = threadIdx.x - g * n;
-            if (g < G) {
-                double a = 0.;
-                for (int j = k + g; j < n; j += G) a += Qw[(size_t)j * n + i] * sm.hv[j];
-                sm.part[g * n + i] = a;
-            }
-            __syncthreads();
-            if (g < G) {
-                double a = sm.part[i];
-                for (int q = 1; q < G; ++q) a += sm.part[q * n + i];
-                a *= beta;
-                for (int j = k + g; j < n; j += G) Qw[(size_t)j * n + i] -= a * sm.hv[j];
-            }
-        } else {
-            for (int i = threadIdx.x; i < n; i += WS_NT) {
-                double a = 0.;
-                for (int j = k; j < n; ++j) a += Qw[(size_t)j * n + i] * sm.hv[j];
-                a *= beta;
-                for (int j = k; j < n; ++j) Qw[(size_t)j * n + i] -= a * sm.hv[j];
-            }
-        }
+    const double ir = 1. / sqrt(rho2);
+    double *qk = qcol_w(P, cx, k), *rk = ricol_w(P, cx, k);
+    double uk = 0., lk = 0.;
+    if (track) { uk = (neg_bound(P, cx, r, sgn) - cu) * ir; lk = uk * ir; }
+    for (int i = threadIdx.x; i < P.np; i += WS_NT) {
+        const double q = z[i] * ir;
+        qk[i] = q;
+        if (track) SMV(v)[i] -= q * uk;
     }
-    const double rkk = -sg * rho, irkk = 1. / rkk;
-    double *Rc = sp.R + tri_off(k), *Ric = sp.Ri + tri_off(k);
-    for (int i = threadIdx.x; i < k; i += WS_NT) { Rc[i] = sm.c[i]; Ric[i] = -sm.t[i] * irkk; }
+    for (int i = threadIdx.x; i < k; i += WS_NT) {
+        const double ti = t[i];
+        rk[i] = -ti * ir;
+        if (track) SMV(ls)[i] -= ti * lk;
+    }
     if (threadIdx.x == 0) {
-        Rc[k] = rkk; Ric[k] = irkk;
-        sm.row[k] = r; sm.side[k] = sgn; sm.lam[k] = 0.;
+        rk[k] = ir;
+        SMI(irow)[k] = r; SMI(iside)[k] = sgn; SMV(lam)[k] = 0.;
+        if (track) { SMV(u)[k] = uk; SMV(ls)[k] = lk; }
     }
     k += 1;
     __syncthreads();
     return 1;
 }
 
-// Remove position kp from the working set: delete column kp of R, restore triangularity by Givens
-// rotations of rows (i, i+1), i = kp..k-2; the same rotations act on the columns of Q and of R^-1.
-__device__ inline void qr_remove(const DevProblem &P, const SlotPtrs &sp, Smem &sm, int &k, int kp) {
-    const int n = P.n, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const double *R = sp.R;
-    double *Rn = sp.tmp;                  // new R (columns kp .. k-2), built out of place
-    // ---- 1. warp 0: Givens chain.  Old column j (> kp) becomes new column j-1.  A lane owns one
-    // column of a block of 32 and carries its running entry in a register: entries of R are read once
-    // (no read-after-write through L2).  The other warps copy the untouched rows < kp meanwhile.
+// Remove position kp from the working set (u, ls, v follow).  Returns the smallest position >= kp whose
+// diagonal of R collapsed (|Ri_ii| >= 1 / tol_sing) after the removal, or -1.
+__device__ inline int thin_remove(const DevProblem &P, const Ctx &cx, int &k, int kp) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, tid = (int)threadIdx.x;
+    double *gc = SMV(gc), *gs = SMV(gs), *u = SMV(u);
+    int *row = SMI(irow), *side = SMI(iside), *flag = SMI(ired) + 2 * WS_NW;
+    if (tid == 0) *flag = 0x7fffffff;
+    if (kp == k - 1) {
+        // last position: Q1, Ri lose their last column; v += q_last u_last
+        const double ul = u[kp];
+        const double *qk = qcol_w(P, cx, kp);
+        for (int i = tid; i < P.np; i += WS_NT) SMV(v)[i] += qk[i] * ul;
+        k -= 1;
+        __syncthreads();
+        ri_matvec(P, cx, k, u, SMV(ls));
+        return -1;
+    }
+    // ---- 1. warp 0: rotations i = kp .. k-2 of the column pairs (i, i+1) from prefix sums of squares of row kp of Ri
     if (w == 0) {
-        for (int j0 = kp + 1; j0 < k; j0 += 32) {
-            const int j = j0 + lane;
-            const bool has = j < k;
-            const double *col = R + tri_off(has ? j : kp);
-            double *out = Rn + tri_off(has ? j - 1 : kp);
-            double carry = has ? col[kp] : 0.;
-            // rotations defined by earlier blocks: i = kp .. j0-2
-#pragma unroll 4
-            for (int i = kp; i < j0 - 1; ++i) {
-                const double b = has ? col[i + 1] : 0.;
-                const double cs = sm.gc[i], sn = sm.gs[i];
-                if (has) out[i] = cs * carry + sn * b;
-                carry = -sn * carry + cs * b;
+        const double wkp = ricol_w(P, cx, kp)[kp];
+        double run = 0.;
+        for (int b = kp; b < k; b += 32) {
+            const int j = b + lane;
+            const double wj = j < k ? ricol_w(P, cx, j)[kp] : 0.;
+            double s = wj * wj;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const double y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
+            s += run;                                             // sigma_j^2 (inclusive)
+            double excl = __shfl_up_sync(0xffffffffu, s, 1);      // sigma_{j-1}^2
+            if (lane == 0) excl = run;
+            if (j > kp && j < k) {
+                const double isj = 1. / sqrt(s);
+                const double tau = (j - 1 == kp) ? wkp : sqrt(excl);
+                gc[j - 1] = wj * isj; gs[j - 1] = -tau * isj;
             }
-            // stage rows j0 .. j of the own column (the triangular part of the block)
-            for (int q = 0; q < 32; ++q) sm.stage[q * 33 + lane] = (has && j0 + q <= j) ? col[j0 + q] : 0.;
-            __syncwarp();
-            const int iend = (j0 + 32 < k ? j0 + 32 : k) - 1;          // rotations i = j0-1 .. iend-1
-            for (int i = j0 - 1; i < iend; ++i) {
-                const int q = i + 1 - j0;                               // defining column = lane q, its row i+1
-                const double b = sm.stage[q * 33 + lane];
-                const double a_d = __shfl_sync(0xffffffffu, carry, q), b_d = __shfl_sync(0xffffffffu, b, q);
-                double cs = 1., sn = 0.;
-                const double hyp = sqrt(a_d * a_d + b_d * b_d);
-                if (hyp > 0.) { const double ih = 1. / hyp; cs = a_d * ih; sn = b_d * ih; }
-                if (lane == 0) { sm.gc[i] = cs; sm.gs[i] = sn; }
-                if (has && j >= i + 1) {
-                    out[i] = cs * carry + sn * b;
-                    carry = -sn * carry + cs * b;
+            run = __shfl_sync(0xffffffffu, s, 31);
+        }
+    }
+    // bookkeeping shift: read now, write after the first barrier of the sweep
+    int rw = 0, sd = 0; double lm = 0.;
+    const int tsrc = kp + 1 + tid;
+    if (tsrc < k) { rw = row[tsrc]; sd = side[tsrc]; lm = SMV(lam)[tsrc]; }
+    // ---- 2. sweep over the columns in chunks: Q rows in threads [0, np), Ri rows in threads WS_NT-1 .. downwards,
+    //         the u chain in thread np (first thread without a row of Q1)
+    const int qr = tid < P.np ? tid : -1;                                   // row of Q1
+    const int rr = (WS_NT - 1 - tid) < k - 1 ? WS_NT - 1 - tid : -1;        // new row of Ri (k - 1 <= WS_NT)
+    const int ro = rr < kp ? rr : rr + 1;                                   // its old row
+    const bool uth = tid == (P.np < WS_NT ? P.np : 0);
+    const double big = 1. / P.tol_sing;
+    __syncthreads();                                                        // gc, gs visible
+    double qcarry = qr >= 0 ? qcol_w(P, cx, kp)[qr] : 0.;
+    double rcarry = (rr >= 0 && ro <= kp) ? ricol_w(P, cx, kp)[ro] : 0.;
+    double ucarry = uth ? u[kp] : 0.;
+    for (int i0 = kp; i0 < k - 1; i0 += WS_CH) {
+        double b[WS_CH];
+        if (rr >= 0) {
+#pragma unroll
+            for (int q = 0; q < WS_CH; ++q) { const int i = i0 + q; b[q] = (i < k - 1 && ro <= i + 1) ? ricol_w(P, cx, i + 1)[ro] : 0.; }
+        }
+        __syncthreads();                                                    // every old entry of the chunk has been read
+        if (i0 == kp && tsrc < k) { row[tsrc - 1] = rw; side[tsrc - 1] = sd; SMV(lam)[tsrc - 1] = lm; }
+        if (rr >= 0 && ro <= i0 + WS_CH) {
+#pragma unroll
+            for (int q = 0; q < WS_CH; ++q) {
+                const int i = i0 + q;
+                if (i < k - 1) {
+                    const double cs = gc[i], sn = gs[i];
+                    const double o = cs * rcarry + sn * b[q];
+                    rcarry = -sn * rcarry + cs * b[q];
+                    if (rr <= i) {
+                        ricol_w(P, cx, i)[rr] = o;
+                        if (rr == i && fabs(o) >= big) atomicMin(flag, rr);
+                    }
                 }
             }
-            __syncwarp();
         }
-    } else {
-        // rows < kp of the shifted columns are unchanged
-        for (int j = kp + 1 + (w - 1); j < k; j += WS_NW - 1) {
-            const double *col = R + tri_off(j);
-            double *out = Rn + tri_off(j - 1);
-            for (int i = lane; i < kp; i += 32) out[i] = col[i];
-        }
-    }
-    __syncthreads();
-    // ---- 2. copy the new columns back
-    {
-        const int a0 = tri_off(kp), a1 = tri_off(k - 1);
-        for (int a = a0 + threadIdx.x; a < a1; a += WS_NT) sp.R[a] = Rn[a];
-    }
-    // ---- 3. Q columns: q_i <- c q_i + s q_{i+1} ; carry the other combination (thread per row)
-    {
-        double *Qw = sm.Q;
-        for (int r = threadIdx.x; r < n; r += WS_NT) {
-            double carry = Qw[(size_t)kp * n + r];
-#pragma unroll 4
-            for (int i = kp; i < k - 1; ++i) {
-                const double b = Qw[(size_t)(i + 1) * n + r];
-                const double cs = sm.gc[i], sn = sm.gs[i];
-                Qw[(size_t)i * n + r] = cs * carry + sn * b;
-                carry = -sn * carry + cs * b;
+        const int iend = (i0 + WS_CH < k - 1) ? i0 + WS_CH : k - 1;
+        if (qr >= 0) {
+            for (int i = i0; i < iend; ++i) {
+                const double bq = qcol_w(P, cx, i + 1)[qr];
+                const double cs = gc[i], sn = gs[i];
+                qcol_w(P, cx, i)[qr] = cs * qcarry + sn * bq;
+                qcarry = -sn * qcarry + cs * bq;
             }
-            Qw[(size_t)(k - 1) * n + r] = carry;
+        }
+        if (uth) {
+            for (int i = i0; i < iend; ++i) {
+                const double bu_ = u[i + 1];
+                const double cs = gc[i], sn = gs[i];
+                u[i] = cs * ucarry + sn * bu_;
+                ucarry = -sn * ucarry + cs * bu_;
+            }
         }
     }
-    // ---- 4. Ri: delete row kp, rotate columns, drop the last column.  new row rr <- old row
-    // (rr < kp ? rr : rr+1).  Written to tmp2 then copied back (threads own rows, columns interleave).
-    // Threads WS_NT/2.. take the rows from the top so that both halves of the CTA have work.
-    for (int rr = threadIdx.x; rr < k - 1; rr += WS_NT) {
-        const int ro = rr < kp ? rr : rr + 1;
-        // X[rr][j] = old Ri[ro][j] if ro <= j else 0
-        double carry = (ro <= kp) ? sp.Ri[tri_off(kp) + ro] : 0.;
-#pragma unroll 4
-        for (int i = kp; i < k - 1; ++i) {
-            const double b = (ro <= i + 1) ? sp.Ri[tri_off(i + 1) + ro] : 0.;
-            const double cs = sm.gc[i], sn = sm.gs[i];
-            if (rr <= i) sp.tmp2[tri_off(i) + rr] = cs * carry + sn * b;
-            carry = -sn * carry + cs * b;
-        }
-    }
-    __syncthreads();
-    {
-        const int a0 = tri_off(kp), a1 = tri_off(k - 1);
-        for (int a = a0 + threadIdx.x; a < a1; a += WS_NT) sp.Ri[a] = sp.tmp2[a];
-    }
-    // ---- 5. shift the bookkeeping (chunked: k may exceed the block size)
-    __syncthreads();
-    for (int base = kp + 1; base < k; base += WS_NT) {
-        const int tsrc = base + threadIdx.x;
-        int rw = 0, sd = 0; double lm = 0.;
-        if (tsrc < k) { rw = sm.row[tsrc]; sd = sm.side[tsrc]; lm = sm.lam[tsrc]; }
-        __syncthreads();
-        if (tsrc < k) { sm.row[tsrc - 1] = rw; sm.side[tsrc - 1] = sd; sm.lam[tsrc - 1] = lm; }
-        __syncthreads();
-    }
+    if (uth) SMV(red)[2 * WS_NW] = ucarry;                                  // (G u)_last
     k -= 1;
     __syncthreads();
+    // v = -Q1_new u_new = v_old + q_last (G u)_last
+    if (qr >= 0) SMV(v)[qr] += qcarry * SMV(red)[2 * WS_NW];
+    const int bad = *flag;
+    __syncthreads();
+    ri_matvec(P, cx, k, u, SMV(ls));
+    return bad == 0x7fffffff ? -1 : bad;
 }
 
-// remove position kp, then every row whose diagonal of R collapsed (see oracle/qp_core.c ws_remove)
-__device__ inline void ws_remove(const DevProblem &P, const SlotPtrs &sp, Smem &sm, int &k, int kp) {
-    if (threadIdx.x == 0) sm.inW[sm.row[kp]] = 0;
+// remove position kp, then every row whose diagonal of R collapsed (see oracle/qp_core.c thin_ws_remove)
+__device__ inline void ws_remove(const DevProblem &P, const Ctx &cx, int &k, int kp) {
+    signed char *inW = reinterpret_cast<signed char *>(SMB(binW));
+    if (threadIdx.x == 0) inW[SMI(irow)[kp]] = 0;
     __syncthreads();
-    qr_remove(P, sp, sm, k, kp);
-    for (;;) {
-        double val = 0.; int bad = -1;
-        for (int i = kp + threadIdx.x; i < k; i += WS_NT)
-            if (fabs(sp.R[tri_off(i) + i]) <= P.tol_sing && (bad < 0 || i < bad)) bad = i;
-        // smallest index wins: encode as arg-max of -index
-        val = bad >= 0 ? -(double)bad : 0.;
-        block_argmax(val, bad, sm.red, sm.ired);
-        if (bad < 0) break;
-        if (threadIdx.x == 0) sm.inW[sm.row[bad]] = 0;
+    int bad = thin_remove(P, cx, k, kp);
+    while (bad >= 0) {
+        if (threadIdx.x == 0) inW[SMI(irow)[bad]] = 0;
         __syncthreads();
-        qr_remove(P, sp, sm, k, bad);
-        kp = bad;
+        bad = thin_remove(P, cx, k, bad);
     }
 }
 
@@ -453,221 +556,289 @@ __device__ inline void ws_remove(const DevProblem &P, const SlotPtrs &sp, Smem &
 //   xi = Wf x  (ns = n + T nx entries: inputs zeta_t, then states xi_1 .. xi_T of the homogeneous dynamics)
 //   row (t, i):  sv = (F_t[i] . xi_t + G_t[i] . zeta_t) / nrm_r   (xi_0 = 0: the x0 part is in the bounds)
 //   binary (t, i): sv = zeta_t[nuc + i] / nrm_r
+// WfT is the operator transposed (n x ns2): a thread owns two adjacent outputs and streams 16-byte words,
+// gp groups split the columns.
 template <class Fn>
-__device__ inline void price_rows(const DevProblem &P, Smem &sm, const double *x, Fn f) {
-    const int n = P.n, m = P.m, mc = P.mc, nx = P.nx, nu = P.nu, ns = P.ns;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    // xi = Wf x : warp per row of Wf (row major, coalesced over lanes), two rows in flight
-    for (int r = w; r < ns; r += 2 * WS_NW) {
-        const int r2 = r + WS_NW;
-        const double *w0 = P.Wf + (size_t)r * n, *w1 = P.Wf + (size_t)(r2 < ns ? r2 : r) * n;
-        double s0 = 0., s1 = 0.;
-        for (int c = lane; c < n; c += 32) { const double xc = x[c]; s0 += w0[c] * xc; s1 += w1[c] * xc; }
-        s0 = warp_sum(s0); s1 = warp_sum(s1);
-        if (lane == 0) { sm.xi[r] = s0; if (r2 < ns) sm.xi[r2] = s1; }
+__device__ inline void price_rows(const DevProblem &P, const Ctx &cx, const double *x, Fn f) {
+    const int n = P.n, m = P.m, mc = P.mc, nx = P.nx, nu = P.nu;
+    const int hs = P.ns2 >> 1;
+    double *xi = SMV(xi);
+    {
+        double2 *part2 = reinterpret_cast<double2 *>(SMV(part));
+        if (cx.pg < P.gp) {
+            const double2 *w2 = reinterpret_cast<const double2 *>(P.WfT) + cx.prp;
+            double ax = 0., ay = 0., bx = 0., by = 0., ex = 0., ey = 0., dx = 0., dy = 0.;
+            int c = cx.pg;
+            const int G = P.gp;
+            for (; c + 3 * G < n; c += 4 * G) {
+                const double2 a = __ldg(w2 + (size_t)c * hs), b = __ldg(w2 + (size_t)(c + G) * hs),
+                              e = __ldg(w2 + (size_t)(c + 2 * G) * hs), d = __ldg(w2 + (size_t)(c + 3 * G) * hs);
+                const double xa = x[c], xb = x[c + G], xe = x[c + 2 * G], xd = x[c + 3 * G];
+                ax += a.x * xa; ay += a.y * xa; bx += b.x * xb; by += b.y * xb;
+                ex += e.x * xe; ey += e.y * xe; dx += d.x * xd; dy += d.y * xd;
+            }
+            for (; c < n; c += G) { const double2 a = __ldg(w2 + (size_t)c * hs); const double xa = x[c]; ax += a.x * xa; ay += a.y * xa; }
+            part2[cx.pg * hs + cx.prp] = make_double2((ax + bx) + (ex + dx), (ay + by) + (ey + dy));
+        }
+        __syncthreads();
+        const double *part = SMV(part);
+        for (int r = threadIdx.x; r < P.ns2; r += WS_NT) {
+            double s = part[r];
+            for (int q = 1; q < P.gp; ++q) s += part[q * P.ns2 + r];
+            xi[r] = s;
+        }
+        __syncthreads();
     }
-    __syncthreads();
+    const int *rinfo = SMI(rinfo);
+    const double *inr = SMV(inr);
     for (int r = threadIdx.x; r < m; r += WS_NT) {
         double s;
+        const int info = rinfo[r];
         if (r < mc) {
-            int t = r / P.nh; if (t > P.T - 1) t = P.T - 1;
-            const int i = r - t * P.nh;
-            const double *Fr = (t < P.T - 1 ? P.F : P.F1) + (size_t)i * nx;
-            const double *Gr = (t < P.T - 1 ? P.G : P.G1) + (size_t)i * nu;
-            const double *zt = sm.xi + (size_t)t * nu;
-            s = 0.;
-            for (int c = 0; c < nu; ++c) s += Gr[c] * zt[c];
+            const int t = info >> 16, i = info & 0xffff;
+            const bool last = t == P.T - 1;
+            const double *Fr = (last ? SMV(sF1) : SMV(sF)) + i * nx;
+            const double *Gr = (last ? SMV(sG1) : SMV(sG)) + i * nu;
+            const double *zt = xi + t * nu;
+            double s0 = 0., s1 = 0.;
+            int c = 0;
+            for (; c + 1 < nu; c += 2) { s0 += Gr[c] * zt[c]; s1 += Gr[c + 1] * zt[c + 1]; }
+            if (c < nu) s0 += Gr[c] * zt[c];
             if (t > 0) {
-                const double *xt = sm.xi + n + (size_t)(t - 1) * nx;
-                for (int c = 0; c < nx; ++c) s += Fr[c] * xt[c];
+                const double *xt = xi + n + (t - 1) * nx;
+                c = 0;
+                for (; c + 1 < nx; c += 2) { s0 += Fr[c] * xt[c]; s1 += Fr[c + 1] * xt[c + 1]; }
+                if (c < nx) s0 += Fr[c] * xt[c];
             }
+            s = s0 + s1;
         } else {
-            s = sm.xi[P.bin_idx[r - mc]];
+            s = xi[info];
         }
-        f(r, s * P.inr[r]);
+        f(r, s * inr[r]);
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// the solver.  Inputs: x0 (global), lb/ub (global, nb).  Slot state must be loaded (load_slot).
-// Outputs: status; sm.yc = solution in orthonormal coordinates (if optimal); y_out (global, m):
-// signed multipliers of the ORIGINAL rows (>0 upper side, <0 lower side; Farkas ray if infeasible).
+// slot state
 // ---------------------------------------------------------------------------------------------
-__device__ inline void load_slot(const DevProblem &P, const SlotPtrs &sp, Smem &sm, int &k, bool reset) {
+
+// once per kernel launch: shared copies of the stage rows, row scalings and the row -> (stage, index) map
+__device__ inline void init_shared_tables(const DevProblem &P, const Ctx &cx) {
+    for (int i = threadIdx.x; i < P.nh * P.nx; i += WS_NT) SMV(sF)[i] = P.F[i];
+    for (int i = threadIdx.x; i < P.nh * P.nu; i += WS_NT) SMV(sG)[i] = P.G[i];
+    for (int i = threadIdx.x; i < P.nh1 * P.nx; i += WS_NT) SMV(sF1)[i] = P.F1[i];
+    for (int i = threadIdx.x; i < P.nh1 * P.nu; i += WS_NT) SMV(sG1)[i] = P.G1[i];
+    for (int r = threadIdx.x; r < P.m; r += WS_NT) {
+        SMV(inr)[r] = P.inr[r]; SMV(vsc)[r] = P.vscale[r];
+        int info;
+        if (r < P.mc) { int t = r / P.nh; if (t > P.T - 1) t = P.T - 1; info = (t << 16) | (r - t * P.nh); }
+        else info = P.bin_idx[r - P.mc];
+        SMI(rinfo)[r] = info;
+    }
+    for (int i = threadIdx.x; i < P.np + 2; i += WS_NT) { SMV(z)[i] = 0.; SMV(v)[i] = 0.; SMV(wv)[i] = 0.; SMV(yc)[i] = 0.; }
+    for (int i = threadIdx.x; i < P.ns2; i += WS_NT) SMV(xi)[i] = 0.;
+    __syncthreads();
+}
+
+// working set of the slot: empty (reset) or the one stored by the previous launch.  The factor is NOT
+// loaded: every node rebuilds it (rebuild_factor).
+__device__ inline void load_slot(const DevProblem &P, const Ctx &cx, const SlotPtrs &sp, int &k, bool reset) {
     const int n = P.n;
     if (reset) {
-        for (size_t a = threadIdx.x; a < (size_t)n * n; a += WS_NT) sm.Q[a] = 0.;
-        __syncthreads();
-        for (int i = threadIdx.x; i < n; i += WS_NT) { sm.Q[(size_t)i * n + i] = 1.; sm.yc[i] = 0.; }
+        for (int i = threadIdx.x; i < n; i += WS_NT) SMV(yc)[i] = 0.;
         k = 0;
     } else {
         k = *sp.nW;
-        for (int i = threadIdx.x; i < n; i += WS_NT) sm.yc[i] = sp.yc[i];
-        for (int i = threadIdx.x; i < k; i += WS_NT) { sm.row[i] = sp.row[i]; sm.side[i] = sp.side[i]; sm.lam[i] = sp.lam[i]; }
-        if (P.q_in_smem) for (size_t a = threadIdx.x; a < (size_t)n * n; a += WS_NT) sm.Q[a] = sp.Q[a];
+        for (int i = threadIdx.x; i < n; i += WS_NT) SMV(yc)[i] = sp.yc[i];
+        for (int i = threadIdx.x; i < k; i += WS_NT) { SMI(irow)[i] = sp.row[i]; SMI(iside)[i] = sp.side[i]; SMV(lam)[i] = sp.lam[i]; }
     }
-    for (int r = threadIdx.x; r < P.m; r += WS_NT) { sm.inW[r] = 0; sm.ign[r] = 0; sm.nadd[r] = 0; }
-    __syncthreads();
-    for (int i = threadIdx.x; i < k; i += WS_NT) sm.inW[sm.row[i]] = (signed char)sm.side[i];
     __syncthreads();
 }
 
-__device__ inline void store_slot(const DevProblem &P, const SlotPtrs &sp, Smem &sm, int k) {
+__device__ inline void store_slot(const DevProblem &P, const Ctx &cx, const SlotPtrs &sp, int k) {
     const int n = P.n;
-    for (int i = threadIdx.x; i < n; i += WS_NT) sp.yc[i] = sm.yc[i];
-    for (int i = threadIdx.x; i < k; i += WS_NT) { sp.row[i] = sm.row[i]; sp.side[i] = sm.side[i]; sp.lam[i] = sm.lam[i]; }
-    if (P.q_in_smem) for (size_t a = threadIdx.x; a < (size_t)n * n; a += WS_NT) sp.Q[a] = sm.Q[a];
+    for (int i = threadIdx.x; i < n; i += WS_NT) sp.yc[i] = SMV(yc)[i];
+    for (int i = threadIdx.x; i < k; i += WS_NT) { sp.row[i] = SMI(irow)[i]; sp.side[i] = SMI(iside)[i]; sp.lam[i] = SMV(lam)[i]; }
     if (threadIdx.x == 0) *sp.nW = k;
     __syncthreads();
 }
 
-// per-node reset of the anti-cycling bookkeeping (the working set itself is kept)
-__device__ inline void begin_node(const DevProblem &P, Smem &sm) {
-    for (int r = threadIdx.x; r < P.m; r += WS_NT) { sm.ign[r] = 0; sm.nadd[r] = 0; }
+// Start of a node: rebuild the factor of the inherited working set (rows in their stored order, keeping
+// their multipliers, dropping rows that have become dependent) and reset the anti-cycling bookkeeping.
+// Mirrors the warm start of oracle/qp_core.c qp_solve.
+__device__ inline void rebuild_factor(const DevProblem &P, const Ctx &cx, int &k) {
+    signed char *inW = reinterpret_cast<signed char *>(SMB(binW));
+    unsigned char *ign = SMB(bign), *nadd = SMB(bnadd);
+    for (int r = threadIdx.x; r < P.m; r += WS_NT) { inW[r] = 0; ign[r] = 0; nadd[r] = 0; }
+    // the inherited rows are parked in scratch while the factor grows from the front
+    const int k0 = k;
+    double *lam0 = SMV(cw), *lam = SMV(lam);
+    int *row = SMI(irow), *side = SMI(iside);
+    int *row0 = SMI(iscr);                           // (row, side) packed, n + 1 ints
+    __syncthreads();
+    for (int i = threadIdx.x; i < k0; i += WS_NT) { row0[i] = row[i] * 2 + (side[i] > 0 ? 1 : 0); lam0[i] = lam[i]; }
+    __syncthreads();
+    k = 0;
+    for (int i = 0; i < k0; ++i) {
+        const int r = row0[i] >> 1, s = (row0[i] & 1) ? 1 : -1;
+        if (thin_append(P, cx, k, r, s, false)) {
+            if (threadIdx.x == 0) { lam[k - 1] = lam0[i]; inW[r] = (signed char)s; }
+        }
+    }
     __syncthreads();
 }
 
-__device__ inline int qp_solve(const DevProblem &P, const SlotPtrs &sp, Smem &sm, int &k,
+// ---------------------------------------------------------------------------------------------
+// the solver.  Inputs: x0 (global), lb/ub (global, nb).  The working set (rows, sides, lam, k) must be
+// loaded (load_slot) -- its factor is rebuilt here.  Outputs: status; yc = solution in orthonormal
+// coordinates (if optimal); y_out (global, m): signed multipliers of the ORIGINAL rows (>0 upper side,
+// <0 lower side; Farkas ray if infeasible).
+// ---------------------------------------------------------------------------------------------
+__device__ inline int qp_solve(const DevProblem &P, const Ctx &cx, int &k,
                                const double *x0, const double *lb, const double *ub,
                                double *y_out, int *iters_out)
 {
     const int n = P.n, m = P.m, mc = P.mc, nx = P.nx;
+    signed char *inW = reinterpret_cast<signed char *>(SMB(binW));
+    unsigned char *ign = SMB(bign), *nadd = SMB(bnadd);
+    double *lam = SMV(lam), *ls = SMV(ls), *t = SMV(t), *bu = SMV(bu), *blb = SMV(blb), *vsc = SMV(vsc);
+    int *row = SMI(irow), *side = SMI(iside);
+    double *red = SMV(red); int *ired = SMI(ired);
     int it = 0, status = WS_ITER_LIMIT;
+    bool hot = k > 0;
+    int cap = hot ? min(P.hot_cap, P.max_iter) : P.max_iter;
+
+restart:
+    rebuild_factor(P, cx, k);
     int pending = -1, pside = 0, just_added = -1;
     double plam = 0.;
-
     for (int pk = 0; pk < P.max_prox; ++pk) {
         // wv = Kx x0 - eps Rinv' yc     ((Rinv' yc)_c = sum_r Rinv[r][c] yc[r], coalesced over c)
-        grouped_matvec(P.Rinv, n, n, 0, n, sm.yc, sm.part, [&](int c, double a) {
+        grouped_matvec(P.Rinv, n, n, 0, n, SMV(yc), SMV(part), [&](int c, double a) {
             double s = 0.;
             for (int j = 0; j < nx; ++j) s += P.Kx[(size_t)c * nx + j] * x0[j];
-            sm.wv[c] = s - P.eps * a;
+            SMV(wv)[c] = s - P.eps * a;
         });
         // bounds of this proximal sub-problem: g = Mh wv
-        price_rows(P, sm, sm.wv, [&](int r, double g) {
+        price_rows(P, cx, SMV(wv), [&](int r, double g) {
             if (r < mc) {
                 double e = 0.;
                 for (int j = 0; j < nx; ++j) e += P.Eh[(size_t)r * nx + j] * x0[j];
-                sm.bu[r] = P.hh[r] - e + g;
+                bu[r] = P.hh[r] - e + g;
             } else {
                 const int i = r - mc;
-                const double inr = P.inr[r];
-                sm.bu[r] = ub[i] * inr + g;
-                sm.blb[i] = lb[i] * inr + g;
+                const double inr = SMV(inr)[r];
+                bu[r] = ub[i] * inr + g;
+                blb[i] = lb[i] * inr + g;
             }
         });
         __syncthreads();
+        refresh_uv(P, cx, k);
 
         status = WS_ITER_LIMIT;
-        while (it < P.max_iter) {
+        while (it < cap) {
             ++it;
             if (pending < 0) {
-                // u = R^-T (-d_W) ; lam* = R^-1 u ; v = -Q1 u
+                // ratio test on the way to lam* = ls ; sum of the positive multipliers
+                double amin = INFINITY, lpart = 0.; int kmin = -1;
                 for (int i = threadIdx.x; i < k; i += WS_NT) {
-                    const int r = sm.row[i];
-                    sm.c[i] = -(sm.side[i] > 0 ? sm.bu[r] : -sm.blb[r - mc]);
+                    const double l = ls[i];
+                    if (l < -P.tol_d) {
+                        const double a = lam[i] / (lam[i] - l);
+                        if (a < amin || (a == amin && i < kmin)) { amin = a; kmin = i; }
+                    }
+                    lpart += l > 0. ? l : 0.;
                 }
-                __syncthreads();
-                rit_matvec(sp.Ri, k, sm.c, sm.u);
-                ri_matvec(sp.Ri, k, sm.u, sm.ls, sm.part);
-                double amin = INFINITY; int kmin = -1;
-                for (int i = threadIdx.x; i < k; i += WS_NT) if (sm.ls[i] < -P.tol_d) {
-                    const double a = sm.lam[i] / (sm.lam[i] - sm.ls[i]);
-                    if (a < amin || (a == amin && i < kmin)) { amin = a; kmin = i; }
-                }
-                block_argmin(amin, kmin, sm.red, sm.ired);
+                block_argmin_sum(amin, kmin, lpart, red, ired);
+                if (hot && !(lpart < WS_LAM_MAX)) break;          // degenerate hot start: restart cold
                 if (kmin >= 0) {
-                    for (int i = threadIdx.x; i < k; i += WS_NT) sm.lam[i] += amin * (sm.ls[i] - sm.lam[i]);
+                    for (int i = threadIdx.x; i < k; i += WS_NT) lam[i] += amin * (ls[i] - lam[i]);
                     __syncthreads();
                     if (threadIdx.x == 0) {
-                        const int rr = sm.row[kmin];
-                        if (rr == just_added && sm.lam[kmin] == 0.) sm.ign[rr] |= (sm.side[kmin] > 0 ? 1 : 2);
-                        if (amin <= 1e-9 && sm.nadd[rr] < 255) ++sm.nadd[rr];
+                        const int rr = row[kmin];
+                        if (rr == just_added && lam[kmin] == 0.) ign[rr] |= (side[kmin] > 0 ? 1 : 2);
+                        if (amin <= 1e-9 && nadd[rr] < 255) ++nadd[rr];
                     }
                     just_added = -1;
-                    ws_remove(P, sp, sm, k, kmin);
+                    ws_remove(P, cx, k, kmin);
                     continue;
                 }
-                for (int i = threadIdx.x; i < k; i += WS_NT) sm.lam[i] = sm.ls[i] > 0. ? sm.ls[i] : 0.;
-                // v = -Q1 u
-                grouped_matvec(sm.Q, n, n, 0, k, sm.u, sm.part, [&](int i, double s) { sm.v[i] = -s; });
-                double lpart = 0.;
-                for (int i = threadIdx.x; i < k; i += WS_NT) lpart += sm.ls[i] > 0. ? sm.ls[i] : 0.;
-                const double lsum = block_sum(lpart, sm.red);
-                const double vnoise = 1e-14 * lsum, vcap = 100. * P.tol_p;
+                for (int i = threadIdx.x; i < k; i += WS_NT) lam[i] = ls[i] > 0. ? ls[i] : 0.;
+                const double vnoise = 1e-14 * lpart, vcap = 100. * P.tol_p;
                 double vbest = 0.; int ibest = -1;                 // ibest = 2 r + (lower side)
-                price_rows(P, sm, sm.v, [&](int r, double sv) {
-                    if (sm.inW[r]) return;
-                    const int na = sm.nadd[r];
+                price_rows(P, cx, SMV(v), [&](int r, double sv) {
+                    if (inW[r]) return;
+                    const int na = nadd[r];
                     double tolr = P.tol_p * (na == 0 ? 1. : (na == 1 ? 10. : 100.));
-                    const double vs = P.vscale[r];
+                    const double vs = vsc[r];
                     const double fl = vnoise * vs < vcap ? vnoise * vs : vcap;
                     if (fl > tolr) tolr = fl;
-                    if (!(sm.ign[r] & 1)) {
-                        const double vu = (sv - sm.bu[r]) * vs;
+                    const int ig = ign[r];
+                    if (!(ig & 1)) {
+                        const double vu = (sv - bu[r]) * vs;
                         if (vu > tolr && (vu > vbest || (vu == vbest && 2 * r < ibest))) { vbest = vu; ibest = 2 * r; }
                     }
-                    if (r >= mc && !(sm.ign[r] & 2)) {
-                        const double vl = (sm.blb[r - mc] - sv) * vs;
+                    if (r >= mc && !(ig & 2)) {
+                        const double vl = (blb[r - mc] - sv) * vs;
                         if (vl > tolr && (vl > vbest || (vl == vbest && 2 * r + 1 < ibest))) { vbest = vl; ibest = 2 * r + 1; }
                     }
                 });
-                block_argmax(vbest, ibest, sm.red, sm.ired);
+                block_argmax(vbest, ibest, red, ired);
                 if (ibest < 0) { status = WS_OPTIMAL; break; }
                 const int jb = ibest >> 1, sb = (ibest & 1) ? -1 : 1;
-                if (qr_append(P, sp, sm, k, jb, sb)) {
-                    if (threadIdx.x == 0) sm.inW[jb] = (signed char)sb;
+                if (thin_append(P, cx, k, jb, sb, true)) {
+                    if (threadIdx.x == 0) inW[jb] = (signed char)sb;
                     just_added = jb;
                     __syncthreads();
                 } else { pending = jb; pside = sb; plam = 0.; }
             } else {
                 // dependent entering row: dual ray (p_W, 1), p_W = -t
                 double pm = 1.;
-                for (int i = threadIdx.x; i < k; i += WS_NT) pm = fmax(pm, fabs(sm.t[i]));
-                { int dummy = 0; block_argmax(pm, dummy, sm.red, sm.ired); }
+                for (int i = threadIdx.x; i < k; i += WS_NT) pm = fmax(pm, fabs(t[i]));
+                { int dummy = 0; block_argmax(pm, dummy, red, ired); }
                 double amin = INFINITY; int kmin = -1;
-                for (int i = threadIdx.x; i < k; i += WS_NT) if (sm.t[i] > P.tol_ray * pm) {
-                    const double a = sm.lam[i] / sm.t[i];
+                for (int i = threadIdx.x; i < k; i += WS_NT) if (t[i] > P.tol_ray * pm) {
+                    const double a = lam[i] / t[i];
                     if (a < amin || (a == amin && i < kmin)) { amin = a; kmin = i; }
                 }
-                block_argmin(amin, kmin, sm.red, sm.ired);
+                block_argmin(amin, kmin, red, ired);
                 if (kmin < 0) {
                     double cpart = 0., wpart = 0.;
                     for (int i = threadIdx.x; i < k; i += WS_NT) {
-                        const double pi = sm.t[i] < 0. ? -sm.t[i] : 0.;
-                        const int r = sm.row[i];
-                        cpart -= pi * (sm.side[i] > 0 ? sm.bu[r] : -sm.blb[r - mc]);
-                        wpart += pi / P.vscale[r];
+                        const double pi = t[i] < 0. ? -t[i] : 0.;
+                        const int r = row[i];
+                        cpart -= pi * (side[i] > 0 ? bu[r] : -blb[r - mc]);
+                        wpart += pi / vsc[r];
                     }
-                    double cost = block_sum(cpart, sm.red);
-                    double wsum = block_sum(wpart, sm.red);
-                    cost -= (pside > 0 ? sm.bu[pending] : -sm.blb[pending - mc]);
-                    wsum += 1. / P.vscale[pending];
+                    double cost = cpart, wsum = wpart;
+                    block_sum2(cost, wsum, red);
+                    cost -= (pside > 0 ? bu[pending] : -blb[pending - mc]);
+                    wsum += 1. / vsc[pending];
                     if (cost > P.tol_p * wsum) {
                         for (int r = threadIdx.x; r < m; r += WS_NT) y_out[r] = 0.;
                         __syncthreads();
                         for (int i = threadIdx.x; i < k; i += WS_NT) {
-                            const double pi = sm.t[i] < 0. ? -sm.t[i] : 0.;
-                            const int r = sm.row[i];
-                            y_out[r] = (double)sm.side[i] * pi * P.inr[r];
+                            const double pi = t[i] < 0. ? -t[i] : 0.;
+                            const int r = row[i];
+                            y_out[r] = (double)side[i] * pi * SMV(inr)[r];
                         }
-                        if (threadIdx.x == 0) y_out[pending] = (double)pside * P.inr[pending];
+                        if (threadIdx.x == 0) y_out[pending] = (double)pside * SMV(inr)[pending];
                         __syncthreads();
                         status = WS_INFEASIBLE;
                         break;
                     }
-                    if (threadIdx.x == 0) sm.ign[pending] |= (pside > 0 ? 1 : 2);
+                    if (threadIdx.x == 0) ign[pending] |= (pside > 0 ? 1 : 2);
                     pending = -1;
                     __syncthreads();
                     continue;
                 }
-                for (int i = threadIdx.x; i < k; i += WS_NT) sm.lam[i] -= amin * sm.t[i];
+                for (int i = threadIdx.x; i < k; i += WS_NT) lam[i] -= amin * t[i];
                 plam += amin;
                 __syncthreads();
-                if (threadIdx.x == 0 && amin <= 1e-9 * (1. + plam) && sm.nadd[sm.row[kmin]] < 255) ++sm.nadd[sm.row[kmin]];
-                ws_remove(P, sp, sm, k, kmin);
-                if (qr_append(P, sp, sm, k, pending, pside)) {
-                    if (threadIdx.x == 0) { sm.lam[k - 1] = plam; sm.inW[pending] = (signed char)pside; }
+                if (threadIdx.x == 0 && amin <= 1e-9 * (1. + plam) && nadd[row[kmin]] < 255) ++nadd[row[kmin]];
+                ws_remove(P, cx, k, kmin);
+                if (thin_append(P, cx, k, pending, pside, true)) {
+                    if (threadIdx.x == 0) { lam[k - 1] = plam; inW[pending] = (signed char)pside; }
                     pending = -1;
                     __syncthreads();
                 }
@@ -676,24 +847,31 @@ __device__ inline int qp_solve(const DevProblem &P, const SlotPtrs &sp, Smem &sm
         if (status != WS_OPTIMAL) break;
         // yc <- Rinv (v - wv) ; proximal convergence
         __syncthreads();
-        for (int r = threadIdx.x; r < n; r += WS_NT) sm.c[r] = sm.v[r] - sm.wv[r];
+        for (int r = threadIdx.x; r < n; r += WS_NT) SMV(c1)[r] = SMV(v)[r] - SMV(wv)[r];
         __syncthreads();
         double dz = 0.;
-        grouped_matvec(P.RinvT, n, n, 0, n, sm.c, sm.part, [&](int r, double s) {
-            dz = fmax(dz, fabs(s - sm.yc[r]));
-            sm.hv[r] = s;
+        grouped_matvec(P.RinvT, n, n, 0, n, SMV(c1), SMV(part), [&](int r, double s) {
+            dz = fmax(dz, fabs(s - SMV(yc)[r]));
+            SMV(c2)[r] = s;
         });
-        { int dummy = 0; block_argmax(dz, dummy, sm.red, sm.ired); }
-        for (int r = threadIdx.x; r < n; r += WS_NT) sm.yc[r] = sm.hv[r];
+        { int dummy = 0; block_argmax(dz, dummy, red, ired); }
+        for (int r = threadIdx.x; r < n; r += WS_NT) SMV(yc)[r] = SMV(c2)[r];
         __syncthreads();
         if (P.eps * dz <= P.prox_tol) break;
+    }
+    if (status == WS_ITER_LIMIT && hot) {
+        // a hot start from a stale, nearly dependent working set can degenerate: solve once more from scratch
+        hot = false; cap = it + P.max_iter; k = 0;
+        for (int i = threadIdx.x; i < n; i += WS_NT) SMV(yc)[i] = 0.;
+        __syncthreads();
+        goto restart;
     }
     if (status == WS_OPTIMAL) {
         for (int r = threadIdx.x; r < m; r += WS_NT) y_out[r] = 0.;
         __syncthreads();
         for (int i = threadIdx.x; i < k; i += WS_NT) {
-            const int r = sm.row[i];
-            y_out[r] = (double)sm.side[i] * sm.lam[i] * P.inr[r];
+            const int r = row[i];
+            y_out[r] = (double)side[i] * lam[i] * SMV(inr)[r];
         }
         __syncthreads();
     }

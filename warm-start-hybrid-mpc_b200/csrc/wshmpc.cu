@@ -42,24 +42,24 @@ solve_nodes_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, int 
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int slot = blockIdx.x;
-    SlotPtrs sp = slot_ptrs(slot_d, slot_i, slot, P.n);
-    Smem sm = carve_smem(smem_raw, P.n, P.m, P.nb, P.ns, P.q_in_smem, sp.Q);
+    SlotPtrs sp = slot_ptrs(slot_d, slot_i, slot, P.n, P.ld);
+    const Ctx cx = make_ctx(P, smem_raw, sp);
+    init_shared_tables(P, cx);
     double *y = ybuf + (size_t)slot * P.m;
     int k = 0;
     bool loaded = false;
     for (int i = 0; i < n_nodes; ++i) {
         if (slot_of[i] != slot) continue;
         const bool reset = hot[i] == 0;
-        if (!loaded || reset) { load_slot(P, sp, sm, k, reset); loaded = true; }
-        else begin_node(P, sm);
+        if (!loaded || reset) { load_slot(P, cx, sp, k, reset); loaded = true; }
         const double *xi = x0 + (size_t)i * P.nx, *lbi = lb + (size_t)i * P.nb, *ubi = ub + (size_t)i * P.nb;
-        const int st = qp_solve(P, sp, sm, k, xi, lbi, ubi, y, iters + i);
-        build_records(P, st, sm.yc, y, xi, lbi, ubi, primal + (size_t)i * P.n_primal,
-                      dual + (size_t)i * P.n_dual, cost + i, dobj + i, sm.part, sm.red);
+        const int st = qp_solve(P, cx, k, xi, lbi, ubi, y, iters + i);
+        build_records(P, st, SMV(yc), y, xi, lbi, ubi, primal + (size_t)i * P.n_primal,
+                      dual + (size_t)i * P.n_dual, cost + i, dobj + i, SMV(part), SMV(red));
         if (threadIdx.x == 0) status[i] = st;
         __syncthreads();
     }
-    if (loaded) store_slot(P, sp, sm, k);
+    if (loaded) store_slot(P, cx, sp, k);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -100,7 +100,6 @@ extern "C" int wshmpc_create(const wshmpc_problem *p, int device, int n_slots, v
     P.nq = p->nq; P.nqT = p->nqT; P.nr = p->nr; P.n = p->n; P.m = p->m; P.mc = p->mc; P.nb = p->nb; P.ns = p->ns;
     P.eps = p->eps; P.tol_p = p->tol_p; P.tol_d = p->tol_d; P.tol_sing = p->tol_sing; P.tol_ray = p->tol_ray;
     P.prox_tol = p->prox_tol; P.max_iter = p->max_iter; P.max_prox = p->max_prox;
-    P.tri = (p->n + 1) * (p->n + 2) / 2;
     const int nx = p->nx, nu = p->nu, n = p->n, m = p->m;
     int rc = 0;
 #define UP(field, src, cnt) if ((rc = upload(h, src, (size_t)(cnt), &P.field))) { wshmpc_destroy(h); return rc; }
@@ -108,13 +107,18 @@ extern "C" int wshmpc_create(const wshmpc_problem *p, int device, int n_slots, v
     UP(F1, p->F_Tm1, p->nh1 * nx) UP(G1, p->G_Tm1, p->nh1 * nu) UP(h1, p->h_Tm1, p->nh1)
     UP(Q, p->Q, p->nq * nx) UP(R, p->R, p->nr * nu) UP(QT, p->Q_T, p->nqT * nx)
     UP(Mmu, p->M_mu, p->nh * p->nh1) UP(Mrho, p->M_rho, p->nq * p->nqT)
-    UP(Mh, p->Mh, (size_t)m * n) UP(Wf, p->Wf, (size_t)p->ns * n) UP(nrm, p->nrm, m) UP(vscale, p->vscale, m) UP(Eh, p->Eh, (size_t)p->mc * nx)
+    UP(Mh, p->Mh, (size_t)m * n) UP(nrm, p->nrm, m) UP(vscale, p->vscale, m) UP(Eh, p->Eh, (size_t)p->mc * nx)
     UP(hh, p->hh, p->mc) UP(Rinv, p->Rinv, (size_t)n * n) UP(Kx, p->Kx, (size_t)n * nx)
     UP(bin_idx, p->bin_idx, p->nb)
     {
         std::vector<double> ir(m); for (int r = 0; r < m; ++r) ir[r] = 1. / p->nrm[r]; UP(inr, ir.data(), m)
         std::vector<double> r = transpose(p->Rinv, n, n); UP(RinvT, r.data(), (size_t)n * n)
         std::vector<double> z = transpose(p->Zmap, n, n); UP(ZmapT, z.data(), (size_t)n * n)
+        // pricing operator transposed and padded to an even number of outputs: WfT[c * ns2 + r] = Wf[r][c]
+        const int ns2 = (p->ns + 1) & ~1;
+        std::vector<double> wt((size_t)n * ns2, 0.);
+        for (int r2 = 0; r2 < p->ns; ++r2) for (int c = 0; c < n; ++c) wt[(size_t)c * ns2 + r2] = p->Wf[(size_t)r2 * n + c];
+        UP(WfT, wt.data(), (size_t)n * ns2)
     }
 #undef UP
     // record layout (subproblem_solution.py:86-91, 137-166)
@@ -129,17 +133,55 @@ extern "C" int wshmpc_create(const wshmpc_problem *p, int device, int n_slots, v
     L.dual = L.off_sigma + p->T * p->nr;
     P.n_primal = L.primal; P.n_dual = L.dual; P.off_lam = L.off_lam; P.off_mu = L.off_mu; P.off_nulb = L.off_nu_lb;
     P.off_nuub = L.off_nu_ub; P.off_rho = L.off_rho; P.off_sigma = L.off_sigma;
-    // shared memory budget: one CTA per SM; Q lives in shared memory when it fits
+    // shared memory budget: one CTA per SM; the first ks columns of Q1 and of Ri live in shared memory
     cudaDeviceProp prop;
     WS_CUDA(cudaGetDeviceProperties(&prop, device));
     const size_t optin = prop.sharedMemPerBlockOptin;
-    P.q_in_smem = smem_bytes(n, m, p->nb, p->ns, 1) <= optin ? 1 : 0;
-    h->smem = smem_bytes(n, m, p->nb, p->ns, P.q_in_smem);
-    if (h->smem > optin) { wshmpc_destroy(h); WS_FAIL(-4, "problem too large: %zu bytes of shared memory needed, %zu available", h->smem, optin); }
+    if (n > WS_NT) { wshmpc_destroy(h); WS_FAIL(-4, "problem too large: n = %d condensed inputs, at most %d supported", n, WS_NT); }
+    if (p->ns > 2 * WS_NT) { wshmpc_destroy(h); WS_FAIL(-4, "problem too large: ns = %d, at most %d supported", p->ns, 2 * WS_NT); }
+    if (p->T > 32767 || p->nh > 65535 || p->nh1 > 65535) { wshmpc_destroy(h); WS_FAIL(-4, "problem too large for the packed row map"); }
+    P.np = (n + 1) & ~1;
+    P.ns2 = (p->ns + 1) & ~1;
+    P.ld = P.np; while (((P.ld >> 1) & 1) == 0) P.ld += 2;     // even, ld / 2 odd
+    P.kp_ = P.np;
+    P.gb = WS_NT / (P.np >> 1);
+    P.gp = WS_NT / (P.ns2 >> 1);
+    P.hot_cap = 2 * n > 200 ? 2 * n : 200;
+    {
+        SmemOff &so = P.so;
+        const int nvl = P.np + 2;
+        const int part = (2 * WS_NT > WS_NG * P.kp_ ? 2 * WS_NT : WS_NG * P.kp_);
+        if ((size_t)2 * (p->T + 1) * nx > (size_t)part) { wshmpc_destroy(h); WS_FAIL(-4, "problem too large: (T+1) nx = %d", (p->T + 1) * nx); }
+        int o = 0;
+        auto take = [&](int cnt) { const int at = o; o += (cnt + 1) & ~1; return at; };   // keep 16-byte alignment
+        // fixed part first, then Q and Ri take what is left
+        so.z = take(nvl); so.c1 = take(nvl); so.c2 = take(nvl); so.t = take(nvl); so.u = take(nvl); so.ls = take(nvl);
+        so.lam = take(nvl); so.cw = take(nvl); so.yc = take(nvl); so.wv = take(nvl); so.v = take(nvl); so.gc = take(nvl); so.gs = take(nvl);
+        so.bu = take(m); so.blb = take(p->nb); so.inr = take(m); so.vsc = take(m); so.xi = take(P.ns2); so.part = take(part);
+        so.red = take(4 * WS_NW + 8);
+        so.sF = take(p->nh * nx); so.sG = take(p->nh * nu); so.sF1 = take(p->nh1 * nx); so.sG1 = take(p->nh1 * nu);
+        so.ints = o;
+        int io = 0;
+        so.irow = io; io += n + 1; so.iside = io; io += n + 1; so.ired = io; io += 2 * WS_NW + 8; so.iscr = io; io += n + 1;
+        so.rinfo = io; io += m;
+        o += (io + 1) / 2; o = (o + 1) & ~1;
+        so.bytes = o;
+        so.binW = 0; so.bign = m; so.bnadd = 2 * m;
+        o += (3 * m + 7) / 8; o = (o + 1) & ~1;
+        const size_t fixed = (size_t)o * 8;
+        if (fixed + 64 > optin) { wshmpc_destroy(h); WS_FAIL(-4, "problem too large: %zu bytes of shared memory needed, %zu available", fixed, optin); }
+        int ks = 0;
+        while (ks < n && fixed + ((size_t)(ks + 1) * P.ld + (size_t)tri_off(ks + 1) + 2) * 8 <= optin) ++ks;
+        P.ks = ks;
+        so.Q = o; o += ks * P.ld;
+        so.Ri = o; o += (tri_off(ks) + 1) & ~1;
+        so.total_bytes = o * 8;
+        h->smem = (size_t)so.total_bytes;
+    }
     WS_CUDA(cudaFuncSetAttribute(solve_nodes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
     // slot memory
     void *d = nullptr;
-    WS_CUDA(cudaMalloc(&d, (size_t)n_slots * slot_doubles(n) * sizeof(double))); h->allocs.push_back(d); h->slot_d = (double *)d;
+    WS_CUDA(cudaMalloc(&d, (size_t)n_slots * slot_doubles(n, P.ld) * sizeof(double))); h->allocs.push_back(d); h->slot_d = (double *)d;
     WS_CUDA(cudaMalloc(&d, (size_t)n_slots * slot_ints(n) * sizeof(int))); h->allocs.push_back(d); h->slot_i = (int *)d;
     WS_CUDA(cudaMemset(h->slot_i, 0, (size_t)n_slots * slot_ints(n) * sizeof(int)));
     WS_CUDA(cudaMalloc(&d, (size_t)n_slots * m * sizeof(double))); h->allocs.push_back(d); h->ybuf = (double *)d;
