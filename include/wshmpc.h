@@ -145,6 +145,34 @@ int wshmpc_shift_tree(wshmpc_handle *h, int n_inst, const double *d_x0, const do
                       const wshmpc_tree *old_tree, const double *d_inc_cost, const double *d_inc_primal,
                       int *d_active, const wshmpc_tree *new_tree, double *d_x_next, double *d_u0);
 
+/* Fused closed loop -- many receding-horizon steps of a batch of independent instances in ONE launch,
+ * with no barrier between the steps of different instances (a queue of (instance, next step) tasks in
+ * global memory feeds the CTAs).  Replaces the experiment loop of
+ * notebooks/cart_pole_with_walls/statistical_analysis.py:93-196 (cold or warm-started feedforward,
+ * construct_warm_start, x <- x_1|t + e_t on the linear plant) for the whole batch; results are identical to
+ * calling wshmpc_bnb_solve + wshmpc_shift_tree once per step.
+ */
+typedef struct {
+    int n_steps;                      /* receding-horizon steps to run per instance */
+    int warm;                         /* 1: warm start by tree shifting, 0: every step from the root node */
+    int fresh;                        /* 1: step 0 starts from the root node (no tree yet) */
+    int par;                          /* which tree / state buffer (0 or 1) holds the data of step 0 */
+    int *d_queue;                     /* [2 + n_inst * (n_steps + 1)] scratch */
+    int *d_step_of;                   /* [n_inst] scratch */
+    double *d_x;                      /* [2][n_inst][nx] states, buffer `par` holds the current ones */
+    const double *d_e;                /* [n_steps][n_inst][nx] model errors, or NULL */
+    int *d_active;                    /* [n_inst] in/out */
+    double *d_log_cost;               /* [n_steps][n_inst] optimal cost of every step (+inf: infeasible) */
+    double *d_log_u0;                 /* [n_steps][n_inst][nu] applied input (NaN once an instance is off) */
+    int *d_log_solves;                /* [n_steps][n_inst] QP relaxations solved */
+    int *d_log_status;                /* [n_steps][n_inst] status of wshmpc_bnb_solve */
+} wshmpc_loop;
+
+int wshmpc_closed_loop(wshmpc_handle *h, int n_inst, const wshmpc_loop *loop,
+                       const wshmpc_tree *tree0, const wshmpc_tree *tree1, double tol, int max_solves,
+                       double *d_inc_cost, int *d_inc_node, double *d_inc_primal, int *d_n_solves,
+                       int *d_status, unsigned long long *d_totals);
+
 #ifdef __cplusplus
 }
 #endif

@@ -190,3 +190,35 @@ def test_batch_equals_single(cp20):
         r1, _ = ctl.feedforward_batch(x0[k:k + 1], n_slots=1)
         assert float(r1['cost'][0]) == c[k] or (np.isinf(c[k]) and np.isinf(float(r1['cost'][0])))
         assert int(r1['n_solves'][0]) == ns[k]
+
+
+@pytest.mark.parametrize('warm', [True, False])
+def test_fused_closed_loop_equals_lock_step(cp20, warm):
+    """wshmpc_closed_loop (one launch, task queue, no barrier between instances) must reproduce, bit for bit,
+    the lock-step loop wshmpc_bnb_solve + wshmpc_shift_tree per step -- more instances than resident CTAs so
+    that instances migrate between CTAs."""
+    model, ctl = cp20
+    from warm_start_hmpc_b200.closed_loop import ClosedLoop
+    N, S = 200, 4
+    x0 = np.load(os.path.join(GOLDEN, 'cp20_instances.npy'))[:N]
+    rng = np.random.default_rng(5)
+    e = torch.as_tensor(0.003 * rng.standard_normal((S, N, 4)) * model['x_max'], device='cuda')
+    A = ClosedLoop(ctl, N, warm=warm, max_solves=1024, max_roots=512)
+    B = ClosedLoop(ctl, N, warm=warm, max_solves=1024, max_roots=512)
+    A.reset(x0); B.reset(x0)
+    cost, ns, u0 = [], [], []
+    for t in range(S):
+        out = A.step(e=e[t])
+        cost.append(out['cost'].clone()); ns.append(out['n_solves'].clone()); u0.append(A.u0.clone())
+    logs = B.run(S, e=e)
+    torch.cuda.synchronize()
+    assert torch.equal(torch.stack(ns), logs['n_solves'])
+    assert torch.equal(torch.stack(cost), logs['cost'])
+    a, b = torch.stack(u0), logs['u0']
+    assert torch.equal(torch.isnan(a), torch.isnan(b)) and torch.equal(torch.nan_to_num(a), torch.nan_to_num(b))
+    assert torch.equal(A.x, B.x) and torch.equal(A.active, B.active)
+    assert int(A.totals[0]) == int(B.totals[0]) == int(logs['n_solves'].sum())
+    # and the loops can be continued either way
+    o1 = A.step(); l2 = B.run(1)
+    torch.cuda.synchronize()
+    assert torch.equal(o1['cost'], l2['cost'][0])

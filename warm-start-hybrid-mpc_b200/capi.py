@@ -42,7 +42,13 @@ def load_library():
 
 
 EXPORTS = ('wshmpc_last_error', 'wshmpc_create', 'wshmpc_destroy', 'wshmpc_get_layout', 'wshmpc_solve_nodes',
-           'wshmpc_tree_init_root', 'wshmpc_bnb_solve', 'wshmpc_shift_tree')
+           'wshmpc_tree_init_root', 'wshmpc_bnb_solve', 'wshmpc_shift_tree', 'wshmpc_closed_loop')
+
+
+class _Loop(C.Structure):
+    _fields_ = ([(k, C.c_int) for k in ('n_steps', 'warm', 'fresh', 'par')]
+                + [(k, C.c_void_p) for k in ('d_queue', 'd_step_of', 'd_x', 'd_e', 'd_active', 'd_log_cost', 'd_log_u0',
+                                             'd_log_solves', 'd_log_status')])
 
 
 class _Tree(C.Structure):
@@ -183,3 +189,35 @@ class Handle(object):
         P = lambda a: C.c_void_p(a.data_ptr()) if a is not None else None
         _check(self.lib.wshmpc_shift_tree(self._h, old_tree.n_inst, P(x0), P(e0), C.byref(old_tree.c), P(inc_cost),
                                           P(inc_primal), P(active), C.byref(new_tree.c), P(x_next), P(u0)))
+
+    def closed_loop(self, n_steps, warm, fresh, par, xbuf, e, active, trees, out, tol=0., max_solves=1024, totals=None, logs=None):
+        """Fused closed loop (wshmpc_closed_loop): `n_steps` receding-horizon steps of every instance in one
+        launch.  xbuf [2, n_inst, nx]; e [n_steps, n_inst, nx] or None; trees = (tree0, tree1).  Asynchronous.
+        Returns the dict of per-step logs (CUDA tensors)."""
+        import torch
+        dev = self.torch_device
+        N = trees[0].n_inst
+        nx, nu = self.pd.nx, self.pd.nu
+        assert xbuf.is_cuda and xbuf.dtype == torch.float64 and xbuf.is_contiguous() and tuple(xbuf.shape) == (2, N, nx)
+        if e is not None:
+            assert e.is_cuda and e.dtype == torch.float64 and e.is_contiguous() and tuple(e.shape) == (n_steps, N, nx)
+        if logs is None:
+            logs = dict(cost=torch.empty((n_steps, N), dtype=torch.float64, device=dev),
+                        u0=torch.empty((n_steps, N, nu), dtype=torch.float64, device=dev),
+                        n_solves=torch.empty((n_steps, N), dtype=torch.int32, device=dev),
+                        status=torch.empty((n_steps, N), dtype=torch.int32, device=dev))
+        need = 2 + N * (n_steps + 1)
+        if getattr(self, '_queue', None) is None or self._queue.numel() < need:
+            self._queue = torch.empty(need, dtype=torch.int32, device=dev)
+        if getattr(self, '_step_of', None) is None or self._step_of.numel() < N:
+            self._step_of = torch.empty(N, dtype=torch.int32, device=dev)
+        P = lambda a: a.data_ptr() if a is not None else None
+        L = _Loop()
+        L.n_steps, L.warm, L.fresh, L.par = int(n_steps), int(bool(warm)), int(bool(fresh)), int(par) & 1
+        L.d_queue, L.d_step_of, L.d_x, L.d_e, L.d_active = P(self._queue), P(self._step_of), P(xbuf), P(e), P(active)
+        L.d_log_cost, L.d_log_u0, L.d_log_solves, L.d_log_status = P(logs['cost']), P(logs['u0']), P(logs['n_solves']), P(logs['status'])
+        V = lambda a: C.c_void_p(a.data_ptr()) if a is not None else None
+        _check(self.lib.wshmpc_closed_loop(self._h, N, C.byref(L), C.byref(trees[0].c), C.byref(trees[1].c), C.c_double(tol),
+                                           int(max_solves), V(out['cost']), V(out['node']), V(out['primal']), V(out['n_solves']),
+                                           V(out['status']), V(totals)))
+        return logs

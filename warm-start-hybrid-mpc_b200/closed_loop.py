@@ -31,8 +31,8 @@ class ClosedLoop(object):
         self.cur = 0
         nx, nu = controller.mld.nx, controller.mld.nu
         f64 = dict(dtype=torch.float64, device=dev)
-        self.x = torch.zeros((n_inst, nx), **f64)
-        self.x_next = torch.zeros((n_inst, nx), **f64)
+        self.xbuf = torch.zeros((2, n_inst, nx), **f64)     # states, ping-pong (the shift writes the other half)
+        self.xpar = 0
         self.u0 = torch.zeros((n_inst, nu), **f64)
         self.active = torch.ones(n_inst, dtype=torch.int32, device=dev)
         self.out = dict(cost=torch.zeros(n_inst, **f64), node=torch.zeros(n_inst, dtype=torch.int32, device=dev),
@@ -43,6 +43,11 @@ class ClosedLoop(object):
         self.fresh = True
         self.launches = 0
         self.events = None          # list -> (start, after K3, after K2+K4) CUDA events of every step
+
+    @property
+    def x(self):
+        """Current states [n_inst, nx] (CUDA tensor view)."""
+        return self.xbuf[self.xpar]
 
     def nbytes(self):
         return sum(t.nbytes() for t in self.trees)
@@ -77,14 +82,35 @@ class ClosedLoop(object):
         # K2 + K4 (in cold mode only its plant update matters: the next step re-initialises the root)
         new = self.trees[1 - self.cur]
         h.shift_tree(self.x, e, tree, self.out['cost'], self.out['primal'], new, active=self.active,
-                     x_next=self.x_next, u0=self.u0)
+                     x_next=self.xbuf[1 - self.xpar], u0=self.u0)
         self.cur = 1 - self.cur
         self.launches += 1
         if self.events is not None:
             ev[2].record()
             self.events.append(tuple(ev))
-        self.x, self.x_next = self.x_next, self.x
+        self.xpar = 1 - self.xpar
         return self.out
+
+    def run(self, n_steps, e=None, logs=None):
+        """`n_steps` receding-horizon steps of every instance in ONE launch (wshmpc_closed_loop): the fused
+        form of calling step() n_steps times, without a barrier between the steps of different instances.
+        e: [n_steps, n_inst, nx] CUDA tensor of model errors or None.  Returns per-step logs
+        (cost, u0, n_solves, status), each [n_steps, n_inst, ...]; self.x holds the final states."""
+        h = self.h
+        if self.warm:
+            par, fresh = self.cur, self.fresh
+        else:
+            par, fresh = self.cur, True
+        # states and trees flip together: make the state parity equal to the tree parity
+        if self.xpar != par:
+            self.xbuf[par].copy_(self.xbuf[self.xpar]); self.xpar = par
+        logs = h.closed_loop(n_steps, self.warm, fresh, par, self.xbuf, e, self.active, self.trees, self.out,
+                             tol=self.tol, max_solves=self.max_solves, totals=self.totals, logs=logs)
+        self.launches += 2
+        self.fresh = False
+        self.cur = (self.cur + n_steps) & 1
+        self.xpar = (self.xpar + n_steps) & 1
+        return logs
 
 
 def reduce_stats(n_units, elapsed_ms, device=None):

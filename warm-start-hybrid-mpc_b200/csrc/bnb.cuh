@@ -36,6 +36,97 @@ __global__ void init_root_kernel(int n_inst, TreeView tr)
 // ---------------------------------------------------------------------------------------------
 // K3
 // ---------------------------------------------------------------------------------------------
+// branch and bound of ONE instance by the calling CTA (all threads).  Returns the status.
+__device__ inline int bnb_instance(const DevProblem &P, const Ctx &cx, const SlotPtrs &sp, double *y, double *sc, int *iters_s,
+                                   int inst, const double *xi, const TreeView &tr, double tol, int max_solves,
+                                   double *inc_cost, int *inc_node, double *inc_primal, int *n_solves, int *trace,
+                                   unsigned long long *totals)
+{
+    const int nb = P.nb;
+    double *lbv = sc, *ubv = sc + nb, *prim = sc + 2 * nb, *cost_s = prim + P.n_primal, *dobj_s = cost_s + 1;
+    const size_t no = (size_t)inst * tr.cap_nodes;
+    int *depth = tr.depth + no, *alive = tr.alive + no, *rec = tr.rec + no;
+    unsigned int *bits = tr.bits + no * tr.words;
+    double *lb = tr.lb + no;
+    double *rdobj = tr.rec_dobj + (size_t)inst * tr.cap_recs;
+    double *rdual = tr.rec_dual + (size_t)inst * tr.cap_recs * P.n_dual;
+    int *tr_i = trace ? trace + (size_t)inst * 2 * max_solves : nullptr;
+
+    int nn = tr.n_nodes[inst], nr = tr.n_recs[inst];
+    double ub = INFINITY;
+    int inc = -1, solves = 0, st = -1, k = 0;
+    long long iters = 0;
+    bool first = true;
+
+    while (st < 0) {
+        // ---- select: candidates = alive leaves with lb < ub - tol ; best_first = first minimum
+        const double cutoff = ub - tol;
+        double best = INFINITY; int bi = -1;
+        for (int j = threadIdx.x; j < nn; j += WS_NT)
+            if (alive[j]) {
+                const double l = lb[j];
+                if (l < cutoff && (bi < 0 || l < best)) { best = l; bi = j; }
+            }
+        block_argmin(best, bi, SMV(red), SMI(ired));
+        if (bi < 0) { st = inc >= 0 ? BNB_OK : BNB_INFEASIBLE; break; }
+        if (solves >= max_solves || nn + 2 > tr.cap_nodes || nr + 1 > tr.cap_recs) { st = BNB_CAPACITY; break; }
+        // ---- bounds of the node (controller.py:273-298)
+        const int d = depth[bi];
+        const unsigned int *bw = bits + (size_t)bi * tr.words;
+        for (int j = threadIdx.x; j < nb; j += WS_NT) {
+            const double v = (double)((bw[j >> 5] >> (j & 31)) & 1u);
+            lbv[j] = j < d ? v : 0.;
+            ubv[j] = j < d ? v : 1.;
+        }
+        __syncthreads();
+        // ---- solve (K1), hot-started from the working set of the node solved before it
+        if (first) { load_slot(P, cx, sp, k, true); first = false; }
+        const int qs = qp_solve(P, cx, k, xi, lbv, ubv, y, iters_s);
+        if (qs == WS_ITER_LIMIT) { st = BNB_QP_LIMIT; break; }
+        double *dual = rdual + (size_t)nr * P.n_dual;
+        build_records(P, qs, SMV(yc), y, xi, lbv, ubv, prim, dual, cost_s, dobj_s, SMV(part), SMV(red));
+        const double cost = *cost_s;
+        if (threadIdx.x == 0) {
+            lb[bi] = cost; rec[bi] = nr; rdobj[nr] = *dobj_s;
+            if (tr_i) { tr_i[2 * solves] = bi; tr_i[2 * solves + 1] = *iters_s; }
+        }
+        const int myrec = nr;
+        iters += *iters_s;
+        ++nr; ++solves;
+        // ---- prune / incumbent / branch (branch_and_bound.py:476-489)
+        if (cost >= cutoff) {
+            // pruned: the node stays a leaf with its new bound
+        } else if (d == nb) {
+            inc = bi; ub = cost;
+            double *ip = inc_primal + (size_t)inst * P.n_primal;
+            for (int j = threadIdx.x; j < P.n_primal; j += WS_NT) ip[j] = prim[j];
+        } else {
+            // children [value 0, value 1] of binary d = (t, i); bound += multiplier of the bound that moves
+            const double l0 = cost + dual[P.off_nuub + d], l1 = cost + dual[P.off_nulb + d];
+            unsigned int *c0 = bits + (size_t)nn * tr.words, *c1 = c0 + tr.words;
+            for (int w = threadIdx.x; w < tr.words; w += WS_NT) {
+                const unsigned int b = bw[w];
+                c0[w] = b & ~((w == (d >> 5)) ? (1u << (d & 31)) : 0u);
+                c1[w] = b | ((w == (d >> 5)) ? (1u << (d & 31)) : 0u);
+            }
+            if (threadIdx.x == 0) {
+                alive[bi] = 0;
+                depth[nn] = d + 1; alive[nn] = 1; rec[nn] = myrec; lb[nn] = l0;
+                depth[nn + 1] = d + 1; alive[nn + 1] = 1; rec[nn + 1] = myrec; lb[nn + 1] = l1;
+            }
+            nn += 2;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        tr.n_nodes[inst] = nn; tr.n_recs[inst] = nr;
+        inc_cost[inst] = ub; inc_node[inst] = inc; n_solves[inst] = solves;
+        if (totals) { atomicAdd(totals, (unsigned long long)solves); atomicAdd(totals + 1, (unsigned long long)iters); }
+    }
+    __syncthreads();
+    return st;
+}
+
 __global__ void __launch_bounds__(WS_NT, 1)
 bnb_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, double *scratch, int *work_counter,
            int n_inst, const double *__restrict__ x0, const int *__restrict__ active, TreeView tr,
@@ -46,13 +137,11 @@ bnb_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, double *scra
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_inst;
     const int slot = blockIdx.x;
-    const int nb = P.nb;
     SlotPtrs sp = slot_ptrs(slot_d, slot_i, slot, P.n, P.ld);
     const Ctx cx = make_ctx(P, smem_raw, sp);
     init_shared_tables(P, cx);
     double *y = ybuf + (size_t)slot * P.m;
-    double *sc = scratch + (size_t)slot * bnb_scratch_doubles(nb, P.n_primal);
-    double *lbv = sc, *ubv = sc + nb, *prim = sc + 2 * nb, *cost_s = prim + P.n_primal, *dobj_s = cost_s + 1;
+    double *sc = scratch + (size_t)slot * bnb_scratch_doubles(P.nb, P.n_primal);
     int *iters_s = slot_i + (size_t)slot * slot_ints(P.n) + 2 * (P.n + 1) + 1;
 
     for (;;) {
@@ -65,87 +154,9 @@ bnb_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, double *scra
             if (threadIdx.x == 0) { inc_cost[inst] = INFINITY; inc_node[inst] = -1; n_solves[inst] = 0; status_out[inst] = BNB_INFEASIBLE; }
             continue;
         }
-
-        const size_t no = (size_t)inst * tr.cap_nodes;
-        int *depth = tr.depth + no, *alive = tr.alive + no, *rec = tr.rec + no;
-        unsigned int *bits = tr.bits + no * tr.words;
-        double *lb = tr.lb + no;
-        double *rdobj = tr.rec_dobj + (size_t)inst * tr.cap_recs;
-        double *rdual = tr.rec_dual + (size_t)inst * tr.cap_recs * P.n_dual;
-        const double *xi = x0 + (size_t)inst * P.nx;
-        int *tr_i = trace ? trace + (size_t)inst * 2 * max_solves : nullptr;
-
-        int nn = tr.n_nodes[inst], nr = tr.n_recs[inst];
-        double ub = INFINITY;
-        int inc = -1, solves = 0, st = -1, k = 0;
-        long long iters = 0;
-        bool first = true;
-
-        while (st < 0) {
-            // ---- select: candidates = alive leaves with lb < ub - tol ; best_first = first minimum
-            const double cutoff = ub - tol;
-            double best = INFINITY; int bi = -1;
-            for (int j = threadIdx.x; j < nn; j += WS_NT)
-                if (alive[j]) {
-                    const double l = lb[j];
-                    if (l < cutoff && (bi < 0 || l < best)) { best = l; bi = j; }
-                }
-            block_argmin(best, bi, SMV(red), SMI(ired));
-            if (bi < 0) { st = inc >= 0 ? BNB_OK : BNB_INFEASIBLE; break; }
-            if (solves >= max_solves || nn + 2 > tr.cap_nodes || nr + 1 > tr.cap_recs) { st = BNB_CAPACITY; break; }
-            // ---- bounds of the node (controller.py:273-298)
-            const int d = depth[bi];
-            const unsigned int *bw = bits + (size_t)bi * tr.words;
-            for (int j = threadIdx.x; j < nb; j += WS_NT) {
-                const double v = (double)((bw[j >> 5] >> (j & 31)) & 1u);
-                lbv[j] = j < d ? v : 0.;
-                ubv[j] = j < d ? v : 1.;
-            }
-            __syncthreads();
-            // ---- solve (K1), hot-started from the node solved before it
-            if (first) { load_slot(P, cx, sp, k, true); first = false; }
-            const int qs = qp_solve(P, cx, k, xi, lbv, ubv, y, iters_s);
-            if (qs == WS_ITER_LIMIT) { st = BNB_QP_LIMIT; break; }
-            double *dual = rdual + (size_t)nr * P.n_dual;
-            build_records(P, qs, SMV(yc), y, xi, lbv, ubv, prim, dual, cost_s, dobj_s, SMV(part), SMV(red));
-            const double cost = *cost_s;
-            if (threadIdx.x == 0) {
-                lb[bi] = cost; rec[bi] = nr; rdobj[nr] = *dobj_s;
-                if (tr_i) { tr_i[2 * solves] = bi; tr_i[2 * solves + 1] = *iters_s; }
-            }
-            const int myrec = nr;
-            iters += *iters_s;
-            ++nr; ++solves;
-            // ---- prune / incumbent / branch (branch_and_bound.py:476-489)
-            if (cost >= cutoff) {
-                // pruned: the node stays a leaf with its new bound
-            } else if (d == nb) {
-                inc = bi; ub = cost;
-                double *ip = inc_primal + (size_t)inst * P.n_primal;
-                for (int j = threadIdx.x; j < P.n_primal; j += WS_NT) ip[j] = prim[j];
-            } else {
-                // children [value 0, value 1] of binary d = (t, i); bound += multiplier of the bound that moves
-                const double l0 = cost + dual[P.off_nuub + d], l1 = cost + dual[P.off_nulb + d];
-                unsigned int *c0 = bits + (size_t)nn * tr.words, *c1 = c0 + tr.words;
-                for (int w = threadIdx.x; w < tr.words; w += WS_NT) {
-                    const unsigned int b = bw[w];
-                    c0[w] = b & ~((w == (d >> 5)) ? (1u << (d & 31)) : 0u);
-                    c1[w] = b | ((w == (d >> 5)) ? (1u << (d & 31)) : 0u);
-                }
-                if (threadIdx.x == 0) {
-                    alive[bi] = 0;
-                    depth[nn] = d + 1; alive[nn] = 1; rec[nn] = myrec; lb[nn] = l0;
-                    depth[nn + 1] = d + 1; alive[nn + 1] = 1; rec[nn + 1] = myrec; lb[nn + 1] = l1;
-                }
-                nn += 2;
-            }
-            __syncthreads();
-        }
-        if (threadIdx.x == 0) {
-            tr.n_nodes[inst] = nn; tr.n_recs[inst] = nr;
-            inc_cost[inst] = ub; inc_node[inst] = inc; n_solves[inst] = solves; status_out[inst] = st;
-            if (totals) { atomicAdd(totals, (unsigned long long)solves); atomicAdd(totals + 1, (unsigned long long)iters); }
-        }
+        const int st = bnb_instance(P, cx, sp, y, sc, iters_s, inst, x0 + (size_t)inst * P.nx, tr, tol, max_solves,
+                                    inc_cost, inc_node, inc_primal, n_solves, trace, totals);
+        if (threadIdx.x == 0) status_out[inst] = st;
     }
 }
 
@@ -155,6 +166,184 @@ bnb_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, double *scra
 #define SH_NT 256
 #define SH_NW (SH_NT / 32)
 
+// doubles of shared scratch the shift needs with NT threads
+__host__ __device__ inline size_t shift_smem_doubles(const DevProblem &P, int nt) {
+    return (size_t)2 * P.nx + P.nu + P.nq + P.nr + P.nh + (size_t)(nt / 32) * (P.nh1 + P.nqT + P.nh + P.nq) + 8;
+}
+
+// warm start of ONE instance by the calling CTA (NT threads): shm = shared scratch (shift_smem_doubles),
+// s_wsum (NT / 32 ints) and s_base (1 int) shared as well.
+template <int NT>
+__device__ inline void shift_instance(const DevProblem &P, double *shm, int *s_wsum, int *s_base_p, int inst,
+                                      const double *__restrict__ x0, const double *__restrict__ e0,
+                                      const TreeView &ot, const double *__restrict__ inc_cost, const double *__restrict__ inc_primal,
+                                      int *active, const TreeView &nt, double *x_next, double *u0_out)
+{
+    const int nx = P.nx, nu = P.nu, nub = P.nub, nuc = P.nuc, T = P.T, nh = P.nh, nh1 = P.nh1;
+    const int nq = P.nq, nqT = P.nqT, nr_ = P.nr;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    // shared: x0 | u0 | e0 | Qx0 | Ru0 | res_mu | per-warp scratch (nh1 + nqT each)
+    double *xs = shm, *us = xs + nx, *es = us + nu, *Qx = es + nx, *Ru = Qx + nq, *rmu = Ru + nr_;
+    double *wscr = rmu + nh + (size_t)w * (nh1 + nqT + nh + nq);
+#define s_base (*s_base_p)
+    __syncthreads();
+    const double *ip = inc_primal + (size_t)inst * P.n_primal;
+    const bool on = (!active || active[inst]) && inc_cost[inst] < INFINITY;
+    if (!on) {
+        if (threadIdx.x == 0) {
+            if (active) active[inst] = 0;
+            nt.n_nodes[inst] = 0; nt.n_recs[inst] = 0;
+        }
+        for (int j = threadIdx.x; j < nx; j += NT) if (x_next) x_next[(size_t)inst * nx + j] = x0[(size_t)inst * nx + j];
+        for (int j = threadIdx.x; j < nu; j += NT) if (u0_out) u0_out[(size_t)inst * nu + j] = nan("");
+        return;
+    }
+    for (int j = threadIdx.x; j < nx; j += NT) { xs[j] = x0[(size_t)inst * nx + j]; es[j] = e0 ? e0[(size_t)inst * nx + j] : 0.; }
+    for (int j = threadIdx.x; j < nu; j += NT) us[j] = ip[(size_t)(T + 1) * nx + j];
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < nq; i += NT) { double s = 0.; for (int c = 0; c < nx; ++c) s += P.Q[i * nx + c] * xs[c]; Qx[i] = s; }
+    for (int i = threadIdx.x; i < nr_; i += NT) { double s = 0.; for (int c = 0; c < nu; ++c) s += P.R[i * nu + c] * us[c]; Ru[i] = s; }
+    for (int i = threadIdx.x; i < nh; i += NT) {
+        double s = -P.h[i];
+        for (int c = 0; c < nx; ++c) s += P.F[i * nx + c] * xs[c];
+        for (int c = 0; c < nu; ++c) s += P.G[i * nu + c] * us[c];
+        rmu[i] = s;
+    }
+    // plant update and applied input
+    for (int j = threadIdx.x; j < nx; j += NT) if (x_next) x_next[(size_t)inst * nx + j] = ip[nx + j] + es[j];
+    for (int j = threadIdx.x; j < nu; j += NT) if (u0_out) u0_out[(size_t)inst * nu + j] = us[j];
+    __syncthreads();
+
+    const size_t oo = (size_t)inst * ot.cap_nodes, on_ = (size_t)inst * nt.cap_nodes;
+    const int nn = ot.n_nodes[inst];
+    // ---- pass 1: _retain_leaf (controller.py:615-633) + ordered compaction + identifier shift (:476)
+    for (int base = 0; base < nn; base += NT) {
+        const int j = base + threadIdx.x;
+        int keep = 0;
+        if (j < nn && ot.alive[oo + j]) {
+            keep = 1;
+            const int d = ot.depth[oo + j];
+            const unsigned int b0 = ot.bits[(oo + j) * ot.words];
+            const int lim = d < nub ? d : nub;
+            for (int i = 0; i < lim; ++i)
+                if ((double)((b0 >> i) & 1u) != us[nuc + i]) keep = 0;
+        }
+        const unsigned int bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_wsum[w] = __popc(bal);
+        __syncthreads();
+        int pre = s_base;
+        for (int q = 0; q < w; ++q) pre += s_wsum[q];
+        const int idx = pre + __popc(bal & ((1u << lane) - 1u));
+        if (keep && idx < nt.cap_nodes) {
+            const int d = ot.depth[oo + j];
+            const int dn = d > nub ? d - nub : 0;
+            nt.depth[on_ + idx] = dn; nt.alive[on_ + idx] = 1; nt.rec[on_ + idx] = j;   // rec = source node (pass 2 rewrites it)
+            const unsigned int *src = ot.bits + (oo + j) * ot.words;
+            unsigned int *dst = nt.bits + (on_ + idx) * nt.words;
+            for (int q = 0; q < nt.words; ++q) {
+                // shift the bit string right by nub bits
+                const int sb = q * 32 + nub;
+                const int wq = sb >> 5, sh = sb & 31;
+                unsigned int lo = wq < ot.words ? src[wq] : 0u, hi = wq + 1 < ot.words ? src[wq + 1] : 0u;
+                unsigned int v = sh ? ((lo >> sh) | (hi << (32 - sh))) : lo;
+                const int valid = dn - q * 32;      // keep only bits < dn
+                if (valid <= 0) v = 0u; else if (valid < 32) v &= (1u << valid) - 1u;
+                dst[q] = v;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { int s = s_base; for (int q = 0; q < (NT / 32); ++q) s += s_wsum[q]; s_base = s; }
+        __syncthreads();
+    }
+    const int nnew = s_base < nt.cap_nodes ? s_base : nt.cap_nodes;
+    // ---- pass 2: one warp per retained leaf
+    for (int idx = w; idx < nnew; idx += (NT / 32)) {
+        const int j = nt.rec[on_ + idx];
+        const int ro = ot.rec[oo + j];
+        const double lbo = ot.lb[oo + j];
+        double *E = nt.rec_dual + ((size_t)inst * nt.cap_recs + idx) * P.n_dual;
+        if (ro < 0) {
+            // dual = None (controller.py:556-558 on the previous step, never solved since): trivial bound
+            for (int e = lane; e < P.n_dual; e += 32) E[e] = 0.;
+            if (lane == 0) { nt.lb[on_ + idx] = 0.; nt.rec[on_ + idx] = -1; nt.rec_dobj[(size_t)inst * nt.cap_recs + idx] = 0.; }
+            return;
+        }
+        const double *D = ot.rec_dual + ((size_t)inst * ot.cap_recs + ro) * P.n_dual;
+        const int d_old = ot.depth[oo + j];
+        const unsigned int b0 = ot.bits[(oo + j) * ot.words];
+        double acc = 0.;                     // pi_sum + pi3, lane-partial
+        // lam: drop t = 0, append zero ; pi3 = -lam'_0 . e0 (controller.py:544)
+        {
+            const double *s = D + P.off_lam + nx; double *t = E + P.off_lam;
+            for (int e = lane; e < T * nx; e += 32) { const double v = s[e]; t[e] = v; if (e < nx) acc -= v * es[e]; }
+            for (int e = lane; e < nx; e += 32) t[T * nx + e] = 0.;
+        }
+        // nu_lb, nu_ub: complementarity terms with the OLD identifier's bounds at t = 0 (controller.py:703-709)
+        {
+            const double *sl = D + P.off_nulb, *su = D + P.off_nuub;
+            double *tl = E + P.off_nulb, *tu = E + P.off_nuub;
+            for (int e = lane; e < (T - 1) * nub; e += 32) { tl[e] = sl[nub + e]; tu[e] = su[nub + e]; }
+            for (int e = lane; e < nub; e += 32) {
+                tl[(T - 1) * nub + e] = 0.; tu[(T - 1) * nub + e] = 0.;
+                const double bit = (double)((b0 >> e) & 1u);
+                const double l0 = e < d_old ? bit : 0., u0b = e < d_old ? bit : 1.;
+                const double vu = us[nuc + e];
+                acc -= (l0 - vu) * sl[e] + (vu - u0b) * su[e];
+            }
+        }
+        // sigma: suboptimality term |sigma_0 / 2 - R u0|^2 - |R u0|^2
+        {
+            const double *s = D + P.off_sigma; double *t = E + P.off_sigma;
+            for (int e = lane; e < (T - 1) * nr_; e += 32) t[e] = s[nr_ + e];
+            for (int e = lane; e < nr_; e += 32) { t[(T - 1) * nr_ + e] = 0.; const double a = .5 * s[e] - Ru[e]; acc += a * a - Ru[e] * Ru[e]; }
+        }
+        // rho: rho'_{T-1} = M_rho rho_T (controller.py:96, 662-664)
+        {
+            const double *s = D + P.off_rho; double *t = E + P.off_rho;
+            for (int e = lane; e < (T - 1) * nq; e += 32) t[e] = s[nq + e];
+            for (int e = lane; e < nq; e += 32) { const double a = .5 * s[e] - Qx[e]; acc += a * a - Qx[e] * Qx[e]; }
+            double *rT = wscr;                              // rho_T staged for the small mat-vec
+            for (int e = lane; e < nqT; e += 32) { const double v = s[T * nq + e]; rT[e] = v; acc += .25 * v * v; t[T * nq + e] = 0.; }
+            __syncwarp();
+            for (int i = lane; i < nq; i += 32) {
+                double v = 0.;
+                for (int c = 0; c < nqT; ++c) v += P.Mrho[i * nqT + c] * rT[c];
+                t[(T - 1) * nq + i] = v; acc -= .25 * v * v;
+            }
+        }
+        // mu: mu'_{T-2} = M_mu mu_{T-1} (controller.py:186-227, 662-664)
+        {
+            const double *s = D + P.off_mu; double *t = E + P.off_mu;
+            for (int e = lane; e < (T - 2) * nh; e += 32) t[e] = s[nh + e];
+            for (int e = lane; e < nh; e += 32) acc -= rmu[e] * s[e];
+            double *mT = wscr + nqT;
+            for (int e = lane; e < nh1; e += 32) { const double v = s[(T - 1) * nh + e]; mT[e] = v; acc += P.h1[e] * v; t[(T - 1) * nh + e] = 0.; }
+            __syncwarp();
+            for (int i = lane; i < nh; i += 32) {
+                double v = 0.;
+                for (int c = 0; c < nh1; ++c) v += P.Mmu[(size_t)i * nh1 + c] * mT[c];
+                t[(T - 2) * nh + i] = v; acc -= P.h[i] * v;
+            }
+            __syncwarp();
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            double obj = ot.rec_dobj[(size_t)inst * ot.cap_recs + ro] + acc;
+            obj = obj > 0. ? obj : 0.;                     // controller.py:546
+            double lbn; int rn = idx;
+            if (!isinf(lbo)) lbn = obj;                    // :550-551
+            else if (obj <= 0.) { lbn = 0.; rn = -1; }     // :555-558
+            else lbn = INFINITY;
+            nt.lb[on_ + idx] = lbn; nt.rec[on_ + idx] = rn; nt.rec_dobj[(size_t)inst * nt.cap_recs + idx] = obj;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { nt.n_nodes[inst] = nnew; nt.n_recs[inst] = nnew; }
+
+#undef s_base
+}
+
 __global__ void __launch_bounds__(SH_NT)
 shift_tree_kernel(DevProblem P, int n_inst, const double *__restrict__ x0, const double *__restrict__ e0,
                   TreeView ot, const double *__restrict__ inc_cost, const double *__restrict__ inc_primal,
@@ -162,172 +351,120 @@ shift_tree_kernel(DevProblem P, int n_inst, const double *__restrict__ x0, const
 {
     extern __shared__ __align__(16) double shm[];
     __shared__ int s_wsum[SH_NW];
-    __shared__ int s_base;
-    const int nx = P.nx, nu = P.nu, nub = P.nub, nuc = P.nuc, T = P.T, nh = P.nh, nh1 = P.nh1;
-    const int nq = P.nq, nqT = P.nqT, nr_ = P.nr;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    // shared: x0 | u0 | e0 | Qx0 | Ru0 | res_mu | per-warp scratch (nh1 + nqT each)
-    double *xs = shm, *us = xs + nx, *es = us + nu, *Qx = es + nx, *Ru = Qx + nq, *rmu = Ru + nr_;
-    double *wscr = rmu + nh + (size_t)w * (nh1 + nqT + nh + nq);
-
+    __shared__ int s_base_v;
     for (int inst = blockIdx.x; inst < n_inst; inst += gridDim.x) {
         __syncthreads();
-        const double *ip = inc_primal + (size_t)inst * P.n_primal;
-        const bool on = (!active || active[inst]) && inc_cost[inst] < INFINITY;
-        if (!on) {
-            if (threadIdx.x == 0) {
-                if (active) active[inst] = 0;
-                nt.n_nodes[inst] = 0; nt.n_recs[inst] = 0;
-            }
-            for (int j = threadIdx.x; j < nx; j += SH_NT) if (x_next) x_next[(size_t)inst * nx + j] = x0[(size_t)inst * nx + j];
-            for (int j = threadIdx.x; j < nu; j += SH_NT) if (u0_out) u0_out[(size_t)inst * nu + j] = nan("");
-            continue;
-        }
-        for (int j = threadIdx.x; j < nx; j += SH_NT) { xs[j] = x0[(size_t)inst * nx + j]; es[j] = e0 ? e0[(size_t)inst * nx + j] : 0.; }
-        for (int j = threadIdx.x; j < nu; j += SH_NT) us[j] = ip[(size_t)(T + 1) * nx + j];
-        if (threadIdx.x == 0) s_base = 0;
-        __syncthreads();
-        for (int i = threadIdx.x; i < nq; i += SH_NT) { double s = 0.; for (int c = 0; c < nx; ++c) s += P.Q[i * nx + c] * xs[c]; Qx[i] = s; }
-        for (int i = threadIdx.x; i < nr_; i += SH_NT) { double s = 0.; for (int c = 0; c < nu; ++c) s += P.R[i * nu + c] * us[c]; Ru[i] = s; }
-        for (int i = threadIdx.x; i < nh; i += SH_NT) {
-            double s = -P.h[i];
-            for (int c = 0; c < nx; ++c) s += P.F[i * nx + c] * xs[c];
-            for (int c = 0; c < nu; ++c) s += P.G[i * nu + c] * us[c];
-            rmu[i] = s;
-        }
-        // plant update and applied input
-        for (int j = threadIdx.x; j < nx; j += SH_NT) if (x_next) x_next[(size_t)inst * nx + j] = ip[nx + j] + es[j];
-        for (int j = threadIdx.x; j < nu; j += SH_NT) if (u0_out) u0_out[(size_t)inst * nu + j] = us[j];
-        __syncthreads();
-
-        const size_t oo = (size_t)inst * ot.cap_nodes, on_ = (size_t)inst * nt.cap_nodes;
-        const int nn = ot.n_nodes[inst];
-        // ---- pass 1: _retain_leaf (controller.py:615-633) + ordered compaction + identifier shift (:476)
-        for (int base = 0; base < nn; base += SH_NT) {
-            const int j = base + threadIdx.x;
-            int keep = 0;
-            if (j < nn && ot.alive[oo + j]) {
-                keep = 1;
-                const int d = ot.depth[oo + j];
-                const unsigned int b0 = ot.bits[(oo + j) * ot.words];
-                const int lim = d < nub ? d : nub;
-                for (int i = 0; i < lim; ++i)
-                    if ((double)((b0 >> i) & 1u) != us[nuc + i]) keep = 0;
-            }
-            const unsigned int bal = __ballot_sync(0xffffffffu, keep);
-            if (lane == 0) s_wsum[w] = __popc(bal);
-            __syncthreads();
-            int pre = s_base;
-            for (int q = 0; q < w; ++q) pre += s_wsum[q];
-            const int idx = pre + __popc(bal & ((1u << lane) - 1u));
-            if (keep && idx < nt.cap_nodes) {
-                const int d = ot.depth[oo + j];
-                const int dn = d > nub ? d - nub : 0;
-                nt.depth[on_ + idx] = dn; nt.alive[on_ + idx] = 1; nt.rec[on_ + idx] = j;   // rec = source node (pass 2 rewrites it)
-                const unsigned int *src = ot.bits + (oo + j) * ot.words;
-                unsigned int *dst = nt.bits + (on_ + idx) * nt.words;
-                for (int q = 0; q < nt.words; ++q) {
-                    // shift the bit string right by nub bits
-                    const int sb = q * 32 + nub;
-                    const int wq = sb >> 5, sh = sb & 31;
-                    unsigned int lo = wq < ot.words ? src[wq] : 0u, hi = wq + 1 < ot.words ? src[wq + 1] : 0u;
-                    unsigned int v = sh ? ((lo >> sh) | (hi << (32 - sh))) : lo;
-                    const int valid = dn - q * 32;      // keep only bits < dn
-                    if (valid <= 0) v = 0u; else if (valid < 32) v &= (1u << valid) - 1u;
-                    dst[q] = v;
-                }
-            }
-            __syncthreads();
-            if (threadIdx.x == 0) { int s = s_base; for (int q = 0; q < SH_NW; ++q) s += s_wsum[q]; s_base = s; }
-            __syncthreads();
-        }
-        const int nnew = s_base < nt.cap_nodes ? s_base : nt.cap_nodes;
-        // ---- pass 2: one warp per retained leaf
-        for (int idx = w; idx < nnew; idx += SH_NW) {
-            const int j = nt.rec[on_ + idx];
-            const int ro = ot.rec[oo + j];
-            const double lbo = ot.lb[oo + j];
-            double *E = nt.rec_dual + ((size_t)inst * nt.cap_recs + idx) * P.n_dual;
-            if (ro < 0) {
-                // dual = None (controller.py:556-558 on the previous step, never solved since): trivial bound
-                for (int e = lane; e < P.n_dual; e += 32) E[e] = 0.;
-                if (lane == 0) { nt.lb[on_ + idx] = 0.; nt.rec[on_ + idx] = -1; nt.rec_dobj[(size_t)inst * nt.cap_recs + idx] = 0.; }
-                continue;
-            }
-            const double *D = ot.rec_dual + ((size_t)inst * ot.cap_recs + ro) * P.n_dual;
-            const int d_old = ot.depth[oo + j];
-            const unsigned int b0 = ot.bits[(oo + j) * ot.words];
-            double acc = 0.;                     // pi_sum + pi3, lane-partial
-            // lam: drop t = 0, append zero ; pi3 = -lam'_0 . e0 (controller.py:544)
-            {
-                const double *s = D + P.off_lam + nx; double *t = E + P.off_lam;
-                for (int e = lane; e < T * nx; e += 32) { const double v = s[e]; t[e] = v; if (e < nx) acc -= v * es[e]; }
-                for (int e = lane; e < nx; e += 32) t[T * nx + e] = 0.;
-            }
-            // nu_lb, nu_ub: complementarity terms with the OLD identifier's bounds at t = 0 (controller.py:703-709)
-            {
-                const double *sl = D + P.off_nulb, *su = D + P.off_nuub;
-                double *tl = E + P.off_nulb, *tu = E + P.off_nuub;
-                for (int e = lane; e < (T - 1) * nub; e += 32) { tl[e] = sl[nub + e]; tu[e] = su[nub + e]; }
-                for (int e = lane; e < nub; e += 32) {
-                    tl[(T - 1) * nub + e] = 0.; tu[(T - 1) * nub + e] = 0.;
-                    const double bit = (double)((b0 >> e) & 1u);
-                    const double l0 = e < d_old ? bit : 0., u0b = e < d_old ? bit : 1.;
-                    const double vu = us[nuc + e];
-                    acc -= (l0 - vu) * sl[e] + (vu - u0b) * su[e];
-                }
-            }
-            // sigma: suboptimality term |sigma_0 / 2 - R u0|^2 - |R u0|^2
-            {
-                const double *s = D + P.off_sigma; double *t = E + P.off_sigma;
-                for (int e = lane; e < (T - 1) * nr_; e += 32) t[e] = s[nr_ + e];
-                for (int e = lane; e < nr_; e += 32) { t[(T - 1) * nr_ + e] = 0.; const double a = .5 * s[e] - Ru[e]; acc += a * a - Ru[e] * Ru[e]; }
-            }
-            // rho: rho'_{T-1} = M_rho rho_T (controller.py:96, 662-664)
-            {
-                const double *s = D + P.off_rho; double *t = E + P.off_rho;
-                for (int e = lane; e < (T - 1) * nq; e += 32) t[e] = s[nq + e];
-                for (int e = lane; e < nq; e += 32) { const double a = .5 * s[e] - Qx[e]; acc += a * a - Qx[e] * Qx[e]; }
-                double *rT = wscr;                              // rho_T staged for the small mat-vec
-                for (int e = lane; e < nqT; e += 32) { const double v = s[T * nq + e]; rT[e] = v; acc += .25 * v * v; t[T * nq + e] = 0.; }
-                __syncwarp();
-                for (int i = lane; i < nq; i += 32) {
-                    double v = 0.;
-                    for (int c = 0; c < nqT; ++c) v += P.Mrho[i * nqT + c] * rT[c];
-                    t[(T - 1) * nq + i] = v; acc -= .25 * v * v;
-                }
-            }
-            // mu: mu'_{T-2} = M_mu mu_{T-1} (controller.py:186-227, 662-664)
-            {
-                const double *s = D + P.off_mu; double *t = E + P.off_mu;
-                for (int e = lane; e < (T - 2) * nh; e += 32) t[e] = s[nh + e];
-                for (int e = lane; e < nh; e += 32) acc -= rmu[e] * s[e];
-                double *mT = wscr + nqT;
-                for (int e = lane; e < nh1; e += 32) { const double v = s[(T - 1) * nh + e]; mT[e] = v; acc += P.h1[e] * v; t[(T - 1) * nh + e] = 0.; }
-                __syncwarp();
-                for (int i = lane; i < nh; i += 32) {
-                    double v = 0.;
-                    for (int c = 0; c < nh1; ++c) v += P.Mmu[(size_t)i * nh1 + c] * mT[c];
-                    t[(T - 2) * nh + i] = v; acc -= P.h[i] * v;
-                }
-                __syncwarp();
-            }
-            acc = warp_sum(acc);
-            if (lane == 0) {
-                double obj = ot.rec_dobj[(size_t)inst * ot.cap_recs + ro] + acc;
-                obj = obj > 0. ? obj : 0.;                     // controller.py:546
-                double lbn; int rn = idx;
-                if (!isinf(lbo)) lbn = obj;                    // :550-551
-                else if (obj <= 0.) { lbn = 0.; rn = -1; }     // :555-558
-                else lbn = INFINITY;
-                nt.lb[on_ + idx] = lbn; nt.rec[on_ + idx] = rn; nt.rec_dobj[(size_t)inst * nt.cap_recs + idx] = obj;
-            }
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) { nt.n_nodes[inst] = nnew; nt.n_recs[inst] = nnew; }
+        shift_instance<SH_NT>(P, shm, s_wsum, &s_base_v, inst, x0, e0, ot, inc_cost, inc_primal, active, nt, x_next, u0_out);
     }
 }
 
-__host__ inline size_t shift_smem_bytes(const DevProblem &P) {
-    return sizeof(double) * ((size_t)2 * P.nx + P.nu + P.nq + P.nr + P.nh + (size_t)SH_NW * (P.nh1 + P.nqT + P.nh + P.nq) + 8);
+__host__ inline size_t shift_smem_bytes(const DevProblem &P) { return sizeof(double) * shift_smem_doubles(P, SH_NT); }
+
+
+// ---------------------------------------------------------------------------------------------
+// Fused closed loop (K3 + K2/K4 of many receding-horizon steps in ONE launch).
+// Restates the experiment driver notebooks/cart_pole_with_walls/statistical_analysis.py:93-196 (linear
+// plant + model error, no Gurobi legs) for a batch of independent instances WITHOUT a barrier between
+// the steps of different instances: a task is (instance, its next step); CTAs pop tasks from a queue in
+// global memory, run branch and bound + warm-start construction + plant update for that step, and push
+// the instance back.  An instance is owned by one CTA at a time; its trees and state live in global
+// memory, so any CTA can continue it.  Results are identical to stepping the batch in lock step.
+// ---------------------------------------------------------------------------------------------
+struct LoopView {
+    int n_steps, warm, fresh, par;
+    int *q;                 // [0] head, [1] tail, [2 ...] items
+    int *step_of;           // [n_inst]
+    double *x;              // [2][n_inst][nx]
+    const double *e;        // [n_steps][n_inst][nx] or null
+    int *active;            // [n_inst]
+    double *log_cost;       // [n_steps][n_inst]
+    double *log_u0;         // [n_steps][n_inst][nu]
+    int *log_solves;        // [n_steps][n_inst]
+    int *log_status;        // [n_steps][n_inst]
+};
+
+__global__ void loop_init_kernel(int n_inst, int n_items, LoopView L)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) { L.q[0] = 0; L.q[1] = n_inst; }
+    if (i < n_items) L.q[2 + i] = i < n_inst ? i : -1;
+    if (i < n_inst) L.step_of[i] = 0;
+}
+
+__device__ inline void init_root(const TreeView &tr, int k)
+{
+    const size_t o = (size_t)k * tr.cap_nodes;
+    tr.n_nodes[k] = 1; tr.n_recs[k] = 0;
+    tr.depth[o] = 0; tr.alive[o] = 1; tr.rec[o] = -1; tr.lb[o] = -INFINITY;
+    for (int w = 0; w < tr.words; ++w) tr.bits[o * tr.words + w] = 0u;
+}
+
+__global__ void __launch_bounds__(WS_NT, 1)
+closed_loop_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, double *scratch, LoopView L, int n_inst,
+                   TreeView t0, TreeView t1, double tol, int max_solves,
+                   double *inc_cost, int *inc_node, double *inc_primal, int *n_solves, int *status_out,
+                   unsigned long long *totals)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_inst;
+    const int slot = blockIdx.x;
+    SlotPtrs sp = slot_ptrs(slot_d, slot_i, slot, P.n, P.ld);
+    const Ctx cx = make_ctx(P, smem_raw, sp);
+    init_shared_tables(P, cx);
+    double *y = ybuf + (size_t)slot * P.m;
+    double *sc = scratch + (size_t)slot * bnb_scratch_doubles(P.nb, P.n_primal);
+    int *iters_s = slot_i + (size_t)slot * slot_ints(P.n) + 2 * (P.n + 1) + 1;
+    const int total = n_inst * L.n_steps;
+    const size_t xs = (size_t)n_inst * P.nx;
+
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int pos = atomicAdd(L.q, 1);
+            int inst = -1;
+            if (pos < total) {
+                volatile int *item = L.q + 2 + pos;
+                while ((inst = *item) < 0) __nanosleep(256);
+            }
+            s_inst = inst;
+        }
+        __syncthreads();
+        const int inst = s_inst;
+        if (inst < 0) break;
+        __threadfence();                                   // acquire: drop stale L1 lines of the instance's data
+        const int t = L.step_of[inst];
+        const int par = (L.par + t) & 1;
+        const TreeView &cur = par ? t1 : t0;
+        const TreeView &nxt = par ? t0 : t1;
+        const double *xc = L.x + (size_t)par * xs;
+        double *xn = L.x + (size_t)(par ^ 1) * xs;
+        if (!L.warm || (t == 0 && L.fresh)) {
+            if (threadIdx.x == 0) init_root(cur, inst);
+            __syncthreads();
+        }
+        int st;
+        if (!L.active[inst]) {
+            if (threadIdx.x == 0) { inc_cost[inst] = INFINITY; inc_node[inst] = -1; n_solves[inst] = 0; }
+            st = BNB_INFEASIBLE;
+            __syncthreads();
+        } else {
+            st = bnb_instance(P, cx, sp, y, sc, iters_s, inst, xc + (size_t)inst * P.nx, cur, tol, max_solves,
+                              inc_cost, inc_node, inc_primal, n_solves, nullptr, totals);
+        }
+        if (threadIdx.x == 0) {
+            status_out[inst] = st;
+            const size_t lo = (size_t)t * n_inst + inst;
+            L.log_cost[lo] = inc_cost[inst]; L.log_solves[lo] = n_solves[inst]; L.log_status[lo] = st;
+        }
+        __syncthreads();
+        shift_instance<WS_NT>(P, SMV(Q), SMI(ired), SMI(ired) + WS_NW, inst, xc, L.e ? L.e + (size_t)t * xs : nullptr,
+                              cur, inc_cost, inc_primal, L.active, nxt, xn, L.log_u0 + (size_t)t * n_inst * P.nu);
+        if (threadIdx.x == 0) L.step_of[inst] = t + 1;
+        __threadfence();                                   // release: the instance's data before the token
+        __syncthreads();
+        if (threadIdx.x == 0 && t + 1 < L.n_steps) {
+            const int p = atomicAdd(L.q + 1, 1);
+            atomicExch(L.q + 2 + p, inst);
+        }
+    }
 }

@@ -132,6 +132,12 @@ __device__ __forceinline__ double warp_sum(double x) {
     return x;
 }
 
+// The block-wide reductions below reduce inside each warp by shuffles, park one value per warp in shared
+// memory, and finish with a second shuffle tree over the WS_NW per-warp values (every warp does it
+// redundantly, so the result reaches all threads with two barriers and ~25 instructions).
+#define WS_FULL 0xffffffffu
+static_assert(WS_NW == 16, "the two-level reductions assume 16 warps per CTA");
+
 // block-wide sum, result to all threads
 __device__ inline double block_sum(double x, double *red) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -139,10 +145,10 @@ __device__ inline double block_sum(double x, double *red) {
     __syncthreads();
     if (lane == 0) red[w] = x;
     __syncthreads();
-    double s = 0.;
+    double s = lane < WS_NW ? red[lane] : 0.;
 #pragma unroll
-    for (int i = 0; i < WS_NW; ++i) s += red[i];
-    return s;
+    for (int o = WS_NW / 2; o > 0; o >>= 1) s += __shfl_xor_sync(WS_FULL, s, o);
+    return __shfl_sync(WS_FULL, s, 0);
 }
 
 // two block-wide sums at once
@@ -152,10 +158,15 @@ __device__ inline void block_sum2(double &x, double &y, double *red) {
     __syncthreads();
     if (lane == 0) { red[w] = x; red[WS_NW + w] = y; }
     __syncthreads();
-    double s = 0., q = 0.;
+    // lanes 0..15 take the x partials, lanes 16..31 the y partials (WS_NW == 16)
+    double s = red[lane];
 #pragma unroll
-    for (int i = 0; i < WS_NW; ++i) { s += red[i]; q += red[WS_NW + i]; }
-    x = s; y = q;
+    for (int o = WS_NW / 2; o > 0; o >>= 1) s += __shfl_xor_sync(WS_FULL, s, o);
+    x = __shfl_sync(WS_FULL, s, 0); y = __shfl_sync(WS_FULL, s, WS_NW);
+}
+
+__device__ __forceinline__ bool better_max(double ov, int oi, double val, int idx) {
+    return oi >= 0 && (idx < 0 || ov > val || (ov == val && oi < idx));
 }
 
 // block-wide arg-max of (val, idx): larger val wins, ties -> smaller idx.  idx < 0 = no candidate.
@@ -163,19 +174,35 @@ __device__ inline void block_argmax(double &val, int &idx, double *red, int *ire
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        const double ov = __shfl_xor_sync(0xffffffffu, val, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-        if (oi >= 0 && (idx < 0 || ov > val || (ov == val && oi < idx))) { val = ov; idx = oi; }
+        const double ov = __shfl_xor_sync(WS_FULL, val, o);
+        const int oi = __shfl_xor_sync(WS_FULL, idx, o);
+        if (better_max(ov, oi, val, idx)) { val = ov; idx = oi; }
     }
     __syncthreads();
     if (lane == 0) { red[w] = val; ired[w] = idx; }
     __syncthreads();
-    val = red[0]; idx = ired[0];
+    val = lane < WS_NW ? red[lane] : 0.; idx = lane < WS_NW ? ired[lane] : -1;
 #pragma unroll
-    for (int i = 1; i < WS_NW; ++i) {
-        const double ov = red[i]; const int oi = ired[i];
-        if (oi >= 0 && (idx < 0 || ov > val || (ov == val && oi < idx))) { val = ov; idx = oi; }
+    for (int o = WS_NW / 2; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(WS_FULL, val, o);
+        const int oi = __shfl_xor_sync(WS_FULL, idx, o);
+        if (better_max(ov, oi, val, idx)) { val = ov; idx = oi; }
     }
+    val = __shfl_sync(WS_FULL, val, 0); idx = __shfl_sync(WS_FULL, idx, 0);
+}
+
+// block-wide max of a non-negative value
+__device__ inline double block_max(double x, double *red) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(WS_FULL, x, o));
+    __syncthreads();
+    if (lane == 0) red[w] = x;
+    __syncthreads();
+    double s = lane < WS_NW ? red[lane] : 0.;
+#pragma unroll
+    for (int o = WS_NW / 2; o > 0; o >>= 1) s = fmax(s, __shfl_xor_sync(WS_FULL, s, o));
+    return __shfl_sync(WS_FULL, s, 0);
 }
 
 // block-wide arg-min (ratio tests): smaller val wins, ties -> smaller idx
@@ -188,23 +215,27 @@ __device__ inline void block_argmin(double &val, int &idx, double *red, int *ire
 // arg-min and a sum in one pass (ratio test + sum of the positive multipliers)
 __device__ inline void block_argmin_sum(double &val, int &idx, double &sum, double *red, int *ired) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    double nv = -val;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        const double ov = __shfl_xor_sync(0xffffffffu, val, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-        sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        if (oi >= 0 && (idx < 0 || ov < val || (ov == val && oi < idx))) { val = ov; idx = oi; }
+        const double ov = __shfl_xor_sync(WS_FULL, nv, o);
+        const int oi = __shfl_xor_sync(WS_FULL, idx, o);
+        sum += __shfl_xor_sync(WS_FULL, sum, o);
+        if (better_max(ov, oi, nv, idx)) { nv = ov; idx = oi; }
     }
     __syncthreads();
-    if (lane == 0) { red[w] = val; ired[w] = idx; red[WS_NW + w] = sum; }
+    if (lane == 0) { red[w] = nv; ired[w] = idx; red[WS_NW + w] = sum; }
     __syncthreads();
-    val = red[0]; idx = ired[0]; sum = red[WS_NW];
+    nv = lane < WS_NW ? red[lane] : 0.; idx = lane < WS_NW ? ired[lane] : -1;
+    sum = lane < WS_NW ? red[WS_NW + lane] : 0.;
 #pragma unroll
-    for (int i = 1; i < WS_NW; ++i) {
-        const double ov = red[i]; const int oi = ired[i];
-        sum += red[WS_NW + i];
-        if (oi >= 0 && (idx < 0 || ov < val || (ov == val && oi < idx))) { val = ov; idx = oi; }
+    for (int o = WS_NW / 2; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(WS_FULL, nv, o);
+        const int oi = __shfl_xor_sync(WS_FULL, idx, o);
+        sum += __shfl_xor_sync(WS_FULL, sum, o);
+        if (better_max(ov, oi, nv, idx)) { nv = ov; idx = oi; }
     }
+    val = -__shfl_sync(WS_FULL, nv, 0); idx = __shfl_sync(WS_FULL, idx, 0); sum = __shfl_sync(WS_FULL, sum, 0);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -795,7 +826,7 @@ restart:
                 // dependent entering row: dual ray (p_W, 1), p_W = -t
                 double pm = 1.;
                 for (int i = threadIdx.x; i < k; i += WS_NT) pm = fmax(pm, fabs(t[i]));
-                { int dummy = 0; block_argmax(pm, dummy, red, ired); }
+                pm = block_max(pm, red);
                 double amin = INFINITY; int kmin = -1;
                 for (int i = threadIdx.x; i < k; i += WS_NT) if (t[i] > P.tol_ray * pm) {
                     const double a = lam[i] / t[i];
@@ -854,7 +885,7 @@ restart:
             dz = fmax(dz, fabs(s - SMV(yc)[r]));
             SMV(c2)[r] = s;
         });
-        { int dummy = 0; block_argmax(dz, dummy, red, ired); }
+        dz = block_max(dz, red);
         for (int r = threadIdx.x; r < n; r += WS_NT) SMV(yc)[r] = SMV(c2)[r];
         __syncthreads();
         if (P.eps * dz <= P.prox_tol) break;

@@ -186,6 +186,7 @@ extern "C" int wshmpc_create(const wshmpc_problem *p, int device, int n_slots, v
     WS_CUDA(cudaMemset(h->slot_i, 0, (size_t)n_slots * slot_ints(n) * sizeof(int)));
     WS_CUDA(cudaMalloc(&d, (size_t)n_slots * m * sizeof(double))); h->allocs.push_back(d); h->ybuf = (double *)d;
     WS_CUDA(cudaFuncSetAttribute(bnb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+    WS_CUDA(cudaFuncSetAttribute(closed_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
     WS_CUDA(cudaMalloc(&d, (size_t)n_slots * bnb_scratch_doubles(p->nb, L.primal) * sizeof(double))); h->allocs.push_back(d); h->scratch = (double *)d;
     WS_CUDA(cudaMalloc(&d, 64)); h->allocs.push_back(d); h->work_counter = (int *)d;
     h->shift_smem = shift_smem_bytes(P);
@@ -288,6 +289,40 @@ extern "C" int wshmpc_shift_tree(wshmpc_handle *h, int n_inst, const double *d_x
     WS_CUDA(cudaSetDevice(h->device));
     shift_tree_kernel<<<n_inst, SH_NT, h->shift_smem, h->stream>>>(
         h->P, n_inst, d_x0, d_e0, ov, d_inc_cost, d_inc_primal, d_active, nv, d_x_next, d_u0);
+    WS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int wshmpc_closed_loop(wshmpc_handle *h, int n_inst, const wshmpc_loop *loop,
+                                  const wshmpc_tree *tree0, const wshmpc_tree *tree1, double tol, int max_solves,
+                                  double *d_inc_cost, int *d_inc_node, double *d_inc_primal, int *d_n_solves,
+                                  int *d_status, unsigned long long *d_totals)
+{
+    if (!h || !loop) WS_FAIL(-1, "null argument");
+    if (n_inst <= 0 || loop->n_steps <= 0) return 0;
+    if (max_solves <= 0) WS_FAIL(-1, "max_solves must be positive");
+    if (!loop->d_queue || !loop->d_step_of || !loop->d_x || !loop->d_active || !loop->d_log_cost || !loop->d_log_u0 ||
+        !loop->d_log_solves || !loop->d_log_status || !d_inc_cost || !d_inc_node || !d_inc_primal || !d_n_solves || !d_status)
+        WS_FAIL(-1, "null argument");
+    if (h->P.T < 2) WS_FAIL(-1, "tree shifting needs T >= 2");
+    if (h->P.nub > 32) WS_FAIL(-1, "tree shifting supports nub <= 32");
+    if ((size_t)h->P.ks * h->P.ld < shift_smem_doubles(h->P, WS_NT)) WS_FAIL(-4, "shared memory too small for the fused warm start");
+    if ((long long)n_inst * (loop->n_steps + 1) > 0x7fffffffLL) WS_FAIL(-1, "too many tasks");
+    TreeView v0, v1; int rc = tree_view(h, tree0, &v0); if (rc) return rc;
+    rc = tree_view(h, tree1, &v1); if (rc) return rc;
+    if (v0.rec_dual == v1.rec_dual || v0.lb == v1.lb) WS_FAIL(-1, "the two trees must be distinct buffers");
+    LoopView L;
+    L.n_steps = loop->n_steps; L.warm = loop->warm; L.fresh = loop->fresh; L.par = loop->par & 1;
+    L.q = loop->d_queue; L.step_of = loop->d_step_of; L.x = loop->d_x; L.e = loop->d_e; L.active = loop->d_active;
+    L.log_cost = loop->d_log_cost; L.log_u0 = loop->d_log_u0; L.log_solves = loop->d_log_solves; L.log_status = loop->d_log_status;
+    WS_CUDA(cudaSetDevice(h->device));
+    const int n_items = n_inst * (loop->n_steps + 1);
+    loop_init_kernel<<<(n_items + 255) / 256, 256, 0, h->stream>>>(n_inst, n_items, L);
+    WS_CUDA(cudaGetLastError());
+    const int grid = n_inst < h->n_slots ? n_inst : h->n_slots;
+    closed_loop_kernel<<<grid, WS_NT, h->smem, h->stream>>>(
+        h->P, h->slot_d, h->slot_i, h->ybuf, h->scratch, L, n_inst, v0, v1, tol, max_solves,
+        d_inc_cost, d_inc_node, d_inc_primal, d_n_solves, d_status, d_totals);
     WS_CUDA(cudaGetLastError());
     return 0;
 }
