@@ -8,9 +8,10 @@
 Workload (BASELINE.json configs[1] per instance, configs[2] = 4096 instances over 8 GPUs as the batch):
 closed loop of the notebook two-wall cart-pole (T = 20), `--instances` independent initial states per GPU
 (tests/golden/cp20_instances.npy), model error e_t = sigma * randn * x_max, warm-started branch and bound
-with tree shifting.  One "step" = one receding-horizon step of the whole batch = K3 (device B&B, K1
-inside) + K2/K4 (tree shift + plant update).  Instances are independent: ranks own contiguous blocks
-of instances, there is no collective on the data path (weak scaling).
+with tree shifting.  One bench "step" = ONE fused launch (wshmpc_closed_loop) that advances every instance of
+the batch by `--window` receding-horizon steps = K3 (device B&B, K1 inside) + K2/K4 (tree shift + plant
+update) per MPC step, with no barrier between instances.  Instances are independent: ranks own contiguous
+blocks of instances, there is no collective on the data path (weak scaling).
 
 Prints ONE JSON line (rank 0).  `value` = QP relaxations solved by all ranks / max-over-ranks device time,
 states resident in HBM; `e2e` = the same loop driven from HOST buffers through the public Python API
@@ -39,8 +40,9 @@ UNIT = 'QP/s'
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--window', type=int, default=10, help='receding-horizon steps per bench step (one fused launch)')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--instances', type=int, default=512, help='independent MPC instances per GPU')
     ap.add_argument('--sigma', type=float, default=0.003, help='model error std (fraction of x_max)')
@@ -56,7 +58,9 @@ def workload_config(args, world):
                         'BASELINE configs[1] per instance, batched as configs[2])',
             'instances_per_gpu': args.instances, 'instances_total': args.instances * world,
             'horizon': 20, 'sigma': args.sigma, 'tol': 0.,
-            'step': 'one receding-horizon step of every instance: device B&B (K3+K1) + tree shift/plant update (K2+K4)',
+            'window': args.window,
+            'step': 'one fused launch = %d receding-horizon steps of every instance: device B&B (K3+K1) + tree shift/plant '
+                    'update (K2+K4) per MPC step, task queue over (instance, step), no barrier between instances' % args.window,
             'search': 'best_first / branch_in_time, reference order, no speculative solves',
             'parallelism': 'instances sharded over %d GPU(s), no data-path collective' % world}
 
@@ -122,7 +126,7 @@ def _cpu_worker(job):
     from oracle.qp_c import CoreC
     from oracle.bnb_ref import OracleController
     model = load_model('cp20')
-    ctl = OracleController(model, CoreC(model), hot_start=True)
+    ctl = OracleController(model, CoreC(model, variant=1), hot_start='record')
     x = x0.copy(); ws = None; rows = []
     t_begin = time.perf_counter()
     for t in range(n_steps):
@@ -149,7 +153,7 @@ def cpu_baseline_sample(args, model, x0, e, seconds):
     solves = sum(r[2] for r in rows)
     return {'value': solves / wall, 'unit': UNIT, 'cores': 1, 'kind': 'port',
             'sample': 'instance 0 of the workload, %d closed-loop steps (1 cold + %d warm), %d QPs in %.1f s; '
-                      'oracle/bnb_ref.py + oracle/qp_core.c (hot-started dual active-set), Python overhead included'
+                      'oracle/bnb_ref.py + oracle/qp_core.c variant 1 (dual active-set, thin QR, each node started from the dual solution it carries -- the same algorithm as the CUDA path), Python overhead included'
                       % (len(rows), len(rows) - 1, solves, wall),
             'qp_only_value': solves / max(qp_time, 1e-9), 'ms_per_qp': 1e3 * wall / max(solves, 1),
             'host_cores_available': os.cpu_count()}
@@ -166,7 +170,8 @@ def run_reference(args):
     qp_c.build()
     model = load_model('cp20')
     cores = max(1, os.cpu_count() or 1)
-    n_steps = args.warmup + args.steps
+    S = args.window
+    n_steps = (args.warmup + args.steps) * S
     x0 = load_instances(0, cores)
     e = noise(model, n_steps, cores, args.sigma, 1000)
     jobs = [(k, x0[k], e[:, k], n_steps, None) for k in range(cores)]
@@ -174,7 +179,7 @@ def run_reference(args):
         res = pool.map(_cpu_worker, jobs)
     solves, t_lo, t_hi = 0, [], []
     for rows, _ in res:
-        timed = rows[args.warmup:]
+        timed = rows[args.warmup * S:]
         if not timed:
             continue
         solves += sum(r[2] for r in timed)
@@ -183,8 +188,8 @@ def run_reference(args):
     elapsed = max(hi - lo for lo, hi in zip(t_lo, t_hi)) if t_lo else float('nan')
     value = solves / elapsed
     cfg = workload_config(args, world)
-    sample = ('%d instances (one per host core) x %d timed closed-loop steps after %d warm-up steps (step 0 = cold solve); '
-              '%d QPs' % (cores, args.steps, args.warmup, solves))
+    sample = ('%d instances (one per host core, fork pool) x %d timed closed-loop MPC steps (= %d bench steps of %d) after %d '
+              'warm-up MPC steps (step 0 = cold solve); %d QPs' % (cores, args.steps * S, args.steps, S, args.warmup * S, solves))
     line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': 1e3 * elapsed / args.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': cfg,
@@ -214,8 +219,9 @@ def fp64_peak_probe(torch, dev):
     return 2. * n ** 3 / (best * 1e-3) / 1e12
 
 
-def timed_loop(torch, dist, loop, e_dev, steps, world, e2e=None):
-    """Times `steps` steps bracketed by barrier + synchronize; returns (elapsed ms max over ranks, QPs, iterations)."""
+def timed_loop(torch, dist, loop, steps, world, body):
+    """Times `steps` bench steps bracketed by barrier + synchronize; body(t) launches step t.
+    Returns (elapsed ms max over ranks, QPs of all ranks, iterations of all ranks, QPs of this rank)."""
     from warm_start_hmpc_b200.closed_loop import reduce_stats
     if world > 1:
         dist.barrier()
@@ -224,10 +230,7 @@ def timed_loop(torch, dist, loop, e_dev, steps, world, e2e=None):
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
     for t in range(steps):
-        if e2e is None:
-            loop.step(e=e_dev[t])
-        else:
-            e2e(t)
+        body(t)
     e.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -260,91 +263,120 @@ def run_b200(args):
     model = load_model('cp20')
     ctl = controller_from_model(model, device=local)
     dev = torch.device('cuda', local)
-    n_inst = args.instances
+    n_inst, S = args.instances, args.window
     lo, hi = shard(n_inst * world, rank, world)
     x0 = load_instances(lo, hi)
-    n_steps = args.warmup + args.steps
-    e_host = noise(model, 2 * n_steps + 8, n_inst, args.sigma, 1000 + rank)
+    n_win = args.warmup + args.steps
+    e_host = noise(model, (2 * n_win + 4) * S, n_inst, args.sigma, 1000 + rank).reshape(2 * n_win + 4, S, n_inst, -1)
     e_dev = torch.as_tensor(e_host, device=dev)
 
     loop = ClosedLoop(ctl, n_inst, warm=True, max_solves=args.max_solves, max_roots=args.max_roots)
     tree_bytes = loop.nbytes()
+    nx, nu = ctl.mld.nx, ctl.mld.nu
+    f64 = dict(dtype=torch.float64, device=dev)
+    logs = dict(cost=torch.empty((S, n_inst), **f64), u0=torch.empty((S, n_inst, nu), **f64),
+                n_solves=torch.empty((S, n_inst), dtype=torch.int32, device=dev),
+                status=torch.empty((S, n_inst), dtype=torch.int32, device=dev))
     loop.reset(x0)
-    for t in range(args.warmup):
-        loop.step(e=e_dev[t])
+    for w in range(args.warmup):
+        loop.run(S, e=e_dev[w], logs=logs)
     torch.cuda.synchronize()
 
-    # ---- device-resident timed region
+    # ---- device-resident timed region: args.steps fused launches
     sampler = ClockSampler(local); sampler.start(); time.sleep(0.3)
-    loop.events = []
+    ev = []
+
+    def dev_step(t):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); loop.run(S, e=e_dev[args.warmup + t], logs=logs); b.record()
+        ev.append((a, b))
     l0 = loop.launches
-    ms, qps, iters, my_qps = timed_loop(torch, dist, loop, e_dev[args.warmup:], args.steps, world)
+    ms, qps, iters, my_qps = timed_loop(torch, dist, loop, args.steps, world, dev_step)
     launches = loop.launches - l0
-    ev = loop.events; loop.events = None
     clocks = sampler.stop()
-    bnb_ms = [a.elapsed_time(b) for a, b, c in ev]; shift_ms = [b.elapsed_time(c) for a, b, c in ev]
+    ker_ms = [a.elapsed_time(b) for a, b in ev]
     n_active = int(loop.active.sum())
     status = loop.out['status'].cpu().numpy()
     value = qps / (ms * 1e-3)
 
-    # ---- end-to-end through the public API with HOST buffers
-    nx, nu = ctl.mld.nx, ctl.mld.nu
+    # ---- end-to-end through the public API with HOST buffers: per bench step H2D of the measured states and of the
+    # window's model errors (pinned), one fused launch, D2H of the applied inputs, costs and final states
     pin = lambda *shape: torch.empty(shape, dtype=torch.float64).pin_memory()
-    xh, eh, uh, ch, xnh = pin(n_inst, nx), pin(n_inst, nx), pin(n_inst, nu), pin(n_inst), pin(n_inst, nx)
-    xd, ed = torch.empty((n_inst, nx), dtype=torch.float64, device=dev), torch.empty((n_inst, nx), dtype=torch.float64, device=dev)
+    xh, eh, uh, ch, xnh = pin(n_inst, nx), pin(S, n_inst, nx), pin(S, n_inst, nu), pin(S, n_inst), pin(n_inst, nx)
+    ed = torch.empty((S, n_inst, nx), **f64)
     xh.copy_(loop.x); torch.cuda.synchronize()
     e_host_t = torch.as_tensor(e_host)
 
     def e2e_step(t):
-        eh.copy_(e_host_t[n_steps + t])
-        xd.copy_(xh, non_blocking=True); ed.copy_(eh, non_blocking=True)          # measured state, model error
-        out = loop.step(e=ed, x=xd)
-        uh.copy_(loop.u0, non_blocking=True); ch.copy_(out['cost'], non_blocking=True); xnh.copy_(loop.x, non_blocking=True)
-        torch.cuda.synchronize()                                                    # the host needs u0 now
+        eh.copy_(e_host_t[n_win + t])
+        loop.x.copy_(xh, non_blocking=True); ed.copy_(eh, non_blocking=True)      # measured states, model errors
+        loop.run(S, e=ed, logs=logs)
+        uh.copy_(logs['u0'], non_blocking=True); ch.copy_(logs['cost'], non_blocking=True); xnh.copy_(loop.x, non_blocking=True)
+        torch.cuda.synchronize()                                                    # the host needs the inputs now
         xh.copy_(xnh)
-    ms_e, qps_e, _, _ = timed_loop(torch, dist, loop, None, args.steps, world, e2e=e2e_step)
-    e2e = {'value': qps_e / (ms_e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': 2 * n_inst * nx * 8,
-           'd2h_bytes_per_step': n_inst * (nu + 1 + nx) * 8, 'ms_per_step': ms_e / args.steps,
-           'api': 'ClosedLoop.step(e, x) of warm_start_hmpc_b200 (ctypes -> C ABI wshmpc_bnb_solve + wshmpc_shift_tree)'}
+    ms_e, qps_e, _, _ = timed_loop(torch, dist, loop, args.steps, world, e2e_step)
+    e2e = {'value': qps_e / (ms_e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': (S + 1) * n_inst * nx * 8,
+           'd2h_bytes_per_step': n_inst * (S * (nu + 1) + nx) * 8, 'ms_per_step': ms_e / args.steps,
+           'ms_per_mpc_step_of_the_batch': ms_e / args.steps / S,
+           'api': 'ClosedLoop.run(n_steps, e) of warm_start_hmpc_b200 (ctypes -> C ABI wshmpc_closed_loop)'}
 
-    # ---- roofline of the dominant kernel (bnb_kernel = K3 with K1 inside)
-    F_iter = 2. * ctl.problem.n ** 2 + 4. * ctl.problem.mc * ctl.problem.n      # flops / iteration
-    flops_per_launch = F_iter * iters / world / max(len(bnb_ms), 1)
-    bnb_avg_ms = float(np.mean(bnb_ms))
-    achieved = flops_per_launch / (bnb_avg_ms * 1e-3) / 1e12
+    # ---- roofline of the dominant kernel (closed_loop_kernel = K3 with K1 inside + K2/K4)
+    pd = ctl.problem
+    F_dense = 2. * pd.n ** 2 + 4. * pd.mc * pd.n                     # dense shared-operator form
+    kbar = pd.n / 2.
+    F_exec = 2. * pd.ns * pd.n + 2. * pd.mc * (pd.nx + pd.nu) + 2. * pd.nb + 4. * pd.n * kbar + kbar ** 2   # factored form executed
+    it_per_launch = iters / world / max(len(ker_ms), 1)
+    ker_avg_ms = float(np.mean(ker_ms))
+    achieved = F_exec * it_per_launch / (ker_avg_ms * 1e-3) / 1e12
     peak = fp64_peak_probe(torch, dev)
-    roofline = {'bound': 'tensor', 'kernel': 'bnb_kernel', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
+    roofline = {'bound': 'tensor', 'kernel': 'closed_loop_kernel', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
                 'frac': achieved / peak, 'traffic': None,
                 'peak_source': 'measured in this run: cuBLAS DGEMM 4096^3 best of 5 (fp64 pipe; MEASURED_PEAKS.json has no fp64 entry)',
-                'algorithmic': 'F_iter = 2 n^2 + 4 m_c n = %.0f flop per active-set iteration (SURVEY 8d), %.1f iterations/QP, '
-                               '%.0f QPs/launch' % (F_iter, iters / max(qps, 1), qps / world / max(len(bnb_ms), 1)),
-                'kernel_ms_avg': bnb_avg_ms, 'kernel_share_of_step': float(np.sum(bnb_ms) / ms),
-                'shift_kernel_ms_avg': float(np.mean(shift_ms))}
+                'algorithmic': 'flops per active-set iteration in the FACTORED form the kernel executes: 2 ns n (pricing operator) + '
+                               '2 mc (nx+nu) (sparse stage rows) + 4 n k + k^2 (Gram-Schmidt append, R^-1 column; k = n/2) = %.0f '
+                               '(the dense shared-operator form of SURVEY 8d would be %.0f); %.1f iterations/QP, %.0f QPs/launch; '
+                               'the kernel is latency bound (dependent phases of one small QP per SM), see DESIGN.md'
+                               % (F_exec, F_dense, iters / max(qps, 1), qps / world / max(len(ker_ms), 1)),
+                'achieved_dense_form_tflops': F_dense * it_per_launch / (ker_avg_ms * 1e-3) / 1e12,
+                'kernel_ms_avg': ker_avg_ms, 'kernel_share_of_step': float(np.sum(ker_ms) / ms)}
     peaks_file = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(peaks_file):
         roofline['hbm_peak_gbs_measured'] = json.load(open(peaks_file)).get('hbm_gbs')
+    traffic_file = os.path.join(ROOT, 'profiles', 'closed_loop_kernel_traffic.json')
+    if os.path.exists(traffic_file):
+        roofline['traffic'] = json.load(open(traffic_file)).get('dram_bytes_per_launch')
 
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(args, world),
             'roofline': roofline, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks,
-            'qp_per_step_per_instance': qps / args.steps / (n_inst * world),
+            'ms_per_mpc_step_of_the_batch': ms / args.steps / S,
+            'qp_per_mpc_step_per_instance': qps / args.steps / S / (n_inst * world),
             'active_instances_rank0': n_active, 'bnb_status_counts_rank0': {int(k): int((status == k).sum()) for k in np.unique(status)}}
     line['config']['l2'] = 'inputs larger than L2: two device trees of %.1f GB per rank, leaf records touched per step >> 126 MB' % (tree_bytes / 2 / 1e9)
 
-    # ---- extras (outside the timed region): cold start, single instance latency, CPU baseline
+    # ---- extras (outside the timed region): cold start, lock-step API, single instance latency, CPU baseline
     if not args.no_extras:
         del loop
         torch.cuda.empty_cache()
         cold = ClosedLoop(ctl, n_inst, warm=False, max_solves=args.max_solves, max_roots=args.max_roots)
         cold.reset(x0)
-        cold.step(e=e_dev[0])
-        ms_c, qps_c, _, _ = timed_loop(torch, dist, cold, e_dev[1:], 2, world)
-        line['cold_start'] = {'value': qps_c / (ms_c * 1e-3), 'unit': UNIT, 'ms_per_step': ms_c / 2,
-                              'qp_per_step_per_instance': qps_c / 2 / (n_inst * world)}
-        line['warm_start'] = {'value': value, 'unit': UNIT, 'ms_per_step': ms / args.steps,
-                              'qp_per_step_per_instance': line['qp_per_step_per_instance']}
+        cold.run(1, e=e_dev[0, :1])
+        ms_c, qps_c, _, _ = timed_loop(torch, dist, cold, 1, world, lambda t: cold.run(2, e=e_dev[1, :2]))
+        line['cold_start'] = {'value': qps_c / (ms_c * 1e-3), 'unit': UNIT, 'ms_per_mpc_step_of_the_batch': ms_c / 2,
+                              'qp_per_mpc_step_per_instance': qps_c / 2 / (n_inst * world)}
+        line['warm_start'] = {'value': value, 'unit': UNIT, 'ms_per_mpc_step_of_the_batch': ms / args.steps / S,
+                              'qp_per_mpc_step_per_instance': line['qp_per_mpc_step_per_instance']}
         del cold
+        torch.cuda.empty_cache()
+        lock = ClosedLoop(ctl, n_inst, warm=True, max_solves=args.max_solves, max_roots=args.max_roots)
+        lock.reset(x0)
+        for t in range(3):
+            lock.step(e=e_dev[0, t])
+        ms_l, qps_l, _, _ = timed_loop(torch, dist, lock, 5, world, lambda t: lock.step(e=e_dev[1, t]))
+        line['lock_step_api'] = {'value': qps_l / (ms_l * 1e-3), 'unit': UNIT, 'ms_per_mpc_step_of_the_batch': ms_l / 5,
+                                 'note': 'ClosedLoop.step(): one launch pair per MPC step, every instance waits for the slowest one'}
+        del lock
         torch.cuda.empty_cache()
         if rank == 0:
             single = {}
@@ -366,7 +398,7 @@ def run_b200(args):
                                              'source': 'BASELINE.md (Gurobi, unknown CPU)'}
             line['single_instance_nominal'] = single
     if rank == 0 and world == 1 and not args.no_extras:
-        line['cpu_baseline'] = cpu_baseline_sample(args, model, x0, e_host, args.cpu_seconds)
+        line['cpu_baseline'] = cpu_baseline_sample(args, model, x0, e_host.reshape(-1, n_inst, nx), args.cpu_seconds)
     elif rank == 0:
         line['cpu_baseline'] = None
     if rank == 0:

@@ -51,6 +51,10 @@ typedef struct {
     int primal;                  /* (T+1)*nx + T*nu : x_0..x_T, u_0..u_{T-1}  (subproblem_solution.py:86-91) */
     int dual;                    /* lam | mu | nu_lb | nu_ub | rho | sigma     (subproblem_solution.py:137-166) */
     int off_lam, off_mu, off_nu_lb, off_nu_ub, off_rho, off_sigma;
+    int rec_stride;              /* doubles per dual record INSIDE a wshmpc_tree: dual + n.  The n extra doubles hold the
+                                    proximal centre (orthonormal coordinates) of the solve the record came from, i.e. the
+                                    `active_set` payload the reference hands from a parent to its children
+                                    (subproblem_solution.py:10, controller.py:426) */
 } wshmpc_layout;
 
 const char *wshmpc_last_error(void);
@@ -69,9 +73,14 @@ int wshmpc_get_layout(const wshmpc_handle *h, wshmpc_layout *out);
  *   d_lb   [n_nodes][nb]     lower bounds on the relaxed binaries, (t,i) -> t*nub+i   (-rhs of 'nu_lb_t')
  *   d_ub   [n_nodes][nb]     upper bounds                                  (rhs of 'nu_ub_t')
  *   d_slot [n_nodes]         solver state used by the node; nodes sharing a slot are solved in index
- *                            order by one CTA, each hot-started from the previous one (any dual
- *                            feasible point of one node is dual feasible for every other node)
- *   d_hot  [n_nodes]         0: reset the slot to the empty working set before the solve, 1: keep it
+ *                            order by one CTA
+ *   d_hot  [n_nodes]         start of the dual active-set method (any multipliers >= 0 are dual feasible for every node):
+ *                            0: empty working set; 1: the working set the slot's previous node ended with;
+ *                            2: the multipliers d_y0 / proximal centre d_yc0 of this node -- what the reference hands
+ *                               from a parent to its children as `active_set` (controller.py:262-264, 426)
+ *   d_y0   [n_nodes][m]      (hot = 2; may be NULL otherwise) signed multipliers of the rows mu_0..mu_{T-1} | binaries:
+ *                            m = layout.off_nu_lb - layout.off_mu + nb; > 0 upper side (mu, nu_ub), < 0 lower (nu_lb)
+ *   d_yc0  [n_nodes][n]      (hot = 2; may be NULL = 0) proximal centre, n = T * nu
  * outputs
  *   d_status [n_nodes]       2 optimal, 3 infeasible (Gurobi status codes, bounded_qp.py:212), 9 iteration limit
  *   d_cost   [n_nodes]       primal objective, +inf if infeasible          (bounded_qp.py:292-311)
@@ -79,11 +88,13 @@ int wshmpc_get_layout(const wshmpc_handle *h, wshmpc_layout *out);
  *   d_iters  [n_nodes]       active-set iterations
  *   d_primal [n_nodes][layout.primal]   (undefined if infeasible)
  *   d_dual   [n_nodes][layout.dual]
+ *   d_yc     [n_nodes][n] or NULL       proximal centre the solve ended at (0 if infeasible): d_yc0 of the children
  */
 int wshmpc_solve_nodes(wshmpc_handle *h, int n_nodes, const double *d_x0, const double *d_lb,
                        const double *d_ub, const int *d_slot, const int *d_hot,
+                       const double *d_y0, const double *d_yc0,
                        int *d_status, double *d_cost, double *d_dobj, int *d_iters,
-                       double *d_primal, double *d_dual);
+                       double *d_primal, double *d_dual, double *d_yc);
 
 /* ---------------------------------------------------------------------------------------------
  * Branch-and-bound trees of a batch of independent MPC instances (device memory, caller-owned:
@@ -93,7 +104,8 @@ int wshmpc_solve_nodes(wshmpc_handle *h, int n_nodes, const double *d_x0, const 
  * node is removed = alive 0).  With the reference's default `branch_in_time` rule (controller.py:13-44)
  * every identifier is a prefix of the chronological order (0,0),(0,1),...,(T-1,nub-1), so a node is
  * (depth, value bits); time shifting keeps it a prefix (controller.py:476).
- * Dual records follow wshmpc_layout.dual; children alias the parent's record (controller.py:426).
+ * Dual records follow the layout struct above (stride rec_stride); children alias the parent's record (controller.py:426)
+ * and start their QP from its multipliers.
  */
 typedef struct {
     int cap_nodes, cap_recs, words;   /* words = ceil(T*nub / 32) uint32 per identifier */
@@ -105,7 +117,7 @@ typedef struct {
     unsigned int *bits;               /* [n_inst][cap_nodes][words]  bit j = value of binary j = t*nub+i, j < depth */
     double *lb;                       /* [n_inst][cap_nodes]  Node.lb */
     double *rec_dobj;                 /* [n_inst][cap_recs]   DualSolution.objective */
-    double *rec_dual;                 /* [n_inst][cap_recs][layout.dual]  DualSolution.variables */
+    double *rec_dual;                 /* [n_inst][cap_recs][layout.rec_stride]  DualSolution.variables | proximal centre */
 } wshmpc_tree;
 
 /* K3 -- device-side branch and bound, one CTA per instance, no host round trip per node.

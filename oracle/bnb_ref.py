@@ -74,7 +74,10 @@ class OracleController(object):
     def __init__(self, model, core, hot_start=True, persistent=False):
         """model: dict of oracle/models.py; core: oracle.qp_c.CoreC (or any object with
         solve(x0, lb, ub, warm=None)).  `hot_start`: each node starts from the working set of the node
-        solved before it (what the CUDA path does); False = every node from scratch.
+        solved before it; 'record' = each node starts from the multipliers of the dual solution IT carries (its
+        parent's, or its own shifted one for a warm-start root) and from its parent's proximal centre -- the
+        reference's dormant `active_set` hand-over (controller.py:262-264, 426) and what the CUDA path does;
+        False = every node from scratch.
         `persistent`: the factorisation itself survives between the nodes of one feedforward call (exactly
         what a CUDA solver slot does) instead of being rebuilt from the inherited working set."""
         self.m = model
@@ -105,6 +108,21 @@ class OracleController(object):
         if self._state is not None:
             out = self.core.solve(x0, lb.ravel(), ub.ravel(), state=self._state, reset=self._reset)
             self._reset = False
+        elif self.hot_start == 'record':
+            warm = None
+            if node.dual is not None:
+                var = node.dual['variables']
+                rows, sides, lam = [], [], []
+                for t in range(T):
+                    for i in np.nonzero(var['mu'][t] > 0)[0]:
+                        rows.append(c.row0[t] + i); sides.append(1); lam.append(var['mu'][t][i])
+                for t in range(T):
+                    for i in range(self.nub):
+                        yy = max(var['nu_ub'][t][i], 0.) - max(var['nu_lb'][t][i], 0.)
+                        if yy != 0.:
+                            rows.append(c.mc + t * self.nub + i); sides.append(1 if yy > 0 else -1); lam.append(abs(yy))
+                warm = dict(rows=rows, sides=sides, lam=lam, z=node.dual.get('yc'))
+            out = self.core.solve(x0, lb.ravel(), ub.ravel(), warm=warm)
         else:
             out = self.core.solve(x0, lb.ravel(), ub.ravel(), warm=self._warm if self.hot_start else None)
         self.qp_time += time.perf_counter() - tic
@@ -135,7 +153,7 @@ class OracleController(object):
             Ft = m['F'] if t < T - 1 else m['F_Tm1']
             lam[t] = A.T.dot(lam[t + 1]) - Q.T.dot(var['rho'][t]) - Ft.T.dot(mu[t])
         var['lam'] = lam
-        node.dual = dict(variables=var, objective=objective)
+        node.dual = dict(variables=var, objective=objective, yc=out['warm']['z'])      # yc: proximal centre (None if infeasible)
         node.binary_feasible = bool(np.array_equal(lb, ub))        # subproblem_solution.py:94-97
 
     # -- controller.py:395-429

@@ -36,9 +36,9 @@ def test_device_bnb_equals_host_bnb(cp20):
     order = []
     orig = ctl._solve_subproblem
 
-    def spy(identifier, x0_, active_set=None, hot=True):
+    def spy(identifier, x0_, active_set=None, hot=True, extra=None):
         order.append(_ident_key(identifier))
-        return orig(identifier, x0_, active_set, hot)
+        return orig(identifier, x0_, active_set, hot, extra)
     ctl._solve_subproblem = spy
     try:
         sol_h, leaves_h, n_h, _ = ctl.feedforward(x0, printing_period=None)
@@ -109,7 +109,8 @@ def _upload_golden_tree(ctl, g):
     tree.depth[0, :n0] = torch.as_tensor(g['depth'], device=dev); tree.alive[0, :n0] = 1
     tree.rec[0, :n0] = torch.as_tensor(g['rec'], device=dev); tree.lb[0, :n0] = torch.as_tensor(g['lb'], device=dev)
     tree.bits[0, :n0] = torch.as_tensor(g['bits'].view(np.int32), device=dev)
-    tree.rec_dual[0, :len(g['dobj'])] = torch.as_tensor(g['recs'], device=dev)
+    tree.rec_dual[0, :len(g['dobj'])] = 0.
+    tree.rec_dual[0, :len(g['dobj']), :g['recs'].shape[1]] = torch.as_tensor(g['recs'], device=dev)
     tree.rec_dobj[0, :len(g['dobj'])] = torch.as_tensor(g['dobj'], device=dev)
     return tree
 
@@ -147,7 +148,7 @@ def test_shift_tree_matches_reference_golden(cp20, tag):
     assert np.allclose(x_next[0].cpu().numpy(), g['x1'] + e0, rtol=0, atol=0)
     if tag == 'rand':
         j = int(g['ws_rand_sample'])
-        rec = new.rec_dual[0, int(new.rec[0, j])].cpu().numpy()
+        rec = new.rec_dual[0, int(new.rec[0, j])].cpu().numpy()[:h.layout.dual]
         assert np.allclose(rec, g['ws_rand_sample_rec'], rtol=1e-13, atol=1e-13)
 
 

@@ -8,7 +8,7 @@ from oracle.bnb_ref import OracleController
 mode = sys.argv[1]
 nsteps = int(sys.argv[2])
 model = load_model('cp20')
-core = CoreC(model)
+core = CoreC(model, variant=1)
 stats = []
 class Ctl(OracleController):
     def solve_node(self, node, x0):
@@ -25,7 +25,7 @@ class Ctl(OracleController):
                     for i in range(self.nub):
                         if var['nu_ub'][t][i] > 0: rows.append(c.mc + t * self.nub + i); sides.append(1); lam.append(var['nu_ub'][t][i])
                         elif var['nu_lb'][t][i] > 0: rows.append(c.mc + t * self.nub + i); sides.append(-1); lam.append(var['nu_lb'][t][i])
-                self._warm = dict(rows=rows, sides=sides, lam=lam, z=node.dual.get('yc'))
+                self._warm = dict(rows=rows, sides=sides, lam=lam, z=(node.dual.get('yc') if os.environ.get('USE_YC', '1') == '1' else None))
         elif mode == 'none':
             self._warm = None
         nW0 = 0 if self._warm is None else len(self._warm['rows'])

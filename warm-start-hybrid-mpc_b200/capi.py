@@ -23,7 +23,7 @@ class _Problem(C.Structure):
 
 class Layout(C.Structure):
     _fields_ = [(k, C.c_int) for k in ('primal', 'dual', 'off_lam', 'off_mu', 'off_nu_lb', 'off_nu_ub',
-                                       'off_rho', 'off_sigma')]
+                                       'off_rho', 'off_sigma', 'rec_stride')]
 
 
 def load_library():
@@ -62,6 +62,7 @@ class Tree(object):
     torch owns the memory; the kernels read and write it in place."""
 
     def __init__(self, n_inst, nb, n_dual, cap_nodes, cap_recs, device):
+        """n_dual = layout.rec_stride: doubles per dual record (reference duals followed by the proximal centre)."""
         import torch
         self.n_inst, self.nb, self.n_dual = n_inst, nb, n_dual
         self.cap_nodes, self.cap_recs, self.words = cap_nodes, cap_recs, (nb + 31) // 32
@@ -132,8 +133,10 @@ class Handle(object):
             pass
 
     # -- K1 -------------------------------------------------------------------------------------
-    def solve_nodes(self, x0, lb, ub, slot=None, hot=None):
-        """x0 [N, nx], lb/ub [N, nb] (torch CUDA fp64 or numpy).  Returns dict of torch CUDA tensors."""
+    def solve_nodes(self, x0, lb, ub, slot=None, hot=None, y0=None, yc0=None):
+        """x0 [N, nx], lb/ub [N, nb] (torch CUDA fp64 or numpy).  hot: 0 empty working set, 1 the slot's previous
+        node, 2 start from the signed multipliers y0 [N, m] (and proximal centre yc0 [N, n]).
+        Returns dict of torch CUDA tensors."""
         import torch
         dev = self.torch_device
         t = lambda a, dt: torch.as_tensor(np.asarray(a) if not torch.is_tensor(a) else a, dtype=dt, device=dev).contiguous()
@@ -149,16 +152,21 @@ class Handle(object):
                    dobj=torch.zeros(N, dtype=torch.float64, device=dev),
                    iters=torch.zeros(N, dtype=torch.int32, device=dev),
                    primal=torch.zeros((N, self.layout.primal), dtype=torch.float64, device=dev),
-                   dual=torch.zeros((N, self.layout.dual), dtype=torch.float64, device=dev))
-        P = lambda a: C.c_void_p(a.data_ptr())
-        _check(self.lib.wshmpc_solve_nodes(self._h, N, P(x0), P(lb), P(ub), P(slot), P(hot), P(out['status']),
+                   dual=torch.zeros((N, self.layout.dual), dtype=torch.float64, device=dev),
+                   yc=torch.zeros((N, self.pd.n), dtype=torch.float64, device=dev))
+        if y0 is not None:
+            y0 = t(y0, torch.float64); assert y0.shape == (N, self.pd.m)
+        if yc0 is not None:
+            yc0 = t(yc0, torch.float64); assert yc0.shape == (N, self.pd.n)
+        P = lambda a: C.c_void_p(a.data_ptr()) if a is not None else None
+        _check(self.lib.wshmpc_solve_nodes(self._h, N, P(x0), P(lb), P(ub), P(slot), P(hot), P(y0), P(yc0), P(out['status']),
                                            P(out['cost']), P(out['dobj']), P(out['iters']), P(out['primal']),
-                                           P(out['dual'])))
+                                           P(out['dual']), P(out['yc'])))
         return out
 
     # -- trees / K3 / K2+K4 ---------------------------------------------------------------------
     def new_tree(self, n_inst, cap_nodes, cap_recs):
-        return Tree(n_inst, self.pd.nb, self.layout.dual, cap_nodes, cap_recs, self.torch_device)
+        return Tree(n_inst, self.pd.nb, self.layout.rec_stride, cap_nodes, cap_recs, self.torch_device)
 
     def tree_init_root(self, tree):
         _check(self.lib.wshmpc_tree_init_root(self._h, tree.n_inst, C.byref(tree.c)))

@@ -132,16 +132,35 @@ class HybridModelPredictiveController(object):
             ub_ub[k] = v
         return ub_lb, ub_ub
 
-    def _solve_subproblem(self, identifier, x0, active_set=None, hot=True):
-        """controller.py:229-271: one node = one K1 launch on slot 0.  `hot` keeps the solver state
-        of the previously solved node (any dual feasible point is dual feasible for every node)."""
+    def _start_from(self, extra):
+        """Signed multipliers (and proximal centre) a node starts its dual active-set solve from: the dual
+        solution it carries -- its parent's (controller.py:426) or its own shifted one (controller.py:487) --
+        and the parent's `active_set` (controller.py:262-264).  None = empty working set."""
+        if extra is None or extra.dual is None:
+            return None, None
+        v = extra.dual.variables
+        y0 = np.concatenate([np.maximum(m_, 0.) for m_ in v['mu']]
+                            + [np.maximum(np.concatenate(v['nu_ub']), 0.) - np.maximum(np.concatenate(v['nu_lb']), 0.)])
+        return y0, extra.active_set
+
+    def _solve_subproblem(self, identifier, x0, active_set=None, hot=True, extra=None):
+        """controller.py:229-271: one node = one K1 launch on slot 0.  `extra` (the SubproblemSolution the node
+        carries) gives the start of the solve, see _start_from; without it `hot` keeps the working set of the
+        previously solved node (any multipliers >= 0 are dual feasible for every node)."""
         import torch
         h = self.handle()
         lb, ub = self._get_bound_binaries(identifier)
+        y0, yc0 = self._start_from(extra)
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         start.record()
-        out = h.solve_nodes(np.asarray(x0, dtype=float)[None], lb.reshape(1, -1), ub.reshape(1, -1),
-                            slot=np.zeros(1, np.int32), hot=np.array([1 if hot else 0], np.int32))
+        if extra is not None:
+            mode = 2 if y0 is not None else 0
+            out = h.solve_nodes(np.asarray(x0, dtype=float)[None], lb.reshape(1, -1), ub.reshape(1, -1),
+                                slot=np.zeros(1, np.int32), hot=np.array([mode], np.int32),
+                                y0=None if y0 is None else y0[None], yc0=None if yc0 is None else np.asarray(yc0)[None])
+        else:
+            out = h.solve_nodes(np.asarray(x0, dtype=float)[None], lb.reshape(1, -1), ub.reshape(1, -1),
+                                slot=np.zeros(1, np.int32), hot=np.array([1 if hot else 0], np.int32))
         end.record()
         end.synchronize()
         solve_time = start.elapsed_time(end) * 1e-3
@@ -153,7 +172,8 @@ class HybridModelPredictiveController(object):
         primal = PrimalSolution.from_record(self.problem, out['primal'][0].cpu().numpy(), float(out['cost'][0]),
                                             binary_feasible, status == 2)
         dual = DualSolution.from_record(self.problem, h.layout, out['dual'][0].cpu().numpy(), float(out['dobj'][0]))
-        sol = SubproblemSolution(primal, dual, None)
+        # active_set = proximal centre of this solve: what the children start from (controller.py:426)
+        sol = SubproblemSolution(primal, dual, out['yc'][0].cpu().numpy() if status == 2 else None)
         sol.iters = int(out['iters'][0])
         return sol, solve_time
 
@@ -168,11 +188,9 @@ class HybridModelPredictiveController(object):
             ws = kwargs.get('warm_start')
             if ws is None or all(_is_prefix(l.identifier, self.mld.nub) for l in ws):
                 return self._feedforward_device(x0, kwargs.get('tol', 0.), ws)
-        first = [True]
-
         def solver(identifier, cutoff, extra):
-            solution, solve_time = self._solve_subproblem(identifier, x0, None, hot=not first[0])
-            first[0] = False
+            solution, solve_time = self._solve_subproblem(identifier, x0, None, extra=extra if extra is not None
+                                                          else SubproblemSolution(None, None, None))
             return solution.primal.objective, solution.primal.binary_feasible, solve_time, solution
 
         def brancher(parent):
@@ -348,8 +366,9 @@ class HybridModelPredictiveController(object):
                 extra = SubproblemSolution(None, None) if depth[j] or np.isfinite(lb[j]) else None
             else:
                 if r not in cache:          # children alias the parent's dual object (controller.py:426)
-                    cache[r] = DualSolution.from_record(self.problem, h.layout, duals[r], dobj[r])
-                extra = SubproblemSolution(None, cache[r])
+                    cache[r] = (DualSolution.from_record(self.problem, h.layout, duals[r], dobj[r]),
+                                duals[r][h.layout.dual:h.layout.rec_stride].copy())
+                extra = SubproblemSolution(None, cache[r][0], cache[r][1])
             node = Node(ident, float(lb[j]), extra)
             node.index = j
             leaves.append(node)
@@ -377,7 +396,8 @@ class HybridModelPredictiveController(object):
             if dual is not None:
                 if id(dual) not in seen:
                     seen[id(dual)] = len(recs)
-                    recs.append(DualSolution.to_record(self.problem, h.layout, dual.variables))
+                    yc = np.zeros(h.layout.rec_stride - h.layout.dual) if l.extra.active_set is None else np.asarray(l.extra.active_set)
+                    recs.append(np.concatenate((DualSolution.to_record(self.problem, h.layout, dual.variables), yc)))
                     dobj.append(dual.objective)
                 rec[j] = seen[id(dual)]
         dev = tree.lb.device

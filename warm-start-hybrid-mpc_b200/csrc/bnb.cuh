@@ -49,14 +49,13 @@ __device__ inline int bnb_instance(const DevProblem &P, const Ctx &cx, const Slo
     unsigned int *bits = tr.bits + no * tr.words;
     double *lb = tr.lb + no;
     double *rdobj = tr.rec_dobj + (size_t)inst * tr.cap_recs;
-    double *rdual = tr.rec_dual + (size_t)inst * tr.cap_recs * P.n_dual;
+    double *rdual = tr.rec_dual + (size_t)inst * tr.cap_recs * P.n_rec;
     int *tr_i = trace ? trace + (size_t)inst * 2 * max_solves : nullptr;
 
     int nn = tr.n_nodes[inst], nr = tr.n_recs[inst];
     double ub = INFINITY;
     int inc = -1, solves = 0, st = -1, k = 0;
     long long iters = 0;
-    bool first = true;
 
     while (st < 0) {
         // ---- select: candidates = alive leaves with lb < ub - tol ; best_first = first minimum
@@ -79,12 +78,25 @@ __device__ inline int bnb_instance(const DevProblem &P, const Ctx &cx, const Slo
             ubv[j] = j < d ? v : 1.;
         }
         __syncthreads();
-        // ---- solve (K1), hot-started from the working set of the node solved before it
-        if (first) { load_slot(P, cx, sp, k, true); first = false; }
+        // ---- solve (K1), started from the node's OWN dual record: the multipliers (and proximal centre) of its
+        //      parent, or its shifted dual solution for a warm-start root (controller.py:262-264, 426, 487);
+        //      no record (root node, dual = None) = empty working set
+        {
+            const int r0 = rec[bi];
+            if (r0 >= 0) {
+                const double *D = rdual + (size_t)r0 * P.n_rec;
+                const double *mu = D + P.off_mu, *nl = D + P.off_nulb, *nu_ = D + P.off_nuub;
+                const int mc = P.mc;
+                load_ws_from_multipliers(P, cx, [&](int r) { return r < mc ? mu[r] : nu_[r - mc] - nl[r - mc]; }, D + P.n_dual, k);
+            } else {
+                load_slot(P, cx, sp, k, true);
+            }
+        }
         const int qs = qp_solve(P, cx, k, xi, lbv, ubv, y, iters_s);
         if (qs == WS_ITER_LIMIT) { st = BNB_QP_LIMIT; break; }
-        double *dual = rdual + (size_t)nr * P.n_dual;
+        double *dual = rdual + (size_t)nr * P.n_rec;
         build_records(P, qs, SMV(yc), y, xi, lbv, ubv, prim, dual, cost_s, dobj_s, SMV(part), SMV(red));
+        for (int j = threadIdx.x; j < P.n; j += WS_NT) dual[P.n_dual + j] = qs == WS_OPTIMAL ? SMV(yc)[j] : 0.;
         const double cost = *cost_s;
         if (threadIdx.x == 0) {
             lb[bi] = cost; rec[bi] = nr; rdobj[nr] = *dobj_s;
@@ -262,14 +274,15 @@ __device__ inline void shift_instance(const DevProblem &P, double *shm, int *s_w
         const int j = nt.rec[on_ + idx];
         const int ro = ot.rec[oo + j];
         const double lbo = ot.lb[oo + j];
-        double *E = nt.rec_dual + ((size_t)inst * nt.cap_recs + idx) * P.n_dual;
+        double *E = nt.rec_dual + ((size_t)inst * nt.cap_recs + idx) * P.n_rec;
         if (ro < 0) {
             // dual = None (controller.py:556-558 on the previous step, never solved since): trivial bound
-            for (int e = lane; e < P.n_dual; e += 32) E[e] = 0.;
+            for (int e = lane; e < P.n_rec; e += 32) E[e] = 0.;
             if (lane == 0) { nt.lb[on_ + idx] = 0.; nt.rec[on_ + idx] = -1; nt.rec_dobj[(size_t)inst * nt.cap_recs + idx] = 0.; }
             return;
         }
-        const double *D = ot.rec_dual + ((size_t)inst * ot.cap_recs + ro) * P.n_dual;
+        const double *D = ot.rec_dual + ((size_t)inst * ot.cap_recs + ro) * P.n_rec;
+        for (int e = P.n_dual + lane; e < P.n_rec; e += 32) E[e] = 0.;          // a shifted root starts from the centre 0
         const int d_old = ot.depth[oo + j];
         const unsigned int b0 = ot.bits[(oo + j) * ot.words];
         double acc = 0.;                     // pi_sum + pi3, lane-partial
@@ -457,7 +470,7 @@ closed_loop_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, doub
             L.log_cost[lo] = inc_cost[inst]; L.log_solves[lo] = n_solves[inst]; L.log_status[lo] = st;
         }
         __syncthreads();
-        shift_instance<WS_NT>(P, SMV(Q), SMI(ired), SMI(ired) + WS_NW, inst, xc, L.e ? L.e + (size_t)t * xs : nullptr,
+        shift_instance<WS_NT>(P, SMV(Q), SMI(ired), SMI(ired) + 16, inst, xc, L.e ? L.e + (size_t)t * xs : nullptr,
                               cur, inc_cost, inc_primal, L.active, nxt, xn, L.log_u0 + (size_t)t * n_inst * P.nu);
         if (threadIdx.x == 0) L.step_of[inst] = t + 1;
         __threadfence();                                   // release: the instance's data before the token

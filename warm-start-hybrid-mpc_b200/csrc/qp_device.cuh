@@ -34,7 +34,9 @@
 #include <math.h>
 #include <stdint.h>
 
+#ifndef WS_NT
 #define WS_NT 512
+#endif
 #define WS_NW (WS_NT / 32)
 #define WS_JW 128               // lanes of the k-indexed phases (columns of Q1 / rows of Ri)
 #define WS_NG (WS_NT / WS_JW)   // groups splitting the long dimension of those phases
@@ -72,6 +74,7 @@ struct DevProblem {
     SmemOff so;
     // record layout
     int n_primal, n_dual, off_lam, off_mu, off_nulb, off_nuub, off_rho, off_sigma;
+    int n_rec;               // stride of a dual record in a tree: n_dual + n (the proximal centre of the solve follows the duals)
 };
 
 __host__ __device__ __forceinline__ int tri_off(int j) { return j * (j + 1) / 2; }
@@ -136,7 +139,7 @@ __device__ __forceinline__ double warp_sum(double x) {
 // memory, and finish with a second shuffle tree over the WS_NW per-warp values (every warp does it
 // redundantly, so the result reaches all threads with two barriers and ~25 instructions).
 #define WS_FULL 0xffffffffu
-static_assert(WS_NW == 16, "the two-level reductions assume 16 warps per CTA");
+static_assert(WS_NW == 16 || WS_NW == 8, "the two-level reductions assume 8 or 16 warps per CTA");
 
 // block-wide sum, result to all threads
 __device__ inline double block_sum(double x, double *red) {
@@ -156,13 +159,13 @@ __device__ inline void block_sum2(double &x, double &y, double *red) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     x = warp_sum(x); y = warp_sum(y);
     __syncthreads();
-    if (lane == 0) { red[w] = x; red[WS_NW + w] = y; }
+    if (lane == 0) { red[w] = x; red[16 + w] = y; }
     __syncthreads();
-    // lanes 0..15 take the x partials, lanes 16..31 the y partials (WS_NW == 16)
-    double s = red[lane];
+    // lanes 0..15 take the x partials, lanes 16..31 the y partials
+    double s = (lane & 15) < WS_NW ? red[lane] : 0.;
 #pragma unroll
-    for (int o = WS_NW / 2; o > 0; o >>= 1) s += __shfl_xor_sync(WS_FULL, s, o);
-    x = __shfl_sync(WS_FULL, s, 0); y = __shfl_sync(WS_FULL, s, WS_NW);
+    for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(WS_FULL, s, o);
+    x = __shfl_sync(WS_FULL, s, 0); y = __shfl_sync(WS_FULL, s, 16);
 }
 
 __device__ __forceinline__ bool better_max(double ov, int oi, double val, int idx) {
@@ -224,10 +227,10 @@ __device__ inline void block_argmin_sum(double &val, int &idx, double &sum, doub
         if (better_max(ov, oi, nv, idx)) { nv = ov; idx = oi; }
     }
     __syncthreads();
-    if (lane == 0) { red[w] = nv; ired[w] = idx; red[WS_NW + w] = sum; }
+    if (lane == 0) { red[w] = nv; ired[w] = idx; red[16 + w] = sum; }
     __syncthreads();
     nv = lane < WS_NW ? red[lane] : 0.; idx = lane < WS_NW ? ired[lane] : -1;
-    sum = lane < WS_NW ? red[WS_NW + lane] : 0.;
+    sum = lane < WS_NW ? red[16 + lane] : 0.;
 #pragma unroll
     for (int o = WS_NW / 2; o > 0; o >>= 1) {
         const double ov = __shfl_xor_sync(WS_FULL, nv, o);
@@ -290,7 +293,7 @@ __device__ inline void grouped_matvec(const double *__restrict__ M, int ld, int 
 // through `part` (stride kp_).  Ends with a barrier.
 __device__ inline void qt_dots(const DevProblem &P, const Ctx &cx, int k, const double *x, double *out) {
     double *part = SMV(part);
-    const int g = threadIdx.x >> 7, jl = threadIdx.x & (WS_JW - 1);
+    const int g = threadIdx.x / WS_JW, jl = threadIdx.x & (WS_JW - 1);
     const int h = P.np >> 1, cp = (h + WS_NG - 1) / WS_NG;
     const int p0 = g * cp, p1 = min(p0 + cp, h);
     const double2 *x2 = reinterpret_cast<const double2 *>(x);
@@ -356,7 +359,7 @@ __device__ inline double q_apply(const DevProblem &P, const Ctx &cx, int k, cons
 // columns j = i + g, i + g + WS_NG, ...  Ends with a barrier.
 __device__ inline void ri_matvec(const DevProblem &P, const Ctx &cx, int k, const double *c, double *t) {
     double *part = SMV(part);
-    const int g = threadIdx.x >> 7, il = threadIdx.x & (WS_JW - 1);
+    const int g = threadIdx.x / WS_JW, il = threadIdx.x & (WS_JW - 1);
     const int ke = min(k, P.ks);
     for (int i = il; i < k; i += WS_JW) {
         double s0 = 0., s1 = 0.;
@@ -380,7 +383,7 @@ __device__ inline void ri_matvec(const DevProblem &P, const Ctx &cx, int k, cons
 // u = Ri' * d[:k]  (u_j = sum_{i <= j} Ri[tri_off(j) + i] d_i).  Refresh path only.  Ends with a barrier.
 __device__ inline void rit_matvec(const DevProblem &P, const Ctx &cx, int k, const double *d, double *u) {
     double *part = SMV(part);
-    const int g = threadIdx.x >> 7, jl = threadIdx.x & (WS_JW - 1);
+    const int g = threadIdx.x / WS_JW, jl = threadIdx.x & (WS_JW - 1);
     for (int j = jl; j < k; j += WS_JW) {
         const double *col = (j < P.ks ? SMV(Ri) : cx.gRi) + tri_off(j);
         double s = 0.;
@@ -470,7 +473,7 @@ __device__ inline int thin_append(const DevProblem &P, const Ctx &cx, int &k, in
 __device__ inline int thin_remove(const DevProblem &P, const Ctx &cx, int &k, int kp) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, tid = (int)threadIdx.x;
     double *gc = SMV(gc), *gs = SMV(gs), *u = SMV(u);
-    int *row = SMI(irow), *side = SMI(iside), *flag = SMI(ired) + 2 * WS_NW;
+    int *row = SMI(irow), *side = SMI(iside), *flag = SMI(ired) + 32;
     if (tid == 0) *flag = 0x7fffffff;
     if (kp == k - 1) {
         // last position: Q1, Ri lose their last column; v += q_last u_last
@@ -559,11 +562,11 @@ __device__ inline int thin_remove(const DevProblem &P, const Ctx &cx, int &k, in
             }
         }
     }
-    if (uth) SMV(red)[2 * WS_NW] = ucarry;                                  // (G u)_last
+    if (uth) SMV(red)[40] = ucarry;                                  // (G u)_last
     k -= 1;
     __syncthreads();
     // v = -Q1_new u_new = v_old + q_last (G u)_last
-    if (qr >= 0) SMV(v)[qr] += qcarry * SMV(red)[2 * WS_NW];
+    if (qr >= 0) SMV(v)[qr] += qcarry * SMV(red)[40];
     const int bad = *flag;
     __syncthreads();
     ri_matvec(P, cx, k, u, SMV(ls));
@@ -691,6 +694,37 @@ __device__ inline void store_slot(const DevProblem &P, const Ctx &cx, const Slot
     for (int i = threadIdx.x; i < n; i += WS_NT) sp.yc[i] = SMV(yc)[i];
     for (int i = threadIdx.x; i < k; i += WS_NT) { sp.row[i] = SMI(irow)[i]; sp.side[i] = SMI(iside)[i]; sp.lam[i] = SMV(lam)[i]; }
     if (threadIdx.x == 0) *sp.nW = k;
+    __syncthreads();
+}
+
+// Working set from signed multipliers of the ORIGINAL rows (ysigned(r) > 0: upper side, < 0: lower side) and a
+// proximal centre: the start the reference hands from a parent to its children (`active_set`,
+// controller.py:262-264, 426) and what a shifted dual solution gives a warm-start root.  Rows keep their
+// natural order.  yc0 may be null (centre 0).
+template <class Y>
+__device__ inline void load_ws_from_multipliers(const DevProblem &P, const Ctx &cx, Y ysigned, const double *yc0, int &k) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int *wsum = SMI(ired);                       // WS_NW ints
+    int *row = SMI(irow), *side = SMI(iside);
+    double *lam = SMV(lam);
+    for (int i = threadIdx.x; i < P.n; i += WS_NT) SMV(yc)[i] = yc0 ? yc0[i] : 0.;
+    int base = 0;
+    for (int r0 = 0; r0 < P.m; r0 += WS_NT) {
+        const int r = r0 + threadIdx.x;
+        double yv = 0.;
+        if (r < P.m) yv = ysigned(r);
+        const int keep = yv != 0. && base < P.n;
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        __syncthreads();
+        if (lane == 0) wsum[w] = __popc(bal);
+        __syncthreads();
+        int pre = base, tot = 0;
+        for (int q = 0; q < WS_NW; ++q) { const int c = wsum[q]; if (q < w) pre += c; tot += c; }
+        const int idx = pre + __popc(bal & ((1u << lane) - 1u));
+        if (keep && idx < P.n) { row[idx] = r; side[idx] = yv > 0. ? 1 : -1; lam[idx] = fabs(yv) * P.nrm[r]; }
+        base += tot;
+    }
+    k = base < P.n ? base : P.n;
     __syncthreads();
 }
 

@@ -38,7 +38,8 @@ __global__ void __launch_bounds__(WS_NT, 1)
 solve_nodes_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, int n_nodes,
                    const double *__restrict__ x0, const double *__restrict__ lb, const double *__restrict__ ub,
                    const int *__restrict__ slot_of, const int *__restrict__ hot,
-                   int *status, double *cost, double *dobj, int *iters, double *primal, double *dual)
+                   const double *__restrict__ y0, const double *__restrict__ yc0,
+                   int *status, double *cost, double *dobj, int *iters, double *primal, double *dual, double *yc_out)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int slot = blockIdx.x;
@@ -50,12 +51,20 @@ solve_nodes_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, int 
     bool loaded = false;
     for (int i = 0; i < n_nodes; ++i) {
         if (slot_of[i] != slot) continue;
-        const bool reset = hot[i] == 0;
-        if (!loaded || reset) { load_slot(P, cx, sp, k, reset); loaded = true; }
+        const int hm = hot[i];
+        if (hm == 2 && y0) {
+            const double *yy = y0 + (size_t)i * P.m;
+            load_ws_from_multipliers(P, cx, [&](int r) { return yy[r]; }, yc0 ? yc0 + (size_t)i * P.n : nullptr, k);
+            loaded = true;
+        } else {
+            const bool reset = hm == 0;
+            if (!loaded || reset) { load_slot(P, cx, sp, k, reset); loaded = true; }
+        }
         const double *xi = x0 + (size_t)i * P.nx, *lbi = lb + (size_t)i * P.nb, *ubi = ub + (size_t)i * P.nb;
         const int st = qp_solve(P, cx, k, xi, lbi, ubi, y, iters + i);
         build_records(P, st, SMV(yc), y, xi, lbi, ubi, primal + (size_t)i * P.n_primal,
                       dual + (size_t)i * P.n_dual, cost + i, dobj + i, SMV(part), SMV(red));
+        if (yc_out) for (int j = threadIdx.x; j < P.n; j += WS_NT) yc_out[(size_t)i * P.n + j] = st == WS_OPTIMAL ? SMV(yc)[j] : 0.;
         if (threadIdx.x == 0) status[i] = st;
         __syncthreads();
     }
@@ -131,7 +140,8 @@ extern "C" int wshmpc_create(const wshmpc_problem *p, int device, int n_slots, v
     L.off_rho = L.off_nu_ub + p->nb;
     L.off_sigma = L.off_rho + p->T * p->nq + p->nqT;
     L.dual = L.off_sigma + p->T * p->nr;
-    P.n_primal = L.primal; P.n_dual = L.dual; P.off_lam = L.off_lam; P.off_mu = L.off_mu; P.off_nulb = L.off_nu_lb;
+    L.rec_stride = L.dual + n;
+    P.n_primal = L.primal; P.n_dual = L.dual; P.n_rec = L.rec_stride; P.off_lam = L.off_lam; P.off_mu = L.off_mu; P.off_nulb = L.off_nu_lb;
     P.off_nuub = L.off_nu_ub; P.off_rho = L.off_rho; P.off_sigma = L.off_sigma;
     // shared memory budget: one CTA per SM; the first ks columns of Q1 and of Ri live in shared memory
     cudaDeviceProp prop;
@@ -158,11 +168,11 @@ extern "C" int wshmpc_create(const wshmpc_problem *p, int device, int n_slots, v
         so.z = take(nvl); so.c1 = take(nvl); so.c2 = take(nvl); so.t = take(nvl); so.u = take(nvl); so.ls = take(nvl);
         so.lam = take(nvl); so.cw = take(nvl); so.yc = take(nvl); so.wv = take(nvl); so.v = take(nvl); so.gc = take(nvl); so.gs = take(nvl);
         so.bu = take(m); so.blb = take(p->nb); so.inr = take(m); so.vsc = take(m); so.xi = take(P.ns2); so.part = take(part);
-        so.red = take(4 * WS_NW + 8);
+        so.red = take(72);
         so.sF = take(p->nh * nx); so.sG = take(p->nh * nu); so.sF1 = take(p->nh1 * nx); so.sG1 = take(p->nh1 * nu);
         so.ints = o;
         int io = 0;
-        so.irow = io; io += n + 1; so.iside = io; io += n + 1; so.ired = io; io += 2 * WS_NW + 8; so.iscr = io; io += n + 1;
+        so.irow = io; io += n + 1; so.iside = io; io += n + 1; so.ired = io; io += 40; so.iscr = io; io += n + 1;
         so.rinfo = io; io += m;
         o += (io + 1) / 2; o = (o + 1) & ~1;
         so.bytes = o;
@@ -214,15 +224,16 @@ extern "C" int wshmpc_get_layout(const wshmpc_handle *h, wshmpc_layout *out)
 
 extern "C" int wshmpc_solve_nodes(wshmpc_handle *h, int n_nodes, const double *d_x0, const double *d_lb,
                                   const double *d_ub, const int *d_slot, const int *d_hot,
+                                  const double *d_y0, const double *d_yc0,
                                   int *d_status, double *d_cost, double *d_dobj, int *d_iters,
-                                  double *d_primal, double *d_dual)
+                                  double *d_primal, double *d_dual, double *d_yc)
 {
     if (!h) WS_FAIL(-1, "null handle");
     if (n_nodes <= 0) return 0;
     WS_CUDA(cudaSetDevice(h->device));
     solve_nodes_kernel<<<h->n_slots, WS_NT, h->smem, h->stream>>>(
-        h->P, h->slot_d, h->slot_i, h->ybuf, n_nodes, d_x0, d_lb, d_ub, d_slot, d_hot,
-        d_status, d_cost, d_dobj, d_iters, d_primal, d_dual);
+        h->P, h->slot_d, h->slot_i, h->ybuf, n_nodes, d_x0, d_lb, d_ub, d_slot, d_hot, d_y0, d_yc0,
+        d_status, d_cost, d_dobj, d_iters, d_primal, d_dual, d_yc);
     WS_CUDA(cudaGetLastError());
     return 0;
 }
