@@ -167,3 +167,40 @@ def test_bnb_restatement_equals_reference(cp20):
     s2, l2, n2, _ = rc.feedforward(x1, warm_start=ws, printing_period=None)
     i2, ol2, on2 = oc.feedforward(x1, warm_start=ows)
     assert on2 == n2 and i2.primal['objective'] == s2.objective
+
+
+def test_thin_factor_variant_agrees_with_full_factor():
+    """oracle/qp_core.c variant 1 (thin Q1 + R^-1, the CUDA kernel's factorisation) against variant 0
+    (full Q + R by Householder): same status on every node, same cost to 1e-9, certificates hold."""
+    from tests.util import random_nodes
+    model = load_model('cp20')
+    a, b = CoreC(model, variant=0), CoreC(model, variant=1)
+    cond = Condensed(model)
+    x0, lb, ub = random_nodes(model, 24, seed=4)
+    same_iters = 0
+    for i in range(len(x0)):
+        ra, rb = a.solve(x0[i], lb[i], ub[i]), b.solve(x0[i], lb[i], ub[i])
+        assert ra['status'] == rb['status']
+        same_iters += ra['iters'] == rb['iters']
+        if ra['status'] == OPTIMAL:
+            assert abs(ra['cost'] - rb['cost']) <= 1e-9 * abs(ra['cost'])
+            bl, bu = cond.bounds(x0[i], lb[i], ub[i])
+            r = cond.Aall.dot(rb['z'])
+            assert np.all(r <= bu + 2e-4) and np.all(r >= bl - 2e-4)      # same tolerance as tests/test_gpu_qp.py (tol_p is in scaled rows)
+    assert same_iters >= len(x0) - 4          # same pivoting rules: identical paths except at rounding-level ties
+
+
+def test_persistent_state_and_record_start_reach_the_same_optimum():
+    """The three start policies of the oracle (from scratch / persistent factor = a CUDA slot / the dual
+    solution the node carries = the reference's active_set hand-over) give the same branch and bound
+    optimum and mode sequence on the nominal instance."""
+    model = load_model('cp20')
+    ref = None
+    for kw in (dict(hot_start=False), dict(persistent=True), dict(hot_start='record')):
+        ctl = OracleController(model, CoreC(model, variant=1), **kw)
+        inc, leaves, solves = ctl.feedforward(model['x0_nominal'])
+        assert inc is not None and abs(solves - 160) <= 2
+        cur = (inc.primal['objective'], inc.primal['u'][:, ctl.nuc:].copy())
+        if ref is None:
+            ref = cur
+        assert abs(cur[0] - ref[0]) <= 1e-9 * abs(ref[0]) and np.array_equal(cur[1], ref[1])
