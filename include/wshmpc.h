@@ -41,6 +41,9 @@ typedef struct {
     const double *Kx;            /* n x nx */
     const double *Zmap;          /* n x n */
     const int *bin_idx;          /* nb */
+    const double *Linv;          /* nb x nb, lower triangular: inverse of the leading block of the binaries' bound rows
+                                    Mh[mc + j][0..j] (problem.py rotates v so that these rows are lower triangular) */
+    int n_elim;                  /* leading binaries (chronological order) that may be eliminated when pinned; 0 = off */
     /* solver parameters */
     double eps, tol_p, tol_d, tol_sing, tol_ray, prox_tol;
     int max_iter, max_prox;
@@ -133,7 +136,8 @@ typedef struct {
  *   d_n_solves  [n_inst]          number of QP relaxations solved
  *   d_status    [n_inst]          0 optimal, 1 infeasible MIQP, 2 capacity reached, 3 QP iteration limit
  *   d_trace     [n_inst][2*max_solves] or NULL : (node index, active-set iterations) of every solve, in order
- *   d_totals    [2] or NULL : running 64-bit counters, += QP relaxations solved, += active-set iterations
+ *   d_totals    [4] or NULL : running 64-bit counters: += QP relaxations solved, += active-set iterations,
+ *                             += working-set size at the end of every solve, max= largest working set seen
  */
 int wshmpc_bnb_solve(wshmpc_handle *h, int n_inst, const double *d_x0, const int *d_active,
                      const wshmpc_tree *tree, double tol, int max_solves,

@@ -16,4 +16,4 @@ for w in range(6):
     torch.cuda.synchronize(); t0 = time.time(); b = L.totals.clone()
     logs = L.run(S, e=e[w])
     torch.cuda.synchronize(); dt = time.time() - t0; d = (L.totals - b).cpu().numpy()
-    print('window', w, '%.1f ms' % (dt * 1e3), 'QPs', d[0], 'iters/QP %.1f' % (d[1] / d[0]), '%.0f QP/s' % (d[0] / dt), '%.2f us/iter/SM' % (dt * 1e6 * 148 / d[1]), 'active', int(L.active.sum()), flush=True)
+    print('window', w, '%.1f ms' % (dt * 1e3), 'QPs', d[0], 'iters/QP %.1f' % (d[1] / d[0]), '%.0f QP/s' % (d[0] / dt), '%.2f us/iter/SM' % (dt * 1e6 * 148 / d[1]), 'active', int(L.active.sum()), 'k mean %.1f max %d' % (d[2] / d[0], int(L.totals[3])), flush=True)

@@ -16,7 +16,8 @@ class _Problem(C.Structure):
     _fields_ = ([(k, C.c_int) for k in ('nx', 'nu', 'nub', 'T', 'nh', 'nh1', 'nq', 'nqT', 'nr', 'n', 'm', 'mc', 'nb', 'ns')]
                 + [(k, C.c_void_p) for k in ('A', 'B', 'F', 'G', 'h', 'F_Tm1', 'G_Tm1', 'h_Tm1', 'Q', 'R', 'Q_T',
                                              'M_mu', 'M_rho', 'Mh', 'Wf', 'nrm', 'vscale', 'Eh', 'hh', 'Rinv', 'Kx',
-                                             'Zmap', 'bin_idx')]
+                                             'Zmap', 'bin_idx', 'Linv')]
+                + [('n_elim', C.c_int)]
                 + [(k, C.c_double) for k in ('eps', 'tol_p', 'tol_d', 'tol_sing', 'tol_ray', 'prox_tol')]
                 + [(k, C.c_int) for k in ('max_iter', 'max_prox')])
 
@@ -106,11 +107,11 @@ class Handle(object):
         self.torch_device = torch.device('cuda', device)
         self.n_slots = n_slots
         p = _Problem()
-        for k in ('nx', 'nu', 'nub', 'T', 'nh', 'nh1', 'nq', 'nqT', 'nr', 'n', 'm', 'mc', 'nb', 'ns', 'max_iter', 'max_prox',
+        for k in ('nx', 'nu', 'nub', 'T', 'nh', 'nh1', 'nq', 'nqT', 'nr', 'n', 'm', 'mc', 'nb', 'ns', 'n_elim', 'max_iter', 'max_prox',
                   'eps', 'tol_p', 'tol_d', 'tol_sing', 'tol_ray', 'prox_tol'):
             setattr(p, k, getattr(pd, k))
         for k in ('A', 'B', 'F', 'G', 'h', 'F_Tm1', 'G_Tm1', 'h_Tm1', 'Q', 'R', 'Q_T', 'M_mu', 'M_rho', 'Mh', 'Wf', 'nrm',
-                  'vscale', 'Eh', 'hh', 'Rinv', 'Kx', 'Zmap', 'bin_idx'):
+                  'vscale', 'Eh', 'hh', 'Rinv', 'Kx', 'Zmap', 'bin_idx', 'Linv'):
             a = getattr(pd, k)
             assert a.flags['C_CONTIGUOUS']
             setattr(p, k, a.ctypes.data)

@@ -55,7 +55,8 @@ __device__ inline int bnb_instance(const DevProblem &P, const Ctx &cx, const Slo
     int nn = tr.n_nodes[inst], nr = tr.n_recs[inst];
     double ub = INFINITY;
     int inc = -1, solves = 0, st = -1, k = 0;
-    long long iters = 0;
+    long long iters = 0, ksum = 0;
+    int kmx = 0;
 
     while (st < 0) {
         // ---- select: candidates = alive leaves with lb < ub - tol ; best_first = first minimum
@@ -77,6 +78,7 @@ __device__ inline int bnb_instance(const DevProblem &P, const Ctx &cx, const Slo
             lbv[j] = j < d ? v : 0.;
             ubv[j] = j < d ? v : 1.;
         }
+        set_node_prefix_known(P, cx, d);
         __syncthreads();
         // ---- solve (K1), started from the node's OWN dual record: the multipliers (and proximal centre) of its
         //      parent, or its shifted dual solution for a warm-start root (controller.py:262-264, 426, 487);
@@ -92,7 +94,7 @@ __device__ inline int bnb_instance(const DevProblem &P, const Ctx &cx, const Slo
                 load_slot(P, cx, sp, k, true);
             }
         }
-        const int qs = qp_solve(P, cx, k, xi, lbv, ubv, y, iters_s);
+        const int qs = qp_solve(P, cx, k, xi, lbv, ubv, y, iters_s, iters_s + 1);
         if (qs == WS_ITER_LIMIT) { st = BNB_QP_LIMIT; break; }
         double *dual = rdual + (size_t)nr * P.n_rec;
         build_records(P, qs, SMV(yc), y, xi, lbv, ubv, prim, dual, cost_s, dobj_s, SMV(part), SMV(red));
@@ -103,7 +105,7 @@ __device__ inline int bnb_instance(const DevProblem &P, const Ctx &cx, const Slo
             if (tr_i) { tr_i[2 * solves] = bi; tr_i[2 * solves + 1] = *iters_s; }
         }
         const int myrec = nr;
-        iters += *iters_s;
+        iters += *iters_s; ksum += k; kmx = max(kmx, iters_s[1]);
         ++nr; ++solves;
         // ---- prune / incumbent / branch (branch_and_bound.py:476-489)
         if (cost >= cutoff) {
@@ -133,7 +135,10 @@ __device__ inline int bnb_instance(const DevProblem &P, const Ctx &cx, const Slo
     if (threadIdx.x == 0) {
         tr.n_nodes[inst] = nn; tr.n_recs[inst] = nr;
         inc_cost[inst] = ub; inc_node[inst] = inc; n_solves[inst] = solves;
-        if (totals) { atomicAdd(totals, (unsigned long long)solves); atomicAdd(totals + 1, (unsigned long long)iters); }
+        if (totals) {
+            atomicAdd(totals, (unsigned long long)solves); atomicAdd(totals + 1, (unsigned long long)iters);
+            atomicAdd(totals + 2, (unsigned long long)ksum); atomicMax(totals + 3, (unsigned long long)kmx);
+        }
     }
     __syncthreads();
     return st;

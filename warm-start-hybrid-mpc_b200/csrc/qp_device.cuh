@@ -50,7 +50,9 @@
 // offsets (in doubles unless noted) of the shared-memory arrays, resolved on the host (wshmpc_create)
 struct SmemOff {
     int Q, Ri, z, c1, c2, t, u, ls, lam, cw, yc, wv, v, gc, gs, bu, blb, inr, vsc, xi, part, red, sF, sG, sF1, sG1;
+    int vf0, vf;                          // eliminated coordinates of v: node-constant part / value in the current proximal pass
     int irow, iside, ired, iscr, rinfo;   // int offsets (from the start of the int area)
+    int idep;                             // [0] number of eliminated (pinned prefix) binaries of the node being solved
     int ints;                             // start of the int area, in doubles
     int binW, bign, bnadd;                // byte offsets from the start of the byte area
     int bytes;                            // start of the byte area, in doubles
@@ -60,8 +62,9 @@ struct SmemOff {
 struct DevProblem {
     int nx, nu, nub, nuc, T, nh, nh1, nq, nqT, nr, n, m, mc, nb, ns;
     const double *A, *B, *F, *G, *h, *F1, *G1, *h1, *Q, *R, *QT, *Mmu, *Mrho;
-    const double *Mh, *WfT, *nrm, *inr, *vscale, *Eh, *hh, *Rinv, *RinvT, *Kx, *ZmapT;
+    const double *Mh, *WfT, *nrm, *inr, *vscale, *Eh, *hh, *Rinv, *RinvT, *Kx, *ZmapT, *Linv, *LinvT;
     const int *bin_idx;
+    int n_elim;              // leading binaries that may be eliminated when pinned (0 = never)
     double eps, tol_p, tol_d, tol_sing, tol_ray, prox_tol;
     int max_iter, max_prox;
     int ks;                  // columns of Q1 and of Ri held in shared memory
@@ -423,9 +426,9 @@ __device__ inline void refresh_uv(const DevProblem &P, const Ctx &cx, int k) {
 // numerically in the span of the working rows; either way t = R^-1 Q1' mj  (mj = Mw' t if dependent).
 // `track`: also bring u, ls, v up to date (false while the factor of an inherited working set is rebuilt).
 __device__ inline int thin_append(const DevProblem &P, const Ctx &cx, int &k, int r, int sgn, bool track) {
-    const int n = P.n;
+    const int n = P.n, d = SMI(idep)[0];
     double *z = SMV(z), *c1 = SMV(c1), *t = SMV(t);
-    for (int i = threadIdx.x; i < P.np; i += WS_NT) z[i] = i < n ? (double)sgn * __ldg(P.Mh + (size_t)r * n + i) : 0.;
+    for (int i = threadIdx.x; i < P.np; i += WS_NT) z[i] = (i < n && i >= d) ? (double)sgn * __ldg(P.Mh + (size_t)r * n + i) : 0.;
     __syncthreads();
     qt_dots(P, cx, k, z, c1);
     double zz = q_apply(P, cx, k, c1, z);
@@ -443,7 +446,7 @@ __device__ inline int thin_append(const DevProblem &P, const Ctx &cx, int &k, in
         rho2 = zz; cu += cu2;
     }
     ri_matvec(P, cx, k, c1, t);
-    if (k >= n || rho2 <= P.tol_sing * P.tol_sing) return 0;
+    if (k >= n - d || rho2 <= P.tol_sing * P.tol_sing) return 0;
     const double ir = 1. / sqrt(rho2);
     double *qk = qcol_w(P, cx, k), *rk = ricol_w(P, cx, k);
     double uk = 0., lk = 0.;
@@ -592,8 +595,9 @@ __device__ inline void ws_remove(const DevProblem &P, const Ctx &cx, int &k, int
 //   binary (t, i): sv = zeta_t[nuc + i] / nrm_r
 // WfT is the operator transposed (n x ns2): a thread owns two adjacent outputs and streams 16-byte words,
 // gp groups split the columns.
+// x[c] = 0 for c < c0 (the eliminated coordinates): those columns of the operator are skipped.
 template <class Fn>
-__device__ inline void price_rows(const DevProblem &P, const Ctx &cx, const double *x, Fn f) {
+__device__ inline void price_rows(const DevProblem &P, const Ctx &cx, const double *x, int c0, Fn f) {
     const int n = P.n, m = P.m, mc = P.mc, nx = P.nx, nu = P.nu;
     const int hs = P.ns2 >> 1;
     double *xi = SMV(xi);
@@ -602,7 +606,7 @@ __device__ inline void price_rows(const DevProblem &P, const Ctx &cx, const doub
         if (cx.pg < P.gp) {
             const double2 *w2 = reinterpret_cast<const double2 *>(P.WfT) + cx.prp;
             double ax = 0., ay = 0., bx = 0., by = 0., ex = 0., ey = 0., dx = 0., dy = 0.;
-            int c = cx.pg;
+            int c = c0 + cx.pg;
             const int G = P.gp;
             for (; c + 3 * G < n; c += 4 * G) {
                 const double2 a = __ldg(w2 + (size_t)c * hs), b = __ldg(w2 + (size_t)(c + G) * hs),
@@ -707,13 +711,14 @@ __device__ inline void load_ws_from_multipliers(const DevProblem &P, const Ctx &
     int *wsum = SMI(ired);                       // WS_NW ints
     int *row = SMI(irow), *side = SMI(iside);
     double *lam = SMV(lam);
+    const int d = SMI(idep)[0];
     for (int i = threadIdx.x; i < P.n; i += WS_NT) SMV(yc)[i] = yc0 ? yc0[i] : 0.;
     int base = 0;
     for (int r0 = 0; r0 < P.m; r0 += WS_NT) {
         const int r = r0 + threadIdx.x;
         double yv = 0.;
         if (r < P.m) yv = ysigned(r);
-        const int keep = yv != 0. && base < P.n;
+        const int keep = yv != 0. && base < P.n && !(r >= P.mc && r - P.mc < d);   // eliminated rows carry no working-set entry
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
         __syncthreads();
         if (lane == 0) wsum[w] = __popc(bal);
@@ -734,7 +739,8 @@ __device__ inline void load_ws_from_multipliers(const DevProblem &P, const Ctx &
 __device__ inline void rebuild_factor(const DevProblem &P, const Ctx &cx, int &k) {
     signed char *inW = reinterpret_cast<signed char *>(SMB(binW));
     unsigned char *ign = SMB(bign), *nadd = SMB(bnadd);
-    for (int r = threadIdx.x; r < P.m; r += WS_NT) { inW[r] = 0; ign[r] = 0; nadd[r] = 0; }
+    const int d = SMI(idep)[0];
+    for (int r = threadIdx.x; r < P.m; r += WS_NT) { inW[r] = 0; ign[r] = (r >= P.mc && r - P.mc < d) ? 3 : 0; nadd[r] = 0; }
     // the inherited rows are parked in scratch while the factor grows from the front
     const int k0 = k;
     double *lam0 = SMV(cw), *lam = SMV(lam);
@@ -746,9 +752,60 @@ __device__ inline void rebuild_factor(const DevProblem &P, const Ctx &cx, int &k
     k = 0;
     for (int i = 0; i < k0; ++i) {
         const int r = row0[i] >> 1, s = (row0[i] & 1) ? 1 : -1;
+        if (r >= P.mc && r - P.mc < d) continue;          // eliminated in this node
         if (thin_append(P, cx, k, r, s, false)) {
             if (threadIdx.x == 0) { lam[k - 1] = lam0[i]; inW[r] = (signed char)s; }
         }
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// pinned-prefix elimination.  problem.py rotates v so that the bound row of binary j (chronological order) has
+// its non-zeros in columns 0..j.  A node whose first d binaries are pinned (lb == ub: every node branch_in_time
+// creates, controller.py:13-44) has v[:d] fixed by those d rows; the solver works in the coordinates d..n-1
+// (rows enter the factor with their first d entries dropped, the bounds are shifted by mh_r[:d] . v_f) and
+// the multipliers of the d eliminated rows follow from stationarity in the eliminated coordinates.
+// ---------------------------------------------------------------------------------------------
+
+// d from the bounds of the node.  Ends with a barrier.
+__device__ inline void set_node_prefix(const DevProblem &P, const Ctx &cx, const double *lb, const double *ub) {
+    double far = 0.;                                        // nb - (first binary that is not pinned)
+    for (int j = threadIdx.x; j < P.nb; j += WS_NT) if (lb[j] != ub[j]) far = fmax(far, (double)(P.nb - j));
+    far = block_max(far, SMV(red));
+    if (threadIdx.x == 0) { const int d = P.nb - (int)far; SMI(idep)[0] = d < P.n_elim ? d : P.n_elim; }
+    __syncthreads();
+}
+
+// d known by the caller (depth of a branch_in_time node).  The caller provides the barrier.
+__device__ inline void set_node_prefix_known(const DevProblem &P, const Ctx &cx, int d) {
+    if (threadIdx.x == 0) SMI(idep)[0] = d < P.n_elim ? d : P.n_elim;
+}
+
+// y_out of the eliminated rows:  L' eta = -( [v_f] + sum_i coef_i mh_{row_i}[:d] + pcoef mh_pend[:d] )
+__device__ inline void pinned_multipliers(const DevProblem &P, const Ctx &cx, int k, int d, const double *coef,
+                                          int pend, double pcoef, bool with_v, double *y_out) {
+    if (d == 0) return;
+    double *g = SMV(c2);
+    const int *row = SMI(irow);
+    for (int c = threadIdx.x; c < d; c += WS_NT) {
+        double s0 = with_v ? SMV(vf)[c] : 0., s1 = 0.;
+        int i = 0;
+        for (; i + 1 < k; i += 2) {
+            s0 += coef[i] * __ldg(P.Mh + (size_t)row[i] * P.n + c);
+            s1 += coef[i + 1] * __ldg(P.Mh + (size_t)row[i + 1] * P.n + c);
+        }
+        if (i < k) s0 += coef[i] * __ldg(P.Mh + (size_t)row[i] * P.n + c);
+        if (pend >= 0) s1 += pcoef * __ldg(P.Mh + (size_t)pend * P.n + c);
+        g[c] = s0 + s1;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < d; j += WS_NT) {
+        double s0 = 0., s1 = 0.;
+        int c = j;
+        for (; c + 1 < d; c += 2) { s0 += __ldg(P.Linv + (size_t)c * P.nb + j) * g[c]; s1 += __ldg(P.Linv + (size_t)(c + 1) * P.nb + j) * g[c + 1]; }
+        if (c < d) s0 += __ldg(P.Linv + (size_t)c * P.nb + j) * g[c];
+        y_out[P.mc + j] = -(s0 + s1) * SMV(inr)[P.mc + j];
     }
     __syncthreads();
 }
@@ -761,7 +818,7 @@ __device__ inline void rebuild_factor(const DevProblem &P, const Ctx &cx, int &k
 // ---------------------------------------------------------------------------------------------
 __device__ inline int qp_solve(const DevProblem &P, const Ctx &cx, int &k,
                                const double *x0, const double *lb, const double *ub,
-                               double *y_out, int *iters_out)
+                               double *y_out, int *iters_out, int *kmax_out = nullptr)
 {
     const int n = P.n, m = P.m, mc = P.mc, nx = P.nx;
     signed char *inW = reinterpret_cast<signed char *>(SMB(binW));
@@ -769,12 +826,27 @@ __device__ inline int qp_solve(const DevProblem &P, const Ctx &cx, int &k,
     double *lam = SMV(lam), *ls = SMV(ls), *t = SMV(t), *bu = SMV(bu), *blb = SMV(blb), *vsc = SMV(vsc);
     int *row = SMI(irow), *side = SMI(iside);
     double *red = SMV(red); int *ired = SMI(ired);
-    int it = 0, status = WS_ITER_LIMIT;
+    int it = 0, status = WS_ITER_LIMIT, kmax = 0;
     bool hot = k > 0;
     int cap = hot ? min(P.hot_cap, P.max_iter) : P.max_iter;
 
+    // eliminated coordinates: L v_f = b with b_j = ub_j / nrm_j + (Mh wv)_j  =>  v_f = vf0 + wv[:d], vf0 = L^-1 (ub / nrm)
+    const int d = SMI(idep)[0];
+    for (int c = threadIdx.x; c < d; c += WS_NT) {
+        double s0 = 0., s1 = 0.;
+        int j = 0;
+        for (; j + 1 <= c; j += 2) {
+            s0 += __ldg(P.LinvT + (size_t)j * P.nb + c) * (ub[j] * SMV(inr)[mc + j]);
+            s1 += __ldg(P.LinvT + (size_t)(j + 1) * P.nb + c) * (ub[j + 1] * SMV(inr)[mc + j + 1]);
+        }
+        if (j <= c) s0 += __ldg(P.LinvT + (size_t)j * P.nb + c) * (ub[j] * SMV(inr)[mc + j]);
+        SMV(vf0)[c] = s0 + s1;
+    }
+    __syncthreads();
+
 restart:
     rebuild_factor(P, cx, k);
+    kmax = max(kmax, k);
     int pending = -1, pside = 0, just_added = -1;
     double plam = 0.;
     for (int pk = 0; pk < P.max_prox; ++pk) {
@@ -782,10 +854,12 @@ restart:
         grouped_matvec(P.Rinv, n, n, 0, n, SMV(yc), SMV(part), [&](int c, double a) {
             double s = 0.;
             for (int j = 0; j < nx; ++j) s += P.Kx[(size_t)c * nx + j] * x0[j];
-            SMV(wv)[c] = s - P.eps * a;
+            const double w = s - P.eps * a;
+            if (c < d) { SMV(vf)[c] = SMV(vf0)[c] + w; SMV(wv)[c] = -SMV(vf0)[c]; }      // wv - [v_f; 0]: the bounds below come out shifted
+            else SMV(wv)[c] = w;
         });
         // bounds of this proximal sub-problem: g = Mh wv
-        price_rows(P, cx, SMV(wv), [&](int r, double g) {
+        price_rows(P, cx, SMV(wv), 0, [&](int r, double g) {
             if (r < mc) {
                 double e = 0.;
                 for (int j = 0; j < nx; ++j) e += P.Eh[(size_t)r * nx + j] * x0[j];
@@ -831,7 +905,7 @@ restart:
                 for (int i = threadIdx.x; i < k; i += WS_NT) lam[i] = ls[i] > 0. ? ls[i] : 0.;
                 const double vnoise = 1e-14 * lpart, vcap = 100. * P.tol_p;
                 double vbest = 0.; int ibest = -1;                 // ibest = 2 r + (lower side)
-                price_rows(P, cx, SMV(v), [&](int r, double sv) {
+                price_rows(P, cx, SMV(v), d, [&](int r, double sv) {
                     if (inW[r]) return;
                     const int na = nadd[r];
                     double tolr = P.tol_p * (na == 0 ? 1. : (na == 1 ? 10. : 100.));
@@ -852,6 +926,7 @@ restart:
                 if (ibest < 0) { status = WS_OPTIMAL; break; }
                 const int jb = ibest >> 1, sb = (ibest & 1) ? -1 : 1;
                 if (thin_append(P, cx, k, jb, sb, true)) {
+                    kmax = max(kmax, k);
                     if (threadIdx.x == 0) inW[jb] = (signed char)sb;
                     just_added = jb;
                     __syncthreads();
@@ -888,7 +963,9 @@ restart:
                             y_out[r] = (double)side[i] * pi * SMV(inr)[r];
                         }
                         if (threadIdx.x == 0) y_out[pending] = (double)pside * SMV(inr)[pending];
+                        for (int i = threadIdx.x; i < k; i += WS_NT) SMV(cw)[i] = (double)side[i] * (t[i] < 0. ? -t[i] : 0.);
                         __syncthreads();
+                        pinned_multipliers(P, cx, k, d, SMV(cw), pending, (double)pside, false, y_out);
                         status = WS_INFEASIBLE;
                         break;
                     }
@@ -937,9 +1014,11 @@ restart:
         for (int i = threadIdx.x; i < k; i += WS_NT) {
             const int r = row[i];
             y_out[r] = (double)side[i] * lam[i] * SMV(inr)[r];
+            SMV(cw)[i] = (double)side[i] * lam[i];
         }
         __syncthreads();
+        pinned_multipliers(P, cx, k, d, SMV(cw), -1, 0., true, y_out);
     }
-    if (threadIdx.x == 0) *iters_out = it;
+    if (threadIdx.x == 0) { *iters_out = it; if (kmax_out) *kmax_out = kmax; }
     return status;
 }

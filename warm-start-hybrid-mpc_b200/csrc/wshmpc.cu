@@ -52,6 +52,8 @@ solve_nodes_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, int 
     for (int i = 0; i < n_nodes; ++i) {
         if (slot_of[i] != slot) continue;
         const int hm = hot[i];
+        const double *xi = x0 + (size_t)i * P.nx, *lbi = lb + (size_t)i * P.nb, *ubi = ub + (size_t)i * P.nb;
+        set_node_prefix(P, cx, lbi, ubi);
         if (hm == 2 && y0) {
             const double *yy = y0 + (size_t)i * P.m;
             load_ws_from_multipliers(P, cx, [&](int r) { return yy[r]; }, yc0 ? yc0 + (size_t)i * P.n : nullptr, k);
@@ -60,7 +62,6 @@ solve_nodes_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, int 
             const bool reset = hm == 0;
             if (!loaded || reset) { load_slot(P, cx, sp, k, reset); loaded = true; }
         }
-        const double *xi = x0 + (size_t)i * P.nx, *lbi = lb + (size_t)i * P.nb, *ubi = ub + (size_t)i * P.nb;
         const int st = qp_solve(P, cx, k, xi, lbi, ubi, y, iters + i);
         build_records(P, st, SMV(yc), y, xi, lbi, ubi, primal + (size_t)i * P.n_primal,
                       dual + (size_t)i * P.n_dual, cost + i, dobj + i, SMV(part), SMV(red));
@@ -119,6 +120,14 @@ extern "C" int wshmpc_create(const wshmpc_problem *p, int device, int n_slots, v
     UP(Mh, p->Mh, (size_t)m * n) UP(nrm, p->nrm, m) UP(vscale, p->vscale, m) UP(Eh, p->Eh, (size_t)p->mc * nx)
     UP(hh, p->hh, p->mc) UP(Rinv, p->Rinv, (size_t)n * n) UP(Kx, p->Kx, (size_t)n * nx)
     UP(bin_idx, p->bin_idx, p->nb)
+    P.n_elim = p->n_elim;
+    if (p->n_elim < 0 || p->n_elim > p->nb || (p->n_elim > 0 && !p->Linv)) { wshmpc_destroy(h); WS_FAIL(-1, "n_elim = %d out of range or Linv missing", p->n_elim); }
+    {
+        std::vector<double> li((size_t)p->nb * p->nb, 0.);
+        if (p->Linv) memcpy(li.data(), p->Linv, li.size() * sizeof(double));
+        UP(Linv, li.data(), li.size())
+        std::vector<double> lt = transpose(li.data(), p->nb, p->nb); UP(LinvT, lt.data(), lt.size())
+    }
     {
         std::vector<double> ir(m); for (int r = 0; r < m; ++r) ir[r] = 1. / p->nrm[r]; UP(inr, ir.data(), m)
         std::vector<double> r = transpose(p->Rinv, n, n); UP(RinvT, r.data(), (size_t)n * n)
@@ -167,6 +176,7 @@ extern "C" int wshmpc_create(const wshmpc_problem *p, int device, int n_slots, v
         // fixed part first, then Q and Ri take what is left
         so.z = take(nvl); so.c1 = take(nvl); so.c2 = take(nvl); so.t = take(nvl); so.u = take(nvl); so.ls = take(nvl);
         so.lam = take(nvl); so.cw = take(nvl); so.yc = take(nvl); so.wv = take(nvl); so.v = take(nvl); so.gc = take(nvl); so.gs = take(nvl);
+        so.vf0 = take(nvl); so.vf = take(nvl);
         so.bu = take(m); so.blb = take(p->nb); so.inr = take(m); so.vsc = take(m); so.xi = take(P.ns2); so.part = take(part);
         so.red = take(72);
         so.sF = take(p->nh * nx); so.sG = take(p->nh * nu); so.sF1 = take(p->nh1 * nx); so.sG1 = take(p->nh1 * nu);
@@ -174,6 +184,7 @@ extern "C" int wshmpc_create(const wshmpc_problem *p, int device, int n_slots, v
         int io = 0;
         so.irow = io; io += n + 1; so.iside = io; io += n + 1; so.ired = io; io += 40; so.iscr = io; io += n + 1;
         so.rinfo = io; io += m;
+        so.idep = io; io += 2;
         o += (io + 1) / 2; o = (o + 1) & ~1;
         so.bytes = o;
         so.binW = 0; so.bign = m; so.bnadd = 2 * m;

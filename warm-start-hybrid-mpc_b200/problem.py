@@ -102,8 +102,30 @@ class ProblemData(object):
             eps = 1e-2 * float(pos.min())
         self.eps = float(eps)
         Rinv = U / np.sqrt(np.maximum(lamb, 0.) + self.eps)[None, :]
+        # Rinv is fixed only up to an orthogonal factor on the right.  Choose it so that the bound rows of
+        # the binaries, taken in chronological order (t, i) -- the order branch_in_time pins them in,
+        # controller.py:13-44 -- are LOWER TRIANGULAR in v: row j has its non-zeros in columns 0..j.  A node
+        # whose first d binaries are pinned then fixes v[:d] by one forward substitution and the kernel
+        # solves its QP in the remaining n - d coordinates (working set, factor and pricing all shrink).
         M = Ay.dot(Rinv)
         nrm = np.linalg.norm(M, axis=1); nrm[nrm == 0.] = 1.
+        nb = self.nb
+        Qrot, Rr = np.linalg.qr((M[self.mc:] / nrm[self.mc:, None]).T, mode='complete')
+        sgn = np.sign(np.diag(Rr[:nb, :nb])); sgn[sgn == 0.] = 1.
+        Qrot[:, :nb] *= sgn[None, :]
+        Rinv = Rinv.dot(Qrot)
+        M = Ay.dot(Rinv)
+        for j in range(nb):
+            M[self.mc + j, j + 1:] = 0.
+        nrm = np.linalg.norm(M, axis=1); nrm[nrm == 0.] = 1.
+        L = M[self.mc:, :nb] / nrm[self.mc:, None]
+        dg = np.abs(np.diag(L))
+        bad = np.nonzero(dg < 1e-6)[0]
+        self.n_elim = int(bad[0]) if bad.size else nb
+        Linv = np.zeros((nb, nb))
+        if self.n_elim:
+            Linv[:self.n_elim, :self.n_elim] = np.tril(np.linalg.inv(L[:self.n_elim, :self.n_elim]))
+        self.Linv = np.ascontiguousarray(Linv)
         arow = np.concatenate((np.linalg.norm(As, axis=1), np.ones(self.nb)))
         c = np.ascontiguousarray
         self.Mh = c(M / nrm[:, None]); self.nrm = c(nrm); self.vscale = c(nrm / np.maximum(1., arow))
