@@ -62,6 +62,9 @@ typedef struct {
 
 const char *wshmpc_last_error(void);
 
+/* solver CTAs the library keeps resident per SM (a build constant): n_slots = SMs x this fills the GPU */
+int wshmpc_ctas_per_sm(void);
+
 /* create / destroy.  `n_slots` = number of independent solver states (one per concurrently solved
  * MPC instance); `stream` is a cudaStream_t passed as void* (0 = default stream). */
 int wshmpc_create(const wshmpc_problem *p, int device, int n_slots, void *stream, wshmpc_handle **out);
@@ -116,7 +119,8 @@ typedef struct {
     int *n_recs;                      /* [n_inst] */
     int *depth;                       /* [n_inst][cap_nodes]  number of pinned binaries */
     int *alive;                       /* [n_inst][cap_nodes]  1 = leaf, 0 = branched (removed from `leaves`) */
-    int *rec;                         /* [n_inst][cap_nodes]  dual record of the node, -1 = None */
+    int *rec;                         /* [n_inst][cap_nodes]  dual record of the node, < 0 = None (-2 - r: None, but record r
+                                         holds the shifted ray of a leaf whose proof lapsed: used to start its QP) */
     unsigned int *bits;               /* [n_inst][cap_nodes][words]  bit j = value of binary j = t*nub+i, j < depth */
     double *lb;                       /* [n_inst][cap_nodes]  Node.lb */
     double *rec_dobj;                 /* [n_inst][cap_recs]   DualSolution.objective */
@@ -173,7 +177,7 @@ typedef struct {
     int warm;                         /* 1: warm start by tree shifting, 0: every step from the root node */
     int fresh;                        /* 1: step 0 starts from the root node (no tree yet) */
     int par;                          /* which tree / state buffer (0 or 1) holds the data of step 0 */
-    int *d_queue;                     /* [2 + n_inst * (n_steps + 1)] scratch */
+    int *d_queue;                     /* [4 + 2 * n_steps + n_inst * (n_steps + 1)] scratch (per-step task queues) */
     int *d_step_of;                   /* [n_inst] scratch */
     double *d_x;                      /* [2][n_inst][nx] states, buffer `par` holds the current ones */
     const double *d_e;                /* [n_steps][n_inst][nx] model errors, or NULL */

@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libwshmpc.so')
+LIB_PATH = os.environ.get('WSHMPC_LIB') or os.path.join(_HERE, 'libwshmpc.so')   # WSHMPC_LIB: experiment builds (tools/)
 _lib = None
 
 
@@ -42,7 +42,7 @@ def load_library():
     return _lib
 
 
-EXPORTS = ('wshmpc_last_error', 'wshmpc_create', 'wshmpc_destroy', 'wshmpc_get_layout', 'wshmpc_solve_nodes',
+EXPORTS = ('wshmpc_last_error', 'wshmpc_ctas_per_sm', 'wshmpc_create', 'wshmpc_destroy', 'wshmpc_get_layout', 'wshmpc_solve_nodes',
            'wshmpc_tree_init_root', 'wshmpc_bnb_solve', 'wshmpc_shift_tree', 'wshmpc_closed_loop')
 
 
@@ -215,7 +215,7 @@ class Handle(object):
                         u0=torch.empty((n_steps, N, nu), dtype=torch.float64, device=dev),
                         n_solves=torch.empty((n_steps, N), dtype=torch.int32, device=dev),
                         status=torch.empty((n_steps, N), dtype=torch.int32, device=dev))
-        need = 2 + N * (n_steps + 1)
+        need = 4 + 2 * n_steps + N * (n_steps + 1)
         if getattr(self, '_queue', None) is None or self._queue.numel() < need:
             self._queue = torch.empty(need, dtype=torch.int32, device=dev)
         if getattr(self, '_step_of', None) is None or self._step_of.numel() < N:

@@ -340,9 +340,10 @@ class HybridModelPredictiveController(object):
 
     @staticmethod
     def default_slots():
-        """Solver states resident at once: one 512-thread CTA per SM (148 on a B200)."""
+        """Solver states resident at once: SMs (148 on a B200) x solver CTAs per SM of the library build."""
         import torch
-        return torch.cuda.get_device_properties(0).multi_processor_count
+        from .capi import load_library
+        return torch.cuda.get_device_properties(0).multi_processor_count * int(load_library().wshmpc_ctas_per_sm())
 
     # -- tree <-> reference Node lists ---------------------------------------------------------------
     def tree_to_leaves(self, tree, inst=0):

@@ -80,11 +80,16 @@ __device__ inline int bnb_instance(const DevProblem &P, const Ctx &cx, const Slo
         }
         set_node_prefix_known(P, cx, d);
         __syncthreads();
+        prof_mark(0);
         // ---- solve (K1), started from the node's OWN dual record: the multipliers (and proximal centre) of its
         //      parent, or its shifted dual solution for a warm-start root (controller.py:262-264, 426, 487);
         //      no record (root node, dual = None) = empty working set
         {
-            const int r0 = rec[bi];
+            // rec <= -2: dual = None for the reference's bookkeeping (the shifted Farkas proof of an infeasible leaf no longer
+            // holds, controller.py:555-558), but record -2 - rec still holds that shifted ray: its rows are where the new
+            // proof (or the optimum) is most likely found, and any multipliers >= 0 are a valid start of the dual method
+            const int r00 = rec[bi];
+            const int r0 = r00 <= -2 ? -2 - r00 : r00;
             if (r0 >= 0) {
                 const double *D = rdual + (size_t)r0 * P.n_rec;
                 const double *mu = D + P.off_mu, *nl = D + P.off_nulb, *nu_ = D + P.off_nuub;
@@ -94,15 +99,22 @@ __device__ inline int bnb_instance(const DevProblem &P, const Ctx &cx, const Slo
                 load_slot(P, cx, sp, k, true);
             }
         }
+        prof_mark(1);
         const int qs = qp_solve(P, cx, k, xi, lbv, ubv, y, iters_s, iters_s + 1);
         if (qs == WS_ITER_LIMIT) { st = BNB_QP_LIMIT; break; }
         double *dual = rdual + (size_t)nr * P.n_rec;
         build_records(P, qs, SMV(yc), y, xi, lbv, ubv, prim, dual, cost_s, dobj_s, SMV(part), SMV(red));
         for (int j = threadIdx.x; j < P.n; j += WS_NT) dual[P.n_dual + j] = qs == WS_OPTIMAL ? SMV(yc)[j] : 0.;
+        prof_mark(17);
         const double cost = *cost_s;
         if (threadIdx.x == 0) {
             lb[bi] = cost; rec[bi] = nr; rdobj[nr] = *dobj_s;
+#ifdef WS_PROF
+            // experiment builds: iterations | k after the rebuild << 12 | final k << 20 | infeasible << 28 | proximal passes << 29
+            if (tr_i) { tr_i[2 * solves] = bi | (d << 16); tr_i[2 * solves + 1] = (*iters_s & 0xfff) | ((iters_s[2] & 0xff) << 12) | ((k & 0xff) << 20) | ((qs == WS_INFEASIBLE) << 28) | (((iters_s[2] >> 16) & 3) << 29); }
+#else
             if (tr_i) { tr_i[2 * solves] = bi; tr_i[2 * solves + 1] = *iters_s; }
+#endif
         }
         const int myrec = nr;
         iters += *iters_s; ksum += k; kmx = max(kmx, iters_s[1]);
@@ -131,6 +143,7 @@ __device__ inline int bnb_instance(const DevProblem &P, const Ctx &cx, const Slo
             nn += 2;
         }
         __syncthreads();
+        prof_mark(18);
     }
     if (threadIdx.x == 0) {
         tr.n_nodes[inst] = nn; tr.n_recs[inst] = nr;
@@ -144,7 +157,7 @@ __device__ inline int bnb_instance(const DevProblem &P, const Ctx &cx, const Slo
     return st;
 }
 
-__global__ void __launch_bounds__(WS_NT, 1)
+__global__ void __launch_bounds__(WS_NT, WS_MINB)
 bnb_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, double *scratch, int *work_counter,
            int n_inst, const double *__restrict__ x0, const int *__restrict__ active, TreeView tr,
            double tol, int max_solves,
@@ -351,7 +364,7 @@ __device__ inline void shift_instance(const DevProblem &P, double *shm, int *s_w
             obj = obj > 0. ? obj : 0.;                     // controller.py:546
             double lbn; int rn = idx;
             if (!isinf(lbo)) lbn = obj;                    // :550-551
-            else if (obj <= 0.) { lbn = 0.; rn = -1; }     // :555-558
+            else if (obj <= 0.) { lbn = 0.; rn = -2 - idx; }   // :555-558: dual = None; the shifted ray stays in record idx as a START for the node's QP
             else lbn = INFINITY;
             nt.lb[on_ + idx] = lbn; nt.rec[on_ + idx] = rn; nt.rec_dobj[(size_t)inst * nt.cap_recs + idx] = obj;
         }
@@ -404,8 +417,12 @@ struct LoopView {
 __global__ void loop_init_kernel(int n_inst, int n_items, LoopView L)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) { L.q[0] = 0; L.q[1] = n_inst; }
-    if (i < n_items) L.q[2 + i] = i < n_inst ? i : -1;
+    // q: [0] tasks completed, [1] lowest step with unclaimed tasks (hint), [4 + s] head of step s, [4 + S + s] tail of
+    // step s, [4 + 2 S + s n_inst + pos] instances ready for step s in the order they became ready
+    const int S = L.n_steps;
+    if (i == 0) { L.q[0] = 0; L.q[1] = 0; L.q[2] = 0; L.q[3] = 0; }
+    if (i < S) { L.q[4 + i] = 0; L.q[4 + S + i] = i == 0 ? n_inst : 0; }
+    if (i < n_items) L.q[4 + 2 * S + i] = i < n_inst ? i : -1;
     if (i < n_inst) L.step_of[i] = 0;
 }
 
@@ -417,7 +434,7 @@ __device__ inline void init_root(const TreeView &tr, int k)
     for (int w = 0; w < tr.words; ++w) tr.bits[o * tr.words + w] = 0u;
 }
 
-__global__ void __launch_bounds__(WS_NT, 1)
+__global__ void __launch_bounds__(WS_NT, WS_MINB)
 closed_loop_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, double *scratch, LoopView L, int n_inst,
                    TreeView t0, TreeView t1, double tol, int max_solves,
                    double *inc_cost, int *inc_node, double *inc_primal, int *n_solves, int *status_out,
@@ -434,20 +451,43 @@ closed_loop_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, doub
     int *iters_s = slot_i + (size_t)slot * slot_ints(P.n) + 2 * (P.n + 1) + 1;
     const int total = n_inst * L.n_steps;
     const size_t xs = (size_t)n_inst * P.nx;
+    prof_mark(127);
 
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) {
-            const int pos = atomicAdd(L.q, 1);
+            // pop a ready task of the LOWEST step: the instance that lags behind never waits in a queue, so the launch
+            // ends with the longest chain of solves of one instance, not with that chain plus its queueing delays
+            const int S = L.n_steps;
+            volatile int *q = L.q;
+            int *head = L.q + 4, *items = L.q + 4 + 2 * S;
+            volatile int *tail = L.q + 4 + S;
             int inst = -1;
-            if (pos < total) {
-                volatile int *item = L.q + 2 + pos;
-                while ((inst = *item) < 0) __nanosleep(256);
+            for (;;) {
+                int s = q[1];
+                bool claimed = false;
+                while (s < S) {
+                    const int hd = ((volatile int *)head)[s];
+                    if (hd >= n_inst) { if (s == q[1]) atomicMax(L.q + 1, s + 1); ++s; continue; }
+                    if (hd < tail[s]) {
+                        if (atomicCAS(head + s, hd, hd + 1) == hd) {
+                            volatile int *item = items + (size_t)s * n_inst + hd;
+                            while ((inst = *item) < 0) __nanosleep(64);
+                            claimed = true;
+                            break;
+                        }
+                        continue;                          // lost the race: look at the same step again
+                    }
+                    ++s;
+                }
+                if (claimed || q[0] >= total) break;
+                __nanosleep(256);
             }
             s_inst = inst;
         }
         __syncthreads();
         const int inst = s_inst;
+        prof_mark(20);
         if (inst < 0) break;
         __threadfence();                                   // acquire: drop stale L1 lines of the instance's data
         const int t = L.step_of[inst];
@@ -477,12 +517,15 @@ closed_loop_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, doub
         __syncthreads();
         shift_instance<WS_NT>(P, SMV(Q), SMI(ired), SMI(ired) + 16, inst, xc, L.e ? L.e + (size_t)t * xs : nullptr,
                               cur, inc_cost, inc_primal, L.active, nxt, xn, L.log_u0 + (size_t)t * n_inst * P.nu);
+        prof_mark(19);
         if (threadIdx.x == 0) L.step_of[inst] = t + 1;
         __threadfence();                                   // release: the instance's data before the token
         __syncthreads();
         if (threadIdx.x == 0 && t + 1 < L.n_steps) {
-            const int p = atomicAdd(L.q + 1, 1);
-            atomicExch(L.q + 2 + p, inst);
+            const int S = L.n_steps;
+            const int p = atomicAdd(L.q + 4 + S + (t + 1), 1);
+            atomicExch(L.q + 4 + 2 * S + (size_t)(t + 1) * n_inst + p, inst);
         }
+        if (threadIdx.x == 0) atomicAdd(L.q, 1);
     }
 }

@@ -35,7 +35,10 @@
 #include <stdint.h>
 
 #ifndef WS_NT
-#define WS_NT 512
+#define WS_NT 256            // threads per solver CTA (phases are short: more warps cost more at the barriers than they save)
+#endif
+#ifndef WS_MINB
+#define WS_MINB 1               // resident CTAs (= concurrently solved QPs) per SM
 #endif
 #define WS_NW (WS_NT / 32)
 #define WS_JW 128               // lanes of the k-indexed phases (columns of Q1 / rows of Ri)
@@ -44,12 +47,12 @@
 #define WS_OPTIMAL 2
 #define WS_INFEASIBLE 3
 #define WS_ITER_LIMIT 9
-#define WS_REORTH 1e-2          // re-orthogonalise when |z|^2 < WS_REORTH |m_j|^2  (|m_j| = 1)
+#define WS_REORTH 1e-2          // re-orthogonalise when |z|^2 < WS_REORTH |m_j[d:]|^2
 #define WS_LAM_MAX 1e13         // sum of multipliers beyond which a hot-started solve is declared degenerate
 
 // offsets (in doubles unless noted) of the shared-memory arrays, resolved on the host (wshmpc_create)
 struct SmemOff {
-    int Q, Ri, z, c1, c2, t, u, ls, lam, cw, yc, wv, v, gc, gs, bu, blb, inr, vsc, xi, part, red, sF, sG, sF1, sG1;
+    int Q, Ri, z, z2, c1, c2, t, u, ls, lam, cw, yc, wv, v, gc, gs, bu, blb, inr, vsc, xi, part, red, sF, sG, sF1, sG1;
     int vf0, vf;                          // eliminated coordinates of v: node-constant part / value in the current proximal pass
     int irow, iside, ired, iscr, rinfo;   // int offsets (from the start of the int area)
     int idep;                             // [0] number of eliminated (pinned prefix) binaries of the node being solved
@@ -62,7 +65,7 @@ struct SmemOff {
 struct DevProblem {
     int nx, nu, nub, nuc, T, nh, nh1, nq, nqT, nr, n, m, mc, nb, ns;
     const double *A, *B, *F, *G, *h, *F1, *G1, *h1, *Q, *R, *QT, *Mmu, *Mrho;
-    const double *Mh, *WfT, *nrm, *inr, *vscale, *Eh, *hh, *Rinv, *RinvT, *Kx, *ZmapT, *Linv, *LinvT;
+    const double *Mh, *WfT, *nrm, *inr, *vscale, *Eh, *hh, *Rinv, *RinvT, *Kx, *ZmapT, *Linv, *LinvT, *Msq;
     const int *bin_idx;
     int n_elim;              // leading binaries that may be eliminated when pinned (0 = never)
     double eps, tol_p, tol_d, tol_sing, tol_ray, prox_tol;
@@ -79,6 +82,22 @@ struct DevProblem {
     int n_primal, n_dual, off_lam, off_mu, off_nulb, off_nuub, off_rho, off_sigma;
     int n_rec;               // stride of a dual record in a tree: n_dual + n (the proximal centre of the solve follows the duals)
 };
+
+// Phase timing of the critical path (experiment builds only, -DWS_PROF; read back by tools/ through
+// wshmpc_prof_read): mark(id) charges the cycles since the previous mark of this CTA's thread 0 to phase `id`.
+#ifdef WS_PROF
+__device__ unsigned long long g_prof[256];
+__device__ __forceinline__ void prof_mark(int id) {
+    __shared__ long long s_prof_last;
+    if (threadIdx.x == 0) {
+        const long long t = clock64();
+        atomicAdd(&g_prof[2 * id], (unsigned long long)(t - s_prof_last)); atomicAdd(&g_prof[2 * id + 1], 1ull);
+        s_prof_last = clock64();
+    }
+}
+#else
+#define prof_mark(id) ((void)0)
+#endif
 
 __host__ __device__ __forceinline__ int tri_off(int j) { return j * (j + 1) / 2; }
 
@@ -142,7 +161,7 @@ __device__ __forceinline__ double warp_sum(double x) {
 // memory, and finish with a second shuffle tree over the WS_NW per-warp values (every warp does it
 // redundantly, so the result reaches all threads with two barriers and ~25 instructions).
 #define WS_FULL 0xffffffffu
-static_assert(WS_NW == 16 || WS_NW == 8, "the two-level reductions assume 8 or 16 warps per CTA");
+static_assert(WS_NW == 16 || WS_NW == 8 || WS_NW == 4 || WS_NW == 2, "the two-level reductions assume 2, 4, 8 or 16 warps per CTA");
 
 // block-wide sum, result to all threads
 __device__ inline double block_sum(double x, double *red) {
@@ -215,6 +234,19 @@ __device__ inline double block_max(double x, double *red) {
 __device__ inline void block_argmin(double &val, int &idx, double *red, int *ired) {
     double nv = -val;
     block_argmax(nv, idx, red, ired);
+    val = -nv;
+}
+
+// warp-wide arg-min (ties -> smaller idx) and sum, result in every lane
+__device__ inline void warp_argmin_sum(double &val, int &idx, double &sum) {
+    double nv = -val;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(WS_FULL, nv, o);
+        const int oi = __shfl_xor_sync(WS_FULL, idx, o);
+        sum += __shfl_xor_sync(WS_FULL, sum, o);
+        if (better_max(ov, oi, nv, idx)) { nv = ov; idx = oi; }
+    }
     val = -nv;
 }
 
@@ -292,41 +324,44 @@ __device__ inline void grouped_matvec(const double *__restrict__ M, int ld, int 
 // thin factor: products with Q1 and Ri.  Columns < ks in shared memory, the rest in the global home.
 // ---------------------------------------------------------------------------------------------
 
-// out[j] = q_j . x  for j < k.  Thread (g, jl): column j = jl (+ WS_JW ...), rows of group g; partial sums
-// through `part` (stride kp_).  Ends with a barrier.
+// The k-indexed phases (one output per working-set position) give every output to a team of ng = 2^lg ADJACENT lanes
+// that split the other dimension and combine by shuffles: WS_NT / ng outputs per pass, no partial sums through
+// shared memory, one barrier.  ng is the largest power of two <= 32 with k ng <= WS_NT (so all warps have work).
+__device__ __forceinline__ int team_log2(int k) { return k >= WS_NT ? 0 : min(5, 31 - __clz(WS_NT / max(k, 1))); }
+
+__device__ __forceinline__ double team_sum(double s, int lg) {
+    for (int o = 1; o < (1 << lg); o <<= 1) s += __shfl_xor_sync(WS_FULL, s, o);
+    return s;
+}
+
+// out[j] = q_j . x  for j < k.  Ends with a barrier.
 __device__ inline void qt_dots(const DevProblem &P, const Ctx &cx, int k, const double *x, double *out) {
-    double *part = SMV(part);
-    const int g = threadIdx.x / WS_JW, jl = threadIdx.x & (WS_JW - 1);
-    const int h = P.np >> 1, cp = (h + WS_NG - 1) / WS_NG;
+    const int lg = team_log2(k), ng = 1 << lg, g = threadIdx.x & (ng - 1), jw = WS_NT >> lg;
+    const int h = P.np >> 1, cp = (h + ng - 1) >> lg;
     const int p0 = g * cp, p1 = min(p0 + cp, h);
     const double2 *x2 = reinterpret_cast<const double2 *>(x);
-    int j = jl;
-    const int ke = min(k, P.ks);
-    for (; j < ke; j += WS_JW) {
-        const double2 *q2 = reinterpret_cast<const double2 *>(SMV(Q) + j * P.ld);
+    const int kr = (k + jw - 1) & ~(jw - 1);                       // whole teams take part in the shuffles
+    for (int j = threadIdx.x >> lg; j < kr; j += jw) {
         double s0 = 0., s1 = 0.;
+        if (j < k) {
+            if (j < P.ks) {
+                const double2 *q2 = reinterpret_cast<const double2 *>(SMV(Q) + j * P.ld);
 #pragma unroll 4
-        for (int p = p0; p < p1; ++p) { const double2 a = q2[p], b = x2[p]; s0 += a.x * b.x; s1 += a.y * b.y; }
-        part[g * P.kp_ + j] = s0 + s1;
-    }
-    for (; j < k; j += WS_JW) {
-        const double2 *q2 = reinterpret_cast<const double2 *>(cx.gQ + (size_t)j * P.ld);
-        double s0 = 0., s1 = 0.;
-        for (int p = p0; p < p1; ++p) { const double2 a = q2[p], b = x2[p]; s0 += a.x * b.x; s1 += a.y * b.y; }
-        part[g * P.kp_ + j] = s0 + s1;
-    }
-    __syncthreads();
-    for (int jj = threadIdx.x; jj < k; jj += WS_NT) {
-        double s = part[jj];
-#pragma unroll
-        for (int q = 1; q < WS_NG; ++q) s += part[q * P.kp_ + jj];
-        out[jj] = s;
+                for (int p = p0; p < p1; ++p) { const double2 a = q2[p], b = x2[p]; s0 += a.x * b.x; s1 += a.y * b.y; }
+            } else {
+                const double2 *q2 = reinterpret_cast<const double2 *>(cx.gQ + (size_t)j * P.ld);
+                for (int p = p0; p < p1; ++p) { const double2 a = q2[p], b = x2[p]; s0 += a.x * b.x; s1 += a.y * b.y; }
+            }
+        }
+        const double s = team_sum(s0 + s1, lg);
+        if (g == 0 && j < k) out[j] = s;
     }
     __syncthreads();
 }
 
-// z[i] -= sum_{j < k} q_j[i] c[j] ; returns this thread's share of |z|^2 (threads < np).  Ends with a barrier.
-__device__ inline double q_apply(const DevProblem &P, const Ctx &cx, int k, const double *c, double *z) {
+// zout = zin - sum_{j < k} q_j c[j]  (zin == nullptr: zero; zout may alias zin); returns this thread's share of
+// |zout|^2.  Ends with a barrier.
+__device__ inline double q_apply(const DevProblem &P, const Ctx &cx, int k, const double *c, const double *zin, double *zout) {
     double2 *part2 = reinterpret_cast<double2 *>(SMV(part));
     const int h = P.np >> 1;
     if (cx.bg < P.gb) {
@@ -346,59 +381,51 @@ __device__ inline double q_apply(const DevProblem &P, const Ctx &cx, int k, cons
         part2[cx.bg * h + cx.bip] = make_double2(ax + bx, ay + by);
     }
     __syncthreads();
+    const double *part = SMV(part);
     double zz = 0.;
-    if (threadIdx.x < P.np) {
-        const double *part = SMV(part);
-        double s = part[threadIdx.x];
-        for (int q = 1; q < P.gb; ++q) s += part[q * P.np + threadIdx.x];
-        const double zi = z[threadIdx.x] - s;
-        z[threadIdx.x] = zi; zz = zi * zi;
+    for (int i = threadIdx.x; i < P.np; i += WS_NT) {
+        double s = part[i];
+        for (int q = 1; q < P.gb; ++q) s += part[q * P.np + i];
+        const double zi = (zin ? zin[i] : 0.) - s;
+        zout[i] = zi; zz += zi * zi;
     }
     __syncthreads();
     return zz;
 }
 
-// t = Ri * c[:k]   (t_i = sum_{j >= i} Ri[tri_off(j) + i] c_j).  Thread (g, il): row i = il (+ WS_JW ...),
-// columns j = i + g, i + g + WS_NG, ...  Ends with a barrier.
+// t = Ri * c[:k]   (t_i = sum_{j >= i} Ri[tri_off(j) + i] c_j).  Team of row i: columns j = i + g, i + g + ng, ...
+// Ends with a barrier.
 __device__ inline void ri_matvec(const DevProblem &P, const Ctx &cx, int k, const double *c, double *t) {
-    double *part = SMV(part);
-    const int g = threadIdx.x / WS_JW, il = threadIdx.x & (WS_JW - 1);
+    const int lg = team_log2(k), ng = 1 << lg, g = threadIdx.x & (ng - 1), jw = WS_NT >> lg;
     const int ke = min(k, P.ks);
-    for (int i = il; i < k; i += WS_JW) {
+    const int kr = (k + jw - 1) & ~(jw - 1);
+    const double *Ri = SMV(Ri);
+    for (int i = threadIdx.x >> lg; i < kr; i += jw) {
         double s0 = 0., s1 = 0.;
-        int j = i + g;
-        const double *Ri = SMV(Ri);
-        for (; j + WS_NG < ke; j += 2 * WS_NG) { s0 += Ri[tri_off(j) + i] * c[j]; s1 += Ri[tri_off(j + WS_NG) + i] * c[j + WS_NG]; }
-        for (; j < ke; j += WS_NG) s0 += Ri[tri_off(j) + i] * c[j];
-        for (; j < k; j += WS_NG) s0 += cx.gRi[tri_off(j) + i] * c[j];
-        part[g * P.kp_ + i] = s0 + s1;
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < k; i += WS_NT) {
-        double s = part[i];
-#pragma unroll
-        for (int q = 1; q < WS_NG; ++q) s += part[q * P.kp_ + i];
-        t[i] = s;
+        if (i < k) {
+            int j = i + g;
+            for (; j + ng < ke; j += 2 * ng) { s0 += Ri[tri_off(j) + i] * c[j]; s1 += Ri[tri_off(j + ng) + i] * c[j + ng]; }
+            for (; j < ke; j += ng) s0 += Ri[tri_off(j) + i] * c[j];
+            for (; j < k; j += ng) s0 += cx.gRi[tri_off(j) + i] * c[j];
+        }
+        const double s = team_sum(s0 + s1, lg);
+        if (g == 0 && i < k) t[i] = s;
     }
     __syncthreads();
 }
 
 // u = Ri' * d[:k]  (u_j = sum_{i <= j} Ri[tri_off(j) + i] d_i).  Refresh path only.  Ends with a barrier.
 __device__ inline void rit_matvec(const DevProblem &P, const Ctx &cx, int k, const double *d, double *u) {
-    double *part = SMV(part);
-    const int g = threadIdx.x / WS_JW, jl = threadIdx.x & (WS_JW - 1);
-    for (int j = jl; j < k; j += WS_JW) {
-        const double *col = (j < P.ks ? SMV(Ri) : cx.gRi) + tri_off(j);
+    const int lg = team_log2(k), ng = 1 << lg, g = threadIdx.x & (ng - 1), jw = WS_NT >> lg;
+    const int kr = (k + jw - 1) & ~(jw - 1);
+    for (int j = threadIdx.x >> lg; j < kr; j += jw) {
         double s = 0.;
-        for (int i = g; i <= j; i += WS_NG) s += col[i] * d[i];
-        part[g * P.kp_ + j] = s;
-    }
-    __syncthreads();
-    for (int j = threadIdx.x; j < k; j += WS_NT) {
-        double s = part[j];
-#pragma unroll
-        for (int q = 1; q < WS_NG; ++q) s += part[q * P.kp_ + j];
-        u[j] = s;
+        if (j < k) {
+            if (j < P.ks) { const double *col = SMV(Ri) + tri_off(j); for (int i = g; i <= j; i += ng) s += col[i] * d[i]; }
+            else { const double *col = cx.gRi + tri_off(j); for (int i = g; i <= j; i += ng) s += col[i] * d[i]; }
+        }
+        s = team_sum(s, lg);
+        if (g == 0 && j < k) u[j] = s;
     }
     __syncthreads();
 }
@@ -419,33 +446,42 @@ __device__ inline void refresh_uv(const DevProblem &P, const Ctx &cx, int k) {
     __syncthreads();
     rit_matvec(P, cx, k, SMV(cw), SMV(u));
     ri_matvec(P, cx, k, SMV(u), SMV(ls));
-    q_apply(P, cx, k, SMV(u), SMV(v));
+    q_apply(P, cx, k, SMV(u), nullptr, SMV(v));
 }
 
 // Try to append the sign-normalised row (r, sgn).  Returns 1 if appended (lam = 0), 0 if the row is
 // numerically in the span of the working rows; either way t = R^-1 Q1' mj  (mj = Mw' t if dependent).
+// Returns -1 (nothing done) if the working set is at the capacity of the removal sweep (WS_NT positions).
 // `track`: also bring u, ls, v up to date (false while the factor of an inherited working set is rebuilt).
 __device__ inline int thin_append(const DevProblem &P, const Ctx &cx, int &k, int r, int sgn, bool track) {
     const int n = P.n, d = SMI(idep)[0];
+    if (k >= WS_NT) return -1;
     double *z = SMV(z), *c1 = SMV(c1), *t = SMV(t);
+    const int pb = track ? 30 : 40;
     for (int i = threadIdx.x; i < P.np; i += WS_NT) z[i] = (i < n && i >= d) ? (double)sgn * __ldg(P.Mh + (size_t)r * n + i) : 0.;
     __syncthreads();
+    prof_mark(pb);
     qt_dots(P, cx, k, z, c1);
-    double zz = q_apply(P, cx, k, c1, z);
+    prof_mark(pb + 1);
+    double zz = q_apply(P, cx, k, c1, z, z);
+    prof_mark(pb + 2);
     double cu = 0.;
     if (track) for (int j = threadIdx.x; j < k; j += WS_NT) cu += c1[j] * SMV(u)[j];
     block_sum2(zz, cu, SMV(red));
+    prof_mark(pb + 3);
     double rho2 = zz;
-    if (k > 0 && rho2 < WS_REORTH) {
+    if (k > 0 && rho2 < WS_REORTH * __ldg(P.Msq + (size_t)r * (P.nb + 1) + d)) {
         double *c2 = SMV(c2);
         qt_dots(P, cx, k, z, c2);
-        zz = q_apply(P, cx, k, c2, z);
+        zz = q_apply(P, cx, k, c2, z, z);
         double cu2 = 0.;
-        for (int j = threadIdx.x; j < k; j += WS_NT) { const double d = c2[j]; c1[j] += d; if (track) cu2 += d * SMV(u)[j]; }
+        for (int j = threadIdx.x; j < k; j += WS_NT) { const double dc = c2[j]; c1[j] += dc; if (track) cu2 += dc * SMV(u)[j]; }
         block_sum2(zz, cu2, SMV(red));
         rho2 = zz; cu += cu2;
+        prof_mark(pb + 4);
     }
     ri_matvec(P, cx, k, c1, t);
+    prof_mark(pb + 5);
     if (k >= n - d || rho2 <= P.tol_sing * P.tol_sing) return 0;
     const double ir = 1. / sqrt(rho2);
     double *qk = qcol_w(P, cx, k), *rk = ricol_w(P, cx, k);
@@ -468,12 +504,18 @@ __device__ inline int thin_append(const DevProblem &P, const Ctx &cx, int &k, in
     }
     k += 1;
     __syncthreads();
+    prof_mark(pb + 6);
     return 1;
 }
 
 // Remove position kp from the working set (u, ls, v follow).  Returns the smallest position >= kp whose
 // diagonal of R collapsed (|Ri_ii| >= 1 / tol_sing) after the removal, or -1.
-__device__ inline int thin_remove(const DevProblem &P, const Ctx &cx, int &k, int kp) {
+// SM: every column of the factor is in shared memory (k <= ks): plain shared-memory addressing instead of the
+// per-access shared / global choice.
+template <bool SM>
+__device__ inline int thin_remove_impl(const DevProblem &P, const Ctx &cx, int &k, int kp) {
+    auto QC = [&](int j) -> double * { return SM ? SMV(Q) + j * P.ld : qcol_w(P, cx, j); };
+    auto RC = [&](int j) -> double * { return SM ? SMV(Ri) + tri_off(j) : ricol_w(P, cx, j); };
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, tid = (int)threadIdx.x;
     double *gc = SMV(gc), *gs = SMV(gs), *u = SMV(u);
     int *row = SMI(irow), *side = SMI(iside), *flag = SMI(ired) + 32;
@@ -481,20 +523,21 @@ __device__ inline int thin_remove(const DevProblem &P, const Ctx &cx, int &k, in
     if (kp == k - 1) {
         // last position: Q1, Ri lose their last column; v += q_last u_last
         const double ul = u[kp];
-        const double *qk = qcol_w(P, cx, kp);
+        const double *qk = QC(kp);
         for (int i = tid; i < P.np; i += WS_NT) SMV(v)[i] += qk[i] * ul;
         k -= 1;
         __syncthreads();
         ri_matvec(P, cx, k, u, SMV(ls));
+        prof_mark(50);
         return -1;
     }
     // ---- 1. warp 0: rotations i = kp .. k-2 of the column pairs (i, i+1) from prefix sums of squares of row kp of Ri
     if (w == 0) {
-        const double wkp = ricol_w(P, cx, kp)[kp];
+        const double wkp = RC(kp)[kp];
         double run = 0.;
         for (int b = kp; b < k; b += 32) {
             const int j = b + lane;
-            const double wj = j < k ? ricol_w(P, cx, j)[kp] : 0.;
+            const double wj = j < k ? RC(j)[kp] : 0.;
             double s = wj * wj;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const double y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
@@ -516,19 +559,22 @@ __device__ inline int thin_remove(const DevProblem &P, const Ctx &cx, int &k, in
     // ---- 2. sweep over the columns in chunks: Q rows in threads [0, np), Ri rows in threads WS_NT-1 .. downwards,
     //         the u chain in thread np (first thread without a row of Q1)
     const int qr = tid < P.np ? tid : -1;                                   // row of Q1
+    const int qr2 = tid + WS_NT < P.np ? tid + WS_NT : -1;                  // second row (n <= 2 WS_NT)
     const int rr = (WS_NT - 1 - tid) < k - 1 ? WS_NT - 1 - tid : -1;        // new row of Ri (k - 1 <= WS_NT)
     const int ro = rr < kp ? rr : rr + 1;                                   // its old row
     const bool uth = tid == (P.np < WS_NT ? P.np : 0);
     const double big = 1. / P.tol_sing;
     __syncthreads();                                                        // gc, gs visible
-    double qcarry = qr >= 0 ? qcol_w(P, cx, kp)[qr] : 0.;
-    double rcarry = (rr >= 0 && ro <= kp) ? ricol_w(P, cx, kp)[ro] : 0.;
+    prof_mark(51);
+    double qcarry = qr >= 0 ? QC(kp)[qr] : 0.;
+    double qcarry2 = qr2 >= 0 ? QC(kp)[qr2] : 0.;
+    double rcarry = (rr >= 0 && ro <= kp) ? RC(kp)[ro] : 0.;
     double ucarry = uth ? u[kp] : 0.;
     for (int i0 = kp; i0 < k - 1; i0 += WS_CH) {
         double b[WS_CH];
         if (rr >= 0) {
 #pragma unroll
-            for (int q = 0; q < WS_CH; ++q) { const int i = i0 + q; b[q] = (i < k - 1 && ro <= i + 1) ? ricol_w(P, cx, i + 1)[ro] : 0.; }
+            for (int q = 0; q < WS_CH; ++q) { const int i = i0 + q; b[q] = (i < k - 1 && ro <= i + 1) ? RC(i + 1)[ro] : 0.; }
         }
         __syncthreads();                                                    // every old entry of the chunk has been read
         if (i0 == kp && tsrc < k) { row[tsrc - 1] = rw; side[tsrc - 1] = sd; SMV(lam)[tsrc - 1] = lm; }
@@ -541,7 +587,7 @@ __device__ inline int thin_remove(const DevProblem &P, const Ctx &cx, int &k, in
                     const double o = cs * rcarry + sn * b[q];
                     rcarry = -sn * rcarry + cs * b[q];
                     if (rr <= i) {
-                        ricol_w(P, cx, i)[rr] = o;
+                        RC(i)[rr] = o;
                         if (rr == i && fabs(o) >= big) atomicMin(flag, rr);
                     }
                 }
@@ -550,10 +596,18 @@ __device__ inline int thin_remove(const DevProblem &P, const Ctx &cx, int &k, in
         const int iend = (i0 + WS_CH < k - 1) ? i0 + WS_CH : k - 1;
         if (qr >= 0) {
             for (int i = i0; i < iend; ++i) {
-                const double bq = qcol_w(P, cx, i + 1)[qr];
+                const double bq = QC(i + 1)[qr];
                 const double cs = gc[i], sn = gs[i];
-                qcol_w(P, cx, i)[qr] = cs * qcarry + sn * bq;
+                QC(i)[qr] = cs * qcarry + sn * bq;
                 qcarry = -sn * qcarry + cs * bq;
+            }
+        }
+        if (qr2 >= 0) {
+            for (int i = i0; i < iend; ++i) {
+                const double bq = QC(i + 1)[qr2];
+                const double cs = gc[i], sn = gs[i];
+                QC(i)[qr2] = cs * qcarry2 + sn * bq;
+                qcarry2 = -sn * qcarry2 + cs * bq;
             }
         }
         if (uth) {
@@ -568,12 +622,19 @@ __device__ inline int thin_remove(const DevProblem &P, const Ctx &cx, int &k, in
     if (uth) SMV(red)[40] = ucarry;                                  // (G u)_last
     k -= 1;
     __syncthreads();
+    prof_mark(52);
     // v = -Q1_new u_new = v_old + q_last (G u)_last
     if (qr >= 0) SMV(v)[qr] += qcarry * SMV(red)[40];
+    if (qr2 >= 0) SMV(v)[qr2] += qcarry2 * SMV(red)[40];
     const int bad = *flag;
     __syncthreads();
     ri_matvec(P, cx, k, u, SMV(ls));
+    prof_mark(53);
     return bad == 0x7fffffff ? -1 : bad;
+}
+
+__device__ inline int thin_remove(const DevProblem &P, const Ctx &cx, int &k, int kp) {
+    return k <= P.ks ? thin_remove_impl<true>(P, cx, k, kp) : thin_remove_impl<false>(P, cx, k, kp);
 }
 
 // remove position kp, then every row whose diagonal of R collapsed (see oracle/qp_core.c thin_ws_remove)
@@ -597,7 +658,7 @@ __device__ inline void ws_remove(const DevProblem &P, const Ctx &cx, int &k, int
 // gp groups split the columns.
 // x[c] = 0 for c < c0 (the eliminated coordinates): those columns of the operator are skipped.
 template <class Fn>
-__device__ inline void price_rows(const DevProblem &P, const Ctx &cx, const double *x, int c0, Fn f) {
+__device__ inline void price_rows(const DevProblem &P, const Ctx &cx, const double *x, int c0, int pid, Fn f) {
     const int n = P.n, m = P.m, mc = P.mc, nx = P.nx, nu = P.nu;
     const int hs = P.ns2 >> 1;
     double *xi = SMV(xi);
@@ -618,14 +679,33 @@ __device__ inline void price_rows(const DevProblem &P, const Ctx &cx, const doub
             for (; c < n; c += G) { const double2 a = __ldg(w2 + (size_t)c * hs); const double xa = x[c]; ax += a.x * xa; ay += a.y * xa; }
             part2[cx.pg * hs + cx.prp] = make_double2((ax + bx) + (ex + dx), (ay + by) + (ey + dy));
         }
-        __syncthreads();
-        const double *part = SMV(part);
-        for (int r = threadIdx.x; r < P.ns2; r += WS_NT) {
-            double s = part[r];
-            for (int q = 1; q < P.gp; ++q) s += part[q * P.ns2 + r];
-            xi[r] = s;
+        if (P.gp == 0) {
+            // more output pairs than threads: a thread owns the pairs tid, tid + WS_NT, ... and all columns
+            double2 *xi2 = reinterpret_cast<double2 *>(xi);
+            for (int pp = threadIdx.x; pp < hs; pp += WS_NT) {
+                const double2 *w2 = reinterpret_cast<const double2 *>(P.WfT) + pp;
+                double ax = 0., ay = 0., bx = 0., by = 0.;
+                int c = c0;
+                for (; c + 1 < n; c += 2) {
+                    const double2 a = __ldg(w2 + (size_t)c * hs), b = __ldg(w2 + (size_t)(c + 1) * hs);
+                    const double xa = x[c], xb = x[c + 1];
+                    ax += a.x * xa; ay += a.y * xa; bx += b.x * xb; by += b.y * xb;
+                }
+                if (c < n) { const double2 a = __ldg(w2 + (size_t)c * hs); const double xa = x[c]; ax += a.x * xa; ay += a.y * xa; }
+                xi2[pp] = make_double2(ax + bx, ay + by);
+            }
         }
         __syncthreads();
+        if (P.gp > 0) {
+            const double *part = SMV(part);
+            for (int r = threadIdx.x; r < P.ns2; r += WS_NT) {
+                double s = part[r];
+                for (int q = 1; q < P.gp; ++q) s += part[q * P.ns2 + r];
+                xi[r] = s;
+            }
+        }
+        __syncthreads();
+        prof_mark(pid);
     }
     const int *rinfo = SMI(rinfo);
     const double *inr = SMV(inr);
@@ -635,18 +715,19 @@ __device__ inline void price_rows(const DevProblem &P, const Ctx &cx, const doub
         if (r < mc) {
             const int t = info >> 16, i = info & 0xffff;
             const bool last = t == P.T - 1;
-            const double *Fr = (last ? SMV(sF1) : SMV(sF)) + i * nx;
-            const double *Gr = (last ? SMV(sG1) : SMV(sG)) + i * nu;
+            const int rs = last ? P.nh1 : P.nh;                   // rows of the stage = stride of the transposed tables
+            const double *Fr = (last ? SMV(sF1) : SMV(sF)) + i;
+            const double *Gr = (last ? SMV(sG1) : SMV(sG)) + i;
             const double *zt = xi + t * nu;
             double s0 = 0., s1 = 0.;
             int c = 0;
-            for (; c + 1 < nu; c += 2) { s0 += Gr[c] * zt[c]; s1 += Gr[c + 1] * zt[c + 1]; }
-            if (c < nu) s0 += Gr[c] * zt[c];
+            for (; c + 1 < nu; c += 2) { s0 += Gr[c * rs] * zt[c]; s1 += Gr[(c + 1) * rs] * zt[c + 1]; }
+            if (c < nu) s0 += Gr[c * rs] * zt[c];
             if (t > 0) {
                 const double *xt = xi + n + (t - 1) * nx;
                 c = 0;
-                for (; c + 1 < nx; c += 2) { s0 += Fr[c] * xt[c]; s1 += Fr[c + 1] * xt[c + 1]; }
-                if (c < nx) s0 += Fr[c] * xt[c];
+                for (; c + 1 < nx; c += 2) { s0 += Fr[c * rs] * xt[c]; s1 += Fr[(c + 1) * rs] * xt[c + 1]; }
+                if (c < nx) s0 += Fr[c * rs] * xt[c];
             }
             s = s0 + s1;
         } else {
@@ -662,10 +743,12 @@ __device__ inline void price_rows(const DevProblem &P, const Ctx &cx, const doub
 
 // once per kernel launch: shared copies of the stage rows, row scalings and the row -> (stage, index) map
 __device__ inline void init_shared_tables(const DevProblem &P, const Ctx &cx) {
-    for (int i = threadIdx.x; i < P.nh * P.nx; i += WS_NT) SMV(sF)[i] = P.F[i];
-    for (int i = threadIdx.x; i < P.nh * P.nu; i += WS_NT) SMV(sG)[i] = P.G[i];
-    for (int i = threadIdx.x; i < P.nh1 * P.nx; i += WS_NT) SMV(sF1)[i] = P.F1[i];
-    for (int i = threadIdx.x; i < P.nh1 * P.nu; i += WS_NT) SMV(sG1)[i] = P.G1[i];
+    // stage rows TRANSPOSED (entry (row i, column c) at c * rows + i): adjacent threads price adjacent rows, so
+    // their reads of one column are consecutive words (no bank conflicts)
+    for (int e = threadIdx.x; e < P.nh * P.nx; e += WS_NT) { const int i = e / P.nx, c = e - i * P.nx; SMV(sF)[c * P.nh + i] = P.F[e]; }
+    for (int e = threadIdx.x; e < P.nh * P.nu; e += WS_NT) { const int i = e / P.nu, c = e - i * P.nu; SMV(sG)[c * P.nh + i] = P.G[e]; }
+    for (int e = threadIdx.x; e < P.nh1 * P.nx; e += WS_NT) { const int i = e / P.nx, c = e - i * P.nx; SMV(sF1)[c * P.nh1 + i] = P.F1[e]; }
+    for (int e = threadIdx.x; e < P.nh1 * P.nu; e += WS_NT) { const int i = e / P.nu, c = e - i * P.nu; SMV(sG1)[c * P.nh1 + i] = P.G1[e]; }
     for (int r = threadIdx.x; r < P.m; r += WS_NT) {
         SMV(inr)[r] = P.inr[r]; SMV(vsc)[r] = P.vscale[r];
         int info;
@@ -753,7 +836,7 @@ __device__ inline void rebuild_factor(const DevProblem &P, const Ctx &cx, int &k
     for (int i = 0; i < k0; ++i) {
         const int r = row0[i] >> 1, s = (row0[i] & 1) ? 1 : -1;
         if (r >= P.mc && r - P.mc < d) continue;          // eliminated in this node
-        if (thin_append(P, cx, k, r, s, false)) {
+        if (thin_append(P, cx, k, r, s, false) > 0) {
             if (threadIdx.x == 0) { lam[k - 1] = lam0[i]; inW[r] = (signed char)s; }
         }
     }
@@ -843,13 +926,17 @@ __device__ inline int qp_solve(const DevProblem &P, const Ctx &cx, int &k,
         SMV(vf0)[c] = s0 + s1;
     }
     __syncthreads();
+    prof_mark(2);
 
 restart:
     rebuild_factor(P, cx, k);
+    prof_mark(3);
     kmax = max(kmax, k);
+    const int k_start = k; int n_prox = 0;
     int pending = -1, pside = 0, just_added = -1;
     double plam = 0.;
     for (int pk = 0; pk < P.max_prox; ++pk) {
+        ++n_prox;
         // wv = Kx x0 - eps Rinv' yc     ((Rinv' yc)_c = sum_r Rinv[r][c] yc[r], coalesced over c)
         grouped_matvec(P.Rinv, n, n, 0, n, SMV(yc), SMV(part), [&](int c, double a) {
             double s = 0.;
@@ -858,8 +945,9 @@ restart:
             if (c < d) { SMV(vf)[c] = SMV(vf0)[c] + w; SMV(wv)[c] = -SMV(vf0)[c]; }      // wv - [v_f; 0]: the bounds below come out shifted
             else SMV(wv)[c] = w;
         });
+        prof_mark(4);
         // bounds of this proximal sub-problem: g = Mh wv
-        price_rows(P, cx, SMV(wv), 0, [&](int r, double g) {
+        price_rows(P, cx, SMV(wv), 0, 60, [&](int r, double g) {
             if (r < mc) {
                 double e = 0.;
                 for (int j = 0; j < nx; ++j) e += P.Eh[(size_t)r * nx + j] * x0[j];
@@ -872,15 +960,18 @@ restart:
             }
         });
         __syncthreads();
+        prof_mark(5);
         refresh_uv(P, cx, k);
+        prof_mark(6);
 
         status = WS_ITER_LIMIT;
         while (it < cap) {
             ++it;
             if (pending < 0) {
                 // ratio test on the way to lam* = ls ; sum of the positive multipliers
+                // every warp runs the whole test (k / 32 entries per lane): no barrier, same bits in every thread
                 double amin = INFINITY, lpart = 0.; int kmin = -1;
-                for (int i = threadIdx.x; i < k; i += WS_NT) {
+                for (int i = threadIdx.x & 31; i < k; i += 32) {
                     const double l = ls[i];
                     if (l < -P.tol_d) {
                         const double a = lam[i] / (lam[i] - l);
@@ -888,7 +979,9 @@ restart:
                     }
                     lpart += l > 0. ? l : 0.;
                 }
-                block_argmin_sum(amin, kmin, lpart, red, ired);
+                warp_argmin_sum(amin, kmin, lpart);
+                __syncthreads();                                  // every warp has read lam, ls before they change
+                prof_mark(7);
                 if (hot && !(lpart < WS_LAM_MAX)) break;          // degenerate hot start: restart cold
                 if (kmin >= 0) {
                     for (int i = threadIdx.x; i < k; i += WS_NT) lam[i] += amin * (ls[i] - lam[i]);
@@ -899,13 +992,14 @@ restart:
                         if (amin <= 1e-9 && nadd[rr] < 255) ++nadd[rr];
                     }
                     just_added = -1;
+                    prof_mark(8);
                     ws_remove(P, cx, k, kmin);
                     continue;
                 }
                 for (int i = threadIdx.x; i < k; i += WS_NT) lam[i] = ls[i] > 0. ? ls[i] : 0.;
                 const double vnoise = 1e-14 * lpart, vcap = 100. * P.tol_p;
                 double vbest = 0.; int ibest = -1;                 // ibest = 2 r + (lower side)
-                price_rows(P, cx, SMV(v), d, [&](int r, double sv) {
+                price_rows(P, cx, SMV(v), d, 62, [&](int r, double sv) {
                     if (inW[r]) return;
                     const int na = nadd[r];
                     double tolr = P.tol_p * (na == 0 ? 1. : (na == 1 ? 10. : 100.));
@@ -922,10 +1016,14 @@ restart:
                         if (vl > tolr && (vl > vbest || (vl == vbest && 2 * r + 1 < ibest))) { vbest = vl; ibest = 2 * r + 1; }
                     }
                 });
+                prof_mark(10);
                 block_argmax(vbest, ibest, red, ired);
+                prof_mark(11);
                 if (ibest < 0) { status = WS_OPTIMAL; break; }
                 const int jb = ibest >> 1, sb = (ibest & 1) ? -1 : 1;
-                if (thin_append(P, cx, k, jb, sb, true)) {
+                const int ar = thin_append(P, cx, k, jb, sb, true);
+                if (ar < 0) break;                                  // capacity: reported as iteration limit
+                if (ar) {
                     kmax = max(kmax, k);
                     if (threadIdx.x == 0) inW[jb] = (signed char)sb;
                     just_added = jb;
@@ -942,6 +1040,7 @@ restart:
                     if (a < amin || (a == amin && i < kmin)) { amin = a; kmin = i; }
                 }
                 block_argmin(amin, kmin, red, ired);
+                prof_mark(13);
                 if (kmin < 0) {
                     double cpart = 0., wpart = 0.;
                     for (int i = threadIdx.x; i < k; i += WS_NT) {
@@ -979,7 +1078,7 @@ restart:
                 __syncthreads();
                 if (threadIdx.x == 0 && amin <= 1e-9 * (1. + plam) && nadd[row[kmin]] < 255) ++nadd[row[kmin]];
                 ws_remove(P, cx, k, kmin);
-                if (thin_append(P, cx, k, pending, pside, true)) {
+                if (thin_append(P, cx, k, pending, pside, true) > 0) {
                     if (threadIdx.x == 0) { lam[k - 1] = plam; inW[pending] = (signed char)pside; }
                     pending = -1;
                     __syncthreads();
@@ -997,6 +1096,7 @@ restart:
             SMV(c2)[r] = s;
         });
         dz = block_max(dz, red);
+        prof_mark(15);
         for (int r = threadIdx.x; r < n; r += WS_NT) SMV(yc)[r] = SMV(c2)[r];
         __syncthreads();
         if (P.eps * dz <= P.prox_tol) break;
@@ -1013,12 +1113,17 @@ restart:
         __syncthreads();
         for (int i = threadIdx.x; i < k; i += WS_NT) {
             const int r = row[i];
+#ifdef WS_KEEPW
+            y_out[r] = (double)side[i] * fmax(lam[i], 1e-200) * SMV(inr)[r];
+#else
             y_out[r] = (double)side[i] * lam[i] * SMV(inr)[r];
+#endif
             SMV(cw)[i] = (double)side[i] * lam[i];
         }
         __syncthreads();
         pinned_multipliers(P, cx, k, d, SMV(cw), -1, 0., true, y_out);
     }
-    if (threadIdx.x == 0) { *iters_out = it; if (kmax_out) *kmax_out = kmax; }
+    prof_mark(16);
+    if (threadIdx.x == 0) { *iters_out = it; if (kmax_out) { kmax_out[0] = kmax; kmax_out[1] = k_start | (n_prox << 16); } }
     return status;
 }

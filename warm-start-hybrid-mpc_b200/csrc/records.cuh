@@ -26,14 +26,37 @@ __device__ inline void build_records(const DevProblem &P, int status, const doub
         for (int i = threadIdx.x; i < nb; i += WS_NT) if (lb[i] == ub[i]) U[P.bin_idx[i]] = lb[i];
         for (int j = threadIdx.x; j < nx; j += WS_NT) X[j] = x0[j];
         __syncthreads();
-        for (int t = 0; t < T; ++t) {
-            for (int j = threadIdx.x; j < nx; j += WS_NT) {
+        if (nx <= 32) {
+            // x_{t+1} = A x_t + B u_t: the input terms of all stages in parallel, then ONE warp runs the recursion with
+            // the state in registers (lane j holds x_t[j]) -- no barrier per stage
+            for (int e = threadIdx.x; e < T * nx; e += WS_NT) {
+                const int t = e / nx, j = e - t * nx;
                 double s = 0.;
-                for (int c = 0; c < nx; ++c) s += P.A[j * nx + c] * X[(size_t)t * nx + c];
                 for (int c = 0; c < nu; ++c) s += P.B[j * nu + c] * U[(size_t)t * nu + c];
                 X[(size_t)(t + 1) * nx + j] = s;
             }
             __syncthreads();
+            if (threadIdx.x < 32) {
+                const int j = threadIdx.x < nx ? threadIdx.x : 0;
+                double xj = X[j];
+                for (int t = 0; t < T; ++t) {
+                    double s = X[(size_t)(t + 1) * nx + j];
+                    for (int c = 0; c < nx; ++c) s += P.A[j * nx + c] * __shfl_sync(0xffffffffu, xj, c);
+                    if (threadIdx.x < nx) X[(size_t)(t + 1) * nx + j] = s;
+                    xj = s;
+                }
+            }
+            __syncthreads();
+        } else {
+            for (int t = 0; t < T; ++t) {
+                for (int j = threadIdx.x; j < nx; j += WS_NT) {
+                    double s = 0.;
+                    for (int c = 0; c < nx; ++c) s += P.A[j * nx + c] * X[(size_t)t * nx + c];
+                    for (int c = 0; c < nu; ++c) s += P.B[j * nu + c] * U[(size_t)t * nu + c];
+                    X[(size_t)(t + 1) * nx + j] = s;
+                }
+                __syncthreads();
+            }
         }
         // rho_t = 2 Q x_t, rho_T = 2 Q_T x_T, sigma_t = 2 R u_t ; cost = 1/4 (|rho|^2 + |sigma|^2)
         double part = 0.;
@@ -74,18 +97,48 @@ __device__ inline void build_records(const DevProblem &P, int status, const doub
         lam[(size_t)T * nx + j] = -s;
     }
     __syncthreads();
-    for (int t = T - 1; t >= 0; --t) {
-        const double *Ft = t < T - 1 ? P.F : P.F1;
-        const int k = t < T - 1 ? P.nh : P.nh1;
-        const double *mut = mu + (size_t)t * P.nh;
-        for (int j = threadIdx.x; j < nx; j += WS_NT) {
-            double s = 0.;
-            for (int c = 0; c < nx; ++c) s += P.A[c * nx + j] * lam[(size_t)(t + 1) * nx + c];
-            for (int i = 0; i < P.nq; ++i) s -= P.Q[i * nx + j] * rho[(size_t)t * P.nq + i];
-            for (int i = 0; i < k; ++i) s -= Ft[i * nx + j] * mut[i];
-            lam[(size_t)t * nx + j] = s;
+    if (nx <= 32) {
+        // lam_t = A' lam_{t+1} - g_t,  g_t = Q' rho_t + F_t' mu_t: one warp per stage forms g_t (lanes split the rows,
+        // one shuffle reduction per state), then ONE warp runs the backward recursion in registers
+        const int lane = threadIdx.x & 31;
+        for (int t = threadIdx.x >> 5; t < T; t += WS_NW) {
+            const double *Ft = t < T - 1 ? P.F : P.F1;
+            const int k = t < T - 1 ? P.nh : P.nh1;
+            const double *mut = mu + (size_t)t * P.nh;
+            for (int j = 0; j < nx; ++j) {
+                double s = 0.;
+                for (int i = lane; i < k; i += 32) s += Ft[i * nx + j] * mut[i];
+                for (int i = lane; i < P.nq; i += 32) s += P.Q[i * nx + j] * rho[(size_t)t * P.nq + i];
+                s = warp_sum(s);
+                if (lane == 0) lam[(size_t)t * nx + j] = -s;
+            }
         }
         __syncthreads();
+        if (threadIdx.x < 32) {
+            const int j = threadIdx.x < nx ? threadIdx.x : 0;
+            double lj = lam[(size_t)T * nx + j];
+            for (int t = T - 1; t >= 0; --t) {
+                double s = lam[(size_t)t * nx + j];
+                for (int c = 0; c < nx; ++c) s += P.A[c * nx + j] * __shfl_sync(0xffffffffu, lj, c);
+                if (threadIdx.x < nx) lam[(size_t)t * nx + j] = s;
+                lj = s;
+            }
+        }
+        __syncthreads();
+    } else {
+        for (int t = T - 1; t >= 0; --t) {
+            const double *Ft = t < T - 1 ? P.F : P.F1;
+            const int k = t < T - 1 ? P.nh : P.nh1;
+            const double *mut = mu + (size_t)t * P.nh;
+            for (int j = threadIdx.x; j < nx; j += WS_NT) {
+                double s = 0.;
+                for (int c = 0; c < nx; ++c) s += P.A[c * nx + j] * lam[(size_t)(t + 1) * nx + c];
+                for (int i = 0; i < P.nq; ++i) s -= P.Q[i * nx + j] * rho[(size_t)t * P.nq + i];
+                for (int i = 0; i < k; ++i) s -= Ft[i * nx + j] * mut[i];
+                lam[(size_t)t * nx + j] = s;
+            }
+            __syncthreads();
+        }
     }
     double dobj = cost;
     if (!opt) {

@@ -30,11 +30,20 @@ struct wshmpc_handle {
 };
 
 extern "C" const char *wshmpc_last_error(void) { return g_err.c_str(); }
+extern "C" int wshmpc_ctas_per_sm(void) { return WS_MINB; }
+#ifdef WS_PROF
+// experiment builds only: [2 id] cycles, [2 id + 1] visits of phase id (see prof_mark)
+extern "C" int wshmpc_prof_read(unsigned long long *out, int reset) {
+    if (out) cudaMemcpyFromSymbol(out, g_prof, sizeof(g_prof));
+    if (reset) { static unsigned long long z[256]; cudaMemcpyToSymbol(g_prof, z, sizeof(z)); }
+    return 0;
+}
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // K1: one CTA per solver slot; the CTA solves, in index order, every node assigned to its slot
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(WS_NT, 1)
+__global__ void __launch_bounds__(WS_NT, WS_MINB)
 solve_nodes_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, int n_nodes,
                    const double *__restrict__ x0, const double *__restrict__ lb, const double *__restrict__ ub,
                    const int *__restrict__ slot_of, const int *__restrict__ hot,
@@ -120,6 +129,18 @@ extern "C" int wshmpc_create(const wshmpc_problem *p, int device, int n_slots, v
     UP(Mh, p->Mh, (size_t)m * n) UP(nrm, p->nrm, m) UP(vscale, p->vscale, m) UP(Eh, p->Eh, (size_t)p->mc * nx)
     UP(hh, p->hh, p->mc) UP(Rinv, p->Rinv, (size_t)n * n) UP(Kx, p->Kx, (size_t)n * nx)
     UP(bin_idx, p->bin_idx, p->nb)
+    {
+        // Msq[r][d] = |mh_r[d:]|^2 for d <= nb: the length of a row once the first d coordinates are eliminated
+        const int nb1 = p->nb + 1;
+        std::vector<double> sq((size_t)m * nb1);
+        for (int r = 0; r < m; ++r) {
+            double s = 0.;
+            for (int c = n - 1; c >= p->nb; --c) s += p->Mh[(size_t)r * n + c] * p->Mh[(size_t)r * n + c];
+            sq[(size_t)r * nb1 + p->nb] = s;
+            for (int c = p->nb - 1; c >= 0; --c) { s += p->Mh[(size_t)r * n + c] * p->Mh[(size_t)r * n + c]; sq[(size_t)r * nb1 + c] = s; }
+        }
+        UP(Msq, sq.data(), sq.size())
+    }
     P.n_elim = p->n_elim;
     if (p->n_elim < 0 || p->n_elim > p->nb || (p->n_elim > 0 && !p->Linv)) { wshmpc_destroy(h); WS_FAIL(-1, "n_elim = %d out of range or Linv missing", p->n_elim); }
     {
@@ -155,9 +176,13 @@ extern "C" int wshmpc_create(const wshmpc_problem *p, int device, int n_slots, v
     // shared memory budget: one CTA per SM; the first ks columns of Q1 and of Ri live in shared memory
     cudaDeviceProp prop;
     WS_CUDA(cudaGetDeviceProperties(&prop, device));
-    const size_t optin = prop.sharedMemPerBlockOptin;
-    if (n > WS_NT) { wshmpc_destroy(h); WS_FAIL(-4, "problem too large: n = %d condensed inputs, at most %d supported", n, WS_NT); }
-    if (p->ns > 2 * WS_NT) { wshmpc_destroy(h); WS_FAIL(-4, "problem too large: ns = %d, at most %d supported", p->ns, 2 * WS_NT); }
+    size_t optin = prop.sharedMemPerBlockOptin;
+    if (WS_MINB > 1) {
+        // WS_MINB CTAs per SM: each gets an equal share of the SM's shared memory (1 KB per CTA is reserved by the system)
+        const size_t share = prop.sharedMemPerMultiprocessor / WS_MINB - 1024;
+        if (share < optin) optin = share & ~(size_t)15;
+    }
+    if (n > 2 * WS_NT) { wshmpc_destroy(h); WS_FAIL(-4, "problem too large: n = %d condensed inputs, at most %d supported", n, 2 * WS_NT); }
     if (p->T > 32767 || p->nh > 65535 || p->nh1 > 65535) { wshmpc_destroy(h); WS_FAIL(-4, "problem too large for the packed row map"); }
     P.np = (n + 1) & ~1;
     P.ns2 = (p->ns + 1) & ~1;
@@ -169,12 +194,12 @@ extern "C" int wshmpc_create(const wshmpc_problem *p, int device, int n_slots, v
     {
         SmemOff &so = P.so;
         const int nvl = P.np + 2;
-        const int part = (2 * WS_NT > WS_NG * P.kp_ ? 2 * WS_NT : WS_NG * P.kp_);
-        if ((size_t)2 * (p->T + 1) * nx > (size_t)part) { wshmpc_destroy(h); WS_FAIL(-4, "problem too large: (T+1) nx = %d", (p->T + 1) * nx); }
+        int part = 2 * WS_NT > P.np + 2 ? 2 * WS_NT : P.np + 2;
+        if (part < 2 * (p->T + 1) * nx) part = 2 * (p->T + 1) * nx;         // scratch of the record epilogue
         int o = 0;
         auto take = [&](int cnt) { const int at = o; o += (cnt + 1) & ~1; return at; };   // keep 16-byte alignment
         // fixed part first, then Q and Ri take what is left
-        so.z = take(nvl); so.c1 = take(nvl); so.c2 = take(nvl); so.t = take(nvl); so.u = take(nvl); so.ls = take(nvl);
+        so.z = take(nvl); so.z2 = take(nvl); so.c1 = take(nvl); so.c2 = take(nvl); so.t = take(nvl); so.u = take(nvl); so.ls = take(nvl);
         so.lam = take(nvl); so.cw = take(nvl); so.yc = take(nvl); so.wv = take(nvl); so.v = take(nvl); so.gc = take(nvl); so.gs = take(nvl);
         so.vf0 = take(nvl); so.vf = take(nvl);
         so.bu = take(m); so.blb = take(p->nb); so.inr = take(m); so.vsc = take(m); so.xi = take(P.ns2); so.part = take(part);
