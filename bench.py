@@ -42,7 +42,7 @@ def parse_args():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--window', type=int, default=10, help='receding-horizon steps per bench step (one fused launch)')
+    ap.add_argument('--window', type=int, default=20, help='receding-horizon steps per bench step (one fused launch)')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--instances', type=int, default=512, help='independent MPC instances per GPU')
     ap.add_argument('--sigma', type=float, default=0.003, help='model error std (fraction of x_max)')
@@ -153,7 +153,7 @@ def cpu_baseline_sample(args, model, x0, e, seconds):
     solves = sum(r[2] for r in rows)
     return {'value': solves / wall, 'unit': UNIT, 'cores': 1, 'kind': 'port',
             'sample': 'instance 0 of the workload, %d closed-loop steps (1 cold + %d warm), %d QPs in %.1f s; '
-                      'oracle/bnb_ref.py + oracle/qp_core.c variant 1 (dual active-set, thin QR, each node started from the dual solution it carries -- the same algorithm as the CUDA path), Python overhead included'
+                      'oracle/bnb_ref.py + oracle/qp_core.c variant 1 (dual active-set, thin QR, each node started from the dual solution it carries; no pinned-prefix elimination), Python overhead included'
                       % (len(rows), len(rows) - 1, solves, wall),
             'qp_only_value': solves / max(qp_time, 1e-9), 'ms_per_qp': 1e3 * wall / max(solves, 1),
             'host_cores_available': os.cpu_count()}
@@ -221,7 +221,8 @@ def fp64_peak_probe(torch, dev):
 
 def timed_loop(torch, dist, loop, steps, world, body):
     """Times `steps` bench steps bracketed by barrier + synchronize; body(t) launches step t.
-    Returns (elapsed ms max over ranks, QPs of all ranks, iterations of all ranks, QPs of this rank)."""
+    Returns (elapsed ms max over ranks, QPs of all ranks, iterations of all ranks, QPs of this rank); the counter deltas
+    of this rank (wshmpc.h d_totals) are left in timed_loop.last."""
     from warm_start_hmpc_b200.closed_loop import reduce_stats
     if world > 1:
         dist.barrier()
@@ -237,6 +238,7 @@ def timed_loop(torch, dist, loop, steps, world, body):
         dist.barrier()
     ms = s.elapsed_time(e)
     d = (loop.totals - before).cpu().numpy()
+    timed_loop.last = d
     qps, ms_max = reduce_stats(int(d[0]), ms)
     iters, _ = reduce_stats(int(d[1]), ms)
     return ms_max, qps, iters, int(d[0])
@@ -292,6 +294,7 @@ def run_b200(args):
         ev.append((a, b))
     l0 = loop.launches
     ms, qps, iters, my_qps = timed_loop(torch, dist, loop, args.steps, world, dev_step)
+    cnt = timed_loop.last.astype(float)
     launches = loop.launches - l0
     clocks = sampler.stop()
     ker_ms = [a.elapsed_time(b) for a, b in ev]
@@ -323,20 +326,28 @@ def run_b200(args):
     # ---- roofline of the dominant kernel (closed_loop_kernel = K3 with K1 inside + K2/K4)
     pd = ctl.problem
     F_dense = 2. * pd.n ** 2 + 4. * pd.mc * pd.n                     # dense shared-operator form
-    kbar = pd.n / 2.
-    F_exec = 2. * pd.ns * pd.n + 2. * pd.mc * (pd.nx + pd.nu) + 2. * pd.nb + 4. * pd.n * kbar + kbar ** 2   # factored form executed
+    # executed form, with the MEASURED mean sizes of this rank's timed solves: a node with d pinned binaries is solved in
+    # n_eff = n - d coordinates with a working set of k rows (wshmpc.h d_totals[2], [4], [5])
+    my_q = max(cnt[0], 1.)
+    kbar, n_eff, k0bar = cnt[2] / my_q, pd.n - cnt[4] / my_q, cnt[5] / my_q
+    F_iter = 2. * pd.ns * n_eff + 2. * pd.mc * (pd.nx + pd.nu) + 2. * pd.nb + 4. * n_eff * kbar + kbar ** 2   # pricing + one append
+    F_rebuild = k0bar * (4. * n_eff * k0bar / 2. + (k0bar / 2.) ** 2)                                       # k0 appends at growing k
+    it_per_qp = iters / max(qps, 1)
+    F_qp = it_per_qp * F_iter + F_rebuild
+    qp_per_launch = qps / world / max(len(ker_ms), 1)
     it_per_launch = iters / world / max(len(ker_ms), 1)
     ker_avg_ms = float(np.mean(ker_ms))
-    achieved = F_exec * it_per_launch / (ker_avg_ms * 1e-3) / 1e12
+    achieved = F_qp * qp_per_launch / (ker_avg_ms * 1e-3) / 1e12
     peak = fp64_peak_probe(torch, dev)
     roofline = {'bound': 'tensor', 'kernel': 'closed_loop_kernel', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
                 'frac': achieved / peak, 'traffic': None,
                 'peak_source': 'measured in this run: cuBLAS DGEMM 4096^3 best of 5 (fp64 pipe; MEASURED_PEAKS.json has no fp64 entry)',
-                'algorithmic': 'flops per active-set iteration in the FACTORED form the kernel executes: 2 ns n (pricing operator) + '
-                               '2 mc (nx+nu) (sparse stage rows) + 4 n k + k^2 (Gram-Schmidt append, R^-1 column; k = n/2) = %.0f '
-                               '(the dense shared-operator form of SURVEY 8d would be %.0f); %.1f iterations/QP, %.0f QPs/launch; '
-                               'the kernel is latency bound (dependent phases of one small QP per SM), see DESIGN.md'
-                               % (F_exec, F_dense, iters / max(qps, 1), qps / world / max(len(ker_ms), 1)),
+                'algorithmic': 'flops per QP in the form the kernel executes: iterations x [2 ns n_eff (pricing operator) + 2 mc (nx+nu) '
+                               '(stage rows) + 4 n_eff k + k^2 (Gram-Schmidt append, R^-1 column)] + re-factorisation of the k0 inherited '
+                               'rows, with the measured means n_eff = n - d = %.1f, k = %.1f, k0 = %.1f, %.1f iterations/QP: %.0f flop/iteration, '
+                               '%.0f flop/QP (the dense shared-operator form of SURVEY 8d would be %.0f flop/iteration); %.0f QPs/launch; '
+                               'the kernel is latency bound (dependent phases of one small QP per CTA), see DESIGN.md'
+                               % (n_eff, kbar, k0bar, it_per_qp, F_iter, F_qp, F_dense, qp_per_launch),
                 'achieved_dense_form_tflops': F_dense * it_per_launch / (ker_avg_ms * 1e-3) / 1e12,
                 'kernel_ms_avg': ker_avg_ms, 'kernel_share_of_step': float(np.sum(ker_ms) / ms)}
     peaks_file = os.path.join(ROOT, 'MEASURED_PEAKS.json')

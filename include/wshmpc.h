@@ -140,8 +140,10 @@ typedef struct {
  *   d_n_solves  [n_inst]          number of QP relaxations solved
  *   d_status    [n_inst]          0 optimal, 1 infeasible MIQP, 2 capacity reached, 3 QP iteration limit
  *   d_trace     [n_inst][2*max_solves] or NULL : (node index, active-set iterations) of every solve, in order
- *   d_totals    [4] or NULL : running 64-bit counters: += QP relaxations solved, += active-set iterations,
- *                             += working-set size at the end of every solve, max= largest working set seen
+ *   d_totals    [8] or NULL : running 64-bit counters: [0] += QP relaxations solved, [1] += active-set iterations,
+ *                             [2] += working-set size at the end of every solve, [3] max= largest working set seen,
+ *                             [4] += eliminated (pinned-prefix) coordinates of every solve, [5] += rows of the inherited
+ *                             working set re-factorised at the start of every solve, [6..7] reserved
  */
 int wshmpc_bnb_solve(wshmpc_handle *h, int n_inst, const double *d_x0, const int *d_active,
                      const wshmpc_tree *tree, double tol, int max_solves,

@@ -39,7 +39,7 @@ class ClosedLoop(object):
                         primal=torch.zeros((n_inst, h.layout.primal), **f64),
                         n_solves=torch.zeros(n_inst, dtype=torch.int32, device=dev),
                         status=torch.zeros(n_inst, dtype=torch.int32, device=dev))
-        self.totals = torch.zeros(4, dtype=torch.int64, device=dev)     # QP solves, active-set iterations, sum / max of working-set sizes
+        self.totals = torch.zeros(8, dtype=torch.int64, device=dev)     # wshmpc.h d_totals: QP solves, iterations, working-set statistics
         self.fresh = True
         self.launches = 0
         self.events = None          # list -> (start, after K3, after K2+K4) CUDA events of every step

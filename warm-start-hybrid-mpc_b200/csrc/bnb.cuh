@@ -55,7 +55,7 @@ __device__ inline int bnb_instance(const DevProblem &P, const Ctx &cx, const Slo
     int nn = tr.n_nodes[inst], nr = tr.n_recs[inst];
     double ub = INFINITY;
     int inc = -1, solves = 0, st = -1, k = 0;
-    long long iters = 0, ksum = 0;
+    long long iters = 0, ksum = 0, dsum = 0, k0sum = 0;
     int kmx = 0;
 
     while (st < 0) {
@@ -117,7 +117,7 @@ __device__ inline int bnb_instance(const DevProblem &P, const Ctx &cx, const Slo
 #endif
         }
         const int myrec = nr;
-        iters += *iters_s; ksum += k; kmx = max(kmx, iters_s[1]);
+        iters += *iters_s; ksum += k; kmx = max(kmx, iters_s[1]); dsum += min(d, P.n_elim); k0sum += iters_s[2] & 0xffff;
         ++nr; ++solves;
         // ---- prune / incumbent / branch (branch_and_bound.py:476-489)
         if (cost >= cutoff) {
@@ -151,6 +151,7 @@ __device__ inline int bnb_instance(const DevProblem &P, const Ctx &cx, const Slo
         if (totals) {
             atomicAdd(totals, (unsigned long long)solves); atomicAdd(totals + 1, (unsigned long long)iters);
             atomicAdd(totals + 2, (unsigned long long)ksum); atomicMax(totals + 3, (unsigned long long)kmx);
+            atomicAdd(totals + 4, (unsigned long long)dsum); atomicAdd(totals + 5, (unsigned long long)k0sum);
         }
     }
     __syncthreads();

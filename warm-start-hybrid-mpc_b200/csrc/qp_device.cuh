@@ -359,9 +359,11 @@ __device__ inline void qt_dots(const DevProblem &P, const Ctx &cx, int k, const 
     __syncthreads();
 }
 
-// zout = zin - sum_{j < k} q_j c[j]  (zin == nullptr: zero; zout may alias zin); returns this thread's share of
-// |zout|^2.  Ends with a barrier.
-__device__ inline double q_apply(const DevProblem &P, const Ctx &cx, int k, const double *c, const double *zin, double *zout) {
+// zout = zin - sum_{j < k} q_j c[j]  (zin == nullptr: zero; zout may alias zin).  Returns |zout|^2 and the block-wide
+// sum of `extra` (a second quantity the caller wants reduced: it rides on the barrier this phase needs anyway) in
+// every thread.  Ends with a barrier.
+__device__ inline double q_apply(const DevProblem &P, const Ctx &cx, int k, const double *c, const double *zin, double *zout,
+                                 double extra = 0., double *extra_sum = nullptr) {
     double2 *part2 = reinterpret_cast<double2 *>(SMV(part));
     const int h = P.np >> 1;
     if (cx.bg < P.gb) {
@@ -389,7 +391,18 @@ __device__ inline double q_apply(const DevProblem &P, const Ctx &cx, int k, cons
         const double zi = (zin ? zin[i] : 0.) - s;
         zout[i] = zi; zz += zi * zi;
     }
-    __syncthreads();
+    {
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        double *red = SMV(red) + 72;                     // [w]: |z|^2 partials, [16 + w]: partials of `extra`
+        zz = warp_sum(zz); extra = warp_sum(extra);
+        if (lane == 0) { red[w] = zz; red[16 + w] = extra; }
+        __syncthreads();
+        double sv = (lane & 15) < WS_NW ? red[lane] : 0.;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) sv += __shfl_xor_sync(WS_FULL, sv, o);
+        zz = __shfl_sync(WS_FULL, sv, 0);
+        if (extra_sum) *extra_sum = __shfl_sync(WS_FULL, sv, 16);
+    }
     return zz;
 }
 
@@ -453,31 +466,41 @@ __device__ inline void refresh_uv(const DevProblem &P, const Ctx &cx, int k) {
 // numerically in the span of the working rows; either way t = R^-1 Q1' mj  (mj = Mw' t if dependent).
 // Returns -1 (nothing done) if the working set is at the capacity of the removal sweep (WS_NT positions).
 // `track`: also bring u, ls, v up to date (false while the factor of an inherited working set is rebuilt).
-__device__ inline int thin_append(const DevProblem &P, const Ctx &cx, int &k, int r, int sgn, bool track) {
+// `pre`: entries tid and tid + WS_NT of the row, already loaded by the caller (rebuild: the load of the next row
+// overlaps the append of the current one).
+__device__ __forceinline__ double2 load_row_entries(const DevProblem &P, int r, int d) {
+    const int i0 = threadIdx.x, i1 = threadIdx.x + WS_NT;
+    double2 e;
+    e.x = (i0 < P.n && i0 >= d) ? __ldg(P.Mh + (size_t)r * P.n + i0) : 0.;
+    e.y = (i1 < P.n && i1 >= d) ? __ldg(P.Mh + (size_t)r * P.n + i1) : 0.;
+    return e;
+}
+
+__device__ inline int thin_append(const DevProblem &P, const Ctx &cx, int &k, int r, int sgn, bool track, const double2 *pre = nullptr) {
     const int n = P.n, d = SMI(idep)[0];
     if (k >= WS_NT) return -1;
     double *z = SMV(z), *c1 = SMV(c1), *t = SMV(t);
     const int pb = track ? 30 : 40;
-    for (int i = threadIdx.x; i < P.np; i += WS_NT) z[i] = (i < n && i >= d) ? (double)sgn * __ldg(P.Mh + (size_t)r * n + i) : 0.;
+    {
+        const double2 e = pre ? *pre : load_row_entries(P, r, d);
+        if (threadIdx.x < P.np) z[threadIdx.x] = (double)sgn * e.x;
+        if (threadIdx.x + WS_NT < P.np) z[threadIdx.x + WS_NT] = (double)sgn * e.y;
+    }
     __syncthreads();
     prof_mark(pb);
     qt_dots(P, cx, k, z, c1);
     prof_mark(pb + 1);
-    double zz = q_apply(P, cx, k, c1, z, z);
-    prof_mark(pb + 2);
     double cu = 0.;
     if (track) for (int j = threadIdx.x; j < k; j += WS_NT) cu += c1[j] * SMV(u)[j];
-    block_sum2(zz, cu, SMV(red));
-    prof_mark(pb + 3);
-    double rho2 = zz;
+    double rho2 = q_apply(P, cx, k, c1, z, z, cu, &cu);
+    prof_mark(pb + 2);
     if (k > 0 && rho2 < WS_REORTH * __ldg(P.Msq + (size_t)r * (P.nb + 1) + d)) {
         double *c2 = SMV(c2);
         qt_dots(P, cx, k, z, c2);
-        zz = q_apply(P, cx, k, c2, z, z);
         double cu2 = 0.;
         for (int j = threadIdx.x; j < k; j += WS_NT) { const double dc = c2[j]; c1[j] += dc; if (track) cu2 += dc * SMV(u)[j]; }
-        block_sum2(zz, cu2, SMV(red));
-        rho2 = zz; cu += cu2;
+        rho2 = q_apply(P, cx, k, c2, z, z, cu2, &cu2);
+        cu += cu2;
         prof_mark(pb + 4);
     }
     ri_matvec(P, cx, k, c1, t);
@@ -669,6 +692,18 @@ __device__ inline void price_rows(const DevProblem &P, const Ctx &cx, const doub
             double ax = 0., ay = 0., bx = 0., by = 0., ex = 0., ey = 0., dx = 0., dy = 0.;
             int c = c0 + cx.pg;
             const int G = P.gp;
+            // 8 independent 16-byte loads in flight per thread: the operator comes from L2 (~700 cycles a round trip)
+            for (; c + 7 * G < n; c += 8 * G) {
+                double2 w[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) w[q] = __ldg(w2 + (size_t)(c + q * G) * hs);
+#pragma unroll
+                for (int q = 0; q < 8; q += 4) {
+                    const double xa = x[c + q * G], xb = x[c + (q + 1) * G], xe = x[c + (q + 2) * G], xd = x[c + (q + 3) * G];
+                    ax += w[q].x * xa; ay += w[q].y * xa; bx += w[q + 1].x * xb; by += w[q + 1].y * xb;
+                    ex += w[q + 2].x * xe; ey += w[q + 2].y * xe; dx += w[q + 3].x * xd; dy += w[q + 3].y * xd;
+                }
+            }
             for (; c + 3 * G < n; c += 4 * G) {
                 const double2 a = __ldg(w2 + (size_t)c * hs), b = __ldg(w2 + (size_t)(c + G) * hs),
                               e = __ldg(w2 + (size_t)(c + 2 * G) * hs), d = __ldg(w2 + (size_t)(c + 3 * G) * hs);
@@ -833,10 +868,13 @@ __device__ inline void rebuild_factor(const DevProblem &P, const Ctx &cx, int &k
     for (int i = threadIdx.x; i < k0; i += WS_NT) { row0[i] = row[i] * 2 + (side[i] > 0 ? 1 : 0); lam0[i] = lam[i]; }
     __syncthreads();
     k = 0;
+    double2 pre = k0 > 0 ? load_row_entries(P, row0[0] >> 1, d) : make_double2(0., 0.);
     for (int i = 0; i < k0; ++i) {
         const int r = row0[i] >> 1, s = (row0[i] & 1) ? 1 : -1;
+        const double2 cur = pre;
+        if (i + 1 < k0) pre = load_row_entries(P, row0[i + 1] >> 1, d);      // in flight during this append
         if (r >= P.mc && r - P.mc < d) continue;          // eliminated in this node
-        if (thin_append(P, cx, k, r, s, false) > 0) {
+        if (thin_append(P, cx, k, r, s, false, &cur) > 0) {
             if (threadIdx.x == 0) { lam[k - 1] = lam0[i]; inW[r] = (signed char)s; }
         }
     }

@@ -203,7 +203,7 @@ extern "C" int wshmpc_create(const wshmpc_problem *p, int device, int n_slots, v
         so.lam = take(nvl); so.cw = take(nvl); so.yc = take(nvl); so.wv = take(nvl); so.v = take(nvl); so.gc = take(nvl); so.gs = take(nvl);
         so.vf0 = take(nvl); so.vf = take(nvl);
         so.bu = take(m); so.blb = take(p->nb); so.inr = take(m); so.vsc = take(m); so.xi = take(P.ns2); so.part = take(part);
-        so.red = take(72);
+        so.red = take(112);
         so.sF = take(p->nh * nx); so.sG = take(p->nh * nu); so.sF1 = take(p->nh1 * nx); so.sG1 = take(p->nh1 * nu);
         so.ints = o;
         int io = 0;
