@@ -223,3 +223,24 @@ def test_fused_closed_loop_equals_lock_step(cp20, warm):
     o1 = A.step(); l2 = B.run(1)
     torch.cuda.synchronize()
     assert torch.equal(o1['cost'], l2['cost'][0])
+
+
+def test_cp40_device_bnb_matches_oracle_bnb():
+    """BASELINE configs[3] (horizon 40, deep tree): cold device B&B against the CPU restatement of the reference loop
+    on the oracle QP core: same optimal mode sequence, cost and first input within 1e-6, node count within a few
+    nodes (it depends on which optimal multipliers a solver returns at degenerate nodes)."""
+    from oracle.qp_c import CoreC
+    from oracle.bnb_ref import OracleController
+    model = load_model('cp40')
+    ctl = make_controller(model)
+    x0 = model['x0_nominal']
+    sol, leaves, n_qp, _ = ctl.feedforward(x0, printing_period=None)
+    ref = OracleController(model, CoreC(model, variant=1), hot_start='record')
+    inc, _, n_ref = ref.feedforward(x0)
+    cost_ref = float(inc.lb)
+    assert abs(sol.objective - cost_ref) <= RTOL * abs(cost_ref)
+    nuc = ctl.mld.nu - ctl.mld.nub
+    ub_ref = np.array([u[nuc:] for u in inc.primal['u']])
+    assert np.array_equal(np.array(sol.variables['ub']), np.round(ub_ref))
+    assert np.allclose(sol.variables['uc'][0], inc.primal['u'][0][:nuc], rtol=RTOL, atol=1e-8)
+    assert abs(n_qp - n_ref) <= 6, (n_qp, n_ref)

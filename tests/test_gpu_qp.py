@@ -15,9 +15,9 @@ pytestmark = pytest.mark.gpu
 COST_RTOL = 1e-6
 
 
-def _check_batch(model, N, seed, n_slots):
+def _check_batch(model, N, seed, n_slots, nodes=None):
     ctl = make_controller(model)
-    x0, lb, ub = random_nodes(model, N, seed=seed)
+    x0, lb, ub = random_nodes(model, N, seed=seed) if nodes is None else nodes
     h = ctl.handle(n_slots=n_slots)
     out = h.solve_nodes(x0, lb, ub)
     st = out['status'].cpu().numpy(); cost = out['cost'].cpu().numpy(); dobj = out['dobj'].cpu().numpy()
@@ -74,3 +74,30 @@ def test_cp20_hot_start_equals_cold_cost():
 
 def test_syn30_random_nodes_match_oracle():
     _check_batch(load_model('syn30'), 16, seed=1, n_slots=16)
+
+
+def test_cp40_random_nodes_match_oracle():
+    """BASELINE configs[3]: horizon 40 (n = 280 > threads per CTA, factor columns beyond the shared-memory budget)."""
+    n_inf = _check_batch(load_model('cp40'), 12, seed=2, n_slots=12)
+    assert n_inf > 0
+
+
+def test_pins_outside_the_prefix_match_oracle():
+    """Only the leading run of pinned binaries is eliminated (problem.py rotation); pins behind a gap stay ordinary
+    two-sided rows with lb == ub.  Also the all-pinned leaf (every coordinate of the binaries eliminated)."""
+    model = load_model('cp20')
+    N = 24
+    x0, lb, ub = random_nodes(model, N, seed=5)
+    rng = np.random.default_rng(7)
+    nb = lb.shape[1]
+    for k in range(N - 2):
+        d = int(np.argmax(lb[k] != ub[k])) if np.any(lb[k] != ub[k]) else nb
+        for j in rng.choice(np.arange(min(d + 2, nb - 1), nb), size=3, replace=False):
+            lb[k, j] = ub[k, j] = 0.
+    # two fully pinned identifiers: the optimal mode sequence of the golden run, and all zeros
+    import os
+    from oracle.models import GOLDEN
+    g = np.load(os.path.join(GOLDEN, 'cp20_nodes.npz'))
+    x0[N - 2] = g['x0']; lb[N - 2] = ub[N - 2] = g['opt_ub'].reshape(-1)
+    x0[N - 1] = g['x0']; lb[N - 1] = ub[N - 1] = 0.
+    _check_batch(model, N, seed=0, n_slots=12, nodes=(x0, lb, ub))

@@ -680,8 +680,9 @@ __device__ inline void ws_remove(const DevProblem &P, const Ctx &cx, int &k, int
 // WfT is the operator transposed (n x ns2): a thread owns two adjacent outputs and streams 16-byte words,
 // gp groups split the columns.
 // x[c] = 0 for c < c0 (the eliminated coordinates): those columns of the operator are skipped.
-template <class Fn>
-__device__ inline void price_rows(const DevProblem &P, const Ctx &cx, const double *x, int c0, int pid, Fn f) {
+// skip(r): rows whose value is not wanted (in the working set, eliminated) are dropped BEFORE their products.
+template <class Skip, class Fn>
+__device__ inline void price_rows(const DevProblem &P, const Ctx &cx, const double *x, int c0, int pid, Skip skip, Fn f) {
     const int n = P.n, m = P.m, mc = P.mc, nx = P.nx, nu = P.nu;
     const int hs = P.ns2 >> 1;
     double *xi = SMV(xi);
@@ -745,6 +746,7 @@ __device__ inline void price_rows(const DevProblem &P, const Ctx &cx, const doub
     const int *rinfo = SMI(rinfo);
     const double *inr = SMV(inr);
     for (int r = threadIdx.x; r < m; r += WS_NT) {
+        if (skip(r)) continue;
         double s;
         const int info = rinfo[r];
         if (r < mc) {
@@ -985,7 +987,7 @@ restart:
         });
         prof_mark(4);
         // bounds of this proximal sub-problem: g = Mh wv
-        price_rows(P, cx, SMV(wv), 0, 60, [&](int r, double g) {
+        price_rows(P, cx, SMV(wv), 0, 60, [](int) { return false; }, [&](int r, double g) {
             if (r < mc) {
                 double e = 0.;
                 for (int j = 0; j < nx; ++j) e += P.Eh[(size_t)r * nx + j] * x0[j];
@@ -1037,8 +1039,7 @@ restart:
                 for (int i = threadIdx.x; i < k; i += WS_NT) lam[i] = ls[i] > 0. ? ls[i] : 0.;
                 const double vnoise = 1e-14 * lpart, vcap = 100. * P.tol_p;
                 double vbest = 0.; int ibest = -1;                 // ibest = 2 r + (lower side)
-                price_rows(P, cx, SMV(v), d, 62, [&](int r, double sv) {
-                    if (inW[r]) return;
+                price_rows(P, cx, SMV(v), d, 62, [&](int r) { return inW[r] != 0 || ign[r] == 3; }, [&](int r, double sv) {
                     const int na = nadd[r];
                     double tolr = P.tol_p * (na == 0 ? 1. : (na == 1 ? 10. : 100.));
                     const double vs = vsc[r];
