@@ -30,8 +30,10 @@ torch.cuda.synchronize(); dt = time.time() - t0
 lib.wshmpc_prof_read(buf, 0)
 d = (L.totals - b).cpu().numpy()
 a = np.array(buf[:], dtype=np.float64).reshape(128, 2)
-tot = a[:, 0].sum()
+tot = a[:100, 0].sum()
 print('QPs %d  iters/QP %.1f  %.0f QP/s  cycles/QP (thread-0 timeline) %.0f' % (d[0], d[1] / d[0], d[0] / dt, tot / d[0]))
+print('removals: mean columns rotated %.1f, mean k %.1f' % (a[100, 0] / max(a[100, 1], 1), a[101, 0] / max(a[101, 1], 1)))
+a[100:102] = 0
 for i in np.argsort(-a[:, 0]):
     if a[i, 0] > 0:
         print('%-24s %5.1f%%  visits/QP %6.2f  cycles/visit %8.0f' % (NAMES.get(int(i), str(i)), 100 * a[i, 0] / tot, a[i, 1] / d[0], a[i, 0] / max(a[i, 1], 1)))

@@ -95,8 +95,12 @@ __device__ __forceinline__ void prof_mark(int id) {
         s_prof_last = clock64();
     }
 }
+__device__ __forceinline__ void prof_add(int id, int value) {
+    if (threadIdx.x == 0) { atomicAdd(&g_prof[2 * id], (unsigned long long)value); atomicAdd(&g_prof[2 * id + 1], 1ull); }
+}
 #else
 #define prof_mark(id) ((void)0)
+#define prof_add(id, value) ((void)0)
 #endif
 
 __host__ __device__ __forceinline__ int tri_off(int j) { return j * (j + 1) / 2; }
@@ -543,6 +547,8 @@ __device__ inline int thin_remove_impl(const DevProblem &P, const Ctx &cx, int &
     double *gc = SMV(gc), *gs = SMV(gs), *u = SMV(u);
     int *row = SMI(irow), *side = SMI(iside), *flag = SMI(ired) + 32;
     if (tid == 0) *flag = 0x7fffffff;
+    prof_add(100, k - 1 - kp);
+    prof_add(101, k);
     if (kp == k - 1) {
         // last position: Q1, Ri lose their last column; v += q_last u_last
         const double ul = u[kp];
@@ -585,7 +591,7 @@ __device__ inline int thin_remove_impl(const DevProblem &P, const Ctx &cx, int &
     const int qr2 = tid + WS_NT < P.np ? tid + WS_NT : -1;                  // second row (n <= 2 WS_NT)
     const int rr = (WS_NT - 1 - tid) < k - 1 ? WS_NT - 1 - tid : -1;        // new row of Ri (k - 1 <= WS_NT)
     const int ro = rr < kp ? rr : rr + 1;                                   // its old row
-    const bool uth = tid == (P.np < WS_NT ? P.np : 0);
+    const bool uth = tid == (((P.np + 31) & ~31) < WS_NT ? ((P.np + 31) & ~31) : 0);      // first thread of the first warp without rows of Q1
     const double big = 1. / P.tol_sing;
     __syncthreads();                                                        // gc, gs visible
     prof_mark(51);
@@ -851,6 +857,26 @@ __device__ inline void load_ws_from_multipliers(const DevProblem &P, const Ctx &
     }
     k = base < P.n ? base : P.n;
     __syncthreads();
+#ifndef WS_NO_SORT
+    // Order the start by DECREASING multiplier: the rows the ratio test drops first (small multipliers) sit at the end
+    // of the factor, where a removal rotates few columns (position k - 1 costs nothing); rank by counting, ties by row.
+    {
+        int *scr = SMI(iscr); double *tmp = SMV(cw);
+        for (int i = threadIdx.x; i < k; i += WS_NT) {
+            const double li = lam[i];
+            int rank = 0;
+            for (int j = 0; j < k; ++j) { const double lj = lam[j]; rank += (lj > li || (lj == li && j < i)) ? 1 : 0; }
+            scr[i] = rank | (row[i] << 10) | (side[i] > 0 ? (1 << 30) : 0);     // rank < 1024 (k <= n <= 2 WS_NT), row < 2^20
+            tmp[i] = li;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < k; i += WS_NT) {
+            const int e = scr[i], rank = e & 0x3ff;
+            row[rank] = (e >> 10) & 0xfffff; side[rank] = (e >> 30) & 1 ? 1 : -1; lam[rank] = tmp[i];
+        }
+        __syncthreads();
+    }
+#endif
 }
 
 // Start of a node: rebuild the factor of the inherited working set (rows in their stored order, keeping
