@@ -244,3 +244,33 @@ def test_cp40_device_bnb_matches_oracle_bnb():
     assert np.array_equal(np.array(sol.variables['ub']), np.round(ub_ref))
     assert np.allclose(sol.variables['uc'][0], inc.primal['u'][0][:nuc], rtol=RTOL, atol=1e-8)
     assert abs(n_qp - n_ref) <= 6, (n_qp, n_ref)
+
+
+def test_noisy_closed_loop_warm_equals_cold():
+    """Closed loop WITH model errors (the regime of statistical_analysis.py:93-196, sigma = 0.003): shifted Farkas proofs
+    lapse (controller.py:555-558), leaves are re-solved from their shifted rays, bounds of shifted leaves are only
+    bounds.  Warm-started and cold-started B&B must still find the same optimum at every step of every trajectory
+    (test_controller.py:165-170 on the nominal loop), and warm start must pay off."""
+    from warm_start_hmpc_b200.closed_loop import ClosedLoop
+    model = load_model('cp20')
+    ctl = make_controller(model)
+    N, S = 48, 6
+    x0 = np.load(os.path.join(GOLDEN, 'cp20_instances.npy'))[:N]
+    rng = np.random.default_rng(11)
+    e = torch.as_tensor(0.003 * rng.standard_normal((S, N, 4)) * model['x_max'], device='cuda')
+    W = ClosedLoop(ctl, N, warm=True, max_solves=1024, max_roots=512)
+    Cd = ClosedLoop(ctl, N, warm=False, max_solves=1024, max_roots=512)
+    W.reset(x0); Cd.reset(x0)
+    lw = W.run(S, e=e); lc = Cd.run(S, e=e)
+    torch.cuda.synchronize()
+    cw, cc = lw['cost'].cpu().numpy(), lc['cost'].cpu().numpy()
+    sw, sc = lw['status'].cpu().numpy(), lc['status'].cpu().numpy()
+    assert np.array_equal(sw, sc) and np.all(sw <= 1)
+    fin = np.isfinite(cc)
+    assert np.array_equal(fin, np.isfinite(cw)) and fin.sum() > N * S // 2
+    assert np.all(np.abs(cw[fin] - cc[fin]) <= RTOL * np.abs(cc[fin]))
+    assert np.allclose(torch.nan_to_num(lw['u0']).cpu().numpy()[..., 0], torch.nan_to_num(lc['u0']).cpu().numpy()[..., 0],
+                       rtol=RTOL, atol=1e-8)                                 # the force actually applied
+    assert torch.equal(W.active, Cd.active)
+    nw, nc = lw['n_solves'].cpu().numpy()[1:].sum(), lc['n_solves'].cpu().numpy()[1:].sum()
+    assert nw * 4 < nc

@@ -530,7 +530,9 @@ __device__ inline int thin_append(const DevProblem &P, const Ctx &cx, int &k, in
         if (track) { SMV(u)[k] = uk; SMV(ls)[k] = lk; }
     }
     k += 1;
-    __syncthreads();
+    // while the factor is rebuilt the next append starts with a barrier of its own (after the row is staged) and nothing
+    // in between reads what was written here; rebuild_factor ends with a barrier
+    if (track) __syncthreads();
     prof_mark(pb + 6);
     return 1;
 }
