@@ -131,7 +131,10 @@ def _cpu_worker(job):
     t_begin = time.perf_counter()
     for t in range(n_steps):
         t0 = time.perf_counter()
-        inc, leaves, solves = ctl.feedforward(x, warm_start=ws)
+        try:
+            inc, leaves, solves = ctl.feedforward(x, warm_start=ws)
+        except RuntimeError:                     # the CPU QP core gave up on a node: this trajectory ends here
+            break
         if inc is None:
             rows.append((t0, time.perf_counter(), solves)); break
         u0 = inc.primal['u'][0]

@@ -123,6 +123,10 @@ class OracleController(object):
                             rows.append(c.mc + t * self.nub + i); sides.append(1 if yy > 0 else -1); lam.append(abs(yy))
                 warm = dict(rows=rows, sides=sides, lam=lam, z=node.dual.get('yc'))
             out = self.core.solve(x0, lb.ravel(), ub.ravel(), warm=warm)
+            if out['status'] not in (2, 3) and warm is not None:
+                # a start from a stale, nearly dependent working set can degenerate: once more from the empty working
+                # set (the CUDA solver does the same, qp_device.cuh qp_solve `restart`)
+                out = self.core.solve(x0, lb.ravel(), ub.ravel(), warm=None)
         else:
             out = self.core.solve(x0, lb.ravel(), ub.ravel(), warm=self._warm if self.hot_start else None)
         self.qp_time += time.perf_counter() - tic
