@@ -71,6 +71,11 @@ int wshmpc_create(const wshmpc_problem *p, int device, int n_slots, void *stream
 int wshmpc_destroy(wshmpc_handle *h);
 int wshmpc_get_layout(const wshmpc_handle *h, wshmpc_layout *out);
 
+/* candidate selection of the device-side branch and bound (wshmpc_bnb_solve, wshmpc_closed_loop), the
+ * `candidate_selection` argument of branch_and_bound (branch_and_bound.py:408-416):
+ * 0 best_first (:541-563, default), 1 depth_first (:521-538), 2 breadth_first (:501-518).  Sticky per handle. */
+int wshmpc_set_search_rule(wshmpc_handle *h, int rule);
+
 /* K1 -- batched node QP relaxation.
  * Replaces, per node: controller._solve_subproblem (controller.py:229-271) = _set_bound_binaries
  * (:273-298) + BoundedQP.optimize (bounded_qp.py:200-228) + SubproblemSolution.from_controller

@@ -29,7 +29,10 @@ def _ident_key(identifier):
     return tuple(sorted(identifier.items()))
 
 
-def test_device_bnb_equals_host_bnb(cp20):
+@pytest.mark.parametrize('rule', ['best_first', 'depth_first', 'breadth_first'])
+def test_device_bnb_equals_host_bnb(cp20, rule):
+    import warm_start_hmpc_b200 as ws
+    search_rule = getattr(ws, rule)
     model, ctl = cp20
     x0 = model['x0_nominal']
     ctl.device_search = False
@@ -41,11 +44,15 @@ def test_device_bnb_equals_host_bnb(cp20):
         return orig(identifier, x0_, active_set, hot, extra)
     ctl._solve_subproblem = spy
     try:
-        sol_h, leaves_h, n_h, _ = ctl.feedforward(x0, printing_period=None)
+        sol_h, leaves_h, n_h, _ = ctl.feedforward(x0, search_rule=search_rule, printing_period=None)
     finally:
         ctl._solve_subproblem = orig
         ctl.device_search = True
-    res, tree = ctl.feedforward_batch(x0[None], trace=True, n_slots=1)
+    ctl.handle().set_search_rule({'best_first': 0, 'depth_first': 1, 'breadth_first': 2}[rule])
+    try:
+        res, tree = ctl.feedforward_batch(x0[None], trace=True, n_slots=1)
+    finally:
+        ctl.handle().set_search_rule(0)
     assert int(res['status'][0]) == 0
     n_d = int(res['n_solves'][0])
     assert n_d == n_h
@@ -62,7 +69,7 @@ def test_device_bnb_equals_host_bnb(cp20):
     assert [_ident_key(l.identifier) for l in leaves_d] == [_ident_key(l.identifier) for l in leaves_h]
     assert np.array_equal(np.array([l.lb for l in leaves_d]), np.array([l.lb for l in leaves_h]))
     # drop-in call returns the same thing
-    sol_d, leaves_dd, n_dd, _ = ctl.feedforward(x0, printing_period=None)
+    sol_d, leaves_dd, n_dd, _ = ctl.feedforward(x0, search_rule=search_rule, printing_period=None)
     assert n_dd == n_h and sol_d.objective == sol_h.objective
     for t in range(ctl.T):
         assert np.array_equal(sol_d.variables['ub'][t], sol_h.variables['ub'][t])

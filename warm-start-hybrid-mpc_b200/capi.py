@@ -42,7 +42,7 @@ def load_library():
     return _lib
 
 
-EXPORTS = ('wshmpc_last_error', 'wshmpc_ctas_per_sm', 'wshmpc_create', 'wshmpc_destroy', 'wshmpc_get_layout', 'wshmpc_solve_nodes',
+EXPORTS = ('wshmpc_last_error', 'wshmpc_ctas_per_sm', 'wshmpc_set_search_rule', 'wshmpc_create', 'wshmpc_destroy', 'wshmpc_get_layout', 'wshmpc_solve_nodes',
            'wshmpc_tree_init_root', 'wshmpc_bnb_solve', 'wshmpc_shift_tree', 'wshmpc_closed_loop')
 
 
@@ -121,6 +121,10 @@ class Handle(object):
         _check(self.lib.wshmpc_create(C.byref(p), device, n_slots, sptr, C.byref(self._h)))
         self.layout = Layout()
         _check(self.lib.wshmpc_get_layout(self._h, C.byref(self.layout)))
+
+    def set_search_rule(self, rule):
+        """0 best_first, 1 depth_first, 2 breadth_first (branch_and_bound.py:501-563) for the device-side B&B."""
+        _check(self.lib.wshmpc_set_search_rule(self._h, int(rule)))
 
     def close(self):
         if self._h:

@@ -17,7 +17,7 @@ import gc
 import numpy as np
 from time import time
 
-from .branch_and_bound import Node, branch_and_bound, best_first, depth_first  # noqa: F401
+from .branch_and_bound import Node, branch_and_bound, best_first, depth_first, breadth_first  # noqa: F401
 from .subproblem_solution import SubproblemSolution, PrimalSolution, DualSolution
 from .problem import ProblemData
 
@@ -180,14 +180,15 @@ class HybridModelPredictiveController(object):
     # -- per-solve seam -------------------------------------------------------------------------
     def feedforward(self, x0, gurobi_params={}, search_rule=best_first, branch_rule=branch_in_time, **kwargs):
         """controller.py:329-393.  `gurobi_params` is accepted for signature compatibility and ignored
-        (there is no Gurobi underneath).  With the reference's default rules (best_first, branch_in_time)
-        and `device_search=True` the whole search runs in the device-side B&B kernel (K3); any other
-        rule, or `device_search=False`, runs the reference's host loop with one K1 launch per node --
-        both visit the same nodes in the same order and return bit-identical results."""
-        if self.device_search and search_rule is best_first and branch_rule is branch_in_time:
+        (there is no Gurobi underneath).  With the reference's search rules (best_first, depth_first, breadth_first;
+        branch_and_bound.py:501-563), branch_in_time and `device_search=True` the whole search runs in the device-side
+        B&B kernel (K3); a user-defined rule, or `device_search=False`, runs the reference's host loop with one K1
+        launch per node -- both visit the same nodes in the same order and return bit-identical results."""
+        rules = {best_first: 0, depth_first: 1, breadth_first: 2}
+        if self.device_search and search_rule in rules and branch_rule is branch_in_time:
             ws = kwargs.get('warm_start')
             if ws is None or all(_is_prefix(l.identifier, self.mld.nub) for l in ws):
-                return self._feedforward_device(x0, kwargs.get('tol', 0.), ws)
+                return self._feedforward_device(x0, kwargs.get('tol', 0.), ws, rules[search_rule])
         def solver(identifier, cutoff, extra):
             solution, solve_time = self._solve_subproblem(identifier, x0, None, extra=extra if extra is not None
                                                           else SubproblemSolution(None, None, None))
@@ -411,13 +412,17 @@ class HybridModelPredictiveController(object):
             tree.rec_dobj[0, :len(recs)] = torch.as_tensor(np.array(dobj), device=dev)
         return tree
 
-    def _feedforward_device(self, x0, tol, warm_start):
+    def _feedforward_device(self, x0, tol, warm_start, rule=0):
         import torch
         self._require_gpu()
         tree = None if warm_start is None else self.leaves_to_tree(warm_start)
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         start.record()
-        res, tree = self.feedforward_batch(np.asarray(x0, dtype=float)[None], warm_start=tree, tol=tol, n_slots=1)
+        self.handle().set_search_rule(rule)
+        try:
+            res, tree = self.feedforward_batch(np.asarray(x0, dtype=float)[None], warm_start=tree, tol=tol, n_slots=1)
+        finally:
+            self.handle().set_search_rule(0)
         end.record()
         end.synchronize()
         solver_time = start.elapsed_time(end) * 1e-3

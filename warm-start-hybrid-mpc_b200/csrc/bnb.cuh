@@ -59,13 +59,17 @@ __device__ inline int bnb_instance(const DevProblem &P, const Ctx &cx, const Slo
     int kmx = 0;
 
     while (st < 0) {
-        // ---- select: candidates = alive leaves with lb < ub - tol ; best_first = first minimum
+        // ---- select: candidates = alive leaves with lb < ub - tol, in list (= creation) order ;
+        //      best_first = first minimum of lb (branch_and_bound.py:541-563), depth_first = last candidate (:521-538),
+        //      breadth_first = first candidate (:501-518)
         const double cutoff = ub - tol;
         double best = INFINITY; int bi = -1;
+        const int rule = P.search_rule;
         for (int j = threadIdx.x; j < nn; j += WS_NT)
             if (alive[j]) {
                 const double l = lb[j];
-                if (l < cutoff && (bi < 0 || l < best)) { best = l; bi = j; }
+                const double key = rule == 0 ? l : (rule == 1 ? -(double)j : (double)j);
+                if (l < cutoff && (bi < 0 || key < best)) { best = key; bi = j; }
             }
         block_argmin(best, bi, SMV(red), SMI(ired));
         if (bi < 0) { st = inc >= 0 ? BNB_OK : BNB_INFEASIBLE; break; }

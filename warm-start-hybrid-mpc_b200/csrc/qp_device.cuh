@@ -68,6 +68,7 @@ struct DevProblem {
     const double *Mh, *WfT, *nrm, *inr, *vscale, *Eh, *hh, *Rinv, *RinvT, *Kx, *ZmapT, *Linv, *LinvT, *Msq;
     const int *bin_idx;
     int n_elim;              // leading binaries that may be eliminated when pinned (0 = never)
+    int search_rule;         // candidate selection of the device B&B: 0 best_first, 1 depth_first, 2 breadth_first
     double eps, tol_p, tol_d, tol_sing, tol_ray, prox_tol;
     int max_iter, max_prox;
     int ks;                  // columns of Q1 and of Ri held in shared memory

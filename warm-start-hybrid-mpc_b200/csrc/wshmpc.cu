@@ -251,6 +251,14 @@ extern "C" int wshmpc_destroy(wshmpc_handle *h)
     return 0;
 }
 
+extern "C" int wshmpc_set_search_rule(wshmpc_handle *h, int rule)
+{
+    if (!h) WS_FAIL(-1, "null handle");
+    if (rule < 0 || rule > 2) WS_FAIL(-1, "search rule %d: 0 best_first, 1 depth_first, 2 breadth_first", rule);
+    h->P.search_rule = rule;
+    return 0;
+}
+
 extern "C" int wshmpc_get_layout(const wshmpc_handle *h, wshmpc_layout *out)
 {
     if (!h || !out) WS_FAIL(-1, "null argument");
