@@ -101,3 +101,31 @@ def test_pins_outside_the_prefix_match_oracle():
     x0[N - 2] = g['x0']; lb[N - 2] = ub[N - 2] = g['opt_ub'].reshape(-1)
     x0[N - 1] = g['x0']; lb[N - 1] = ub[N - 1] = 0.
     _check_batch(model, N, seed=0, n_slots=12, nodes=(x0, lb, ub))
+
+
+def test_syn30_dive_nodes_match_golden():
+    """BASELINE configs[4] (nx = 20, 8 binaries/step, N = 30: n = 360, m = 2640): the feasible side of K1 on the
+    synthetic system -- nodes of a dive frozen by oracle/make_syn30_nodes.py (status, cost), plus certificates."""
+    import os
+    from oracle.models import GOLDEN
+    model = load_model('syn30')
+    g = np.load(os.path.join(GOLDEN, 'syn30_nodes.npz'))
+    N = len(g['status'])
+    assert (g['status'] == 2).sum() >= 8
+    ctl = make_controller(model)
+    x0 = np.repeat(g['x0'][None], N, 0)
+    h = ctl.handle(n_slots=N)
+    out = h.solve_nodes(x0, g['lb'], g['ub'])
+    st = out['status'].cpu().numpy(); cost = out['cost'].cpu().numpy()
+    assert np.array_equal(st, g['status'])
+    ok = st == 2
+    assert np.all(np.abs(cost[ok] - g['cost'][ok]) <= COST_RTOL * np.abs(g['cost'][ok]))
+    cond = Condensed(model)
+    P = out['primal'].cpu().numpy(); D = out['dual'].cpu().numpy()
+    for i in np.nonzero(ok)[0][:6]:
+        fam = families_from_records(ctl.problem, h.layout, 2, P[i], D[i])
+        pe, pv = cert.primal_residuals(model, cond, x0[i], g['lb'][i], g['ub'][i], fam)
+        ds, neg = cert.dual_residuals(model, cond, fam)
+        dob = cert.dual_objective(model, cond, x0[i], g['lb'][i], g['ub'][i], fam)
+        assert pe <= 1e-9 and pv <= 2e-4 and ds <= 1e-7 and neg >= 0.
+        assert abs(cost[i] - dob) <= 1e-6 * abs(cost[i])

@@ -204,3 +204,18 @@ def test_persistent_state_and_record_start_reach_the_same_optimum():
         if ref is None:
             ref = cur
         assert abs(cur[0] - ref[0]) <= 1e-9 * abs(ref[0]) and np.array_equal(cur[1], ref[1])
+
+
+def test_syn30_golden_nodes_reproduce():
+    """tests/golden/syn30_nodes.npz (oracle/make_syn30_nodes.py): the frozen statuses and costs are what the oracle
+    computes today (first and last nodes only: the synthetic system is slow on the CPU)."""
+    import os
+    from oracle.models import GOLDEN
+    model = load_model('syn30')
+    g = np.load(os.path.join(GOLDEN, 'syn30_nodes.npz'))
+    core = CoreC(model)
+    for i in (0, len(g['status']) - 2, len(g['status']) - 1):
+        r = core.solve(g['x0'], g['lb'][i], g['ub'][i])
+        assert r['status'] == g['status'][i]
+        if r['status'] == 2:
+            assert abs(r['cost'] - g['cost'][i]) <= 1e-9 * abs(g['cost'][i])
