@@ -411,6 +411,40 @@ def run_b200(args):
             single['reference_published'] = {'cold_ms_per_mpc_step': 530., 'warm_ms_per_mpc_step': 37.4, 'qp_per_s': 300.,
                                              'source': 'BASELINE.md (Gurobi, unknown CPU)'}
             line['single_instance_nominal'] = single
+    if rank == 0 and not args.no_extras:
+        # the other BASELINE configs, as information (they are parity-test cases, not the headline): cold batched B&B
+        # of the horizon-40 cart-pole (configs[3]) and the root relaxation + dive nodes of the synthetic system (configs[4])
+        other = {}
+        try:
+            m40 = load_model('cp40')
+            c40 = controller_from_model(m40, device=local)
+            rng = np.random.default_rng(40)
+            xs = m40['x0_nominal'][None] + rng.uniform(-1, 1, (148, 4)) * np.array([0.02, 0.01, 0.05, 0.05])
+            c40.feedforward_batch(xs[:8], max_solves=2048)
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            res, _ = c40.feedforward_batch(xs, max_solves=2048)
+            torch.cuda.synchronize(); dt = time.perf_counter() - t0
+            ns = res['n_solves'].cpu().numpy(); st = res['status'].cpu().numpy()
+            other['cp40_cold_bnb'] = {'instances': int(len(xs)), 'qp': int(ns.sum()), 'qp_per_s': float(ns.sum() / dt),
+                                      'wall_ms': 1e3 * dt, 'ms_per_qp_of_the_longest_instance': float(1e3 * dt / max(ns.max(), 1)), 'status_counts': {int(k): int((st == k).sum()) for k in np.unique(st)},
+                                      'note': 'horizon 40: n = 280, factor columns beyond the shared-memory budget spill to L2'}
+            del c40
+            g30 = np.load(os.path.join(ROOT, 'tests', 'golden', 'syn30_nodes.npz'))
+            m30 = load_model('syn30')
+            c30 = controller_from_model(m30, device=local)
+            reps = 5
+            N30 = len(g30['status']) * reps
+            x30 = np.repeat(g30['x0'][None], N30, 0); lb30 = np.tile(g30['lb'], (reps, 1)); ub30 = np.tile(g30['ub'], (reps, 1))
+            h30 = c30.handle(n_slots=min(N30, c30.default_slots()))
+            h30.solve_nodes(x30[:8], lb30[:8], ub30[:8]); torch.cuda.synchronize(); t0 = time.perf_counter()
+            out = h30.solve_nodes(x30, lb30, ub30)
+            torch.cuda.synchronize(); dt = time.perf_counter() - t0
+            other['syn30_k1_dive_nodes'] = {'nodes': int(N30), 'qp_per_s': float(N30 / dt), 'iterations_mean': float(out['iters'].float().mean()),
+                                            'note': 'nx = 20, 8 binaries/step, N = 30: n = 360, m = 2640; cold solves of the golden dive nodes'}
+            del c30
+        except Exception as ex:                     # information only
+            other['error'] = repr(ex)
+        line['other_configs'] = other
     if rank == 0 and world == 1 and not args.no_extras:
         line['cpu_baseline'] = cpu_baseline_sample(args, model, x0, e_host.reshape(-1, n_inst, nx), args.cpu_seconds)
     elif rank == 0:
