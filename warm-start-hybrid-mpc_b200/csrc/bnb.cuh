@@ -53,6 +53,8 @@ __device__ inline int bnb_instance(const DevProblem &P, const Ctx &cx, const Slo
     int *tr_i = trace ? trace + (size_t)inst * 2 * max_solves : nullptr;
 
     int nn = tr.n_nodes[inst], nr = tr.n_recs[inst];
+    const int nn0 = nn;                      // nodes >= nn0 are children created by this search
+    int memo_rec = -1, memo_d = -1;          // sibling memo of the slot: (parent record, eliminated prefix) of the parked factor
     double ub = INFINITY;
     int inc = -1, solves = 0, st = -1, k = 0;
     long long iters = 0, ksum = 0, dsum = 0, k0sum = 0;
@@ -88,13 +90,21 @@ __device__ inline int bnb_instance(const DevProblem &P, const Ctx &cx, const Slo
         // ---- solve (K1), started from the node's OWN dual record: the multipliers (and proximal centre) of its
         //      parent, or its shifted dual solution for a warm-start root (controller.py:262-264, 426, 487);
         //      no record (root node, dual = None) = empty working set
+        int memo = 0, memo_r0 = -1;
         {
             // rec <= -2: dual = None for the reference's bookkeeping (the shifted Farkas proof of an infeasible leaf no longer
             // holds, controller.py:555-558), but record -2 - rec still holds that shifted ray: its rows are where the new
             // proof (or the optimum) is most likely found, and any multipliers >= 0 are a valid start of the dual method
             const int r00 = rec[bi];
             const int r0 = r00 <= -2 ? -2 - r00 : r00;
-            if (r0 >= 0) {
+            // children of this search share their parent's record: the second sibling takes the factor the first one built
+            memo = (r0 >= 0 && bi >= nn0) ? ((r0 == memo_rec && min(d, P.n_elim) == memo_d) ? 2 : 1) : 0;
+            memo_r0 = r0;
+            if (memo == 2) {
+                const double *D = rdual + (size_t)r0 * P.n_rec;
+                for (int i = threadIdx.x; i < P.n; i += WS_NT) SMV(yc)[i] = D[P.n_dual + i];      // the proximal centre load_ws would set
+                __syncthreads();
+            } else if (r0 >= 0) {
                 const double *D = rdual + (size_t)r0 * P.n_rec;
                 const double *mu = D + P.off_mu, *nl = D + P.off_nulb, *nu_ = D + P.off_nuub;
                 const int mc = P.mc;
@@ -104,7 +114,9 @@ __device__ inline int bnb_instance(const DevProblem &P, const Ctx &cx, const Slo
             }
         }
         prof_mark(1);
-        const int qs = qp_solve(P, cx, k, xi, lbv, ubv, y, iters_s, iters_s + 1);
+        int memo_saved = 0;
+        const int qs = qp_solve(P, cx, k, xi, lbv, ubv, y, iters_s, iters_s + 1, memo, sp, memo_saved);
+        if (memo == 1) { memo_rec = memo_saved ? memo_r0 : -1; memo_d = min(d, P.n_elim); }
         if (qs == WS_ITER_LIMIT) { st = BNB_QP_LIMIT; break; }
         double *dual = rdual + (size_t)nr * P.n_rec;
         build_records(P, qs, SMV(yc), y, xi, lbv, ubv, prim, dual, cost_s, dobj_s, SMV(part), SMV(red));

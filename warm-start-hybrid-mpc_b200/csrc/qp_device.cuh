@@ -457,7 +457,7 @@ __device__ __forceinline__ double neg_bound(const DevProblem &P, const Ctx &cx, 
 }
 
 // u = R^-T (-d_W), ls = R^-1 u, v = -Q1 u from scratch (new bounds: node start, proximal pass)
-__device__ inline void refresh_uv(const DevProblem &P, const Ctx &cx, int k) {
+__device__ __forceinline__ void refresh_uv(const DevProblem &P, const Ctx &cx, int k) {
     const int *row = SMI(irow), *side = SMI(iside);
     for (int i = threadIdx.x; i < k; i += WS_NT) SMV(cw)[i] = neg_bound(P, cx, row[i], side[i]);
     for (int i = threadIdx.x; i < P.np; i += WS_NT) SMV(v)[i] = 0.;
@@ -670,7 +670,7 @@ __device__ inline int thin_remove(const DevProblem &P, const Ctx &cx, int &k, in
 }
 
 // remove position kp, then every row whose diagonal of R collapsed (see oracle/qp_core.c thin_ws_remove)
-__device__ inline void ws_remove(const DevProblem &P, const Ctx &cx, int &k, int kp) {
+__device__ __forceinline__ void ws_remove(const DevProblem &P, const Ctx &cx, int &k, int kp) {
     signed char *inW = reinterpret_cast<signed char *>(SMB(binW));
     if (threadIdx.x == 0) inW[SMI(irow)[kp]] = 0;
     __syncthreads();
@@ -835,7 +835,7 @@ __device__ inline void store_slot(const DevProblem &P, const Ctx &cx, const Slot
 // controller.py:262-264, 426) and what a shifted dual solution gives a warm-start root.  Rows keep their
 // natural order.  yc0 may be null (centre 0).
 template <class Y>
-__device__ inline void load_ws_from_multipliers(const DevProblem &P, const Ctx &cx, Y ysigned, const double *yc0, int &k) {
+__device__ __forceinline__ void load_ws_from_multipliers(const DevProblem &P, const Ctx &cx, Y ysigned, const double *yc0, int &k) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     int *wsum = SMI(ired);                       // WS_NW ints
     int *row = SMI(irow), *side = SMI(iside);
@@ -885,7 +885,7 @@ __device__ inline void load_ws_from_multipliers(const DevProblem &P, const Ctx &
 // Start of a node: rebuild the factor of the inherited working set (rows in their stored order, keeping
 // their multipliers, dropping rows that have become dependent) and reset the anti-cycling bookkeeping.
 // Mirrors the warm start of oracle/qp_core.c qp_solve.
-__device__ inline void rebuild_factor(const DevProblem &P, const Ctx &cx, int &k) {
+__device__ __forceinline__ void rebuild_factor(const DevProblem &P, const Ctx &cx, int &k) {
     signed char *inW = reinterpret_cast<signed char *>(SMB(binW));
     unsigned char *ign = SMB(bign), *nadd = SMB(bnadd);
     const int d = SMI(idep)[0];
@@ -913,6 +913,43 @@ __device__ inline void rebuild_factor(const DevProblem &P, const Ctx &cx, int &k
 }
 
 // ---------------------------------------------------------------------------------------------
+// Sibling memo.  The two children of a node start from the same rows (their parent's, in the same order) with the same
+// eliminated prefix, so the factor the first one rebuilds is, bit for bit, the factor the second one would rebuild.
+// It is parked in the slot's global home (the columns < ks of the home are otherwise unused) right after the rebuild
+// and read back by the sibling: 2 x 50 KB of L2 traffic instead of ~40 Gram-Schmidt appends.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void save_factor(const DevProblem &P, const Ctx &cx, const SlotPtrs &sp, int k) {
+    const int ldh = P.ld >> 1;
+    const double2 *s2 = reinterpret_cast<const double2 *>(SMV(Q));
+    double2 *g2 = reinterpret_cast<double2 *>(sp.Q);
+    for (int e = threadIdx.x; e < k * ldh; e += WS_NT) g2[e] = s2[e];
+    const int nt = tri_off(k);
+    for (int e = threadIdx.x; e < nt; e += WS_NT) sp.Ri[e] = SMV(Ri)[e];
+    for (int i = threadIdx.x; i < k; i += WS_NT) { sp.row[i] = SMI(irow)[i]; sp.side[i] = SMI(iside)[i]; sp.lam[i] = SMV(lam)[i]; }
+    if (threadIdx.x == 0) *sp.nW = k;
+    __syncthreads();
+}
+
+// the state rebuild_factor leaves behind, from the memo.  Ends with a barrier.
+__device__ __forceinline__ void restore_factor(const DevProblem &P, const Ctx &cx, const SlotPtrs &sp, int &k) {
+    signed char *inW = reinterpret_cast<signed char *>(SMB(binW));
+    unsigned char *ign = SMB(bign), *nadd = SMB(bnadd);
+    const int d = SMI(idep)[0];
+    k = *sp.nW;
+    for (int r = threadIdx.x; r < P.m; r += WS_NT) { inW[r] = 0; ign[r] = (r >= P.mc && r - P.mc < d) ? 3 : 0; nadd[r] = 0; }
+    const int ldh = P.ld >> 1;
+    double2 *s2 = reinterpret_cast<double2 *>(SMV(Q));
+    const double2 *g2 = reinterpret_cast<const double2 *>(sp.Q);
+    for (int e = threadIdx.x; e < k * ldh; e += WS_NT) s2[e] = g2[e];
+    const int nt = tri_off(k);
+    for (int e = threadIdx.x; e < nt; e += WS_NT) SMV(Ri)[e] = sp.Ri[e];
+    for (int i = threadIdx.x; i < k; i += WS_NT) { SMI(irow)[i] = sp.row[i]; SMI(iside)[i] = sp.side[i]; SMV(lam)[i] = sp.lam[i]; }
+    __syncthreads();
+    for (int i = threadIdx.x; i < k; i += WS_NT) inW[SMI(irow)[i]] = (signed char)SMI(iside)[i];
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
 // pinned-prefix elimination.  problem.py rotates v so that the bound row of binary j (chronological order) has
 // its non-zeros in columns 0..j.  A node whose first d binaries are pinned (lb == ub: every node branch_in_time
 // creates, controller.py:13-44) has v[:d] fixed by those d rows; the solver works in the coordinates d..n-1
@@ -935,7 +972,7 @@ __device__ inline void set_node_prefix_known(const DevProblem &P, const Ctx &cx,
 }
 
 // y_out of the eliminated rows:  L' eta = -( [v_f] + sum_i coef_i mh_{row_i}[:d] + pcoef mh_pend[:d] )
-__device__ inline void pinned_multipliers(const DevProblem &P, const Ctx &cx, int k, int d, const double *coef,
+__device__ __forceinline__ void pinned_multipliers(const DevProblem &P, const Ctx &cx, int k, int d, const double *coef,
                                           int pend, double pcoef, bool with_v, double *y_out) {
     if (d == 0) return;
     double *g = SMV(c2);
@@ -968,10 +1005,13 @@ __device__ inline void pinned_multipliers(const DevProblem &P, const Ctx &cx, in
 // coordinates (if optimal); y_out (global, m): signed multipliers of the ORIGINAL rows (>0 upper side,
 // <0 lower side; Farkas ray if infeasible).
 // ---------------------------------------------------------------------------------------------
-__device__ inline int qp_solve(const DevProblem &P, const Ctx &cx, int &k,
+__device__ __forceinline__ int qp_solve(const DevProblem &P, const Ctx &cx, int &k,
                                const double *x0, const double *lb, const double *ub,
-                               double *y_out, int *iters_out, int *kmax_out = nullptr)
+                               double *y_out, int *iters_out, int *kmax_out,
+                               int memo, const SlotPtrs &sp, int &memo_saved)
 {
+    // memo: 0 rebuild the factor of the loaded working set; 1 rebuild it and park it in the slot's home (*memo_saved = 1
+    // if it fitted); 2 the working set was NOT loaded: take it and its factor from the slot's home (sibling memo)
     const int n = P.n, m = P.m, mc = P.mc, nx = P.nx;
     signed char *inW = reinterpret_cast<signed char *>(SMB(binW));
     unsigned char *ign = SMB(bign), *nadd = SMB(bnadd);
@@ -979,8 +1019,9 @@ __device__ inline int qp_solve(const DevProblem &P, const Ctx &cx, int &k,
     int *row = SMI(irow), *side = SMI(iside);
     double *red = SMV(red); int *ired = SMI(ired);
     int it = 0, status = WS_ITER_LIMIT, kmax = 0;
-    bool hot = k > 0;
+    bool hot = k > 0 || memo == 2;
     int cap = hot ? min(P.hot_cap, P.max_iter) : P.max_iter;
+    memo_saved = 0;
 
     // eliminated coordinates: L v_f = b with b_j = ub_j / nrm_j + (Mh wv)_j  =>  v_f = vf0 + wv[:d], vf0 = L^-1 (ub / nrm)
     const int d = SMI(idep)[0];
@@ -998,7 +1039,13 @@ __device__ inline int qp_solve(const DevProblem &P, const Ctx &cx, int &k,
     prof_mark(2);
 
 restart:
-    rebuild_factor(P, cx, k);
+    if (memo == 2) {
+        restore_factor(P, cx, sp, k);
+    } else {
+        rebuild_factor(P, cx, k);
+        if (memo == 1 && k > 0 && k <= P.ks) { save_factor(P, cx, sp, k); memo_saved = 1; }
+    }
+    memo = 0;                                   // a restart from the empty working set rebuilds
     prof_mark(3);
     kmax = max(kmax, k);
     const int k_start = k; int n_prox = 0;

@@ -71,7 +71,8 @@ solve_nodes_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, int 
             const bool reset = hm == 0;
             if (!loaded || reset) { load_slot(P, cx, sp, k, reset); loaded = true; }
         }
-        const int st = qp_solve(P, cx, k, xi, lbi, ubi, y, iters + i);
+        int memo_saved = 0;
+        const int st = qp_solve(P, cx, k, xi, lbi, ubi, y, iters + i, nullptr, 0, sp, memo_saved);
         build_records(P, st, SMV(yc), y, xi, lbi, ubi, primal + (size_t)i * P.n_primal,
                       dual + (size_t)i * P.n_dual, cost + i, dobj + i, SMV(part), SMV(red));
         if (yc_out) for (int j = threadIdx.x; j < P.n; j += WS_NT) yc_out[(size_t)i * P.n + j] = st == WS_OPTIMAL ? SMV(yc)[j] : 0.;
