@@ -420,6 +420,7 @@ def run_b200(args):
             c40 = controller_from_model(m40, device=local)
             rng = np.random.default_rng(40)
             xs = m40['x0_nominal'][None] + rng.uniform(-1, 1, (148, 4)) * np.array([0.02, 0.01, 0.05, 0.05])
+            c40.handle(min(len(xs), c40.default_slots()))
             c40.feedforward_batch(xs[:8], max_solves=2048)
             torch.cuda.synchronize(); t0 = time.perf_counter()
             res, _ = c40.feedforward_batch(xs, max_solves=2048)
