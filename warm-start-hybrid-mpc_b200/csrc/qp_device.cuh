@@ -411,6 +411,27 @@ __device__ inline double q_apply(const DevProblem &P, const Ctx &cx, int k, cons
     return zz;
 }
 
+// t_i = (Ri c[:k])_i = sum_{j >= i} Ri[tri_off(j) + i] c_j handed to out(i, t_i) by the leader of the team of row i
+// (columns j = i + g, i + g + ng, ...).  No barrier.
+template <class Out>
+__device__ inline void ri_matvec_ep(const DevProblem &P, const Ctx &cx, int k, const double *c, Out out) {
+    const int lg = team_log2(k), ng = 1 << lg, g = threadIdx.x & (ng - 1), jw = WS_NT >> lg;
+    const int ke = min(k, P.ks);
+    const int kr = (k + jw - 1) & ~(jw - 1);
+    const double *Ri = SMV(Ri);
+    for (int i = threadIdx.x >> lg; i < kr; i += jw) {
+        double s0 = 0., s1 = 0.;
+        if (i < k) {
+            int j = i + g;
+            for (; j + ng < ke; j += 2 * ng) { s0 += Ri[tri_off(j) + i] * c[j]; s1 += Ri[tri_off(j + ng) + i] * c[j + ng]; }
+            for (; j < ke; j += ng) s0 += Ri[tri_off(j) + i] * c[j];
+            for (; j < k; j += ng) s0 += cx.gRi[tri_off(j) + i] * c[j];
+        }
+        const double sv = team_sum(s0 + s1, lg);
+        if (g == 0 && i < k) out(i, sv);
+    }
+}
+
 // t = Ri * c[:k]   (t_i = sum_{j >= i} Ri[tri_off(j) + i] c_j).  Team of row i: columns j = i + g, i + g + ng, ...
 // Ends with a barrier.
 __device__ inline void ri_matvec(const DevProblem &P, const Ctx &cx, int k, const double *c, double *t) {
@@ -508,22 +529,22 @@ __device__ inline int thin_append(const DevProblem &P, const Ctx &cx, int &k, in
         cu += cu2;
         prof_mark(pb + 4);
     }
-    ri_matvec(P, cx, k, c1, t);
-    prof_mark(pb + 5);
-    if (k >= n - d || rho2 <= P.tol_sing * P.tol_sing) return 0;
-    const double ir = 1. / sqrt(rho2);
+    // t = Ri c1 and, if the row is independent, the new column of Ri / the update of ls straight from the team leaders:
+    // the triangular product and the write-out are ONE phase
+    const bool dep = k >= n - d || rho2 <= P.tol_sing * P.tol_sing;
+    const double ir = dep ? 0. : 1. / sqrt(rho2);
     double *qk = qcol_w(P, cx, k), *rk = ricol_w(P, cx, k);
     double uk = 0., lk = 0.;
-    if (track) { uk = (neg_bound(P, cx, r, sgn) - cu) * ir; lk = uk * ir; }
+    if (track && !dep) { uk = (neg_bound(P, cx, r, sgn) - cu) * ir; lk = uk * ir; }
+    ri_matvec_ep(P, cx, k, c1, [&](int i, double ti) {
+        t[i] = ti;
+        if (!dep) { rk[i] = -ti * ir; if (track) SMV(ls)[i] -= ti * lk; }
+    });
+    if (dep) { __syncthreads(); prof_mark(pb + 5); return 0; }
     for (int i = threadIdx.x; i < P.np; i += WS_NT) {
         const double q = z[i] * ir;
         qk[i] = q;
         if (track) SMV(v)[i] -= q * uk;
-    }
-    for (int i = threadIdx.x; i < k; i += WS_NT) {
-        const double ti = t[i];
-        rk[i] = -ti * ir;
-        if (track) SMV(ls)[i] -= ti * lk;
     }
     if (threadIdx.x == 0) {
         rk[k] = ir;
@@ -557,9 +578,11 @@ __device__ inline int thin_remove_impl(const DevProblem &P, const Ctx &cx, int &
         const double ul = u[kp];
         const double *qk = QC(kp);
         for (int i = tid; i < P.np; i += WS_NT) SMV(v)[i] += qk[i] * ul;
+        // ls = Ri u loses the term of the last column
+        const double *rl = RC(kp);
+        for (int i = tid; i < kp; i += WS_NT) SMV(ls)[i] -= rl[i] * ul;
         k -= 1;
         __syncthreads();
-        ri_matvec(P, cx, k, u, SMV(ls));
         prof_mark(50);
         return -1;
     }
@@ -601,6 +624,7 @@ __device__ inline int thin_remove_impl(const DevProblem &P, const Ctx &cx, int &
     double qcarry = qr >= 0 ? QC(kp)[qr] : 0.;
     double qcarry2 = qr2 >= 0 ? QC(kp)[qr2] : 0.;
     double rcarry = (rr >= 0 && ro <= kp) ? RC(kp)[ro] : 0.;
+    const double ls_old = rr >= 0 ? SMV(ls)[ro] : 0.;                       // read before any thread writes its new entry
     double ucarry = uth ? u[kp] : 0.;
     for (int i0 = kp; i0 < k - 1; i0 += WS_CH) {
         double b[WS_CH];
@@ -658,9 +682,11 @@ __device__ inline int thin_remove_impl(const DevProblem &P, const Ctx &cx, int &
     // v = -Q1_new u_new = v_old + q_last (G u)_last
     if (qr >= 0) SMV(v)[qr] += qcarry * SMV(red)[40];
     if (qr2 >= 0) SMV(v)[qr2] += qcarry2 * SMV(red)[40];
+    // ls = Ri u = (Ri G')(G u): dropping the rotated-out last column leaves  ls_new[rr] = ls_old[ro] - (Ri G')[ro, last] (G u)_last,
+    // and the carry of row rr IS that last-column entry
+    if (rr >= 0) SMV(ls)[rr] = ls_old - rcarry * SMV(red)[40];
     const int bad = *flag;
     __syncthreads();
-    ri_matvec(P, cx, k, u, SMV(ls));
     prof_mark(53);
     return bad == 0x7fffffff ? -1 : bad;
 }
