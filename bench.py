@@ -302,6 +302,7 @@ def run_b200(args):
     clocks = sampler.stop()
     ker_ms = [a.elapsed_time(b) for a, b in ev]
     n_active = int(loop.active.sum())
+    leaves_mean = float(loop.trees[loop.cur].n_nodes.double().mean())      # warm-start roots per instance after the last shift
     status = loop.out['status'].cpu().numpy()
     value = qps / (ms * 1e-3)
 
@@ -356,6 +357,13 @@ def run_b200(args):
     peaks_file = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(peaks_file):
         roofline['hbm_peak_gbs_measured'] = json.load(open(peaks_file)).get('hbm_gbs')
+    # algorithmic HBM bytes of one launch: K1 reads / writes B_node per QP, K2+K4 read and write one dual record
+    # per retained leaf and MPC step (the reference shifts every leaf's dual solution, controller.py:431-501)
+    B_node = 8 * (2 * pd.nb + pd.nx + pd.n + 2 * pd.m) + 12
+    rec_bytes = 8 * loop.h.layout.rec_stride
+    roofline['algorithmic_hbm_bytes_per_launch'] = qp_per_launch * B_node + S * n_inst * leaves_mean * 2 * rec_bytes
+    roofline['algorithmic_hbm_note'] = ('%.0f QPs x %d B (K1) + %d steps x %d instances x %.1f leaves x 2 x %d B (K2+K4 tree shift)'
+                                        % (qp_per_launch, B_node, S, n_inst, leaves_mean, rec_bytes))
     traffic_file = os.path.join(ROOT, 'profiles', 'closed_loop_kernel_traffic.json')
     if os.path.exists(traffic_file):
         roofline['traffic'] = json.load(open(traffic_file)).get('dram_bytes_per_launch')

@@ -297,6 +297,16 @@ __device__ inline void grouped_matvec(const double *__restrict__ M, int ld, int 
         if (g < G) {
             double s0 = 0., s1 = 0., s2 = 0., s3 = 0.;
             int j = j0 + g;
+            // the operators come from L2: 8 independent loads in flight per thread
+            for (; j + 7 * G < j1; j += 8 * G) {
+                double w[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) w[q] = __ldg(M + (size_t)(j + q * G) * ld + i);
+                s0 += w[0] * x[j] + w[4] * x[j + 4 * G];
+                s1 += w[1] * x[j + G] + w[5] * x[j + 5 * G];
+                s2 += w[2] * x[j + 2 * G] + w[6] * x[j + 6 * G];
+                s3 += w[3] * x[j + 3 * G] + w[7] * x[j + 7 * G];
+            }
             for (; j + 3 * G < j1; j += 4 * G) {
                 s0 += M[(size_t)j * ld + i] * x[j];
                 s1 += M[(size_t)(j + G) * ld + i] * x[j + G];
