@@ -213,6 +213,29 @@ bnb_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, double *scra
 #define SH_NT 256
 #define SH_NW (SH_NT / 32)
 
+// a warp asks L2 for the `n` doubles at p (one request per 128-byte line): the dual records of the tree shift are
+// streamed from HBM once, and a leaf's loops would otherwise expose one DRAM latency each
+__device__ __forceinline__ void warp_prefetch_l2(const double *p, int n, int lane) {
+    for (int e = lane * 16; e < n; e += 32 * 16) asm volatile("prefetch.global.L2 [%0];" :: "l"(p + e));
+}
+
+// dst[e] = src[e], e < n, by one warp: eight independent loads in flight per lane (src and dst never overlap)
+__device__ __forceinline__ void warp_copy(double *__restrict__ dst, const double *__restrict__ src, int n, int lane) {
+    int e = lane;
+    for (; e + 224 < n; e += 256) {
+        double v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = src[e + 32 * q];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) dst[e + 32 * q] = v[q];
+    }
+    for (; e + 96 < n; e += 128) {
+        const double v0 = src[e], v1 = src[e + 32], v2 = src[e + 64], v3 = src[e + 96];
+        dst[e] = v0; dst[e + 32] = v1; dst[e + 64] = v2; dst[e + 96] = v3;
+    }
+    for (; e < n; e += 32) dst[e] = src[e];
+}
+
 // doubles of shared scratch the shift needs with NT threads
 __host__ __device__ inline size_t shift_smem_doubles(const DevProblem &P, int nt) {
     return (size_t)2 * P.nx + P.nu + P.nq + P.nr + P.nh + (size_t)(nt / 32) * (P.nh1 + P.nqT + P.nh + P.nq) + 8;
@@ -314,9 +337,17 @@ __device__ inline void shift_instance(const DevProblem &P, double *shm, int *s_w
             // dual = None (controller.py:556-558 on the previous step, never solved since): trivial bound
             for (int e = lane; e < P.n_rec; e += 32) E[e] = 0.;
             if (lane == 0) { nt.lb[on_ + idx] = 0.; nt.rec[on_ + idx] = -1; nt.rec_dobj[(size_t)inst * nt.cap_recs + idx] = 0.; }
-            return;
+            continue;
         }
         const double *D = ot.rec_dual + ((size_t)inst * ot.cap_recs + ro) * P.n_rec;
+        warp_prefetch_l2(D, P.n_dual, lane);
+        {   // ... and the record of the leaf this warp takes next
+            const int nx_idx = idx + (NT / 32);
+            if (nx_idx < nnew) {
+                const int rn_ = ot.rec[oo + nt.rec[on_ + nx_idx]];
+                if (rn_ >= 0) warp_prefetch_l2(ot.rec_dual + ((size_t)inst * ot.cap_recs + rn_) * P.n_rec, P.n_dual, lane);
+            }
+        }
         for (int e = P.n_dual + lane; e < P.n_rec; e += 32) E[e] = 0.;          // a shifted root starts from the centre 0
         const int d_old = ot.depth[oo + j];
         const unsigned int b0 = ot.bits[(oo + j) * ot.words];
@@ -331,7 +362,7 @@ __device__ inline void shift_instance(const DevProblem &P, double *shm, int *s_w
         {
             const double *sl = D + P.off_nulb, *su = D + P.off_nuub;
             double *tl = E + P.off_nulb, *tu = E + P.off_nuub;
-            for (int e = lane; e < (T - 1) * nub; e += 32) { tl[e] = sl[nub + e]; tu[e] = su[nub + e]; }
+            warp_copy(tl, sl + nub, (T - 1) * nub, lane); warp_copy(tu, su + nub, (T - 1) * nub, lane);
             for (int e = lane; e < nub; e += 32) {
                 tl[(T - 1) * nub + e] = 0.; tu[(T - 1) * nub + e] = 0.;
                 const double bit = (double)((b0 >> e) & 1u);
@@ -349,7 +380,7 @@ __device__ inline void shift_instance(const DevProblem &P, double *shm, int *s_w
         // rho: rho'_{T-1} = M_rho rho_T (controller.py:96, 662-664)
         {
             const double *s = D + P.off_rho; double *t = E + P.off_rho;
-            for (int e = lane; e < (T - 1) * nq; e += 32) t[e] = s[nq + e];
+            warp_copy(t, s + nq, (T - 1) * nq, lane);
             for (int e = lane; e < nq; e += 32) { const double a = .5 * s[e] - Qx[e]; acc += a * a - Qx[e] * Qx[e]; }
             double *rT = wscr;                              // rho_T staged for the small mat-vec
             for (int e = lane; e < nqT; e += 32) { const double v = s[T * nq + e]; rT[e] = v; acc += .25 * v * v; t[T * nq + e] = 0.; }
@@ -363,14 +394,22 @@ __device__ inline void shift_instance(const DevProblem &P, double *shm, int *s_w
         // mu: mu'_{T-2} = M_mu mu_{T-1} (controller.py:186-227, 662-664)
         {
             const double *s = D + P.off_mu; double *t = E + P.off_mu;
-            for (int e = lane; e < (T - 2) * nh; e += 32) t[e] = s[nh + e];
+            warp_copy(t, s + nh, (T - 2) * nh, lane);
             for (int e = lane; e < nh; e += 32) acc -= rmu[e] * s[e];
             double *mT = wscr + nqT;
             for (int e = lane; e < nh1; e += 32) { const double v = s[(T - 1) * nh + e]; mT[e] = v; acc += P.h1[e] * v; t[(T - 1) * nh + e] = 0.; }
             __syncwarp();
+            // M_mu stored transposed: the lanes of a warp read consecutive words, four independent chains per lane
             for (int i = lane; i < nh; i += 32) {
-                double v = 0.;
-                for (int c = 0; c < nh1; ++c) v += P.Mmu[(size_t)i * nh1 + c] * mT[c];
+                double v0 = 0., v1 = 0., v2 = 0., v3 = 0.;
+                const double *mc_ = P.MmuT + i;
+                int c = 0;
+                for (; c + 3 < nh1; c += 4) {
+                    v0 += __ldg(mc_ + (size_t)c * nh) * mT[c]; v1 += __ldg(mc_ + (size_t)(c + 1) * nh) * mT[c + 1];
+                    v2 += __ldg(mc_ + (size_t)(c + 2) * nh) * mT[c + 2]; v3 += __ldg(mc_ + (size_t)(c + 3) * nh) * mT[c + 3];
+                }
+                for (; c < nh1; ++c) v0 += __ldg(mc_ + (size_t)c * nh) * mT[c];
+                const double v = (v0 + v1) + (v2 + v3);
                 t[(T - 2) * nh + i] = v; acc -= P.h[i] * v;
             }
             __syncwarp();

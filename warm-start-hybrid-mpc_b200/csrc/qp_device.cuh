@@ -64,7 +64,7 @@ struct SmemOff {
 
 struct DevProblem {
     int nx, nu, nub, nuc, T, nh, nh1, nq, nqT, nr, n, m, mc, nb, ns;
-    const double *A, *B, *F, *G, *h, *F1, *G1, *h1, *Q, *R, *QT, *Mmu, *Mrho;
+    const double *A, *B, *F, *G, *h, *F1, *G1, *h1, *Q, *R, *QT, *Mmu, *MmuT, *Mrho;
     const double *Mh, *WfT, *nrm, *inr, *vscale, *Eh, *hh, *Rinv, *RinvT, *Kx, *ZmapT, *Linv, *LinvT, *Msq;
     const int *bin_idx;
     int n_elim;              // leading binaries that may be eliminated when pinned (0 = never)

@@ -127,6 +127,7 @@ extern "C" int wshmpc_create(const wshmpc_problem *p, int device, int n_slots, v
     UP(F1, p->F_Tm1, p->nh1 * nx) UP(G1, p->G_Tm1, p->nh1 * nu) UP(h1, p->h_Tm1, p->nh1)
     UP(Q, p->Q, p->nq * nx) UP(R, p->R, p->nr * nu) UP(QT, p->Q_T, p->nqT * nx)
     UP(Mmu, p->M_mu, p->nh * p->nh1) UP(Mrho, p->M_rho, p->nq * p->nqT)
+    { std::vector<double> mt = transpose(p->M_mu, p->nh, p->nh1); UP(MmuT, mt.data(), mt.size()) }
     UP(Mh, p->Mh, (size_t)m * n) UP(nrm, p->nrm, m) UP(vscale, p->vscale, m) UP(Eh, p->Eh, (size_t)p->mc * nx)
     UP(hh, p->hh, p->mc) UP(Rinv, p->Rinv, (size_t)n * n) UP(Kx, p->Kx, (size_t)n * nx)
     UP(bin_idx, p->bin_idx, p->nb)
