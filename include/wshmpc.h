@@ -62,9 +62,7 @@ typedef struct {
 
 const char *wshmpc_last_error(void);
 
-/* most solver CTAs the library keeps resident per SM: n_slots = SMs x this fills the GPU.  A call that uses more solver
- * states than there are SMs runs the kernels built for two CTAs per SM (half the shared memory per factor: more QPs in
- * flight, higher latency per QP); a call with fewer runs one CTA per SM.  Results do not depend on the choice. */
+/* solver CTAs the library keeps resident per SM (a build constant): n_slots = SMs x this fills the GPU */
 int wshmpc_ctas_per_sm(void);
 
 /* create / destroy.  `n_slots` = number of independent solver states (one per concurrently solved

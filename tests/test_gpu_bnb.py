@@ -281,21 +281,3 @@ def test_noisy_closed_loop_warm_equals_cold():
     assert torch.equal(W.active, Cd.active)
     nw, nc = lw['n_solves'].cpu().numpy()[1:].sum(), lc['n_solves'].cpu().numpy()[1:].sum()
     assert nw * 4 < nc
-
-
-def test_two_ctas_per_sm_variant_is_bit_identical(cp20):
-    """More solver states than SMs selects the kernels built for two resident CTAs per SM (half the shared memory per
-    factor, 128 registers per thread); they run the same arithmetic: results must not differ by a bit."""
-    model, ctl = cp20
-    sms = torch.cuda.get_device_properties(0).multi_processor_count
-    rng = np.random.default_rng(21)
-    N = sms + 40
-    x0 = model['x0_nominal'][None] + rng.uniform(-1, 1, (N, 4)) * np.array([0.02, 0.01, 0.05, 0.05])
-    one, _ = ctl.feedforward_batch(x0, n_slots=sms // 2)            # fewer states than SMs: one CTA per SM
-    c1 = one['cost'].clone(); n1 = one['n_solves'].clone(); p1 = one['primal'].clone()
-    two, _ = ctl.feedforward_batch(x0, n_slots=N)                   # more states than SMs: two CTAs per SM
-    torch.cuda.synchronize()
-    assert torch.equal(n1, two['n_solves'])
-    assert torch.equal(torch.nan_to_num(c1, posinf=1e300), torch.nan_to_num(two['cost'], posinf=1e300))
-    ok = torch.isfinite(c1)
-    assert torch.equal(p1[ok], two['primal'][ok])

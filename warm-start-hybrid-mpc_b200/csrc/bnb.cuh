@@ -174,8 +174,7 @@ __device__ inline int bnb_instance(const DevProblem &P, const Ctx &cx, const Slo
     return st;
 }
 
-template <int MINB>
-__global__ void __launch_bounds__(WS_NT, MINB)
+__global__ void __launch_bounds__(WS_NT, WS_MINB)
 bnb_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, double *scratch, int *work_counter,
            int n_inst, const double *__restrict__ x0, const int *__restrict__ active, TreeView tr,
            double tol, int max_solves,
@@ -491,8 +490,7 @@ __device__ inline void init_root(const TreeView &tr, int k)
     for (int w = 0; w < tr.words; ++w) tr.bits[o * tr.words + w] = 0u;
 }
 
-template <int MINB>
-__global__ void __launch_bounds__(WS_NT, MINB)
+__global__ void __launch_bounds__(WS_NT, WS_MINB)
 closed_loop_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, double *scratch, LoopView L, int n_inst,
                    TreeView t0, TreeView t1, double tol, int max_solves,
                    double *inc_cost, int *inc_node, double *inc_primal, int *n_solves, int *status_out,

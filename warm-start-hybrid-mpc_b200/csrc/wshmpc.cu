@@ -15,11 +15,7 @@ static thread_local std::string g_err;
 #define WS_CUDA(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) WS_FAIL(-2, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(_e), __FILE__, __LINE__); } while (0)
 
 struct wshmpc_handle {
-    DevProblem P;            // one solver CTA per SM: the whole shared memory of an SM for one factor (lowest latency per QP)
-    DevProblem P2;           // two solver CTAs per SM: half the shared memory each (more QPs in flight; used when the batch is large)
-    bool two;                // the two-CTA layout exists for this problem
-    int sm_count;
-    size_t smem2;
+    DevProblem P;
     int device, n_slots;
     cudaStream_t stream;
     std::vector<void *> allocs;
@@ -34,7 +30,7 @@ struct wshmpc_handle {
 };
 
 extern "C" const char *wshmpc_last_error(void) { return g_err.c_str(); }
-extern "C" int wshmpc_ctas_per_sm(void) { return 2; }
+extern "C" int wshmpc_ctas_per_sm(void) { return WS_MINB; }
 #ifdef WS_PROF
 // experiment builds only: [2 id] cycles, [2 id + 1] visits of phase id (see prof_mark)
 extern "C" int wshmpc_prof_read(unsigned long long *out, int reset) {
@@ -47,8 +43,7 @@ extern "C" int wshmpc_prof_read(unsigned long long *out, int reset) {
 // ---------------------------------------------------------------------------------------------
 // K1: one CTA per solver slot; the CTA solves, in index order, every node assigned to its slot
 // ---------------------------------------------------------------------------------------------
-template <int MINB>
-__global__ void __launch_bounds__(WS_NT, MINB)
+__global__ void __launch_bounds__(WS_NT, WS_MINB)
 solve_nodes_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, int n_nodes,
                    const double *__restrict__ x0, const double *__restrict__ lb, const double *__restrict__ ub,
                    const int *__restrict__ slot_of, const int *__restrict__ hot,
@@ -183,11 +178,12 @@ extern "C" int wshmpc_create(const wshmpc_problem *p, int device, int n_slots, v
     // shared memory budget: one CTA per SM; the first ks columns of Q1 and of Ri live in shared memory
     cudaDeviceProp prop;
     WS_CUDA(cudaGetDeviceProperties(&prop, device));
-    const size_t optin = prop.sharedMemPerBlockOptin;
-    // two CTAs per SM: each gets half of the SM's shared memory (1 KB per CTA is reserved by the system)
-    size_t optin2 = (prop.sharedMemPerMultiprocessor / 2 - 1024) & ~(size_t)15;
-    if (optin2 > optin) optin2 = optin;
-    h->sm_count = prop.multiProcessorCount;
+    size_t optin = prop.sharedMemPerBlockOptin;
+    if (WS_MINB > 1) {
+        // WS_MINB CTAs per SM: each gets an equal share of the SM's shared memory (1 KB per CTA is reserved by the system)
+        const size_t share = prop.sharedMemPerMultiprocessor / WS_MINB - 1024;
+        if (share < optin) optin = share & ~(size_t)15;
+    }
     if (n > 2 * WS_NT) { wshmpc_destroy(h); WS_FAIL(-4, "problem too large: n = %d condensed inputs, at most %d supported", n, 2 * WS_NT); }
     if (p->T > 32767 || p->nh > 65535 || p->nh1 > 65535) { wshmpc_destroy(h); WS_FAIL(-4, "problem too large for the packed row map"); }
     P.np = (n + 1) & ~1;
@@ -229,34 +225,16 @@ extern "C" int wshmpc_create(const wshmpc_problem *p, int device, int n_slots, v
         so.Ri = o; o += (tri_off(ks) + 1) & ~1;
         so.total_bytes = o * 8;
         h->smem = (size_t)so.total_bytes;
-        // the same layout with the smaller budget of the two-CTA variant (only the factor area shrinks)
-        h->P2 = P; h->two = false; h->smem2 = 0;
-        int ks2 = 0;
-        while (ks2 < n && fixed + ((size_t)(ks2 + 1) * P.ld + (size_t)tri_off(ks2 + 1) + 2) * 8 <= optin2) ++ks2;
-        if (fixed + 64 <= optin2 && (size_t)ks2 * P.ld >= shift_smem_doubles(P, WS_NT) && ks2 >= 8) {
-            int o2 = so.Q;
-            h->P2.ks = ks2;
-            o2 += ks2 * P.ld;
-            h->P2.so.Ri = o2; o2 += (tri_off(ks2) + 1) & ~1;
-            h->P2.so.total_bytes = o2 * 8;
-            h->smem2 = (size_t)h->P2.so.total_bytes;
-            h->two = true;
-        }
     }
-    WS_CUDA(cudaFuncSetAttribute(solve_nodes_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
-    if (h->two) {
-        WS_CUDA(cudaFuncSetAttribute(solve_nodes_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem2));
-        WS_CUDA(cudaFuncSetAttribute(bnb_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem2));
-        WS_CUDA(cudaFuncSetAttribute(closed_loop_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem2));
-    }
+    WS_CUDA(cudaFuncSetAttribute(solve_nodes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
     // slot memory
     void *d = nullptr;
     WS_CUDA(cudaMalloc(&d, (size_t)n_slots * slot_doubles(n, P.ld) * sizeof(double))); h->allocs.push_back(d); h->slot_d = (double *)d;
     WS_CUDA(cudaMalloc(&d, (size_t)n_slots * slot_ints(n) * sizeof(int))); h->allocs.push_back(d); h->slot_i = (int *)d;
     WS_CUDA(cudaMemset(h->slot_i, 0, (size_t)n_slots * slot_ints(n) * sizeof(int)));
     WS_CUDA(cudaMalloc(&d, (size_t)n_slots * m * sizeof(double))); h->allocs.push_back(d); h->ybuf = (double *)d;
-    WS_CUDA(cudaFuncSetAttribute(bnb_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
-    WS_CUDA(cudaFuncSetAttribute(closed_loop_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+    WS_CUDA(cudaFuncSetAttribute(bnb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+    WS_CUDA(cudaFuncSetAttribute(closed_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
     WS_CUDA(cudaMalloc(&d, (size_t)n_slots * bnb_scratch_doubles(p->nb, L.primal) * sizeof(double))); h->allocs.push_back(d); h->scratch = (double *)d;
     WS_CUDA(cudaMalloc(&d, 64)); h->allocs.push_back(d); h->work_counter = (int *)d;
     h->shift_smem = shift_smem_bytes(P);
@@ -279,7 +257,7 @@ extern "C" int wshmpc_set_search_rule(wshmpc_handle *h, int rule)
 {
     if (!h) WS_FAIL(-1, "null handle");
     if (rule < 0 || rule > 2) WS_FAIL(-1, "search rule %d: 0 best_first, 1 depth_first, 2 breadth_first", rule);
-    h->P.search_rule = rule; h->P2.search_rule = rule;
+    h->P.search_rule = rule;
     return 0;
 }
 
@@ -299,13 +277,7 @@ extern "C" int wshmpc_solve_nodes(wshmpc_handle *h, int n_nodes, const double *d
     if (!h) WS_FAIL(-1, "null handle");
     if (n_nodes <= 0) return 0;
     WS_CUDA(cudaSetDevice(h->device));
-    // more solver states than SMs: two CTAs per SM (more QPs in flight), else one CTA per SM (lowest latency per QP)
-    if (h->two && h->n_slots > h->sm_count)
-        solve_nodes_kernel<2><<<h->n_slots, WS_NT, h->smem2, h->stream>>>(
-            h->P2, h->slot_d, h->slot_i, h->ybuf, n_nodes, d_x0, d_lb, d_ub, d_slot, d_hot, d_y0, d_yc0,
-            d_status, d_cost, d_dobj, d_iters, d_primal, d_dual, d_yc);
-    else
-    solve_nodes_kernel<1><<<h->n_slots, WS_NT, h->smem, h->stream>>>(
+    solve_nodes_kernel<<<h->n_slots, WS_NT, h->smem, h->stream>>>(
         h->P, h->slot_d, h->slot_i, h->ybuf, n_nodes, d_x0, d_lb, d_ub, d_slot, d_hot, d_y0, d_yc0,
         d_status, d_cost, d_dobj, d_iters, d_primal, d_dual, d_yc);
     WS_CUDA(cudaGetLastError());
@@ -351,18 +323,10 @@ extern "C" int wshmpc_bnb_solve(wshmpc_handle *h, int n_inst, const double *d_x0
     TreeView tv; int rc = tree_view(h, tree, &tv); if (rc) return rc;
     WS_CUDA(cudaSetDevice(h->device));
     WS_CUDA(cudaMemsetAsync(h->work_counter, 0, sizeof(int), h->stream));
-    int grid = n_inst < h->n_slots ? n_inst : h->n_slots;
-    // more instances than SMs: two CTAs per SM (more QPs in flight), else one CTA per SM (lowest latency per QP)
-    const bool two = h->two && grid > h->sm_count;
-    if (!two && grid > h->sm_count) grid = h->sm_count;
-    if (two)
-        bnb_kernel<2><<<grid, WS_NT, h->smem2, h->stream>>>(
-            h->P2, h->slot_d, h->slot_i, h->ybuf, h->scratch, h->work_counter, n_inst, d_x0, d_active, tv, tol, max_solves,
-            d_inc_cost, d_inc_node, d_inc_primal, d_n_solves, d_status, d_trace, d_totals);
-    else
-        bnb_kernel<1><<<grid, WS_NT, h->smem, h->stream>>>(
-            h->P, h->slot_d, h->slot_i, h->ybuf, h->scratch, h->work_counter, n_inst, d_x0, d_active, tv, tol, max_solves,
-            d_inc_cost, d_inc_node, d_inc_primal, d_n_solves, d_status, d_trace, d_totals);
+    const int grid = n_inst < h->n_slots ? n_inst : h->n_slots;
+    bnb_kernel<<<grid, WS_NT, h->smem, h->stream>>>(
+        h->P, h->slot_d, h->slot_i, h->ybuf, h->scratch, h->work_counter, n_inst, d_x0, d_active, tv, tol, max_solves,
+        d_inc_cost, d_inc_node, d_inc_primal, d_n_solves, d_status, d_trace, d_totals);
     WS_CUDA(cudaGetLastError());
     return 0;
 }
@@ -412,17 +376,10 @@ extern "C" int wshmpc_closed_loop(wshmpc_handle *h, int n_inst, const wshmpc_loo
     const int n_items = n_inst * (loop->n_steps + 1);
     loop_init_kernel<<<(n_items + 255) / 256, 256, 0, h->stream>>>(n_inst, n_items, L);
     WS_CUDA(cudaGetLastError());
-    int grid = n_inst < h->n_slots ? n_inst : h->n_slots;
-    const bool two = h->two && grid > h->sm_count;
-    if (!two && grid > h->sm_count) grid = h->sm_count;
-    if (two)
-        closed_loop_kernel<2><<<grid, WS_NT, h->smem2, h->stream>>>(
-            h->P2, h->slot_d, h->slot_i, h->ybuf, h->scratch, L, n_inst, v0, v1, tol, max_solves,
-            d_inc_cost, d_inc_node, d_inc_primal, d_n_solves, d_status, d_totals);
-    else
-        closed_loop_kernel<1><<<grid, WS_NT, h->smem, h->stream>>>(
-            h->P, h->slot_d, h->slot_i, h->ybuf, h->scratch, L, n_inst, v0, v1, tol, max_solves,
-            d_inc_cost, d_inc_node, d_inc_primal, d_n_solves, d_status, d_totals);
+    const int grid = n_inst < h->n_slots ? n_inst : h->n_slots;
+    closed_loop_kernel<<<grid, WS_NT, h->smem, h->stream>>>(
+        h->P, h->slot_d, h->slot_i, h->ybuf, h->scratch, L, n_inst, v0, v1, tol, max_solves,
+        d_inc_cost, d_inc_node, d_inc_primal, d_n_solves, d_status, d_totals);
     WS_CUDA(cudaGetLastError());
     return 0;
 }
