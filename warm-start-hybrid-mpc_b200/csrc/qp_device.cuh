@@ -516,7 +516,8 @@ __device__ inline int thin_append(const DevProblem &P, const Ctx &cx, int &k, in
     const int n = P.n, d = SMI(idep)[0];
     if (k >= WS_NT) return -1;
     double *z = SMV(z), *c1 = SMV(c1), *t = SMV(t);
-    const int pb = track ? 30 : 40;
+    const int pb = track ? 30 : 40;                  // phase ids of the WS_PROF timeline
+    (void)pb;
     {
         const double2 e = pre ? *pre : load_row_entries(P, r, d);
         if (threadIdx.x < P.np) z[threadIdx.x] = (double)sgn * e.x;
