@@ -7,7 +7,7 @@
 
 Workload (BASELINE.json configs[1] per instance, configs[2] = 4096 instances over 8 GPUs as the batch):
 closed loop of the notebook two-wall cart-pole (T = 20), `--instances` independent initial states per GPU
-(tests/golden/cp20_instances.npy), model error e_t = sigma * randn * x_max, warm-started branch and bound
+(warm-start-hybrid-mpc_b200/data/cp20_instances.npy), model error e_t = sigma * randn * x_max, warm-started branch and bound
 with tree shifting.  One bench "step" = ONE fused launch (wshmpc_closed_loop) that advances every instance of
 the batch by `--window` receding-horizon steps = K3 (device B&B, K1 inside) + K2/K4 (tree shift + plant
 update) per MPC step, with no barrier between instances.  Instances are independent: ranks own contiguous
@@ -66,7 +66,7 @@ def workload_config(args, world):
 
 
 def load_instances(lo, hi):
-    x = np.load(os.path.join(ROOT, 'tests', 'golden', 'cp20_instances.npy'))
+    x = np.load(os.path.join(ROOT, 'warm-start-hybrid-mpc_b200', 'data', 'cp20_instances.npy'))
     idx = np.arange(lo, hi) % len(x)
     return np.ascontiguousarray(x[idx])
 

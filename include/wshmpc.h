@@ -93,7 +93,8 @@ int wshmpc_set_search_rule(wshmpc_handle *h, int rule);
  *                            m = layout.off_nu_lb - layout.off_mu + nb; > 0 upper side (mu, nu_ub), < 0 lower (nu_lb)
  *   d_yc0  [n_nodes][n]      (hot = 2; may be NULL = 0) proximal centre, n = T * nu
  * outputs
- *   d_status [n_nodes]       2 optimal, 3 infeasible (Gurobi status codes, bounded_qp.py:212), 9 iteration limit
+ *   d_status [n_nodes]       2 optimal, 3 infeasible (Gurobi status codes, bounded_qp.py:212), 9 iteration limit (also: the
+ *                            proximal outer loop did not converge in max_prox passes, or the working set hit its capacity)
  *   d_cost   [n_nodes]       primal objective, +inf if infeasible          (bounded_qp.py:292-311)
  *   d_dobj   [n_nodes]       dual objective / cost of the Farkas proof     (bounded_qp.py:313-332)
  *   d_iters  [n_nodes]       active-set iterations
@@ -167,6 +168,11 @@ int wshmpc_tree_init_root(wshmpc_handle *h, int n_inst, const wshmpc_tree *tree)
  *   d_inc_cost / d_inc_primal : incumbents of the old tree (u_0 = applied input)
  *   d_active [n_inst] in/out or NULL : instances without incumbent are switched off
  *   d_x_next [n_inst][nx] = x_1 + e0 ; d_u0 [n_inst][nu] applied input (either may be NULL)
+ * Capacity rule: every retained leaf takes one node AND one dual record of `new_tree`, so
+ * min(new_tree.cap_nodes, new_tree.cap_recs) must be >= the number of retained leaves (<= old_tree's n_nodes), and
+ * the search that follows needs 2 more nodes and 1 more record per QP it solves.  An instance whose cover does not
+ * fit is switched off (d_active = 0, empty new tree; in wshmpc_closed_loop its status becomes 2 = capacity) instead
+ * of continuing with a truncated cover, which could report a suboptimal or "infeasible" MIQP as solved.
  */
 int wshmpc_shift_tree(wshmpc_handle *h, int n_inst, const double *d_x0, const double *d_e0,
                       const wshmpc_tree *old_tree, const double *d_inc_cost, const double *d_inc_primal,

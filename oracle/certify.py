@@ -53,6 +53,22 @@ def primal_residuals(model, cond, x0, lb, ub, fam):
     return np.max(np.abs(np.concatenate(eq))), max(0., np.max(np.concatenate(viol)))
 
 
+def primal_violation_scaled(model, cond, x0, lb, ub, fam):
+    """Largest inequality violation with every row divided by max(1, |row of [F G]|): the scaling in which the CUDA
+    solver's primal tolerance is stated (qp_device.cuh pricing: tol_p, escalated to at most 100 tol_p on rows that
+    entered the working set degenerately).  Bound rows have unit norm."""
+    T, nub = cond.T, cond.nub
+    x, u = fam['x'], fam['u']
+    worst = 0.
+    for t in range(T):
+        Ft, Gt, ht = (model['F'], model['G'], model['h']) if t < T - 1 else (model['F_Tm1'], model['G_Tm1'], model['h_Tm1'])
+        sc = np.maximum(1., np.sqrt((Ft ** 2).sum(1) + (Gt ** 2).sum(1)))
+        worst = max(worst, np.max((Ft.dot(x[t]) + Gt.dot(u[t]) - ht) / sc))
+        ubt = u[t, -nub:]
+        worst = max(worst, np.max(lb[t * nub:(t + 1) * nub] - ubt), np.max(ubt - ub[t * nub:(t + 1) * nub]))
+    return max(0., worst)
+
+
 def dual_residuals(model, cond, fam):
     """cart_pole_with_wall.py:207-247 -> (max |stationarity|, most negative multiplier)."""
     T, nuc = cond.T, cond.nuc

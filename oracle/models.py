@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE (oracle side) -- benchmark instance builders.
 
 Builds the problem instances of BASELINE.json / SURVEY.md section 8(d) and freezes them to
-``tests/golden/model_*.npz`` so that CPU oracle and GPU path consume identical bits.
+``warm-start-hybrid-mpc_b200/data/model_*.npz`` (product data; golden VECTORS stay in tests/golden/) so that CPU oracle and GPU path consume identical bits.
 
 * CP20 / CP40: the notebook two-wall cart-pole.  The MLD matrices come from the reference's
   own ``notebooks/cart_pole_with_walls/mld_dynamics.py`` (imported unmodified, sympy);
@@ -19,7 +19,9 @@ import numpy as np
 from scipy.optimize import linprog
 from scipy.linalg import solve_discrete_are
 
-GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden')
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(_ROOT, 'tests', 'golden')
+MODELS = os.path.join(_ROOT, 'warm-start-hybrid-mpc_b200', 'data')
 
 
 # ---------------------------------------------------------------------------------------------
@@ -111,12 +113,12 @@ def pack_model(name, A, B, F, G, h, nub, T, Q, R, Q_T, F_T, h_T, meta=None):
 
 
 def save_model(d):
-    os.makedirs(GOLDEN, exist_ok=True)
-    np.savez_compressed(os.path.join(GOLDEN, 'model_%s.npz' % d['name']), **d)
+    os.makedirs(MODELS, exist_ok=True)
+    np.savez_compressed(os.path.join(MODELS, 'model_%s.npz' % d['name']), **d)
 
 
 def load_model(name):
-    z = np.load(os.path.join(GOLDEN, 'model_%s.npz' % name), allow_pickle=False)
+    z = np.load(os.path.join(MODELS, 'model_%s.npz' % name), allow_pickle=False)
     d = {k: z[k] for k in z.files}
     d['name'] = str(d['name'])
     d['nub'] = int(d['nub'])

@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 import torch
 
-from oracle.models import load_model, GOLDEN
+from oracle.models import load_model, GOLDEN, MODELS
 from tests.util import make_controller
 
 pytestmark = pytest.mark.gpu
@@ -39,9 +39,9 @@ def test_device_bnb_equals_host_bnb(cp20, rule):
     order = []
     orig = ctl._solve_subproblem
 
-    def spy(identifier, x0_, active_set=None, hot=True, extra=None):
+    def spy(identifier, x0_, active_set=None):
         order.append(_ident_key(identifier))
-        return orig(identifier, x0_, active_set, hot, extra)
+        return orig(identifier, x0_, active_set)
     ctl._solve_subproblem = spy
     try:
         sol_h, leaves_h, n_h, _ = ctl.feedforward(x0, search_rule=search_rule, printing_period=None)
@@ -208,7 +208,7 @@ def test_fused_closed_loop_equals_lock_step(cp20, warm):
     model, ctl = cp20
     from warm_start_hmpc_b200.closed_loop import ClosedLoop
     N, S = 200, 4
-    x0 = np.load(os.path.join(GOLDEN, 'cp20_instances.npy'))[:N]
+    x0 = np.load(os.path.join(MODELS, 'cp20_instances.npy'))[:N]
     rng = np.random.default_rng(5)
     e = torch.as_tensor(0.003 * rng.standard_normal((S, N, 4)) * model['x_max'], device='cuda')
     A = ClosedLoop(ctl, N, warm=warm, max_solves=1024, max_roots=512)
@@ -262,7 +262,7 @@ def test_noisy_closed_loop_warm_equals_cold():
     model = load_model('cp20')
     ctl = make_controller(model)
     N, S = 48, 6
-    x0 = np.load(os.path.join(GOLDEN, 'cp20_instances.npy'))[:N]
+    x0 = np.load(os.path.join(MODELS, 'cp20_instances.npy'))[:N]
     rng = np.random.default_rng(11)
     e = torch.as_tensor(0.003 * rng.standard_normal((S, N, 4)) * model['x_max'], device='cuda')
     W = ClosedLoop(ctl, N, warm=True, max_solves=1024, max_roots=512)

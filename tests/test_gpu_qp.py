@@ -13,6 +13,10 @@ pytestmark = pytest.mark.gpu
 
 # relative cost tolerance of north_star ("optimal cost ... within 1e-6 relative")
 COST_RTOL = 1e-6
+# primal inequality tolerance: the kernel accepts a row violated by at most tol_p = 1e-7 in the scaling
+# max(1, |row of [F G]|), escalated to at most 100 tol_p = 1e-5 on rows that entered the working set degenerately
+# (qp_device.cuh pricing; Gurobi's FeasibilityTol default is 1e-6 on rows it scales itself)
+PV_SCALED = 1.0e-5 * (1. + 1e-6)
 
 
 def _check_batch(model, N, seed, n_slots, nodes=None):
@@ -35,8 +39,9 @@ def _check_batch(model, N, seed, n_slots, nodes=None):
         dob = cert.dual_objective(model, cond, x0[i], lb[i], ub[i], fam)
         if st[i] == 2:
             assert abs(cost[i] - ref['cost']) <= COST_RTOL * abs(ref['cost']), (i, cost[i], ref['cost'])
-            pe, pv = cert.primal_residuals(model, cond, x0[i], lb[i], ub[i], fam)
-            assert pe <= 1e-9 and pv <= 2e-4, (i, pe, pv)
+            pe, _ = cert.primal_residuals(model, cond, x0[i], lb[i], ub[i], fam)
+            pv = cert.primal_violation_scaled(model, cond, x0[i], lb[i], ub[i], fam)
+            assert pe <= 1e-9 and pv <= PV_SCALED, (i, pe, pv)
             assert ds <= 1e-7, (i, ds)
             assert abs(cost[i] - dob) <= 1e-6 * abs(cost[i]), (i, cost[i], dob)       # duality gap
             assert dobj[i] == cost[i]
@@ -124,8 +129,9 @@ def test_syn30_dive_nodes_match_golden():
     P = out['primal'].cpu().numpy(); D = out['dual'].cpu().numpy()
     for i in np.nonzero(ok)[0][:6]:
         fam = families_from_records(ctl.problem, h.layout, 2, P[i], D[i])
-        pe, pv = cert.primal_residuals(model, cond, x0[i], g['lb'][i], g['ub'][i], fam)
+        pe, _ = cert.primal_residuals(model, cond, x0[i], g['lb'][i], g['ub'][i], fam)
+        pv = cert.primal_violation_scaled(model, cond, x0[i], g['lb'][i], g['ub'][i], fam)
         ds, neg = cert.dual_residuals(model, cond, fam)
         dob = cert.dual_objective(model, cond, x0[i], g['lb'][i], g['ub'][i], fam)
-        assert pe <= 1e-9 and pv <= 2e-4 and ds <= 1e-7 and neg >= 0.
+        assert pe <= 1e-9 and pv <= PV_SCALED and ds <= 1e-7 and neg >= 0.
         assert abs(cost[i] - dob) <= 1e-6 * abs(cost[i])

@@ -127,17 +127,81 @@ def test_record_round_trip_and_layout():
 
 
 def test_host_construct_warm_start_equals_reference_golden():
-    """The host restatement of construct_warm_start in the product (used by the drop-in API with custom
-    rules) on the reference's golden leaves: bounds equal to the reference code's output."""
+    """The batched host formulation of construct_warm_start in the product (identifiers a user branch rule may
+    produce; prefix identifiers go through kernel K2+K4) on the reference's golden leaves: same cover, same
+    dual = None pattern, bounds equal to the reference code's output to rounding (the sums run in another order)."""
     model = load_model('cp20')
     ctl = make_controller(model)
+    ctl.device_search = False
     g = np.load(os.path.join(GOLDEN, 'cp20_warmstart.npz'))
+    scale = max(1., np.abs(g['dobj']).max())
     for tag, e0 in (('zero', np.zeros(4)), ('rand', g['e_rand'])):
         leaves = [ws.Node(i, lb, ws.SubproblemSolution(None, d)) for i, lb, d in leaves_from_golden(ctl.problem, g)]
         nodes, _, _ = ctl.construct_warm_start(leaves, g['x0'], g['uc0'], g['ub0'], e0)
         assert len(nodes) == 77
-        assert np.array_equal(np.array([n.lb for n in nodes]), g['ws_%s_lb' % tag])
-        assert [n.extra.dual is None for n in nodes] == list(g['ws_%s_none' % tag])
+        lb, ref = np.array([n.lb for n in nodes]), g['ws_%s_lb' % tag]
+        assert np.array_equal(np.isinf(lb), np.isinf(ref))
+        fin = np.isfinite(ref)
+        assert np.all(np.abs(lb[fin] - ref[fin]) <= 1e-11 * scale)
+        none = np.array([n.extra.dual is None for n in nodes])
+        assert np.array_equal(none, g['ws_%s_none' % tag])
+        dobj = np.array([0. if n.extra.dual is None else n.extra.dual.objective for n in nodes])
+        assert np.all(np.abs(dobj[~none] - g['ws_%s_dobj' % tag][~none]) <= 1e-11 * scale)
+        wd = np.array([len(n.identifier) for n in nodes])
+        assert np.array_equal(wd, g['ws_%s_depth' % tag])
+        if tag == 'rand':
+            j = int(g['ws_rand_sample'])
+            rec = DualSolution.to_record(ctl.problem, ctl.problem.layout, nodes[j].extra.dual.variables)
+            assert np.allclose(rec, g['ws_rand_sample_rec'], rtol=1e-13, atol=1e-13)
+        # every node carries the start of its solve (multipliers of its shifted dual solution)
+        assert all(n.extra.active_set is not None and len(n.extra.active_set['c']) == ctl.qp.NumConstrs for n in nodes)
+
+
+def test_bounded_qp_surface_without_gpu():
+    """The named-family surface of the reference's BoundedQP (bounded_qp.py:127-332) that needs no solve:
+    families in the order controller.py:135-166 adds them, rhs edits with the reference's errors, status
+    conventions, parameters."""
+    model = load_model('cp20')
+    ctl = make_controller(model)
+    qp = ctl.qp
+    T, nx, nu, nub = ctl.T, ctl.mld.nx, ctl.mld.nu, ctl.mld.nub
+    assert qp.NumVars == (T + 1) * nx + T * nu and qp.NumConstrs == (T + 1) * nx + 2 * T * nub + ctl.problem.mc
+    names = [c.ConstrName for c in qp.getConstrs()]
+    assert names[:nx] == ['lam_0[%d]' % i for i in range(nx)] and names[nx] == 'nu_lb_0[0]'
+    assert names[nx + 2 * nub] == 'lam_1[0]' and names[2 * nx + 2 * nub] == 'mu_0[0]'
+    assert [v.VarName for v in qp.getVars()][:2 * nx + 1] == ['x_0[%d]' % i for i in range(nx)] + ['x_1[%d]' % i for i in range(nx)] + ['uc_0[0]']
+    assert np.array_equal(qp.get_constraint_rhs('nu_ub_3'), np.ones(nub)) and np.array_equal(qp.get_constraint_rhs('mu_0'), model['h'])
+    assert np.array_equal(qp.get_constraint_rhs('mu_%d' % (T - 1)), ctl.h_Tm1)
+    with pytest.raises(ValueError):
+        qp.set_constraint_rhs('nu_lb_0', np.zeros(nub + 1))
+    with pytest.raises(ValueError):
+        qp.set_constraint_rhs('no_such_family', np.zeros(1))
+    with pytest.raises(NotImplementedError):
+        qp.set_constraint_rhs('mu_0', np.zeros(ctl.problem.nh))
+    with pytest.raises(KeyError):
+        qp.add_variables(3, lb=[0.] * 3)
+    with pytest.raises(ValueError):
+        qp.add_constraints([1, 2], None, [1.])
+    with pytest.raises(RuntimeError):
+        qp.primal_optimizer('x_0')
+    with pytest.raises(RuntimeError):
+        qp.dual_objective()
+    ctl._set_bound_binaries({(0, 0): 1., (2, 3): 0.})
+    assert np.array_equal(qp.get_constraint_rhs('nu_lb_0'), [-1., 0., 0., 0.]) and np.array_equal(qp.get_constraint_rhs('nu_ub_2'), [1., 1., 1., 0.])
+    qp.setParam('Method', -1); assert qp.Params.Method == -1
+    qp.resetParams(); assert qp.Params.Method == 1
+    # active-set payload round trip: CBasis of a row = its multiplier, VBasis of the first T*nu variables = proximal centre
+    rng = np.random.default_rng(0)
+    rec = np.abs(rng.standard_normal(ctl.problem.layout.dual + ctl.problem.n))
+    a = qp.active_set_from_record(rec)
+    y = qp._signed_multipliers(np.array(a['c']))
+    L = ctl.problem.layout
+    assert np.array_equal(y[:ctl.problem.mc], rec[L.off_mu:L.off_nu_lb])
+    assert np.array_equal(y[ctl.problem.mc:], rec[L.off_nu_ub:L.off_rho] - rec[L.off_nu_lb:L.off_nu_ub])
+    assert np.array_equal(np.array(a['v'])[:ctl.problem.n], rec[L.dual:])
+    for c, val in zip(qp.getConstrs(), a['c']):
+        c.setAttr('CBasis', val)
+    assert np.array_equal(qp._cbasis_in, np.array(a['c']))
 
 
 def test_shard_partition():
@@ -146,3 +210,63 @@ def test_shard_partition():
         assert blocks[0][0] == 0 and blocks[-1][1] == n
         assert all(blocks[r][1] == blocks[r + 1][0] for r in range(w - 1))
         assert max(b - a for a, b in blocks) - min(b - a for a, b in blocks) <= 1
+
+
+@pytest.mark.skipif(not reference_available(), reason='/root/reference only exists in the authoring container')
+def test_product_control_flow_equals_reference_on_the_golden_run():
+    """The product's host control flow -- branch_and_bound, best_first, _brancher, _solve_subproblem,
+    SubproblemSolution.from_controller, construct_warm_start -- against the UNMODIFIED reference classes on the golden
+    CP20 run (cold step at x0 = [0, 0, 1, 0], warm start with a model error, warm step), both driving the product's
+    BoundedQP front end (its device call replaced by the CPU oracle core: no GPU here).  Bit-identical explored
+    sequence, leaves, bounds and costs; warm start bounds to 1e-11 (different summation order)."""
+    from oracle.refload import import_reference
+    from tests.util import oracle_launch
+    model = load_model('cp20')
+    ctl = make_controller(model)
+    ctl.device_search = False
+    asked = {'product': [], 'reference': []}
+
+    def spy(tag, launch):
+        def f(x0, lb, ub, y0, yc0):
+            asked[tag].append((lb.tobytes(), ub.tobytes(), x0.tobytes(), None if y0 is None else y0.tobytes()))
+            return launch(x0, lb, ub, y0, yc0)
+        return f
+    ctl.qp._launch = spy('product', oracle_launch(model, ctl.problem))
+    rc, rb, _, rm = import_reference()
+    rqp = ws.BoundedQP(ctl.problem, lambda: None)
+    rqp._launch = spy('reference', oracle_launch(model, ctl.problem))
+
+    class Ref(rc.HybridModelPredictiveController):
+        def _build_mip(self_):
+            return rqp
+
+        def _update_mu(self_):
+            return model['M_mu']
+    ref = Ref(rm.MLDSystem([model['A'], model['B']], [model['F'], model['G'], model['h']], int(model['nub'])),
+              int(model['T']), [model['Q'], model['R'], model['Q_T']], [model['F_T'], model['h_T']])
+    g = np.load(os.path.join(GOLDEN, 'cp20_closed_loop.npz'))
+    x, e = model['x0_nominal'].copy(), g['noisy_e'][0]
+    key = lambda leaves: [sorted(l.identifier.items()) for l in leaves]
+    ws_p = ws_r = None
+    for step in range(2):
+        sp, lp, n_p, _ = ctl.feedforward(x, warm_start=ws_p, printing_period=None)
+        sr, lr, n_r, _ = ref.feedforward(x, warm_start=ws_r, printing_period=None)
+        assert n_p == n_r and asked['product'] == asked['reference']           # same QPs, same starts, same order
+        assert key(lp) == key(lr) and np.array_equal([l.lb for l in lp], [l.lb for l in lr])
+        assert sp.objective == sr.objective
+        if step == 0:
+            assert n_p in (159, 160, 161) and abs(sp.objective - g['noisy_cost'][0]) <= 1e-6 * sp.objective
+        uc0, ub0 = sr.variables['uc'][0], sr.variables['ub'][0]
+        ws_p, _, _ = ctl.construct_warm_start(lp, x, uc0, ub0, e)
+        ws_r, _, _ = ref.construct_warm_start(lr, x, uc0, ub0, e)
+        assert key(ws_p) == key(ws_r) and len(ws_p) == int(g['noisy_cover'][0])
+        a, b = np.array([l.lb for l in ws_p]), np.array([l.lb for l in ws_r])
+        assert np.array_equal(np.isinf(a), np.isinf(b)) and np.all(np.abs(a[np.isfinite(a)] - b[np.isfinite(b)]) <= 1e-11)
+        assert [l.extra.dual is None for l in ws_p] == [l.extra.dual is None for l in ws_r]
+        # the reference's roots carry no active set (controller.py:487): give both sides the same starts and bounds
+        for p, r in zip(ws_p, ws_r):
+            r.extra.active_set = p.extra.active_set
+            r.lb = p.lb
+        x = sr.variables['x'][1] + e
+        asked['product'].clear(); asked['reference'].clear()
+    assert n_p < 40

@@ -66,3 +66,35 @@ def leaves_from_golden(pd, g):
             cache[r] = DualSolution.from_record(pd, pd.layout, g['recs'][r], float(g['dobj'][r]))
         out.append((ident, float(g['lb'][j]), cache.get(r)))
     return out
+
+
+def oracle_launch(model, pd):
+    """A stand-in for BoundedQP._launch (the device call) backed by the CPU oracle core: lets the CPU suite drive the
+    product's and the reference's control flow through the product's BoundedQP front end without a GPU.  Same
+    contract: (x0, lb, ub, y0, yc0) -> dict(status, cost, dobj, iters, primal, dual, yc, runtime)."""
+    from oracle.qp_c import CoreC
+    from oracle.condense import Condensed
+    from oracle import certify as cert
+    core = CoreC(model, variant=1)
+    cond = Condensed(model)
+    L = pd.layout
+
+    def launch(x0, lb, ub, y0, yc0):
+        warm = None
+        if y0 is not None:
+            rows = np.nonzero(y0)[0]
+            warm = dict(rows=rows, sides=np.where(y0[rows] > 0, 1, -1), lam=np.abs(y0[rows]), z=yc0)
+        out = core.solve(x0, lb, ub, warm=warm)
+        if out['status'] not in (2, 3) and warm is not None:
+            out = core.solve(x0, lb, ub, warm=None)
+        fam = cert.families(model, cond, x0, out['status'], out.get('z'), out['y'])
+        dual = np.concatenate([np.concatenate(fam[k]) for k in ('lam', 'mu', 'nu_lb', 'nu_ub', 'rho', 'sigma')])
+        assert dual.size == L.dual
+        primal = np.zeros(L.primal)
+        if out['status'] == 2:
+            primal = np.concatenate((np.asarray(fam['x']).ravel(), np.asarray(fam['u']).ravel()))
+        dobj = out['cost'] if out['status'] == 2 else out['farkas']
+        yc = out['warm']['z'] if out['status'] == 2 else np.zeros(pd.n)
+        return dict(status=out['status'], cost=out['cost'], dobj=dobj, iters=out['iters'], primal=primal, dual=dual,
+                    yc=np.array(yc), runtime=0.)
+    return launch

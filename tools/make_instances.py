@@ -1,4 +1,4 @@
-"""Generates tests/golden/cp20_instances.npy on a GPU box: candidates uniform in
+"""Generates warm-start-hybrid-mpc_b200/data/cp20_instances.npy on a GPU box: candidates uniform in
 +-[0.35, 0.2, 1.0, 0.6] from np.random.default_rng(0), the first 4096 whose step-0 MIQP is feasible.
     gpurun -- python tools/make_instances.py    ->  gpurun_out/cp20_instances.npy
 """

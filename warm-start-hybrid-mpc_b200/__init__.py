@@ -1,7 +1,7 @@
 """B200-native branch-and-bound hot path of warm-start-hybrid-mpc.
 
 Same public names as the reference package ``warm_start_hmpc`` for the hot path:
-``MLDSystem``, ``HybridModelPredictiveController`` (``feedforward`` / ``construct_warm_start``),
+``MLDSystem``, ``BoundedQP``, ``HybridModelPredictiveController`` (``feedforward`` / ``construct_warm_start``),
 ``branch_and_bound``, ``Node``, ``best_first`` / ``depth_first`` / ``breadth_first``,
 ``branch_in_time``, ``SubproblemSolution`` / ``PrimalSolution`` / ``DualSolution``.
 The QP relaxations run in hand-written sm_100a CUDA kernels behind a C ABI (include/wshmpc.h,
@@ -11,3 +11,4 @@ from .mld_system import MLDSystem                                               
 from .subproblem_solution import SubproblemSolution, PrimalSolution, DualSolution  # noqa: F401
 from .branch_and_bound import Node, branch_and_bound, best_first, depth_first, breadth_first  # noqa: F401
 from .controller import HybridModelPredictiveController, branch_in_time          # noqa: F401
+from .bounded_qp import BoundedQP                                                # noqa: F401

@@ -13,13 +13,13 @@ Errors follow the reference: ValueError on inconsistent sizes; an infeasible nod
 Every QP relaxation is solved on the GPU (kernel K1 through the C ABI); host code here is the
 reference's Python control flow.  The all-on-device batched search is ``feedforward_batch``.
 """
-import gc
 import numpy as np
 from time import time
 
 from .branch_and_bound import Node, branch_and_bound, best_first, depth_first, breadth_first  # noqa: F401
 from .subproblem_solution import SubproblemSolution, PrimalSolution, DualSolution
 from .problem import ProblemData
+from .bounded_qp import BoundedQP
 
 
 def _is_prefix(identifier, nub):
@@ -57,9 +57,18 @@ class HybridModelPredictiveController(object):
             self._update['mu'], self._update['rho'], **(qp_options or {}))
         self.device = device
         self._handle = None
+        self._retired = []           # smaller handles handed out earlier stay valid for whoever holds them
         self._n_slots = 1
         self.device_search = True
         self.max_solves = 4096
+        # the QP seam (controller.py:90, _build_mip :119-184)
+        self.qp = self._build_mip()
+
+    def _build_mip(self):
+        """controller.py:119-184: the relaxation of the MIQP as a BoundedQP.  The reference builds a Gurobi model row by
+        row; here the model is the device-resident shared operator compiled by problem.py and the BoundedQP object is its
+        named-family front end (same families, same order)."""
+        return BoundedQP(self.problem, self.handle)
 
     # -- construction ---------------------------------------------------------------------------
     def _check_input_sizes(self):
@@ -115,7 +124,7 @@ class HybridModelPredictiveController(object):
         self._require_gpu()
         if n_slots is not None and (self._handle is None or n_slots > self._handle.n_slots):
             if self._handle is not None:
-                self._handle.close()
+                self._retired.append(self._handle)      # never destroy a handle somebody may still hold
             self._handle = None
             self._n_slots = n_slots
         if self._handle is None:
@@ -132,161 +141,158 @@ class HybridModelPredictiveController(object):
             ub_ub[k] = v
         return ub_lb, ub_ub
 
-    def _start_from(self, extra):
-        """Signed multipliers (and proximal centre) a node starts its dual active-set solve from: the dual
-        solution it carries -- its parent's (controller.py:426) or its own shifted one (controller.py:487) --
-        and the parent's `active_set` (controller.py:262-264).  None = empty working set."""
-        if extra is None or extra.dual is None:
-            return None, None
-        v = extra.dual.variables
-        y0 = np.concatenate([np.maximum(m_, 0.) for m_ in v['mu']]
-                            + [np.maximum(np.concatenate(v['nu_ub']), 0.) - np.maximum(np.concatenate(v['nu_lb']), 0.)])
-        return y0, extra.active_set
-
-    def _solve_subproblem(self, identifier, x0, active_set=None, hot=True, extra=None):
-        """controller.py:229-271: one node = one K1 launch on slot 0.  `extra` (the SubproblemSolution the node
-        carries) gives the start of the solve, see _start_from; without it `hot` keeps the working set of the
-        previously solved node (any multipliers >= 0 are dual feasible for every node)."""
-        import torch
-        h = self.handle()
+    def _set_bound_binaries(self, identifier):
+        """controller.py:273-298: the node's bounds on the binaries as right-hand sides of the rows nu_lb_t, nu_ub_t."""
         lb, ub = self._get_bound_binaries(identifier)
-        y0, yc0 = self._start_from(extra)
-        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        start.record()
-        if extra is not None:
-            mode = 2 if y0 is not None else 0
-            out = h.solve_nodes(np.asarray(x0, dtype=float)[None], lb.reshape(1, -1), ub.reshape(1, -1),
-                                slot=np.zeros(1, np.int32), hot=np.array([mode], np.int32),
-                                y0=None if y0 is None else y0[None], yc0=None if yc0 is None else np.asarray(yc0)[None])
-        else:
-            out = h.solve_nodes(np.asarray(x0, dtype=float)[None], lb.reshape(1, -1), ub.reshape(1, -1),
-                                slot=np.zeros(1, np.int32), hot=np.array([1 if hot else 0], np.int32))
-        end.record()
-        end.synchronize()
-        solve_time = start.elapsed_time(end) * 1e-3
-        status = int(out['status'][0])
-        if status not in (2, 3):
-            raise RuntimeError('QP kernel did not converge (status %d) for identifier %r' % (status, identifier))
-        # subproblem_solution.py:94-97: binary feasible iff EVERY binary is pinned by the identifier
-        binary_feasible = bool(np.array_equal(lb, ub))
-        primal = PrimalSolution.from_record(self.problem, out['primal'][0].cpu().numpy(), float(out['cost'][0]),
-                                            binary_feasible, status == 2)
-        dual = DualSolution.from_record(self.problem, h.layout, out['dual'][0].cpu().numpy(), float(out['dobj'][0]))
-        # active_set = proximal centre of this solve: what the children start from (controller.py:426)
-        sol = SubproblemSolution(primal, dual, out['yc'][0].cpu().numpy() if status == 2 else None)
-        sol.iters = int(out['iters'][0])
-        return sol, solve_time
+        for t in range(self.T):
+            self.qp.set_constraint_rhs('nu_lb_%d' % t, -lb[t])
+            self.qp.set_constraint_rhs('nu_ub_%d' % t, ub[t])
+
+    def _solve_subproblem(self, identifier, x0, active_set=None):
+        """controller.py:229-271, same signature: set the right-hand sides, hand the parent's `active_set` to the solver,
+        optimise (one K1 launch, bounded_qp.BoundedQP.optimize), wrap the solution."""
+        self._set_bound_binaries(identifier)
+        self.qp.set_constraint_rhs('lam_0', np.asarray(x0, dtype=float))
+        if active_set is not None and self.qp.Params.Method == 1:
+            self.qp.set_active_set(active_set)
+        self.qp.optimize()
+        solution = SubproblemSolution.from_controller(self)
+        return solution, self.qp.Runtime
+
+    def _set_gurobi_params(self, gurobi_params):
+        """controller.py:778-796.  Only `Method` means something to the CUDA solver (1 = children start from the parent's
+        active set, the default; anything else = every node from the empty working set); other keys are recorded."""
+        self.qp.resetParams()
+        self.qp.setParam('OutputFlag', 0)
+        for param, value in gurobi_params.items():
+            self.qp.setParam(param, value)
 
     # -- per-solve seam -------------------------------------------------------------------------
     def feedforward(self, x0, gurobi_params={}, search_rule=best_first, branch_rule=branch_in_time, **kwargs):
-        """controller.py:329-393.  `gurobi_params` is accepted for signature compatibility and ignored
-        (there is no Gurobi underneath).  With the reference's search rules (best_first, depth_first, breadth_first;
+        """controller.py:329-393.  With the reference's search rules (best_first, depth_first, breadth_first;
         branch_and_bound.py:501-563), branch_in_time and `device_search=True` the whole search runs in the device-side
         B&B kernel (K3); a user-defined rule, or `device_search=False`, runs the reference's host loop with one K1
-        launch per node -- both visit the same nodes in the same order and return bit-identical results."""
+        launch per node through `self.qp` -- both visit the same nodes in the same order and return bit-identical
+        results."""
+        self._set_gurobi_params(gurobi_params)
+        self.qp.reset()
         rules = {best_first: 0, depth_first: 1, breadth_first: 2}
-        if self.device_search and search_rule in rules and branch_rule is branch_in_time:
+        if self.device_search and self.qp.Params.Method == 1 and search_rule in rules and branch_rule is branch_in_time:
             ws = kwargs.get('warm_start')
             if ws is None or all(_is_prefix(l.identifier, self.mld.nub) for l in ws):
                 return self._feedforward_device(x0, kwargs.get('tol', 0.), ws, rules[search_rule])
+
         def solver(identifier, cutoff, extra):
-            solution, solve_time = self._solve_subproblem(identifier, x0, None, extra=extra if extra is not None
-                                                          else SubproblemSolution(None, None, None))
+            start = extra.active_set if extra is not None else None
+            solution, solve_time = self._solve_subproblem(identifier, x0, start)
             return solution.primal.objective, solution.primal.binary_feasible, solve_time, solution
 
-        def brancher(parent):
-            return self._brancher(parent, branch_rule)
-
-        incumbent, leaves, qp_solves, solver_time = branch_and_bound(solver, search_rule, brancher, **kwargs)
-        if incumbent is None:
-            return None, leaves, qp_solves, solver_time
-        return incumbent.extra.primal, leaves, qp_solves, solver_time
+        incumbent, leaves, qp_solves, solver_time = branch_and_bound(
+            solver, search_rule, lambda parent: self._brancher(parent, branch_rule), **kwargs)
+        primal = None if incumbent is None else incumbent.extra.primal
+        return primal, leaves, qp_solves, solver_time
 
     def _brancher(self, parent, branch_rule):
-        """controller.py:395-429: child bound = parent bound + multiplier of the bound that moves."""
-        branches = branch_rule(parent.identifier, self.mld.nub)
+        """controller.py:395-429: a child's bound is its parent's plus the multiplier of the bound that moves
+        (nu_lb for a binary fixed to 1, nu_ub for 0); children share the parent's dual solution and active set."""
+        nu = parent.extra.dual.variables
         children = []
-        for branch in branches:
-            lb = parent.lb
-            for k, v in branch.items():
-                nu = 'nu_lb' if v == 1 else 'nu_ub' if v == 0 else None
-                lb += parent.extra.dual.variables[nu][k[0]][k[1]]
-            identifier = {**parent.identifier, **branch}
-            solution = SubproblemSolution(None, parent.extra.dual, parent.extra.active_set)
-            children.append(Node(identifier, lb, solution))
+        for branch in branch_rule(parent.identifier, self.mld.nub):
+            moved = sum(nu['nu_lb' if v == 1 else 'nu_ub'][t][i] for (t, i), v in branch.items())
+            children.append(Node({**parent.identifier, **branch}, parent.lb + moved,
+                                 SubproblemSolution(None, parent.extra.dual, parent.extra.active_set)))
         return children
 
-    # -- warm start (host restatement; the batched device version is K4) ------------------------------
-    def _construct_warm_start_interstep(self, leaves, x0, uc0, ub0):
-        """controller.py:431-501."""
-        u0 = np.concatenate((uc0, ub0))
-        gc.disable()
-        construction_time = time()
-        warm_start = []
-        for leaf in leaves:
-            if self._retain_leaf(leaf.identifier, ub0):
-                shifted_identifier = {(k[0] - 1, k[1]): v for k, v in leaf.identifier.items() if k[0] > 0}
-                shifted_variables = self._shift_dual_variables(leaf.extra.dual.variables)
-                pi_sum = self._pi_sum(leaf.identifier, leaf.extra.dual.variables, shifted_variables, x0, u0)
-                shifted_dual = DualSolution(shifted_variables, leaf.extra.dual.objective + pi_sum)
-                warm_start.append(Node(shifted_identifier, leaf.lb, SubproblemSolution(None, shifted_dual)))
-        construction_time = time() - construction_time
-        gc.enable()
-        return warm_start, construction_time
-
+    # -- warm start ---------------------------------------------------------------------------------
     def construct_warm_start(self, leaves, x0, uc0, ub0, e0):
-        """controller.py:503-564."""
-        warm_start, interstep_time = self._construct_warm_start_interstep(leaves, x0, uc0, ub0)
-        gc.disable()
-        construction_time = time()
-        for leaf in warm_start:
-            pi3 = - leaf.extra.dual.variables['lam'][0].dot(e0)
-            leaf.extra.dual.objective += pi3
-            leaf.extra.dual.objective = max(leaf.extra.dual.objective, 0)
-            if not np.isinf(leaf.lb):
-                leaf.lb = leaf.extra.dual.objective
-            else:
-                if leaf.extra.dual.objective <= 0.:
-                    leaf.lb = 0.
-                    leaf.extra.dual = None
-        construction_time = time() - construction_time
-        gc.enable()
-        return warm_start, construction_time, interstep_time
+        """controller.py:503-564 (with :431-501, :615-721 inside): the leaves of this step's search -> the initial cover
+        of the next step's.  Returns (nodes, runtime seconds, inter-step seconds) like the reference; the device kernel
+        does both parts at once, so all its time is reported as run time.
 
-    @staticmethod
-    def _retain_leaf(identifier, ub0):
-        """controller.py:615-633."""
-        return all(v == ub0[k[1]] for k, v in identifier.items() if k[0] == 0)
+        Leaves with chronological-prefix identifiers (everything branch_in_time produces) are shifted by kernel K2+K4
+        (wshmpc_shift_tree): uploaded as a one-instance device tree, shifted, read back.  Other identifiers (user
+        branch rules) take the batched host formulation `_shift_records_host`."""
+        leaves = list(leaves)
+        if self.device_search and all(_is_prefix(l.identifier, self.mld.nub) for l in leaves):
+            return self._construct_warm_start_device(leaves, x0, uc0, ub0, e0)
+        tic = time()
+        nodes = self._shift_records_host(leaves, np.asarray(x0, float), np.concatenate((uc0, ub0)), np.asarray(e0, float))
+        return nodes, time() - tic, 0.
 
-    def _shift_dual_variables(self, variables):
-        """controller.py:635-666."""
-        shifted = {}
-        for k in ['lam', 'nu_lb', 'nu_ub', 'sigma']:
-            shifted[k] = variables[k][1:]
-            shifted[k].append(np.zeros(variables[k][-1].shape))
-        for k in ['mu', 'rho']:
-            shifted[k] = variables[k][1:-1]
-            shifted[k].append(self._update[k].dot(variables[k][-1]))
-            shifted[k].append(np.zeros(variables[k][-1].shape))
-        return shifted
+    def _construct_warm_start_device(self, leaves, x0, uc0, ub0, e0):
+        import torch
+        self._require_gpu()
+        h = self.handle()
+        nx, nu, T = self.mld.nx, self.mld.nu, self.T
+        x0 = np.asarray(x0, dtype=float); u0 = np.concatenate((uc0, ub0)).astype(float)
+        tree = self.leaves_to_tree(leaves, max_solves=0)
+        new = h.new_tree(1, max(len(leaves), 1) + 2, max(len(leaves), 1) + 1)
+        dev = tree.lb.device
+        primal = torch.zeros((1, h.layout.primal), dtype=torch.float64, device=dev)
+        primal[0, nx:2 * nx] = torch.as_tensor(self.mld.A.dot(x0) + self.mld.B.dot(u0), device=dev)
+        primal[0, (T + 1) * nx:(T + 1) * nx + nu] = torch.as_tensor(u0, device=dev)
+        cost = torch.zeros(1, dtype=torch.float64, device=dev)
+        xd = torch.as_tensor(x0[None], device=dev).contiguous()
+        ed = torch.as_tensor(np.asarray(e0, dtype=float)[None], device=dev).contiguous()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        h.shift_tree(xd, ed, tree, cost, primal, new)
+        end.record(); end.synchronize()
+        return self.tree_to_leaves(new, 0), start.elapsed_time(end) * 1e-3, 0.
 
-    def _pi_sum(self, identifier, variables, shifted_variables, x0, u0):
-        """controller.py:668-721."""
-        squared = lambda x: x.dot(x)
-        Qx0 = self.Q.dot(x0)
-        Ru0 = self.R.dot(u0)
-        pi_sum = - squared(Qx0) - squared(Ru0)
-        pi_sum += squared(.5 * variables['rho'][0] - Qx0) + squared(.5 * variables['sigma'][0] - Ru0)
-        ub_lb, ub_ub = self._get_bound_binaries(identifier)
-        residuals = {
-            'mu': self.mld.F.dot(x0) + self.mld.G.dot(u0) - self.mld.h,
-            'nu_lb': ub_lb[0] - self.mld.V.dot(u0),
-            'nu_ub': self.mld.V.dot(u0) - ub_ub[0],
-        }
-        pi_sum -= sum(residual.dot(variables[k][0]) for k, residual in residuals.items())
-        pi_sum += .25 * squared(variables['rho'][self.T]) - .25 * squared(shifted_variables['rho'][self.T - 1])
-        pi_sum += self.h_Tm1.dot(variables['mu'][self.T - 1]) - self.mld.h.dot(shifted_variables['mu'][self.T - 2])
-        return pi_sum
+    def _shift_records_host(self, leaves, x0, u0, e0):
+        """Batched host formulation of the warm start for identifiers that are not chronological prefixes: the same
+        record algebra kernel K2+K4 runs (csrc/bnb.cuh shift_instance), on a [leaves x record] matrix.
+        Follows controller.py:431-564, 615-721."""
+        pd, L = self.problem, self.problem.layout
+        T, nx, nu, nub, nuc, nh, nh1, nq, nqT, nr = pd.T, pd.nx, pd.nu, pd.nub, pd.nuc, pd.nh, pd.nh1, pd.nq, pd.nqT, pd.nr
+        ub0 = u0[nuc:]
+        keep = [l for l in leaves if all(v == ub0[i] for (t, i), v in l.identifier.items() if t == 0)]     # :615-633
+        if not keep:
+            return []
+        D = np.vstack([DualSolution.to_record(pd, L, l.extra.dual.variables) for l in keep])
+        obj = np.array([l.extra.dual.objective for l in keep])
+        lo = np.zeros((len(keep), nub)); hi = np.ones((len(keep), nub))         # old bounds at t = 0
+        for r, l in enumerate(keep):
+            for (t, i), v in l.identifier.items():
+                if t == 0:
+                    lo[r, i] = hi[r, i] = v
+        blk = lambda off, width, t0, t1: D[:, off + t0 * width:off + t1 * width]
+        S = np.zeros_like(D)                                                     # shifted records (:635-666)
+        S[:, L.off_lam:L.off_lam + T * nx] = blk(L.off_lam, nx, 1, T + 1)
+        S[:, L.off_nu_lb:L.off_nu_lb + (T - 1) * nub] = blk(L.off_nu_lb, nub, 1, T)
+        S[:, L.off_nu_ub:L.off_nu_ub + (T - 1) * nub] = blk(L.off_nu_ub, nub, 1, T)
+        S[:, L.off_sigma:L.off_sigma + (T - 1) * nr] = blk(L.off_sigma, nr, 1, T)
+        S[:, L.off_mu:L.off_mu + (T - 2) * nh] = blk(L.off_mu, nh, 1, T - 1)
+        mu_last = D[:, L.off_mu + (T - 1) * nh:L.off_nu_lb]
+        mu_new = mu_last.dot(self._update['mu'].T)
+        S[:, L.off_mu + (T - 2) * nh:L.off_mu + (T - 1) * nh] = mu_new
+        S[:, L.off_rho:L.off_rho + (T - 1) * nq] = blk(L.off_rho, nq, 1, T)
+        rho_T = D[:, L.off_rho + T * nq:L.off_sigma]
+        rho_new = rho_T.dot(self._update['rho'].T)
+        S[:, L.off_rho + (T - 1) * nq:L.off_rho + T * nq] = rho_new
+        # change of the dual objective (:668-721) and the run-time correction pi3 (:541-546)
+        Qx0, Ru0 = self.Q.dot(x0), self.R.dot(u0)
+        rho_0, sig_0 = blk(L.off_rho, nq, 0, 1), blk(L.off_sigma, nr, 0, 1)
+        pi = ((.5 * rho_0 - Qx0) ** 2).sum(1) - Qx0.dot(Qx0) + ((.5 * sig_0 - Ru0) ** 2).sum(1) - Ru0.dot(Ru0)
+        pi -= blk(L.off_mu, nh, 0, 1).dot(self.mld.F.dot(x0) + self.mld.G.dot(u0) - self.mld.h)
+        pi -= ((lo - ub0) * blk(L.off_nu_lb, nub, 0, 1)).sum(1) + ((ub0 - hi) * blk(L.off_nu_ub, nub, 0, 1)).sum(1)
+        pi += .25 * (rho_T ** 2).sum(1) - .25 * (rho_new ** 2).sum(1)
+        pi += mu_last.dot(self.h_Tm1) - mu_new.dot(self.mld.h)
+        pi -= S[:, L.off_lam:L.off_lam + nx].dot(e0)
+        obj = np.maximum(obj + pi, 0.)
+        nodes = []
+        for r, l in enumerate(keep):
+            ident = {(t - 1, i): v for (t, i), v in l.identifier.items() if t > 0}
+            dual = DualSolution.from_record(pd, L, S[r], obj[r])
+            start = self.qp.active_set_from_dual(dual)
+            lb = l.lb
+            if not np.isinf(l.lb):
+                lb = obj[r]                                                      # :550-551
+            elif obj[r] <= 0.:
+                lb, dual = 0., None                                              # :555-558 (the ray stays as a START)
+            nodes.append(Node(ident, lb, SubproblemSolution(None, dual, start)))
+        return nodes
 
     # -- device-resident batch path (K3, K2 + K4) ----------------------------------------------------
     def _as_device(self, a, shape):
@@ -339,12 +345,11 @@ class HybridModelPredictiveController(object):
         h.shift_tree(res['x0'], e0, tree, res['cost'], res['primal'], new_tree, active=active, x_next=x_next, u0=u0)
         return new_tree, x_next, u0
 
-    @staticmethod
-    def default_slots():
+    def default_slots(self):
         """Solver states resident at once: SMs (148 on a B200) x solver CTAs per SM of the library build."""
         import torch
         from .capi import load_library
-        return torch.cuda.get_device_properties(0).multi_processor_count * int(load_library().wshmpc_ctas_per_sm())
+        return torch.cuda.get_device_properties(self.device).multi_processor_count * int(load_library().wshmpc_ctas_per_sm())
 
     # -- tree <-> reference Node lists ---------------------------------------------------------------
     def tree_to_leaves(self, tree, inst=0):
@@ -358,19 +363,24 @@ class HybridModelPredictiveController(object):
         nr = int(tree.n_recs[inst])
         duals = tree.rec_dual[inst, :nr].cpu().numpy(); dobj = tree.rec_dobj[inst, :nr].cpu().numpy()
         cache = {}
+
+        def record(r):                  # children alias the parent's dual object and active set (controller.py:426)
+            if r not in cache:
+                cache[r] = (DualSolution.from_record(self.problem, h.layout, duals[r], dobj[r]),
+                            self.qp.active_set_from_record(duals[r]))
+            return cache[r]
         leaves = []
         for j in range(nn):
             if not alive[j]:
                 continue
             ident = {(q // nub, q % nub): float((bits[j, q >> 5] >> (q & 31)) & 1) for q in range(depth[j])}
             r = int(rec[j])
-            if r < 0:
-                extra = SubproblemSolution(None, None) if depth[j] or np.isfinite(lb[j]) else None
+            if r >= 0:
+                extra = SubproblemSolution(None, record(r)[0], record(r)[1])
+            elif r <= -2:               # dual = None (controller.py:555-558); the shifted ray survives as the START of the solve
+                extra = SubproblemSolution(None, None, record(-2 - r)[1])
             else:
-                if r not in cache:          # children alias the parent's dual object (controller.py:426)
-                    cache[r] = (DualSolution.from_record(self.problem, h.layout, duals[r], dobj[r]),
-                                duals[r][h.layout.dual:h.layout.rec_stride].copy())
-                extra = SubproblemSolution(None, cache[r][0], cache[r][1])
+                extra = SubproblemSolution(None, None) if depth[j] or np.isfinite(lb[j]) else None
             node = Node(ident, float(lb[j]), extra)
             node.index = j
             leaves.append(node)
@@ -387,6 +397,7 @@ class HybridModelPredictiveController(object):
         depth = np.zeros(n0, np.int32); rec = np.full(n0, -1, np.int32); lb = np.zeros(n0)
         bits = np.zeros((n0, tree.words), np.uint32)
         recs, dobj, seen = [], [], {}
+        L, n = h.layout, self.problem.n
         for j, l in enumerate(leaves):
             depth[j] = len(l.identifier)
             for (t, i), v in l.identifier.items():
@@ -395,13 +406,26 @@ class HybridModelPredictiveController(object):
                     bits[j, q >> 5] |= np.uint32(1 << (q & 31))
             lb[j] = l.lb
             dual = None if l.extra is None else l.extra.dual
-            if dual is not None:
-                if id(dual) not in seen:
-                    seen[id(dual)] = len(recs)
-                    yc = np.zeros(h.layout.rec_stride - h.layout.dual) if l.extra.active_set is None else np.asarray(l.extra.active_set)
-                    recs.append(np.concatenate((DualSolution.to_record(self.problem, h.layout, dual.variables), yc)))
+            start = None if l.extra is None else l.extra.active_set
+            key = id(dual) if dual is not None else (id(start) if start is not None else None)
+            if key is None:
+                continue
+            if key not in seen:
+                seen[key] = len(recs)
+                rec_j = np.zeros(L.rec_stride)
+                if dual is not None:
+                    rec_j[:L.dual] = DualSolution.to_record(self.problem, L, dual.variables)
                     dobj.append(dual.objective)
-                rec[j] = seen[id(dual)]
+                else:                   # only the start survives: rebuild the multiplier part of the record from it
+                    y = self.qp._signed_multipliers(np.asarray(start['c'], dtype=float))
+                    rec_j[L.off_mu:L.off_nu_lb] = y[:self.problem.mc]
+                    rec_j[L.off_nu_lb:L.off_nu_ub] = np.maximum(-y[self.problem.mc:], 0.)
+                    rec_j[L.off_nu_ub:L.off_rho] = np.maximum(y[self.problem.mc:], 0.)
+                    dobj.append(0.)
+                if start is not None:
+                    rec_j[L.dual:L.dual + n] = np.asarray(start['v'], dtype=float)[:n]
+                recs.append(rec_j)
+            rec[j] = seen[key] if dual is not None else -2 - seen[key]
         dev = tree.lb.device
         tree.n_nodes[0] = n0; tree.n_recs[0] = len(recs)
         tree.depth[0, :n0] = torch.as_tensor(depth, device=dev); tree.alive[0, :n0] = 1

@@ -243,8 +243,11 @@ __host__ __device__ inline size_t shift_smem_doubles(const DevProblem &P, int nt
 
 // warm start of ONE instance by the calling CTA (NT threads): shm = shared scratch (shift_smem_doubles),
 // s_wsum (NT / 32 ints) and s_base (1 int) shared as well.
+// Returns 0, or 1 if the retained leaves do not fit min(nt.cap_nodes, nt.cap_recs) (every retained leaf takes a node AND a
+// dual record of the new tree): the instance is then switched off (active = 0, empty new tree) instead of continuing
+// with an incomplete cover -- a truncated cover could report a suboptimal or "infeasible" MIQP as solved.
 template <int NT>
-__device__ inline void shift_instance(const DevProblem &P, double *shm, int *s_wsum, int *s_base_p, int inst,
+__device__ inline int shift_instance(const DevProblem &P, double *shm, int *s_wsum, int *s_base_p, int inst,
                                       const double *__restrict__ x0, const double *__restrict__ e0,
                                       const TreeView &ot, const double *__restrict__ inc_cost, const double *__restrict__ inc_primal,
                                       int *active, const TreeView &nt, double *x_next, double *u0_out)
@@ -266,7 +269,7 @@ __device__ inline void shift_instance(const DevProblem &P, double *shm, int *s_w
         }
         for (int j = threadIdx.x; j < nx; j += NT) if (x_next) x_next[(size_t)inst * nx + j] = x0[(size_t)inst * nx + j];
         for (int j = threadIdx.x; j < nu; j += NT) if (u0_out) u0_out[(size_t)inst * nu + j] = nan("");
-        return;
+        return 0;
     }
     for (int j = threadIdx.x; j < nx; j += NT) { xs[j] = x0[(size_t)inst * nx + j]; es[j] = e0 ? e0[(size_t)inst * nx + j] : 0.; }
     for (int j = threadIdx.x; j < nu; j += NT) us[j] = ip[(size_t)(T + 1) * nx + j];
@@ -287,6 +290,7 @@ __device__ inline void shift_instance(const DevProblem &P, double *shm, int *s_w
 
     const size_t oo = (size_t)inst * ot.cap_nodes, on_ = (size_t)inst * nt.cap_nodes;
     const int nn = ot.n_nodes[inst];
+    const int cap_new = nt.cap_nodes < nt.cap_recs ? nt.cap_nodes : nt.cap_recs;
     // ---- pass 1: _retain_leaf (controller.py:615-633) + ordered compaction + identifier shift (:476)
     for (int base = 0; base < nn; base += NT) {
         const int j = base + threadIdx.x;
@@ -305,7 +309,7 @@ __device__ inline void shift_instance(const DevProblem &P, double *shm, int *s_w
         int pre = s_base;
         for (int q = 0; q < w; ++q) pre += s_wsum[q];
         const int idx = pre + __popc(bal & ((1u << lane) - 1u));
-        if (keep && idx < nt.cap_nodes) {
+        if (keep && idx < cap_new) {
             const int d = ot.depth[oo + j];
             const int dn = d > nub ? d - nub : 0;
             nt.depth[on_ + idx] = dn; nt.alive[on_ + idx] = 1; nt.rec[on_ + idx] = j;   // rec = source node (pass 2 rewrites it)
@@ -326,7 +330,13 @@ __device__ inline void shift_instance(const DevProblem &P, double *shm, int *s_w
         if (threadIdx.x == 0) { int s = s_base; for (int q = 0; q < (NT / 32); ++q) s += s_wsum[q]; s_base = s; }
         __syncthreads();
     }
-    const int nnew = s_base < nt.cap_nodes ? s_base : nt.cap_nodes;
+    if (s_base > cap_new) {
+        // capacity of the new tree exceeded: never truncate the cover
+        __syncthreads();
+        if (threadIdx.x == 0) { if (active) active[inst] = 0; nt.n_nodes[inst] = 0; nt.n_recs[inst] = 0; }
+        return 1;
+    }
+    const int nnew = s_base;
     // ---- pass 2: one warp per retained leaf
     for (int idx = w; idx < nnew; idx += (NT / 32)) {
         const int j = nt.rec[on_ + idx];
@@ -427,7 +437,7 @@ __device__ inline void shift_instance(const DevProblem &P, double *shm, int *s_w
     }
     __syncthreads();
     if (threadIdx.x == 0) { nt.n_nodes[inst] = nnew; nt.n_recs[inst] = nnew; }
-
+    return 0;
 #undef s_base
 }
 
@@ -571,8 +581,9 @@ closed_loop_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, doub
             L.log_cost[lo] = inc_cost[inst]; L.log_solves[lo] = n_solves[inst]; L.log_status[lo] = st;
         }
         __syncthreads();
-        shift_instance<WS_NT>(P, SMV(Q), SMI(ired), SMI(ired) + 16, inst, xc, L.e ? L.e + (size_t)t * xs : nullptr,
-                              cur, inc_cost, inc_primal, L.active, nxt, xn, L.log_u0 + (size_t)t * n_inst * P.nu);
+        const int ovf = shift_instance<WS_NT>(P, SMV(Q), SMI(ired), SMI(ired) + 16, inst, xc, L.e ? L.e + (size_t)t * xs : nullptr,
+                                              cur, inc_cost, inc_primal, L.active, nxt, xn, L.log_u0 + (size_t)t * n_inst * P.nu);
+        if (ovf && threadIdx.x == 0) { status_out[inst] = BNB_CAPACITY; L.log_status[(size_t)t * n_inst + inst] = BNB_CAPACITY; }
         prof_mark(19);
         if (threadIdx.x == 0) L.step_of[inst] = t + 1;
         __threadfence();                                   // release: the instance's data before the token

@@ -1086,7 +1086,9 @@ restart:
     prof_mark(3);
     kmax = max(kmax, k);
     const int k_start = k; int n_prox = 0;
-    int pending = -1, pside = 0, just_added = -1;
+    int pending = -1, pside = 0, just_added = -1, n_verify = 0;
+    bool prox_conv = false;
+    if (threadIdx.x == 0) SMI(idep)[1] = 0;
     double plam = 0.;
     for (int pk = 0; pk < P.max_prox; ++pk) {
         ++n_prox;
@@ -1141,7 +1143,7 @@ restart:
                     __syncthreads();
                     if (threadIdx.x == 0) {
                         const int rr = row[kmin];
-                        if (rr == just_added && lam[kmin] == 0.) ign[rr] |= (side[kmin] > 0 ? 1 : 2);
+                        if (rr == just_added && lam[kmin] == 0.) { ign[rr] |= (side[kmin] > 0 ? 1 : 2); SMI(idep)[1] = 1; }
                         if (amin <= 1e-9 && nadd[rr] < 255) ++nadd[rr];
                     }
                     just_added = -1;
@@ -1171,7 +1173,30 @@ restart:
                 prof_mark(10);
                 block_argmax(vbest, ibest, red, ired);
                 prof_mark(11);
-                if (ibest < 0) { status = WS_OPTIMAL; break; }
+                if (ibest < 0) {
+                    // Rows put on the anti-cycling ignore list stay there across the proximal passes although the bounds move:
+                    // before the point is declared optimal, price them once more, unfiltered, against the loosest tolerance the
+                    // pricing ever uses (100 tol_p); a row violated beyond that is given back to the method (at most twice).
+                    if (SMI(idep)[1] != 0 && n_verify < 2) {
+                        double wbest = 0.; int wi = -1;
+                        price_rows(P, cx, SMV(v), d, 63, [&](int r) { return inW[r] != 0 || ign[r] == 3 || ign[r] == 0; }, [&](int r, double sv) {
+                            const double vs = vsc[r];
+                            const double vu = (sv - bu[r]) * vs;
+                            if (vu > vcap && vu > wbest) { wbest = vu; wi = r; }
+                            if (r >= mc) { const double vl = (blb[r - mc] - sv) * vs; if (vl > vcap && vl > wbest) { wbest = vl; wi = r; } }
+                        });
+                        block_argmax(wbest, wi, red, ired);
+                        ++n_verify;
+                        if (threadIdx.x == 0) SMI(idep)[1] = 0;
+                        if (wi >= 0) {
+                            for (int r = threadIdx.x; r < m; r += WS_NT) if (ign[r] != 3) ign[r] = 0;
+                            __syncthreads();
+                            continue;
+                        }
+                        __syncthreads();
+                    }
+                    status = WS_OPTIMAL; break;
+                }
                 const int jb = ibest >> 1, sb = (ibest & 1) ? -1 : 1;
                 const int ar = thin_append(P, cx, k, jb, sb, true);
                 if (ar < 0) break;                                  // capacity: reported as iteration limit
@@ -1220,7 +1245,7 @@ restart:
                         status = WS_INFEASIBLE;
                         break;
                     }
-                    if (threadIdx.x == 0) ign[pending] |= (pside > 0 ? 1 : 2);
+                    if (threadIdx.x == 0) { ign[pending] |= (pside > 0 ? 1 : 2); SMI(idep)[1] = 1; }
                     pending = -1;
                     __syncthreads();
                     continue;
@@ -1251,8 +1276,10 @@ restart:
         prof_mark(15);
         for (int r = threadIdx.x; r < n; r += WS_NT) SMV(yc)[r] = SMV(c2)[r];
         __syncthreads();
-        if (P.eps * dz <= P.prox_tol) break;
+        if (P.eps * dz <= P.prox_tol) { prox_conv = true; break; }
     }
+    // max_prox passes without meeting the proximal tolerance: the iterate is not the optimum -- report it as an iteration limit
+    if (status == WS_OPTIMAL && !prox_conv) status = WS_ITER_LIMIT;
     if (status == WS_ITER_LIMIT && hot) {
         // a hot start from a stale, nearly dependent working set can degenerate: solve once more from scratch
         hot = false; cap = it + P.max_iter; k = 0;

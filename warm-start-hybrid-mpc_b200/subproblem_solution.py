@@ -12,6 +12,15 @@ class SubproblemSolution(object):
         self.dual = dual
         self.active_set = active_set
 
+    @staticmethod
+    def from_controller(controller):
+        """subproblem_solution.py:18-45: primal + dual solution of the QP the controller has just solved, and (with
+        Params.Method == 1) the active set its children start from."""
+        primal = PrimalSolution.from_controller(controller)
+        dual = DualSolution.from_controller(controller)
+        active_set = controller.qp.get_active_set() if controller.qp.Params.Method == 1 else None
+        return SubproblemSolution(primal, dual, active_set)
+
 
 class PrimalSolution(object):
     """variables = {'x': [T+1 arrays], 'uc': [T arrays], 'ub': [T arrays]} (None if infeasible)."""
@@ -20,6 +29,17 @@ class PrimalSolution(object):
         self.variables = variables
         self.objective = objective
         self.binary_feasible = binary_feasible
+
+    @staticmethod
+    def from_controller(controller):
+        """subproblem_solution.py:68-99.  binary_feasible iff EVERY binary is pinned by the node (:94-97)."""
+        qp = controller.qp
+        qp._raise_if_not_solved()
+        T = controller.T
+        lb = np.concatenate([qp.get_constraint_rhs('nu_lb_%d' % t) for t in range(T)])
+        ub = np.concatenate([qp.get_constraint_rhs('nu_ub_%d' % t) for t in range(T)])
+        return PrimalSolution.from_record(controller.problem, qp._primal, qp.primal_objective(),
+                                          bool(np.array_equal(lb, -ub)), qp.status == 2)
 
     @staticmethod
     def from_record(pd, rec, objective, binary_feasible, feasible):
@@ -43,6 +63,14 @@ class DualSolution(object):
     def __init__(self, variables, objective):
         self.variables = variables
         self.objective = objective
+
+    @staticmethod
+    def from_controller(controller):
+        """subproblem_solution.py:119-168.  rho_t = 2 Q x_t, sigma_t = 2 R u_t (zero for a Farkas proof) are part of the
+        record the kernel writes (csrc/records.cuh), so they are the very numbers the device tree holds."""
+        qp = controller.qp
+        qp._raise_if_not_solved()
+        return DualSolution.from_record(controller.problem, controller.problem.layout, qp._dual, qp.dual_objective())
 
     @staticmethod
     def from_record(pd, layout, rec, objective):
