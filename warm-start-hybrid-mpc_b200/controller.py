@@ -349,6 +349,7 @@ class HybridModelPredictiveController(object):
         """Solver states resident at once: SMs (148 on a B200) x solver CTAs per SM of the library build."""
         import torch
         from .capi import load_library
+        self.handle()                # the lanes per CTA are fixed when a handle for THIS problem is created
         return torch.cuda.get_device_properties(self.device).multi_processor_count * int(load_library().wshmpc_ctas_per_sm())
 
     # -- tree <-> reference Node lists ---------------------------------------------------------------

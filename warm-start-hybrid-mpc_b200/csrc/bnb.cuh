@@ -67,7 +67,7 @@ __device__ inline int bnb_instance(const DevProblem &P, const Ctx &cx, const Slo
         const double cutoff = ub - tol;
         double best = INFINITY; int bi = -1;
         const int rule = P.search_rule;
-        for (int j = threadIdx.x; j < nn; j += WS_NT)
+        for (int j = WS_TID; j < nn; j += WS_NT)
             if (alive[j]) {
                 const double l = lb[j];
                 const double key = rule == 0 ? l : (rule == 1 ? -(double)j : (double)j);
@@ -79,13 +79,13 @@ __device__ inline int bnb_instance(const DevProblem &P, const Ctx &cx, const Slo
         // ---- bounds of the node (controller.py:273-298)
         const int d = depth[bi];
         const unsigned int *bw = bits + (size_t)bi * tr.words;
-        for (int j = threadIdx.x; j < nb; j += WS_NT) {
+        for (int j = WS_TID; j < nb; j += WS_NT) {
             const double v = (double)((bw[j >> 5] >> (j & 31)) & 1u);
             lbv[j] = j < d ? v : 0.;
             ubv[j] = j < d ? v : 1.;
         }
         set_node_prefix_known(P, cx, d);
-        __syncthreads();
+        WS_SYNC();
         prof_mark(0);
         // ---- solve (K1), started from the node's OWN dual record: the multipliers (and proximal centre) of its
         //      parent, or its shifted dual solution for a warm-start root (controller.py:262-264, 426, 487);
@@ -102,8 +102,8 @@ __device__ inline int bnb_instance(const DevProblem &P, const Ctx &cx, const Slo
             memo_r0 = r0;
             if (memo == 2) {
                 const double *D = rdual + (size_t)r0 * P.n_rec;
-                for (int i = threadIdx.x; i < P.n; i += WS_NT) SMV(yc)[i] = D[P.n_dual + i];      // the proximal centre load_ws would set
-                __syncthreads();
+                for (int i = WS_TID; i < P.n; i += WS_NT) SMV(yc)[i] = D[P.n_dual + i];      // the proximal centre load_ws would set
+                WS_SYNC();
             } else if (r0 >= 0) {
                 const double *D = rdual + (size_t)r0 * P.n_rec;
                 const double *mu = D + P.off_mu, *nl = D + P.off_nulb, *nu_ = D + P.off_nuub;
@@ -120,10 +120,10 @@ __device__ inline int bnb_instance(const DevProblem &P, const Ctx &cx, const Slo
         if (qs == WS_ITER_LIMIT) { st = BNB_QP_LIMIT; break; }
         double *dual = rdual + (size_t)nr * P.n_rec;
         build_records(P, qs, SMV(yc), y, xi, lbv, ubv, prim, dual, cost_s, dobj_s, SMV(part), SMV(red));
-        for (int j = threadIdx.x; j < P.n; j += WS_NT) dual[P.n_dual + j] = qs == WS_OPTIMAL ? SMV(yc)[j] : 0.;
+        for (int j = WS_TID; j < P.n; j += WS_NT) dual[P.n_dual + j] = qs == WS_OPTIMAL ? SMV(yc)[j] : 0.;
         prof_mark(17);
         const double cost = *cost_s;
-        if (threadIdx.x == 0) {
+        if (WS_TID == 0) {
             lb[bi] = cost; rec[bi] = nr; rdobj[nr] = *dobj_s;
 #ifdef WS_PROF
             // experiment builds: iterations | k after the rebuild << 12 | final k << 20 | infeasible << 28 | proximal passes << 29
@@ -141,27 +141,27 @@ __device__ inline int bnb_instance(const DevProblem &P, const Ctx &cx, const Slo
         } else if (d == nb) {
             inc = bi; ub = cost;
             double *ip = inc_primal + (size_t)inst * P.n_primal;
-            for (int j = threadIdx.x; j < P.n_primal; j += WS_NT) ip[j] = prim[j];
+            for (int j = WS_TID; j < P.n_primal; j += WS_NT) ip[j] = prim[j];
         } else {
             // children [value 0, value 1] of binary d = (t, i); bound += multiplier of the bound that moves
             const double l0 = cost + dual[P.off_nuub + d], l1 = cost + dual[P.off_nulb + d];
             unsigned int *c0 = bits + (size_t)nn * tr.words, *c1 = c0 + tr.words;
-            for (int w = threadIdx.x; w < tr.words; w += WS_NT) {
+            for (int w = WS_TID; w < tr.words; w += WS_NT) {
                 const unsigned int b = bw[w];
                 c0[w] = b & ~((w == (d >> 5)) ? (1u << (d & 31)) : 0u);
                 c1[w] = b | ((w == (d >> 5)) ? (1u << (d & 31)) : 0u);
             }
-            if (threadIdx.x == 0) {
+            if (WS_TID == 0) {
                 alive[bi] = 0;
                 depth[nn] = d + 1; alive[nn] = 1; rec[nn] = myrec; lb[nn] = l0;
                 depth[nn + 1] = d + 1; alive[nn + 1] = 1; rec[nn + 1] = myrec; lb[nn + 1] = l1;
             }
             nn += 2;
         }
-        __syncthreads();
+        WS_SYNC();
         prof_mark(18);
     }
-    if (threadIdx.x == 0) {
+    if (WS_TID == 0) {
         tr.n_nodes[inst] = nn; tr.n_recs[inst] = nr;
         inc_cost[inst] = ub; inc_node[inst] = inc; n_solves[inst] = solves;
         if (totals) {
@@ -170,40 +170,41 @@ __device__ inline int bnb_instance(const DevProblem &P, const Ctx &cx, const Slo
             atomicAdd(totals + 4, (unsigned long long)dsum); atomicAdd(totals + 5, (unsigned long long)k0sum);
         }
     }
-    __syncthreads();
+    WS_SYNC();
     return st;
 }
 
-__global__ void __launch_bounds__(WS_NT, WS_MINB)
-bnb_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, double *scratch, int *work_counter,
+__global__ void __launch_bounds__(WS_MAXL * WS_NT, 1)
+bnb_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, double *scratch, int *work_counter, int n_slots,
            int n_inst, const double *__restrict__ x0, const int *__restrict__ active, TreeView tr,
            double tol, int max_solves,
            double *inc_cost, int *inc_node, double *inc_primal, int *n_solves, int *status_out, int *trace,
            unsigned long long *totals)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ int s_inst;
-    const int slot = blockIdx.x;
-    SlotPtrs sp = slot_ptrs(slot_d, slot_i, slot, P.n, P.ld);
+    __shared__ int s_inst[WS_MAXL];
+    const int slot = blockIdx.x * P.lanes + WS_LANE;
+    SlotPtrs sp = slot_ptrs(slot_d, slot_i, slot < n_slots ? slot : 0, P.n, P.ld);
     const Ctx cx = make_ctx(P, smem_raw, sp);
     init_shared_tables(P, cx);
+    if (slot >= n_slots) return;                       // a lane without a solver state (after the CTA-wide barrier)
     double *y = ybuf + (size_t)slot * P.m;
     double *sc = scratch + (size_t)slot * bnb_scratch_doubles(P.nb, P.n_primal);
     int *iters_s = slot_i + (size_t)slot * slot_ints(P.n) + 2 * (P.n + 1) + 1;
 
     for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_inst = atomicAdd(work_counter, 1);
-        __syncthreads();
-        const int inst = s_inst;
+        WS_SYNC();
+        if (WS_TID == 0) s_inst[WS_LANE] = atomicAdd(work_counter, 1);
+        WS_SYNC();
+        const int inst = s_inst[WS_LANE];
         if (inst >= n_inst) break;
         if (active && !active[inst]) {
-            if (threadIdx.x == 0) { inc_cost[inst] = INFINITY; inc_node[inst] = -1; n_solves[inst] = 0; status_out[inst] = BNB_INFEASIBLE; }
+            if (WS_TID == 0) { inc_cost[inst] = INFINITY; inc_node[inst] = -1; n_solves[inst] = 0; status_out[inst] = BNB_INFEASIBLE; }
             continue;
         }
         const int st = bnb_instance(P, cx, sp, y, sc, iters_s, inst, x0 + (size_t)inst * P.nx, tr, tol, max_solves,
                                     inc_cost, inc_node, inc_primal, n_solves, trace, totals);
-        if (threadIdx.x == 0) status_out[inst] = st;
+        if (WS_TID == 0) status_out[inst] = st;
     }
 }
 
@@ -246,7 +247,9 @@ __host__ __device__ inline size_t shift_smem_doubles(const DevProblem &P, int nt
 // Returns 0, or 1 if the retained leaves do not fit min(nt.cap_nodes, nt.cap_recs) (every retained leaf takes a node AND a
 // dual record of the new tree): the instance is then switched off (active = 0, empty new tree) instead of continuing
 // with an incomplete cover -- a truncated cover could report a suboptimal or "infeasible" MIQP as solved.
-template <int NT>
+// LANE: the caller is a solver lane of WS_NT threads (fused loop): lane-local thread index and the lane's named barrier;
+// otherwise a whole CTA of NT threads.
+template <int NT, bool LANE>
 __device__ inline int shift_instance(const DevProblem &P, double *shm, int *s_wsum, int *s_base_p, int inst,
                                       const double *__restrict__ x0, const double *__restrict__ e0,
                                       const TreeView &ot, const double *__restrict__ inc_cost, const double *__restrict__ inc_primal,
@@ -254,46 +257,48 @@ __device__ inline int shift_instance(const DevProblem &P, double *shm, int *s_ws
 {
     const int nx = P.nx, nu = P.nu, nub = P.nub, nuc = P.nuc, T = P.T, nh = P.nh, nh1 = P.nh1;
     const int nq = P.nq, nqT = P.nqT, nr_ = P.nr;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int tid_ = LANE ? WS_TID : (int)threadIdx.x;
+    auto sync = [] { if (LANE) WS_SYNC(); else __syncthreads(); };
+    const int lane = tid_ & 31, w = tid_ >> 5;
     // shared: x0 | u0 | e0 | Qx0 | Ru0 | res_mu | per-warp scratch (nh1 + nqT each)
     double *xs = shm, *us = xs + nx, *es = us + nu, *Qx = es + nx, *Ru = Qx + nq, *rmu = Ru + nr_;
     double *wscr = rmu + nh + (size_t)w * (nh1 + nqT + nh + nq);
 #define s_base (*s_base_p)
-    __syncthreads();
+    sync();
     const double *ip = inc_primal + (size_t)inst * P.n_primal;
     const bool on = (!active || active[inst]) && inc_cost[inst] < INFINITY;
     if (!on) {
-        if (threadIdx.x == 0) {
+        if (tid_ == 0) {
             if (active) active[inst] = 0;
             nt.n_nodes[inst] = 0; nt.n_recs[inst] = 0;
         }
-        for (int j = threadIdx.x; j < nx; j += NT) if (x_next) x_next[(size_t)inst * nx + j] = x0[(size_t)inst * nx + j];
-        for (int j = threadIdx.x; j < nu; j += NT) if (u0_out) u0_out[(size_t)inst * nu + j] = nan("");
+        for (int j = tid_; j < nx; j += NT) if (x_next) x_next[(size_t)inst * nx + j] = x0[(size_t)inst * nx + j];
+        for (int j = tid_; j < nu; j += NT) if (u0_out) u0_out[(size_t)inst * nu + j] = nan("");
         return 0;
     }
-    for (int j = threadIdx.x; j < nx; j += NT) { xs[j] = x0[(size_t)inst * nx + j]; es[j] = e0 ? e0[(size_t)inst * nx + j] : 0.; }
-    for (int j = threadIdx.x; j < nu; j += NT) us[j] = ip[(size_t)(T + 1) * nx + j];
-    if (threadIdx.x == 0) s_base = 0;
-    __syncthreads();
-    for (int i = threadIdx.x; i < nq; i += NT) { double s = 0.; for (int c = 0; c < nx; ++c) s += P.Q[i * nx + c] * xs[c]; Qx[i] = s; }
-    for (int i = threadIdx.x; i < nr_; i += NT) { double s = 0.; for (int c = 0; c < nu; ++c) s += P.R[i * nu + c] * us[c]; Ru[i] = s; }
-    for (int i = threadIdx.x; i < nh; i += NT) {
+    for (int j = tid_; j < nx; j += NT) { xs[j] = x0[(size_t)inst * nx + j]; es[j] = e0 ? e0[(size_t)inst * nx + j] : 0.; }
+    for (int j = tid_; j < nu; j += NT) us[j] = ip[(size_t)(T + 1) * nx + j];
+    if (tid_ == 0) s_base = 0;
+    sync();
+    for (int i = tid_; i < nq; i += NT) { double s = 0.; for (int c = 0; c < nx; ++c) s += P.Q[i * nx + c] * xs[c]; Qx[i] = s; }
+    for (int i = tid_; i < nr_; i += NT) { double s = 0.; for (int c = 0; c < nu; ++c) s += P.R[i * nu + c] * us[c]; Ru[i] = s; }
+    for (int i = tid_; i < nh; i += NT) {
         double s = -P.h[i];
         for (int c = 0; c < nx; ++c) s += P.F[i * nx + c] * xs[c];
         for (int c = 0; c < nu; ++c) s += P.G[i * nu + c] * us[c];
         rmu[i] = s;
     }
     // plant update and applied input
-    for (int j = threadIdx.x; j < nx; j += NT) if (x_next) x_next[(size_t)inst * nx + j] = ip[nx + j] + es[j];
-    for (int j = threadIdx.x; j < nu; j += NT) if (u0_out) u0_out[(size_t)inst * nu + j] = us[j];
-    __syncthreads();
+    for (int j = tid_; j < nx; j += NT) if (x_next) x_next[(size_t)inst * nx + j] = ip[nx + j] + es[j];
+    for (int j = tid_; j < nu; j += NT) if (u0_out) u0_out[(size_t)inst * nu + j] = us[j];
+    sync();
 
     const size_t oo = (size_t)inst * ot.cap_nodes, on_ = (size_t)inst * nt.cap_nodes;
     const int nn = ot.n_nodes[inst];
     const int cap_new = nt.cap_nodes < nt.cap_recs ? nt.cap_nodes : nt.cap_recs;
     // ---- pass 1: _retain_leaf (controller.py:615-633) + ordered compaction + identifier shift (:476)
     for (int base = 0; base < nn; base += NT) {
-        const int j = base + threadIdx.x;
+        const int j = base + tid_;
         int keep = 0;
         if (j < nn && ot.alive[oo + j]) {
             keep = 1;
@@ -305,7 +310,7 @@ __device__ inline int shift_instance(const DevProblem &P, double *shm, int *s_ws
         }
         const unsigned int bal = __ballot_sync(0xffffffffu, keep);
         if (lane == 0) s_wsum[w] = __popc(bal);
-        __syncthreads();
+        sync();
         int pre = s_base;
         for (int q = 0; q < w; ++q) pre += s_wsum[q];
         const int idx = pre + __popc(bal & ((1u << lane) - 1u));
@@ -326,14 +331,14 @@ __device__ inline int shift_instance(const DevProblem &P, double *shm, int *s_ws
                 dst[q] = v;
             }
         }
-        __syncthreads();
-        if (threadIdx.x == 0) { int s = s_base; for (int q = 0; q < (NT / 32); ++q) s += s_wsum[q]; s_base = s; }
-        __syncthreads();
+        sync();
+        if (tid_ == 0) { int s = s_base; for (int q = 0; q < (NT / 32); ++q) s += s_wsum[q]; s_base = s; }
+        sync();
     }
     if (s_base > cap_new) {
         // capacity of the new tree exceeded: never truncate the cover
-        __syncthreads();
-        if (threadIdx.x == 0) { if (active) active[inst] = 0; nt.n_nodes[inst] = 0; nt.n_recs[inst] = 0; }
+        sync();
+        if (tid_ == 0) { if (active) active[inst] = 0; nt.n_nodes[inst] = 0; nt.n_recs[inst] = 0; }
         return 1;
     }
     const int nnew = s_base;
@@ -435,8 +440,8 @@ __device__ inline int shift_instance(const DevProblem &P, double *shm, int *s_ws
             nt.lb[on_ + idx] = lbn; nt.rec[on_ + idx] = rn; nt.rec_dobj[(size_t)inst * nt.cap_recs + idx] = obj;
         }
     }
-    __syncthreads();
-    if (threadIdx.x == 0) { nt.n_nodes[inst] = nnew; nt.n_recs[inst] = nnew; }
+    sync();
+    if (tid_ == 0) { nt.n_nodes[inst] = nnew; nt.n_recs[inst] = nnew; }
     return 0;
 #undef s_base
 }
@@ -451,7 +456,7 @@ shift_tree_kernel(DevProblem P, int n_inst, const double *__restrict__ x0, const
     __shared__ int s_base_v;
     for (int inst = blockIdx.x; inst < n_inst; inst += gridDim.x) {
         __syncthreads();
-        shift_instance<SH_NT>(P, shm, s_wsum, &s_base_v, inst, x0, e0, ot, inc_cost, inc_primal, active, nt, x_next, u0_out);
+        shift_instance<SH_NT, false>(P, shm, s_wsum, &s_base_v, inst, x0, e0, ot, inc_cost, inc_primal, active, nt, x_next, u0_out);
     }
 }
 
@@ -500,18 +505,20 @@ __device__ inline void init_root(const TreeView &tr, int k)
     for (int w = 0; w < tr.words; ++w) tr.bits[o * tr.words + w] = 0u;
 }
 
-__global__ void __launch_bounds__(WS_NT, WS_MINB)
-closed_loop_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, double *scratch, LoopView L, int n_inst,
+__global__ void __launch_bounds__(WS_MAXL * WS_NT, 1)
+closed_loop_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, double *scratch, LoopView L, int n_slots, int n_inst,
                    TreeView t0, TreeView t1, double tol, int max_solves,
                    double *inc_cost, int *inc_node, double *inc_primal, int *n_solves, int *status_out,
                    unsigned long long *totals)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ int s_inst;
-    const int slot = blockIdx.x;
-    SlotPtrs sp = slot_ptrs(slot_d, slot_i, slot, P.n, P.ld);
+    __shared__ int s_inst_[WS_MAXL];
+    const int slot = blockIdx.x * P.lanes + WS_LANE;
+    SlotPtrs sp = slot_ptrs(slot_d, slot_i, slot < n_slots ? slot : 0, P.n, P.ld);
     const Ctx cx = make_ctx(P, smem_raw, sp);
     init_shared_tables(P, cx);
+    if (slot >= n_slots) return;                       // a lane without a solver state (after the CTA-wide barrier)
+#define s_inst s_inst_[WS_LANE]
     double *y = ybuf + (size_t)slot * P.m;
     double *sc = scratch + (size_t)slot * bnb_scratch_doubles(P.nb, P.n_primal);
     int *iters_s = slot_i + (size_t)slot * slot_ints(P.n) + 2 * (P.n + 1) + 1;
@@ -520,8 +527,8 @@ closed_loop_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, doub
     prof_mark(127);
 
     for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) {
+        WS_SYNC();
+        if (WS_TID == 0) {
             // pop a ready task of the LOWEST step: the instance that lags behind never waits in a queue, so the launch
             // ends with the longest chain of solves of one instance, not with that chain plus its queueing delays
             const int S = L.n_steps;
@@ -551,7 +558,7 @@ closed_loop_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, doub
             }
             s_inst = inst;
         }
-        __syncthreads();
+        WS_SYNC();
         const int inst = s_inst;
         prof_mark(20);
         if (inst < 0) break;
@@ -563,36 +570,37 @@ closed_loop_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, doub
         const double *xc = L.x + (size_t)par * xs;
         double *xn = L.x + (size_t)(par ^ 1) * xs;
         if (!L.warm || (t == 0 && L.fresh)) {
-            if (threadIdx.x == 0) init_root(cur, inst);
-            __syncthreads();
+            if (WS_TID == 0) init_root(cur, inst);
+            WS_SYNC();
         }
         int st;
         if (!L.active[inst]) {
-            if (threadIdx.x == 0) { inc_cost[inst] = INFINITY; inc_node[inst] = -1; n_solves[inst] = 0; }
+            if (WS_TID == 0) { inc_cost[inst] = INFINITY; inc_node[inst] = -1; n_solves[inst] = 0; }
             st = BNB_INFEASIBLE;
-            __syncthreads();
+            WS_SYNC();
         } else {
             st = bnb_instance(P, cx, sp, y, sc, iters_s, inst, xc + (size_t)inst * P.nx, cur, tol, max_solves,
                               inc_cost, inc_node, inc_primal, n_solves, nullptr, totals);
         }
-        if (threadIdx.x == 0) {
+        if (WS_TID == 0) {
             status_out[inst] = st;
             const size_t lo = (size_t)t * n_inst + inst;
             L.log_cost[lo] = inc_cost[inst]; L.log_solves[lo] = n_solves[inst]; L.log_status[lo] = st;
         }
-        __syncthreads();
-        const int ovf = shift_instance<WS_NT>(P, SMV(Q), SMI(ired), SMI(ired) + 16, inst, xc, L.e ? L.e + (size_t)t * xs : nullptr,
+        WS_SYNC();
+        const int ovf = shift_instance<WS_NT, true>(P, SMV(pool), SMI(ired), SMI(ired) + 16, inst, xc, L.e ? L.e + (size_t)t * xs : nullptr,
                                               cur, inc_cost, inc_primal, L.active, nxt, xn, L.log_u0 + (size_t)t * n_inst * P.nu);
-        if (ovf && threadIdx.x == 0) { status_out[inst] = BNB_CAPACITY; L.log_status[(size_t)t * n_inst + inst] = BNB_CAPACITY; }
+        if (ovf && WS_TID == 0) { status_out[inst] = BNB_CAPACITY; L.log_status[(size_t)t * n_inst + inst] = BNB_CAPACITY; }
         prof_mark(19);
-        if (threadIdx.x == 0) L.step_of[inst] = t + 1;
+        if (WS_TID == 0) L.step_of[inst] = t + 1;
         __threadfence();                                   // release: the instance's data before the token
-        __syncthreads();
-        if (threadIdx.x == 0 && t + 1 < L.n_steps) {
+        WS_SYNC();
+        if (WS_TID == 0 && t + 1 < L.n_steps) {
             const int S = L.n_steps;
             const int p = atomicAdd(L.q + 4 + S + (t + 1), 1);
             atomicExch(L.q + 4 + 2 * S + (size_t)(t + 1) * n_inst + p, inst);
         }
-        if (threadIdx.x == 0) atomicAdd(L.q, 1);
+        if (WS_TID == 0) atomicAdd(L.q, 1);
     }
 }
+#undef s_inst

@@ -1,19 +1,27 @@
-// qp_device.cuh -- CTA-cooperative dual active-set solver for one branch-and-bound node QP (K1).
+// qp_device.cuh -- lane-cooperative dual active-set solver for one branch-and-bound node QP (K1).
 //
 // Replaces the Gurobi call of bounded_qp.py:200-228 (reached from controller.py:229-271) for the
 // relaxation of one node.  All nodes of all instances share the least-distance operator
 //     min_v 1/2 |v|^2   s.t.   bl_r <= mh_r . v <= bu_r        (unit rows mh_r, r < m)
 // and differ only in the bounds (x0 and the bounds on the relaxed binaries), see DESIGN.md.
-// One CTA (WS_NT threads, one CTA per SM) owns one solver state ("slot"):
+//
+// Execution model.  A CTA holds up to WS_MAXL independent solver LANES of WS_NT threads each (one CTA per SM); a
+// lane owns one solver state ("slot") and synchronises with a NAMED barrier of its own (bar.sync lane + 1, WS_NT), so
+// the lanes of a CTA run different QPs of different MPC instances at their own pace and hide each other's latencies
+// (every phase of an iteration is a short chain of dependent shared-memory loads and fp64 operations).  The lanes of
+// a CTA SHARE one copy of the read-only tables (stage rows, row scalings, row map) in shared memory; everything else
+// is per lane.  Lane state:
 //     working set W (rows, sides, multipliers lam >= 0 of the sign-normalised rows),
 //     THIN factorisation  Mw' = Q1 R  kept as
-//         Q1  n x k  orthonormal columns, column major (leading dimension ld),
+//         Q1  (n - d) x k  orthonormal columns over the coordinates the node does NOT eliminate (d = pinned prefix),
+//             column major with a per-node leading dimension ldc,
 //         Ri  = R^-1 upper triangular, packed by columns (column j at j (j + 1) / 2),
-//     (no R, no null-space basis); the first `ks` columns of both live in SHARED memory (all of them on the
-//     T = 20 cart-pole), later columns in the slot's global home / L2;
+//     (no R, no null-space basis); the first `ks` columns of both live in the lane's shared-memory POOL, later
+//     columns in the slot's global home / L2.  ks is fixed per node from d (a deep node has short columns, so more of
+//     them fit); every sum runs in an order that does not depend on where a column lives, so results do not depend
+//     on ks, on the number of lanes or on the shared-memory budget;
 //     u = R^-T (-d_W), ls = R^-1 u (the multipliers of the equality-constrained sub-problem) and
-//     v = -Q1 u (its primal point) are kept up to date INCREMENTALLY: O(n + k) per append / removal
-//     instead of two triangular solves and an n x k product per iteration;
+//     v = -Q1 u (its primal point) are kept up to date INCREMENTALLY: O(n + k) per append / removal;
 //     yc = proximal centre.
 // Appending a row is classical Gram-Schmidt against Q1 with one re-orthogonalisation pass when more than
 // a digit was lost (Daniel, Gragg, Kaufman & Stewart 1976); removing position kp rotates the columns of
@@ -24,8 +32,7 @@
 // every CTA, L2 resident, stored transposed so that a thread owns two output rows and streams 16-byte
 // words) and a_r the sparse stage row [F_t G_t] of the MLD system (shared memory), instead of streaming
 // the dense m x n operator (6x less L2 traffic on the cart-pole).
-// Between the nodes of an instance the WORKING SET survives (any lam >= 0 is dual feasible for every
-// node) and its factor is rebuilt at the start of the node, so rounding never accumulates across nodes;
+// Every node rebuilds the factor of the working set it starts from, so rounding never accumulates across nodes;
 // a hot-started solve that degenerates (iteration cap, exploding multipliers) is restarted once from the
 // empty working set.
 // The sequential twin of this file (same pivoting rules, same factorisation) is oracle/qp_core.c variant 1.
@@ -34,31 +41,55 @@
 #include <math.h>
 #include <stdint.h>
 
+// Measured on the 512-instance warm-started cart-pole loop (B200, round 2, tools/loop_timing.py; QP/s):
+//   1 lane  x 256 threads, 255 registers  257 k   (the round-1 configuration: 250 k with the round-1 code)
+//   1 lane  x 256 threads, 128 registers  195 k   (what the register cap of two lanes costs one lane)
+//   2 lanes x 256 threads, 128 registers  342 k   (350 k with 2048 instances)       <- shipped
+//   3 lanes x 128 threads, 168 registers  194 k   (250 k with 2048 instances; a 128-thread lane alone: 126 k)
 #ifndef WS_NT
-#define WS_NT 256            // threads per solver CTA (phases are short: more warps cost more at the barriers than they save)
+#define WS_NT 256            // threads per solver lane
 #endif
-#ifndef WS_MINB
-#define WS_MINB 1               // resident CTAs (= concurrently solved QPs) per SM
+#ifndef WS_MAXL
+#define WS_MAXL 2               // solver lanes per CTA at most (WS_MAXL * WS_NT threads, one CTA per SM)
 #endif
 #define WS_NW (WS_NT / 32)
-#define WS_JW 128               // lanes of the k-indexed phases (columns of Q1 / rows of Ri)
-#define WS_NG (WS_NT / WS_JW)   // groups splitting the long dimension of those phases
-#define WS_CH 8                 // columns per chunk of the removal sweep
+#ifndef WS_RPT
+#define WS_RPT ((384 + WS_NT - 1) / WS_NT)    // rows of Q1 a thread sweeps in a removal: n <= WS_RPT * WS_NT (>= 384)
+#endif
+#ifndef WS_RRT
+#define WS_RRT (256 / WS_NT)    // rows of Ri a thread sweeps in a removal: working sets of up to WS_RRT * WS_NT = 256 rows
+#endif
+#ifndef WS_NOINLINE
+#define WS_NOINLINE inline      // measured: out-of-line phases (__noinline__) shrink the code by a third and cost 25 % (call ABI spills)
+#endif
+#ifndef WS_CH
+#define WS_CH 4                 // columns per chunk of the removal sweep (8 spills under the 128-register cap of two lanes)
+#endif
 #define WS_OPTIMAL 2
 #define WS_INFEASIBLE 3
 #define WS_ITER_LIMIT 9
 #define WS_REORTH 1e-2          // re-orthogonalise when |z|^2 < WS_REORTH |m_j[d:]|^2
 #define WS_LAM_MAX 1e13         // sum of multipliers beyond which a hot-started solve is declared degenerate
 
-// offsets (in doubles unless noted) of the shared-memory arrays, resolved on the host (wshmpc_create)
+// lane-local thread index, lane index inside the CTA, lane barrier
+#define WS_TID ((int)(threadIdx.x & (WS_NT - 1)))
+#define WS_LANE ((int)(threadIdx.x / WS_NT))
+#define WS_SYNC() asm volatile("bar.sync %0, %1;" :: "r"(WS_LANE + 1), "n"(WS_NT) : "memory")
+
+// offsets (in doubles unless noted) of the shared-memory arrays, resolved on the host (wshmpc_create).
+// Per-lane arrays are relative to the lane's base, tables (t_*) to the start of the CTA's shared memory.
 struct SmemOff {
-    int Q, Ri, z, z2, c1, c2, t, u, ls, lam, cw, yc, wv, v, gc, gs, bu, blb, inr, vsc, xi, part, red, sF, sG, sF1, sG1;
+    int z, c1, c2, t, u, ls, lam, cw, yc, wv, v, bu, blb, xi, part, red;
     int vf0, vf;                          // eliminated coordinates of v: node-constant part / value in the current proximal pass
-    int irow, iside, ired, iscr, rinfo;   // int offsets (from the start of the int area)
-    int idep;                             // [0] number of eliminated (pinned prefix) binaries of the node being solved
-    int ints;                             // start of the int area, in doubles
-    int binW, bign, bnadd;                // byte offsets from the start of the byte area
-    int bytes;                            // start of the byte area, in doubles
+    int pool, pool_sz;                    // factor pool of the lane (Ri columns, then Q1 columns) and its size in doubles
+    int irow, iside, ired, iscr;          // int offsets (from the start of the lane's int area)
+    int idep;                             // node geometry: [0] d, [1] ignore-list flag, [2] d0, [3] he, [4] ldc, [5] ks, [6] triR, [7] G, [8] W
+    int ints;                             // start of the lane's int area, in doubles
+    int binW, bign, bnadd;                // byte offsets from the start of the lane's byte area
+    int bytes;                            // start of the lane's byte area, in doubles
+    int lane_doubles;                     // size of a lane's area
+    int t_inr, t_vsc, t_sF, t_sG, t_sF1, t_sG1, t_rinfo;   // shared tables (t_rinfo: doubles offset of an int array)
+    int tab_doubles;                      // size of the table area
     int total_bytes;
 };
 
@@ -71,12 +102,11 @@ struct DevProblem {
     int search_rule;         // candidate selection of the device B&B: 0 best_first, 1 depth_first, 2 breadth_first
     double eps, tol_p, tol_d, tol_sing, tol_ray, prox_tol;
     int max_iter, max_prox;
-    int ks;                  // columns of Q1 and of Ri held in shared memory
-    int ld;                  // leading dimension of Q1 (even, ld / 2 odd: conflict-free 16-byte column reads)
+    int lanes;               // solver lanes per CTA of this handle (<= WS_MAXL)
+    int ld;                  // leading dimension of the global home of Q1 (>= every per-node ldc)
     int np;                  // n rounded up to even
     int ns2;                 // ns rounded up to even
-    int kp_;                 // stride of the k-indexed partial sums (>= n)
-    int gb, gp;              // groups of the n-pair-indexed / ns-pair-indexed phases
+    int gp;                  // groups of the ns-pair-indexed phases
     int hot_cap;             // iteration cap of a hot-started solve before it is restarted cold
     SmemOff so;
     // record layout
@@ -85,7 +115,7 @@ struct DevProblem {
 };
 
 // Phase timing of the critical path (experiment builds only, -DWS_PROF; read back by tools/ through
-// wshmpc_prof_read): mark(id) charges the cycles since the previous mark of this CTA's thread 0 to phase `id`.
+// wshmpc_prof_read): mark(id) charges the cycles since the previous mark of lane 0's thread 0 to phase `id`.
 #ifdef WS_PROF
 __device__ unsigned long long g_prof[256];
 __device__ __forceinline__ void prof_mark(int id) {
@@ -108,7 +138,7 @@ __host__ __device__ __forceinline__ int tri_off(int j) { return j * (j + 1) / 2;
 
 // per-slot persistent state in global memory
 struct SlotPtrs {
-    double *Q;      // n*ld  (home of the columns >= ks of Q1)
+    double *Q;      // n*ld  (home of the columns >= ks of Q1; its first doubles park the sibling memo)
     double *Ri;     // n(n+1)/2
     double *lam;    // n+1
     double *yc;     // n
@@ -136,24 +166,55 @@ __device__ inline SlotPtrs slot_ptrs(double *dbase, int *ibase, int slot, int n,
 
 // what a thread keeps in registers
 struct Ctx {
-    double *smd;             // shared memory base
+    double *smd;             // base of the lane's shared memory
+    double *tab;             // base of the CTA's shared tables
     double *gQ, *gRi;        // global homes of the columns >= ks
-    int bg, bip;             // (group, pair) of the n-pair-indexed phases
     int pg, prp;             // (group, pair) of the ns-pair-indexed phases
 };
 
 #define SMV(name) (cx.smd + P.so.name)
 #define SMI(name) (reinterpret_cast<int *>(cx.smd + P.so.ints) + P.so.name)
 #define SMB(name) (reinterpret_cast<unsigned char *>(cx.smd + P.so.bytes) + P.so.name)
+#define TBV(name) (cx.tab + P.so.t_##name)
+#define TBI(name) (reinterpret_cast<const int *>(cx.tab + P.so.t_##name))
 
 __device__ inline Ctx make_ctx(const DevProblem &P, unsigned char *smem_raw, const SlotPtrs &sp) {
     Ctx cx;
-    cx.smd = reinterpret_cast<double *>(smem_raw);
+    cx.tab = reinterpret_cast<double *>(smem_raw);
+    cx.smd = cx.tab + P.so.tab_doubles + (size_t)WS_LANE * P.so.lane_doubles;
     cx.gQ = sp.Q; cx.gRi = sp.Ri;
-    const int h = P.np >> 1, hs = P.ns2 >> 1;
-    cx.bg = threadIdx.x / h; cx.bip = threadIdx.x - cx.bg * h;
-    cx.pg = threadIdx.x / hs; cx.prp = threadIdx.x - cx.pg * hs;
+    const int hs = P.ns2 >> 1;
+    cx.pg = WS_TID / hs; cx.prp = WS_TID - cx.pg * hs;
     return cx;
+}
+
+// geometry of the node being solved (set_node_prefix*): which coordinates the factor spans and where its columns live
+struct Geom {
+    int d;       // eliminated coordinates (pinned prefix)
+    int d0;      // d rounded down to even: the factor stores coordinates d0 .. np-1 (pairs stay 16-byte aligned)
+    int he;      // pairs of stored coordinates: (np - d0) / 2
+    int ldc;     // leading dimension of the shared-memory columns: 2 (he | 1)  (ldc / 2 odd: conflict-free 16-byte column reads)
+    int ks;      // columns of Q1 and Ri in the lane's pool
+    int triR;    // doubles the Ri part of the pool takes
+    int G, W;    // the pair-indexed phases run as G groups of W threads (W >= he unless he > WS_NT)
+};
+
+__device__ __forceinline__ Geom load_geom(const DevProblem &P, const Ctx &cx) {
+    const int *g = SMI(idep);
+    Geom q;
+    q.d = g[0]; q.d0 = g[2]; q.he = g[3]; q.ldc = g[4]; q.ks = g[5]; q.triR = g[6]; q.G = g[7]; q.W = g[8];
+    return q;
+}
+
+// thread 0 of the lane: geometry for d eliminated coordinates.  The caller provides the barrier.
+__device__ inline void store_geom(const DevProblem &P, const Ctx &cx, int d) {
+    int *g = SMI(idep);
+    d = d < P.n_elim ? d : P.n_elim;
+    const int d0 = d & ~1, he = (P.np - d0) >> 1, ldc = 2 * (he | 1);
+    int ks = P.n - d;                                       // a working set never holds more independent rows
+    while (ks > 0 && (size_t)ks * ldc + ((tri_off(ks) + 1) & ~1) > (size_t)P.so.pool_sz) --ks;
+    const int G = he <= WS_NT ? (WS_NT / he < 8 ? WS_NT / he : 8) : 1;
+    g[0] = d; g[2] = d0; g[3] = he; g[4] = ldc; g[5] = ks; g[6] = (tri_off(ks) + 1) & ~1; g[7] = G; g[8] = WS_NT / G;
 }
 
 __device__ __forceinline__ double warp_sum(double x) {
@@ -162,7 +223,7 @@ __device__ __forceinline__ double warp_sum(double x) {
     return x;
 }
 
-// The block-wide reductions below reduce inside each warp by shuffles, park one value per warp in shared
+// The lane-wide ("block") reductions below reduce inside each warp by shuffles, park one value per warp in shared
 // memory, and finish with a second shuffle tree over the WS_NW per-warp values (every warp does it
 // redundantly, so the result reaches all threads with two barriers and ~25 instructions).
 #define WS_FULL 0xffffffffu
@@ -170,11 +231,11 @@ static_assert(WS_NW == 16 || WS_NW == 8 || WS_NW == 4 || WS_NW == 2, "the two-le
 
 // block-wide sum, result to all threads
 __device__ inline double block_sum(double x, double *red) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int lane = WS_TID & 31, w = WS_TID >> 5;
     x = warp_sum(x);
-    __syncthreads();
+    WS_SYNC();
     if (lane == 0) red[w] = x;
-    __syncthreads();
+    WS_SYNC();
     double s = lane < WS_NW ? red[lane] : 0.;
 #pragma unroll
     for (int o = WS_NW / 2; o > 0; o >>= 1) s += __shfl_xor_sync(WS_FULL, s, o);
@@ -183,11 +244,11 @@ __device__ inline double block_sum(double x, double *red) {
 
 // two block-wide sums at once
 __device__ inline void block_sum2(double &x, double &y, double *red) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int lane = WS_TID & 31, w = WS_TID >> 5;
     x = warp_sum(x); y = warp_sum(y);
-    __syncthreads();
+    WS_SYNC();
     if (lane == 0) { red[w] = x; red[16 + w] = y; }
-    __syncthreads();
+    WS_SYNC();
     // lanes 0..15 take the x partials, lanes 16..31 the y partials
     double s = (lane & 15) < WS_NW ? red[lane] : 0.;
 #pragma unroll
@@ -201,16 +262,16 @@ __device__ __forceinline__ bool better_max(double ov, int oi, double val, int id
 
 // block-wide arg-max of (val, idx): larger val wins, ties -> smaller idx.  idx < 0 = no candidate.
 __device__ inline void block_argmax(double &val, int &idx, double *red, int *ired) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int lane = WS_TID & 31, w = WS_TID >> 5;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const double ov = __shfl_xor_sync(WS_FULL, val, o);
         const int oi = __shfl_xor_sync(WS_FULL, idx, o);
         if (better_max(ov, oi, val, idx)) { val = ov; idx = oi; }
     }
-    __syncthreads();
+    WS_SYNC();
     if (lane == 0) { red[w] = val; ired[w] = idx; }
-    __syncthreads();
+    WS_SYNC();
     val = lane < WS_NW ? red[lane] : 0.; idx = lane < WS_NW ? ired[lane] : -1;
 #pragma unroll
     for (int o = WS_NW / 2; o > 0; o >>= 1) {
@@ -223,12 +284,12 @@ __device__ inline void block_argmax(double &val, int &idx, double *red, int *ire
 
 // block-wide max of a non-negative value
 __device__ inline double block_max(double x, double *red) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int lane = WS_TID & 31, w = WS_TID >> 5;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(WS_FULL, x, o));
-    __syncthreads();
+    WS_SYNC();
     if (lane == 0) red[w] = x;
-    __syncthreads();
+    WS_SYNC();
     double s = lane < WS_NW ? red[lane] : 0.;
 #pragma unroll
     for (int o = WS_NW / 2; o > 0; o >>= 1) s = fmax(s, __shfl_xor_sync(WS_FULL, s, o));
@@ -257,7 +318,7 @@ __device__ inline void warp_argmin_sum(double &val, int &idx, double &sum) {
 
 // arg-min and a sum in one pass (ratio test + sum of the positive multipliers)
 __device__ inline void block_argmin_sum(double &val, int &idx, double &sum, double *red, int *ired) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int lane = WS_TID & 31, w = WS_TID >> 5;
     double nv = -val;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -266,9 +327,9 @@ __device__ inline void block_argmin_sum(double &val, int &idx, double &sum, doub
         sum += __shfl_xor_sync(WS_FULL, sum, o);
         if (better_max(ov, oi, nv, idx)) { nv = ov; idx = oi; }
     }
-    __syncthreads();
+    WS_SYNC();
     if (lane == 0) { red[w] = nv; ired[w] = idx; red[16 + w] = sum; }
-    __syncthreads();
+    WS_SYNC();
     nv = lane < WS_NW ? red[lane] : 0.; idx = lane < WS_NW ? ired[lane] : -1;
     sum = lane < WS_NW ? red[16 + lane] : 0.;
 #pragma unroll
@@ -285,7 +346,7 @@ __device__ inline void block_argmin_sum(double &val, int &idx, double &sum, doub
 // grouped mat-vec with a shared operator:  out(i, sum_{j0 <= j < j1} M[j * ld + i] * x[j])  for i < rows.
 // Adjacent threads take adjacent i (coalesced); when rows <= WS_NT the threads form G = WS_NT / rows
 // groups that split the j range and combine through `part` (>= max(WS_NT, rows) doubles).
-// Ends with a barrier-protected combine; `out` is called once per row.  Contains __syncthreads.
+// Ends with a barrier-protected combine; `out` is called once per row.  Contains lane barriers.
 // (refresh / record paths only: once per proximal pass, not per iteration)
 // ---------------------------------------------------------------------------------------------
 template <class Out>
@@ -293,7 +354,7 @@ __device__ inline void grouped_matvec(const double *__restrict__ M, int ld, int 
                                       const double *x, double *part, Out out) {
     if (rows <= WS_NT) {
         const int G = WS_NT / rows;
-        const int g = threadIdx.x / rows, i = threadIdx.x - g * rows;
+        const int g = WS_TID / rows, i = WS_TID - g * rows;
         if (g < G) {
             double s0 = 0., s1 = 0., s2 = 0., s3 = 0.;
             int j = j0 + g;
@@ -316,102 +377,124 @@ __device__ inline void grouped_matvec(const double *__restrict__ M, int ld, int 
             for (; j < j1; j += G) s0 += M[(size_t)j * ld + i] * x[j];
             part[g * rows + i] = (s0 + s1) + (s2 + s3);
         }
-        __syncthreads();
-        if (threadIdx.x < rows) {
-            double s = part[threadIdx.x];
-            for (int q = 1; q < G; ++q) s += part[q * rows + threadIdx.x];
-            out(threadIdx.x, s);
+        WS_SYNC();
+        if (WS_TID < rows) {
+            double s = part[WS_TID];
+            for (int q = 1; q < G; ++q) s += part[q * rows + WS_TID];
+            out(WS_TID, s);
         }
-        __syncthreads();
+        WS_SYNC();
     } else {
-        for (int i = threadIdx.x; i < rows; i += WS_NT) {
-            double s0 = 0., s1 = 0.;
+        // more rows than threads: a thread owns the rows tid, tid + WS_NT, ... and all columns, 8 loads in flight
+        for (int i = WS_TID; i < rows; i += WS_NT) {
+            double s0 = 0., s1 = 0., s2 = 0., s3 = 0.;
             int j = j0;
-            for (; j + 1 < j1; j += 2) { s0 += M[(size_t)j * ld + i] * x[j]; s1 += M[(size_t)(j + 1) * ld + i] * x[j + 1]; }
-            if (j < j1) s0 += M[(size_t)j * ld + i] * x[j];
-            out(i, s0 + s1);
+            for (; j + 7 < j1; j += 8) {
+                double w[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) w[q] = __ldg(M + (size_t)(j + q) * ld + i);
+                s0 += w[0] * x[j] + w[4] * x[j + 4];
+                s1 += w[1] * x[j + 1] + w[5] * x[j + 5];
+                s2 += w[2] * x[j + 2] + w[6] * x[j + 6];
+                s3 += w[3] * x[j + 3] + w[7] * x[j + 7];
+            }
+            for (; j < j1; ++j) s0 += M[(size_t)j * ld + i] * x[j];
+            out(i, (s0 + s1) + (s2 + s3));
         }
-        __syncthreads();
+        WS_SYNC();
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// thin factor: products with Q1 and Ri.  Columns < ks in shared memory, the rest in the global home.
+// thin factor: products with Q1 and Ri.  Columns < ks in the lane's pool, the rest in the global home.
+// A column of Q1 is addressed by the COORDINATE index i >= d0 (its storage starts at coordinate d0).
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double *pool_Ri(const DevProblem &P, const Ctx &cx) { return SMV(pool); }
+// SM: every column the caller touches is in the pool (the common case): plain shared-memory addressing instead of the
+// per-column shared / global choice.  The arithmetic is the same either way.
+template <bool SM>
+__device__ __forceinline__ double *qcol_w(const DevProblem &P, const Ctx &cx, const Geom &g, int j) {
+    if (SM) return SMV(pool) + g.triR + j * g.ldc - g.d0;
+    return (j < g.ks ? SMV(pool) + g.triR + j * g.ldc : cx.gQ + (size_t)j * P.ld) - g.d0;
+}
+template <bool SM>
+__device__ __forceinline__ double *ricol_w(const DevProblem &P, const Ctx &cx, const Geom &g, int j) {
+    if (SM) return SMV(pool) + tri_off(j);
+    return (j < g.ks ? SMV(pool) : cx.gRi) + tri_off(j);
+}
 
-// The k-indexed phases (one output per working-set position) give every output to a team of ng = 2^lg ADJACENT lanes
-// that split the other dimension and combine by shuffles: WS_NT / ng outputs per pass, no partial sums through
-// shared memory, one barrier.  ng is the largest power of two <= 32 with k ng <= WS_NT (so all warps have work).
+// The k-indexed phases (one output per working-set position) give every output to a team of ng = 2^lg lanes of one warp
+// that split the other dimension and combine by shuffles: WS_NT / ng outputs per pass, no partial sums through shared
+// memory, one barrier.  ng is the largest power of two <= 32 with k ng <= WS_NT (so all warps have work).  The members
+// of a team are the lanes l, l + C, l + 2C, ... (C = 32 / ng outputs per warp): ADJACENT lanes work on adjacent outputs
+// at the same position of the other dimension, i.e. on different columns with an odd 16-byte stride -- no bank conflicts.
 __device__ __forceinline__ int team_log2(int k) { return k >= WS_NT ? 0 : min(5, 31 - __clz(WS_NT / max(k, 1))); }
 
 __device__ __forceinline__ double team_sum(double s, int lg) {
-    for (int o = 1; o < (1 << lg); o <<= 1) s += __shfl_xor_sync(WS_FULL, s, o);
+    for (int o = 32 >> lg; o < 32; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     return s;
 }
 
-// out[j] = q_j . x  for j < k.  Ends with a barrier.
-__device__ inline void qt_dots(const DevProblem &P, const Ctx &cx, int k, const double *x, double *out) {
-    const int lg = team_log2(k), ng = 1 << lg, g = threadIdx.x & (ng - 1), jw = WS_NT >> lg;
-    const int h = P.np >> 1, cp = (h + ng - 1) >> lg;
-    const int p0 = g * cp, p1 = min(p0 + cp, h);
+// out[j] = q_j . x  for j < k  (x indexed by coordinate, entries below d0 ignored).  Ends with a barrier.
+template <bool SM>
+__device__ inline void qt_dots_t(const DevProblem &P, const Ctx &cx, int k, const double *x, double *out) {
+    const Geom gm = load_geom(P, cx);
+    const int lg = team_log2(k), ng = 1 << lg, C = 32 >> lg, jw = WS_NT >> lg;
+    const int lane = WS_TID & 31, g = lane >> (5 - lg), jl = (WS_TID >> 5) * C + (lane & (C - 1));
+    const int p0 = (gm.d0 >> 1) + g, p1 = P.np >> 1;
     const double2 *x2 = reinterpret_cast<const double2 *>(x);
-    const int kr = (k + jw - 1) & ~(jw - 1);                       // whole teams take part in the shuffles
-    for (int j = threadIdx.x >> lg; j < kr; j += jw) {
+    const int kr = (k + jw - 1) / jw * jw;                          // whole warps take part in the shuffles
+    for (int j = jl; j < kr; j += jw) {
         double s0 = 0., s1 = 0.;
         if (j < k) {
-            if (j < P.ks) {
-                const double2 *q2 = reinterpret_cast<const double2 *>(SMV(Q) + j * P.ld);
-#pragma unroll 4
-                for (int p = p0; p < p1; ++p) { const double2 a = q2[p], b = x2[p]; s0 += a.x * b.x; s1 += a.y * b.y; }
-            } else {
-                const double2 *q2 = reinterpret_cast<const double2 *>(cx.gQ + (size_t)j * P.ld);
-                for (int p = p0; p < p1; ++p) { const double2 a = q2[p], b = x2[p]; s0 += a.x * b.x; s1 += a.y * b.y; }
-            }
+            const double2 *q2 = reinterpret_cast<const double2 *>(qcol_w<SM>(P, cx, gm, j));
+            for (int p = p0; p < p1; p += ng) { const double2 a = q2[p], b = x2[p]; s0 += a.x * b.x; s1 += a.y * b.y; }
         }
         const double s = team_sum(s0 + s1, lg);
         if (g == 0 && j < k) out[j] = s;
     }
-    __syncthreads();
+    WS_SYNC();
 }
 
-// zout = zin - sum_{j < k} q_j c[j]  (zin == nullptr: zero; zout may alias zin).  Returns |zout|^2 and the block-wide
-// sum of `extra` (a second quantity the caller wants reduced: it rides on the barrier this phase needs anyway) in
-// every thread.  Ends with a barrier.
-__device__ inline double q_apply(const DevProblem &P, const Ctx &cx, int k, const double *c, const double *zin, double *zout,
+// zout = zin - sum_{j < k} q_j c[j] on the coordinates >= d0 (zin == nullptr: zero; zout may alias zin).  Returns
+// |zout|^2 and the lane-wide sum of `extra` (a second quantity the caller wants reduced: it rides on the barrier this
+// phase needs anyway) in every thread.  Ends with a barrier.
+template <bool SM>
+__device__ inline double q_apply_t(const DevProblem &P, const Ctx &cx, int k, const double *c, const double *zin, double *zout,
                                  double extra = 0., double *extra_sum = nullptr) {
+    const Geom gm = load_geom(P, cx);
     double2 *part2 = reinterpret_cast<double2 *>(SMV(part));
-    const int h = P.np >> 1;
-    if (cx.bg < P.gb) {
-        double ax = 0., ay = 0., bx = 0., by = 0.;
-        int j = cx.bg;
-        const int ke = min(k, P.ks);
-        const double2 *q2 = reinterpret_cast<const double2 *>(SMV(Q)) + cx.bip;
-        const int ldh = P.ld >> 1, G = P.gb;
-        for (; j + G < ke; j += 2 * G) {
-            const double2 a = q2[j * ldh], b = q2[(j + G) * ldh];
-            const double ca = c[j], cb = c[j + G];
-            ax += a.x * ca; ay += a.y * ca; bx += b.x * cb; by += b.y * cb;
+    const int G = gm.G, W = gm.W, he = gm.he, dh = gm.d0 >> 1;
+    const int grp = WS_TID / W, t = WS_TID - grp * W;
+    if (grp < G) {
+        for (int pp = t; pp < he; pp += W) {
+            double ax = 0., ay = 0., bx = 0., by = 0.;
+            int j = grp;
+            for (; j + G < k; j += 2 * G) {
+                const double2 a = reinterpret_cast<const double2 *>(qcol_w<SM>(P, cx, gm, j))[dh + pp];
+                const double2 b = reinterpret_cast<const double2 *>(qcol_w<SM>(P, cx, gm, j + G))[dh + pp];
+                const double ca = c[j], cb = c[j + G];
+                ax += a.x * ca; ay += a.y * ca; bx += b.x * cb; by += b.y * cb;
+            }
+            if (j < k) { const double2 a = reinterpret_cast<const double2 *>(qcol_w<SM>(P, cx, gm, j))[dh + pp]; const double ca = c[j]; ax += a.x * ca; ay += a.y * ca; }
+            part2[grp * he + pp] = make_double2(ax + bx, ay + by);
         }
-        for (; j < ke; j += G) { const double2 a = q2[j * ldh]; const double ca = c[j]; ax += a.x * ca; ay += a.y * ca; }
-        const double2 *g2 = reinterpret_cast<const double2 *>(cx.gQ) + cx.bip;
-        for (; j < k; j += G) { const double2 a = g2[(size_t)j * ldh]; const double ca = c[j]; ax += a.x * ca; ay += a.y * ca; }
-        part2[cx.bg * h + cx.bip] = make_double2(ax + bx, ay + by);
     }
-    __syncthreads();
+    WS_SYNC();
     const double *part = SMV(part);
     double zz = 0.;
-    for (int i = threadIdx.x; i < P.np; i += WS_NT) {
+    for (int i = WS_TID; i < 2 * he; i += WS_NT) {
         double s = part[i];
-        for (int q = 1; q < P.gb; ++q) s += part[q * P.np + i];
-        const double zi = (zin ? zin[i] : 0.) - s;
-        zout[i] = zi; zz += zi * zi;
+        for (int q = 1; q < G; ++q) s += part[q * 2 * he + i];
+        const double zi = (zin ? zin[gm.d0 + i] : 0.) - s;
+        zout[gm.d0 + i] = zi; zz += zi * zi;
     }
     {
-        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        const int lane = WS_TID & 31, w = WS_TID >> 5;
         double *red = SMV(red) + 72;                     // [w]: |z|^2 partials, [16 + w]: partials of `extra`
         zz = warp_sum(zz); extra = warp_sum(extra);
         if (lane == 0) { red[w] = zz; red[16 + w] = extra; }
-        __syncthreads();
+        WS_SYNC();
         double sv = (lane & 15) < WS_NW ? red[lane] : 0.;
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) sv += __shfl_xor_sync(WS_FULL, sv, o);
@@ -423,64 +506,46 @@ __device__ inline double q_apply(const DevProblem &P, const Ctx &cx, int k, cons
 
 // t_i = (Ri c[:k])_i = sum_{j >= i} Ri[tri_off(j) + i] c_j handed to out(i, t_i) by the leader of the team of row i
 // (columns j = i + g, i + g + ng, ...).  No barrier.
-template <class Out>
+template <bool SM, class Out>
 __device__ inline void ri_matvec_ep(const DevProblem &P, const Ctx &cx, int k, const double *c, Out out) {
-    const int lg = team_log2(k), ng = 1 << lg, g = threadIdx.x & (ng - 1), jw = WS_NT >> lg;
-    const int ke = min(k, P.ks);
-    const int kr = (k + jw - 1) & ~(jw - 1);
-    const double *Ri = SMV(Ri);
-    for (int i = threadIdx.x >> lg; i < kr; i += jw) {
+    const Geom gm = load_geom(P, cx);
+    const int lg = team_log2(k), ng = 1 << lg, C = 32 >> lg, jw = WS_NT >> lg;
+    const int lane = WS_TID & 31, g = lane >> (5 - lg), il = (WS_TID >> 5) * C + (lane & (C - 1));
+    const int kr = (k + jw - 1) / jw * jw;
+    for (int i = il; i < kr; i += jw) {
         double s0 = 0., s1 = 0.;
         if (i < k) {
             int j = i + g;
-            for (; j + ng < ke; j += 2 * ng) { s0 += Ri[tri_off(j) + i] * c[j]; s1 += Ri[tri_off(j + ng) + i] * c[j + ng]; }
-            for (; j < ke; j += ng) s0 += Ri[tri_off(j) + i] * c[j];
-            for (; j < k; j += ng) s0 += cx.gRi[tri_off(j) + i] * c[j];
+            for (; j + ng < k; j += 2 * ng) { s0 += ricol_w<SM>(P, cx, gm, j)[i] * c[j]; s1 += ricol_w<SM>(P, cx, gm, j + ng)[i] * c[j + ng]; }
+            if (j < k) s0 += ricol_w<SM>(P, cx, gm, j)[i] * c[j];
         }
         const double sv = team_sum(s0 + s1, lg);
         if (g == 0 && i < k) out(i, sv);
     }
 }
 
-// t = Ri * c[:k]   (t_i = sum_{j >= i} Ri[tri_off(j) + i] c_j).  Team of row i: columns j = i + g, i + g + ng, ...
-// Ends with a barrier.
+// t = Ri * c[:k].  Ends with a barrier.
+template <bool SM>
 __device__ inline void ri_matvec(const DevProblem &P, const Ctx &cx, int k, const double *c, double *t) {
-    const int lg = team_log2(k), ng = 1 << lg, g = threadIdx.x & (ng - 1), jw = WS_NT >> lg;
-    const int ke = min(k, P.ks);
-    const int kr = (k + jw - 1) & ~(jw - 1);
-    const double *Ri = SMV(Ri);
-    for (int i = threadIdx.x >> lg; i < kr; i += jw) {
-        double s0 = 0., s1 = 0.;
-        if (i < k) {
-            int j = i + g;
-            for (; j + ng < ke; j += 2 * ng) { s0 += Ri[tri_off(j) + i] * c[j]; s1 += Ri[tri_off(j + ng) + i] * c[j + ng]; }
-            for (; j < ke; j += ng) s0 += Ri[tri_off(j) + i] * c[j];
-            for (; j < k; j += ng) s0 += cx.gRi[tri_off(j) + i] * c[j];
-        }
-        const double s = team_sum(s0 + s1, lg);
-        if (g == 0 && i < k) t[i] = s;
-    }
-    __syncthreads();
+    ri_matvec_ep<SM>(P, cx, k, c, [&](int i, double s) { t[i] = s; });
+    WS_SYNC();
 }
 
 // u = Ri' * d[:k]  (u_j = sum_{i <= j} Ri[tri_off(j) + i] d_i).  Refresh path only.  Ends with a barrier.
-__device__ inline void rit_matvec(const DevProblem &P, const Ctx &cx, int k, const double *d, double *u) {
-    const int lg = team_log2(k), ng = 1 << lg, g = threadIdx.x & (ng - 1), jw = WS_NT >> lg;
-    const int kr = (k + jw - 1) & ~(jw - 1);
-    for (int j = threadIdx.x >> lg; j < kr; j += jw) {
+template <bool SM>
+__device__ inline void rit_matvec_t(const DevProblem &P, const Ctx &cx, int k, const double *d, double *u) {
+    const Geom gm = load_geom(P, cx);
+    const int lg = team_log2(k), ng = 1 << lg, C = 32 >> lg, jw = WS_NT >> lg;
+    const int lane = WS_TID & 31, g = lane >> (5 - lg), jl = (WS_TID >> 5) * C + (lane & (C - 1));
+    const int kr = (k + jw - 1) / jw * jw;
+    for (int j = jl; j < kr; j += jw) {
         double s = 0.;
-        if (j < k) {
-            if (j < P.ks) { const double *col = SMV(Ri) + tri_off(j); for (int i = g; i <= j; i += ng) s += col[i] * d[i]; }
-            else { const double *col = cx.gRi + tri_off(j); for (int i = g; i <= j; i += ng) s += col[i] * d[i]; }
-        }
+        if (j < k) { const double *col = ricol_w<SM>(P, cx, gm, j); for (int i = g; i <= j; i += ng) s += col[i] * d[i]; }
         s = team_sum(s, lg);
         if (g == 0 && j < k) u[j] = s;
     }
-    __syncthreads();
+    WS_SYNC();
 }
-
-__device__ __forceinline__ double *qcol_w(const DevProblem &P, const Ctx &cx, int j) { return j < P.ks ? SMV(Q) + j * P.ld : cx.gQ + (size_t)j * P.ld; }
-__device__ __forceinline__ double *ricol_w(const DevProblem &P, const Ctx &cx, int j) { return (j < P.ks ? SMV(Ri) : cx.gRi) + tri_off(j); }
 
 // -(signed bound of row r on side s): the entry of c = -d_W
 __device__ __forceinline__ double neg_bound(const DevProblem &P, const Ctx &cx, int r, int s) {
@@ -489,54 +554,61 @@ __device__ __forceinline__ double neg_bound(const DevProblem &P, const Ctx &cx, 
 
 // u = R^-T (-d_W), ls = R^-1 u, v = -Q1 u from scratch (new bounds: node start, proximal pass)
 __device__ __forceinline__ void refresh_uv(const DevProblem &P, const Ctx &cx, int k) {
+    const Geom gm = load_geom(P, cx);
     const int *row = SMI(irow), *side = SMI(iside);
-    for (int i = threadIdx.x; i < k; i += WS_NT) SMV(cw)[i] = neg_bound(P, cx, row[i], side[i]);
-    for (int i = threadIdx.x; i < P.np; i += WS_NT) SMV(v)[i] = 0.;
-    __syncthreads();
-    rit_matvec(P, cx, k, SMV(cw), SMV(u));
-    ri_matvec(P, cx, k, SMV(u), SMV(ls));
-    q_apply(P, cx, k, SMV(u), nullptr, SMV(v));
+    for (int i = WS_TID; i < k; i += WS_NT) SMV(cw)[i] = neg_bound(P, cx, row[i], side[i]);
+    for (int i = WS_TID; i < P.np; i += WS_NT) SMV(v)[i] = 0.;
+    WS_SYNC();
+    if (k <= gm.ks) { rit_matvec_t<true>(P, cx, k, SMV(cw), SMV(u)); ri_matvec<true>(P, cx, k, SMV(u), SMV(ls)); q_apply_t<true>(P, cx, k, SMV(u), nullptr, SMV(v)); }
+    else { rit_matvec_t<false>(P, cx, k, SMV(cw), SMV(u)); ri_matvec<false>(P, cx, k, SMV(u), SMV(ls)); q_apply_t<false>(P, cx, k, SMV(u), nullptr, SMV(v)); }
+}
+
+// entries d0 + tid, d0 + tid + WS_NT, ... of row r (zero below d and beyond n): what a thread stages for an append
+struct RowEnt { double e[WS_RPT]; };
+
+__device__ __forceinline__ RowEnt load_row_entries(const DevProblem &P, int r, int d, int d0) {
+    RowEnt x;
+#pragma unroll
+    for (int q = 0; q < WS_RPT; ++q) {
+        const int i = d0 + WS_TID + q * WS_NT;
+        x.e[q] = (i < P.n && i >= d) ? __ldg(P.Mh + (size_t)r * P.n + i) : 0.;
+    }
+    return x;
 }
 
 // Try to append the sign-normalised row (r, sgn).  Returns 1 if appended (lam = 0), 0 if the row is
 // numerically in the span of the working rows; either way t = R^-1 Q1' mj  (mj = Mw' t if dependent).
-// Returns -1 (nothing done) if the working set is at the capacity of the removal sweep (WS_NT positions).
+// Returns -1 (nothing done) if the working set is at the capacity of the removal sweep (WS_RRT WS_NT positions).
 // `track`: also bring u, ls, v up to date (false while the factor of an inherited working set is rebuilt).
-// `pre`: entries tid and tid + WS_NT of the row, already loaded by the caller (rebuild: the load of the next row
-// overlaps the append of the current one).
-__device__ __forceinline__ double2 load_row_entries(const DevProblem &P, int r, int d) {
-    const int i0 = threadIdx.x, i1 = threadIdx.x + WS_NT;
-    double2 e;
-    e.x = (i0 < P.n && i0 >= d) ? __ldg(P.Mh + (size_t)r * P.n + i0) : 0.;
-    e.y = (i1 < P.n && i1 >= d) ? __ldg(P.Mh + (size_t)r * P.n + i1) : 0.;
-    return e;
-}
-
-__device__ inline int thin_append(const DevProblem &P, const Ctx &cx, int &k, int r, int sgn, bool track, const double2 *pre = nullptr) {
-    const int n = P.n, d = SMI(idep)[0];
-    if (k >= WS_NT) return -1;
+// `pre`: the row's entries, already loaded by the caller (rebuild: the load of the next row overlaps the append of the
+// current one).
+template <bool SM>
+__device__ inline int thin_append_t(const DevProblem &P, const Ctx &cx, int &k, int r, int sgn, bool track, const RowEnt *pre = nullptr) {
+    const Geom gm = load_geom(P, cx);
+    const int n = P.n, d = gm.d;
+    if (k >= WS_RRT * WS_NT) return -1;
     double *z = SMV(z), *c1 = SMV(c1), *t = SMV(t);
     const int pb = track ? 30 : 40;                  // phase ids of the WS_PROF timeline
     (void)pb;
     {
-        const double2 e = pre ? *pre : load_row_entries(P, r, d);
-        if (threadIdx.x < P.np) z[threadIdx.x] = (double)sgn * e.x;
-        if (threadIdx.x + WS_NT < P.np) z[threadIdx.x + WS_NT] = (double)sgn * e.y;
+        const RowEnt e = pre ? *pre : load_row_entries(P, r, d, gm.d0);
+#pragma unroll
+        for (int q = 0; q < WS_RPT; ++q) { const int i = gm.d0 + WS_TID + q * WS_NT; if (i < P.np) z[i] = (double)sgn * e.e[q]; }
     }
-    __syncthreads();
+    WS_SYNC();
     prof_mark(pb);
-    qt_dots(P, cx, k, z, c1);
+    qt_dots_t<SM>(P, cx, k, z, c1);
     prof_mark(pb + 1);
     double cu = 0.;
-    if (track) for (int j = threadIdx.x; j < k; j += WS_NT) cu += c1[j] * SMV(u)[j];
-    double rho2 = q_apply(P, cx, k, c1, z, z, cu, &cu);
+    if (track) for (int j = WS_TID; j < k; j += WS_NT) cu += c1[j] * SMV(u)[j];
+    double rho2 = q_apply_t<SM>(P, cx, k, c1, z, z, cu, &cu);
     prof_mark(pb + 2);
     if (k > 0 && rho2 < WS_REORTH * __ldg(P.Msq + (size_t)r * (P.nb + 1) + d)) {
         double *c2 = SMV(c2);
-        qt_dots(P, cx, k, z, c2);
+        qt_dots_t<SM>(P, cx, k, z, c2);
         double cu2 = 0.;
-        for (int j = threadIdx.x; j < k; j += WS_NT) { const double dc = c2[j]; c1[j] += dc; if (track) cu2 += dc * SMV(u)[j]; }
-        rho2 = q_apply(P, cx, k, c2, z, z, cu2, &cu2);
+        for (int j = WS_TID; j < k; j += WS_NT) { const double dc = c2[j]; c1[j] += dc; if (track) cu2 += dc * SMV(u)[j]; }
+        rho2 = q_apply_t<SM>(P, cx, k, c2, z, z, cu2, &cu2);
         cu += cu2;
         prof_mark(pb + 4);
     }
@@ -544,20 +616,20 @@ __device__ inline int thin_append(const DevProblem &P, const Ctx &cx, int &k, in
     // the triangular product and the write-out are ONE phase
     const bool dep = k >= n - d || rho2 <= P.tol_sing * P.tol_sing;
     const double ir = dep ? 0. : 1. / sqrt(rho2);
-    double *qk = qcol_w(P, cx, k), *rk = ricol_w(P, cx, k);
+    double *qk = qcol_w<SM>(P, cx, gm, k), *rk = ricol_w<SM>(P, cx, gm, k);
     double uk = 0., lk = 0.;
     if (track && !dep) { uk = (neg_bound(P, cx, r, sgn) - cu) * ir; lk = uk * ir; }
-    ri_matvec_ep(P, cx, k, c1, [&](int i, double ti) {
+    ri_matvec_ep<SM>(P, cx, k, c1, [&](int i, double ti) {
         t[i] = ti;
         if (!dep) { rk[i] = -ti * ir; if (track) SMV(ls)[i] -= ti * lk; }
     });
-    if (dep) { __syncthreads(); prof_mark(pb + 5); return 0; }
-    for (int i = threadIdx.x; i < P.np; i += WS_NT) {
+    if (dep) { WS_SYNC(); prof_mark(pb + 5); return 0; }
+    for (int i = gm.d0 + WS_TID; i < P.np; i += WS_NT) {
         const double q = z[i] * ir;
         qk[i] = q;
         if (track) SMV(v)[i] -= q * uk;
     }
-    if (threadIdx.x == 0) {
+    if (WS_TID == 0) {
         rk[k] = ir;
         SMI(irow)[k] = r; SMI(iside)[k] = sgn; SMV(lam)[k] = 0.;
         if (track) { SMV(u)[k] = uk; SMV(ls)[k] = lk; }
@@ -565,21 +637,20 @@ __device__ inline int thin_append(const DevProblem &P, const Ctx &cx, int &k, in
     k += 1;
     // while the factor is rebuilt the next append starts with a barrier of its own (after the row is staged) and nothing
     // in between reads what was written here; rebuild_factor ends with a barrier
-    if (track) __syncthreads();
+    if (track) WS_SYNC();
     prof_mark(pb + 6);
     return 1;
 }
 
 // Remove position kp from the working set (u, ls, v follow).  Returns the smallest position >= kp whose
 // diagonal of R collapsed (|Ri_ii| >= 1 / tol_sing) after the removal, or -1.
-// SM: every column of the factor is in shared memory (k <= ks): plain shared-memory addressing instead of the
-// per-access shared / global choice.
 template <bool SM>
-__device__ inline int thin_remove_impl(const DevProblem &P, const Ctx &cx, int &k, int kp) {
-    auto QC = [&](int j) -> double * { return SM ? SMV(Q) + j * P.ld : qcol_w(P, cx, j); };
-    auto RC = [&](int j) -> double * { return SM ? SMV(Ri) + tri_off(j) : ricol_w(P, cx, j); };
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, tid = (int)threadIdx.x;
-    double *gc = SMV(gc), *gs = SMV(gs), *u = SMV(u);
+__device__ inline int thin_remove_t(const DevProblem &P, const Ctx &cx, int &k, int kp) {
+    const Geom gm = load_geom(P, cx);
+    auto QC = [&](int j) -> double * { return qcol_w<SM>(P, cx, gm, j); };
+    auto RC = [&](int j) -> double * { return ricol_w<SM>(P, cx, gm, j); };
+    const int lane = WS_TID & 31, w = WS_TID >> 5, tid = WS_TID;
+    double *gc = SMV(c2), *gs = SMV(cw), *u = SMV(u);           // rotation cosines / sines (c2, cw are free during a removal)
     int *row = SMI(irow), *side = SMI(iside), *flag = SMI(ired) + 32;
     if (tid == 0) *flag = 0x7fffffff;
     prof_add(100, k - 1 - kp);
@@ -588,12 +659,12 @@ __device__ inline int thin_remove_impl(const DevProblem &P, const Ctx &cx, int &
         // last position: Q1, Ri lose their last column; v += q_last u_last
         const double ul = u[kp];
         const double *qk = QC(kp);
-        for (int i = tid; i < P.np; i += WS_NT) SMV(v)[i] += qk[i] * ul;
+        for (int i = gm.d0 + tid; i < P.np; i += WS_NT) SMV(v)[i] += qk[i] * ul;
         // ls = Ri u loses the term of the last column
         const double *rl = RC(kp);
         for (int i = tid; i < kp; i += WS_NT) SMV(ls)[i] -= rl[i] * ul;
         k -= 1;
-        __syncthreads();
+        WS_SYNC();
         prof_mark(50);
         return -1;
     }
@@ -619,62 +690,77 @@ __device__ inline int thin_remove_impl(const DevProblem &P, const Ctx &cx, int &
         }
     }
     // bookkeeping shift: read now, write after the first barrier of the sweep
-    int rw = 0, sd = 0; double lm = 0.;
-    const int tsrc = kp + 1 + tid;
-    if (tsrc < k) { rw = row[tsrc]; sd = side[tsrc]; lm = SMV(lam)[tsrc]; }
-    // ---- 2. sweep over the columns in chunks: Q rows in threads [0, np), Ri rows in threads WS_NT-1 .. downwards,
-    //         the u chain in thread np (first thread without a row of Q1)
-    const int qr = tid < P.np ? tid : -1;                                   // row of Q1
-    const int qr2 = tid + WS_NT < P.np ? tid + WS_NT : -1;                  // second row (n <= 2 WS_NT)
-    const int rr = (WS_NT - 1 - tid) < k - 1 ? WS_NT - 1 - tid : -1;        // new row of Ri (k - 1 <= WS_NT)
-    const int ro = rr < kp ? rr : rr + 1;                                   // its old row
-    const bool uth = tid == (((P.np + 31) & ~31) < WS_NT ? ((P.np + 31) & ~31) : 0);      // first thread of the first warp without rows of Q1
+    int rw[WS_RRT], sd[WS_RRT]; double lm[WS_RRT];
+#pragma unroll
+    for (int q = 0; q < WS_RRT; ++q) {
+        const int ts = kp + 1 + tid + q * WS_NT;
+        rw[q] = 0; sd[q] = 0; lm[q] = 0.;
+        if (ts < k) { rw[q] = row[ts]; sd[q] = side[ts]; lm[q] = SMV(lam)[ts]; }
+    }
+    // ---- 2. sweep over the columns in chunks: rows d0 + tid + q WS_NT of Q1, rows WS_NT - 1 - tid + q WS_NT of Ri,
+    //         the u chain in the first thread of the first warp without a row of Q1 (thread 0 if every warp has one)
+    int qr[WS_RPT]; double qcarry[WS_RPT];
+#pragma unroll
+    for (int q = 0; q < WS_RPT; ++q) { const int i = gm.d0 + tid + q * WS_NT; qr[q] = i < P.np ? i : -1; }
+    int rr[WS_RRT], ro[WS_RRT]; double rcarry[WS_RRT], ls_old[WS_RRT];
+#pragma unroll
+    for (int q = 0; q < WS_RRT; ++q) {
+        const int r = WS_NT - 1 - tid + q * WS_NT;
+        rr[q] = r < k - 1 ? r : -1;
+        ro[q] = r < kp ? r : r + 1;
+    }
+    const int nq1 = (2 * gm.he + 31) & ~31;
+    const bool uth = tid == (nq1 < WS_NT ? nq1 : 0);
     const double big = 1. / P.tol_sing;
-    __syncthreads();                                                        // gc, gs visible
+    WS_SYNC();                                                              // gc, gs visible
     prof_mark(51);
-    double qcarry = qr >= 0 ? QC(kp)[qr] : 0.;
-    double qcarry2 = qr2 >= 0 ? QC(kp)[qr2] : 0.;
-    double rcarry = (rr >= 0 && ro <= kp) ? RC(kp)[ro] : 0.;
-    const double ls_old = rr >= 0 ? SMV(ls)[ro] : 0.;                       // read before any thread writes its new entry
+#pragma unroll
+    for (int q = 0; q < WS_RPT; ++q) qcarry[q] = qr[q] >= 0 ? QC(kp)[qr[q]] : 0.;
+#pragma unroll
+    for (int q = 0; q < WS_RRT; ++q) {
+        rcarry[q] = (rr[q] >= 0 && ro[q] <= kp) ? RC(kp)[ro[q]] : 0.;
+        ls_old[q] = rr[q] >= 0 ? SMV(ls)[ro[q]] : 0.;                       // read before any thread writes its new entry
+    }
     double ucarry = uth ? u[kp] : 0.;
     for (int i0 = kp; i0 < k - 1; i0 += WS_CH) {
-        double b[WS_CH];
-        if (rr >= 0) {
+        double b[WS_RRT][WS_CH];
 #pragma unroll
-            for (int q = 0; q < WS_CH; ++q) { const int i = i0 + q; b[q] = (i < k - 1 && ro <= i + 1) ? RC(i + 1)[ro] : 0.; }
+        for (int q = 0; q < WS_RRT; ++q) if (rr[q] >= 0) {
+#pragma unroll
+            for (int c = 0; c < WS_CH; ++c) { const int i = i0 + c; b[q][c] = (i < k - 1 && ro[q] <= i + 1) ? RC(i + 1)[ro[q]] : 0.; }
         }
-        __syncthreads();                                                    // every old entry of the chunk has been read
-        if (i0 == kp && tsrc < k) { row[tsrc - 1] = rw; side[tsrc - 1] = sd; SMV(lam)[tsrc - 1] = lm; }
-        if (rr >= 0 && ro <= i0 + WS_CH) {
+        WS_SYNC();                                                          // every old entry of the chunk has been read
+        if (i0 == kp) {
 #pragma unroll
-            for (int q = 0; q < WS_CH; ++q) {
-                const int i = i0 + q;
+            for (int q = 0; q < WS_RRT; ++q) {
+                const int ts = kp + 1 + tid + q * WS_NT;
+                if (ts < k) { row[ts - 1] = rw[q]; side[ts - 1] = sd[q]; SMV(lam)[ts - 1] = lm[q]; }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < WS_RRT; ++q) if (rr[q] >= 0 && ro[q] <= i0 + WS_CH) {
+#pragma unroll
+            for (int c = 0; c < WS_CH; ++c) {
+                const int i = i0 + c;
                 if (i < k - 1) {
                     const double cs = gc[i], sn = gs[i];
-                    const double o = cs * rcarry + sn * b[q];
-                    rcarry = -sn * rcarry + cs * b[q];
-                    if (rr <= i) {
-                        RC(i)[rr] = o;
-                        if (rr == i && fabs(o) >= big) atomicMin(flag, rr);
+                    const double o = cs * rcarry[q] + sn * b[q][c];
+                    rcarry[q] = -sn * rcarry[q] + cs * b[q][c];
+                    if (rr[q] <= i) {
+                        RC(i)[rr[q]] = o;
+                        if (rr[q] == i && fabs(o) >= big) atomicMin(flag, rr[q]);
                     }
                 }
             }
         }
         const int iend = (i0 + WS_CH < k - 1) ? i0 + WS_CH : k - 1;
-        if (qr >= 0) {
+#pragma unroll
+        for (int q = 0; q < WS_RPT; ++q) if (qr[q] >= 0) {
             for (int i = i0; i < iend; ++i) {
-                const double bq = QC(i + 1)[qr];
+                const double bq = QC(i + 1)[qr[q]];
                 const double cs = gc[i], sn = gs[i];
-                QC(i)[qr] = cs * qcarry + sn * bq;
-                qcarry = -sn * qcarry + cs * bq;
-            }
-        }
-        if (qr2 >= 0) {
-            for (int i = i0; i < iend; ++i) {
-                const double bq = QC(i + 1)[qr2];
-                const double cs = gc[i], sn = gs[i];
-                QC(i)[qr2] = cs * qcarry2 + sn * bq;
-                qcarry2 = -sn * qcarry2 + cs * bq;
+                QC(i)[qr[q]] = cs * qcarry[q] + sn * bq;
+                qcarry[q] = -sn * qcarry[q] + cs * bq;
             }
         }
         if (uth) {
@@ -688,33 +774,39 @@ __device__ inline int thin_remove_impl(const DevProblem &P, const Ctx &cx, int &
     }
     if (uth) SMV(red)[40] = ucarry;                                  // (G u)_last
     k -= 1;
-    __syncthreads();
+    WS_SYNC();
     prof_mark(52);
     // v = -Q1_new u_new = v_old + q_last (G u)_last
-    if (qr >= 0) SMV(v)[qr] += qcarry * SMV(red)[40];
-    if (qr2 >= 0) SMV(v)[qr2] += qcarry2 * SMV(red)[40];
+#pragma unroll
+    for (int q = 0; q < WS_RPT; ++q) if (qr[q] >= 0) SMV(v)[qr[q]] += qcarry[q] * SMV(red)[40];
     // ls = Ri u = (Ri G')(G u): dropping the rotated-out last column leaves  ls_new[rr] = ls_old[ro] - (Ri G')[ro, last] (G u)_last,
     // and the carry of row rr IS that last-column entry
-    if (rr >= 0) SMV(ls)[rr] = ls_old - rcarry * SMV(red)[40];
+#pragma unroll
+    for (int q = 0; q < WS_RRT; ++q) if (rr[q] >= 0) SMV(ls)[rr[q]] = ls_old[q] - rcarry[q] * SMV(red)[40];
     const int bad = *flag;
-    __syncthreads();
+    WS_SYNC();
     prof_mark(53);
     return bad == 0x7fffffff ? -1 : bad;
 }
 
+__device__ inline int thin_append(const DevProblem &P, const Ctx &cx, int &k, int r, int sgn, bool track, const RowEnt *pre = nullptr) {
+    const Geom gm = load_geom(P, cx);
+    return k < gm.ks ? thin_append_t<true>(P, cx, k, r, sgn, track, pre) : thin_append_t<false>(P, cx, k, r, sgn, track, pre);
+}
 __device__ inline int thin_remove(const DevProblem &P, const Ctx &cx, int &k, int kp) {
-    return k <= P.ks ? thin_remove_impl<true>(P, cx, k, kp) : thin_remove_impl<false>(P, cx, k, kp);
+    const Geom gm = load_geom(P, cx);
+    return k <= gm.ks ? thin_remove_t<true>(P, cx, k, kp) : thin_remove_t<false>(P, cx, k, kp);
 }
 
 // remove position kp, then every row whose diagonal of R collapsed (see oracle/qp_core.c thin_ws_remove)
 __device__ __forceinline__ void ws_remove(const DevProblem &P, const Ctx &cx, int &k, int kp) {
     signed char *inW = reinterpret_cast<signed char *>(SMB(binW));
-    if (threadIdx.x == 0) inW[SMI(irow)[kp]] = 0;
-    __syncthreads();
+    if (WS_TID == 0) inW[SMI(irow)[kp]] = 0;
+    WS_SYNC();
     int bad = thin_remove(P, cx, k, kp);
     while (bad >= 0) {
-        if (threadIdx.x == 0) inW[SMI(irow)[bad]] = 0;
-        __syncthreads();
+        if (WS_TID == 0) inW[SMI(irow)[bad]] = 0;
+        WS_SYNC();
         bad = thin_remove(P, cx, k, bad);
     }
 }
@@ -764,7 +856,7 @@ __device__ inline void price_rows(const DevProblem &P, const Ctx &cx, const doub
         if (P.gp == 0) {
             // more output pairs than threads: a thread owns the pairs tid, tid + WS_NT, ... and all columns
             double2 *xi2 = reinterpret_cast<double2 *>(xi);
-            for (int pp = threadIdx.x; pp < hs; pp += WS_NT) {
+            for (int pp = WS_TID; pp < hs; pp += WS_NT) {
                 const double2 *w2 = reinterpret_cast<const double2 *>(P.WfT) + pp;
                 double ax = 0., ay = 0., bx = 0., by = 0.;
                 int c = c0;
@@ -777,21 +869,21 @@ __device__ inline void price_rows(const DevProblem &P, const Ctx &cx, const doub
                 xi2[pp] = make_double2(ax + bx, ay + by);
             }
         }
-        __syncthreads();
+        WS_SYNC();
         if (P.gp > 0) {
             const double *part = SMV(part);
-            for (int r = threadIdx.x; r < P.ns2; r += WS_NT) {
+            for (int r = WS_TID; r < P.ns2; r += WS_NT) {
                 double s = part[r];
                 for (int q = 1; q < P.gp; ++q) s += part[q * P.ns2 + r];
                 xi[r] = s;
             }
         }
-        __syncthreads();
+        WS_SYNC();
         prof_mark(pid);
     }
-    const int *rinfo = SMI(rinfo);
-    const double *inr = SMV(inr);
-    for (int r = threadIdx.x; r < m; r += WS_NT) {
+    const int *rinfo = TBI(rinfo);
+    const double *inr = TBV(inr);
+    for (int r = WS_TID; r < m; r += WS_NT) {
         if (skip(r)) continue;
         double s;
         const int info = rinfo[r];
@@ -799,8 +891,8 @@ __device__ inline void price_rows(const DevProblem &P, const Ctx &cx, const doub
             const int t = info >> 16, i = info & 0xffff;
             const bool last = t == P.T - 1;
             const int rs = last ? P.nh1 : P.nh;                   // rows of the stage = stride of the transposed tables
-            const double *Fr = (last ? SMV(sF1) : SMV(sF)) + i;
-            const double *Gr = (last ? SMV(sG1) : SMV(sG)) + i;
+            const double *Fr = (last ? TBV(sF1) : TBV(sF)) + i;
+            const double *Gr = (last ? TBV(sG1) : TBV(sG)) + i;
             const double *zt = xi + t * nu;
             double s0 = 0., s1 = 0.;
             int c = 0;
@@ -824,23 +916,29 @@ __device__ inline void price_rows(const DevProblem &P, const Ctx &cx, const doub
 // slot state
 // ---------------------------------------------------------------------------------------------
 
-// once per kernel launch: shared copies of the stage rows, row scalings and the row -> (stage, index) map
+// once per kernel launch, by ALL threads of the CTA: the shared copies of the stage rows, row scalings and the
+// row -> (stage, index) map (one copy for all lanes), then every lane clears its own vectors.  Contains __syncthreads:
+// call it before any lane leaves the kernel.
 __device__ inline void init_shared_tables(const DevProblem &P, const Ctx &cx) {
     // stage rows TRANSPOSED (entry (row i, column c) at c * rows + i): adjacent threads price adjacent rows, so
     // their reads of one column are consecutive words (no bank conflicts)
-    for (int e = threadIdx.x; e < P.nh * P.nx; e += WS_NT) { const int i = e / P.nx, c = e - i * P.nx; SMV(sF)[c * P.nh + i] = P.F[e]; }
-    for (int e = threadIdx.x; e < P.nh * P.nu; e += WS_NT) { const int i = e / P.nu, c = e - i * P.nu; SMV(sG)[c * P.nh + i] = P.G[e]; }
-    for (int e = threadIdx.x; e < P.nh1 * P.nx; e += WS_NT) { const int i = e / P.nx, c = e - i * P.nx; SMV(sF1)[c * P.nh1 + i] = P.F1[e]; }
-    for (int e = threadIdx.x; e < P.nh1 * P.nu; e += WS_NT) { const int i = e / P.nu, c = e - i * P.nu; SMV(sG1)[c * P.nh1 + i] = P.G1[e]; }
-    for (int r = threadIdx.x; r < P.m; r += WS_NT) {
-        SMV(inr)[r] = P.inr[r]; SMV(vsc)[r] = P.vscale[r];
+    const int nt = blockDim.x, t0 = threadIdx.x;
+    double *sF = cx.tab + P.so.t_sF, *sG = cx.tab + P.so.t_sG, *sF1 = cx.tab + P.so.t_sF1, *sG1 = cx.tab + P.so.t_sG1;
+    for (int e = t0; e < P.nh * P.nx; e += nt) { const int i = e / P.nx, c = e - i * P.nx; sF[c * P.nh + i] = P.F[e]; }
+    for (int e = t0; e < P.nh * P.nu; e += nt) { const int i = e / P.nu, c = e - i * P.nu; sG[c * P.nh + i] = P.G[e]; }
+    for (int e = t0; e < P.nh1 * P.nx; e += nt) { const int i = e / P.nx, c = e - i * P.nx; sF1[c * P.nh1 + i] = P.F1[e]; }
+    for (int e = t0; e < P.nh1 * P.nu; e += nt) { const int i = e / P.nu, c = e - i * P.nu; sG1[c * P.nh1 + i] = P.G1[e]; }
+    int *rinfo = reinterpret_cast<int *>(cx.tab + P.so.t_rinfo);
+    for (int r = t0; r < P.m; r += nt) {
+        (cx.tab + P.so.t_inr)[r] = P.inr[r]; (cx.tab + P.so.t_vsc)[r] = P.vscale[r];
         int info;
         if (r < P.mc) { int t = r / P.nh; if (t > P.T - 1) t = P.T - 1; info = (t << 16) | (r - t * P.nh); }
         else info = P.bin_idx[r - P.mc];
-        SMI(rinfo)[r] = info;
+        rinfo[r] = info;
     }
-    for (int i = threadIdx.x; i < P.np + 2; i += WS_NT) { SMV(z)[i] = 0.; SMV(v)[i] = 0.; SMV(wv)[i] = 0.; SMV(yc)[i] = 0.; }
-    for (int i = threadIdx.x; i < P.ns2; i += WS_NT) SMV(xi)[i] = 0.;
+    for (int i = WS_TID; i < P.np + 2; i += WS_NT) { SMV(z)[i] = 0.; SMV(v)[i] = 0.; SMV(wv)[i] = 0.; SMV(yc)[i] = 0.; }
+    for (int i = WS_TID; i < P.ns2; i += WS_NT) SMV(xi)[i] = 0.;
+    if (WS_TID == 0) store_geom(P, cx, 0);
     __syncthreads();
 }
 
@@ -849,22 +947,22 @@ __device__ inline void init_shared_tables(const DevProblem &P, const Ctx &cx) {
 __device__ inline void load_slot(const DevProblem &P, const Ctx &cx, const SlotPtrs &sp, int &k, bool reset) {
     const int n = P.n;
     if (reset) {
-        for (int i = threadIdx.x; i < n; i += WS_NT) SMV(yc)[i] = 0.;
+        for (int i = WS_TID; i < n; i += WS_NT) SMV(yc)[i] = 0.;
         k = 0;
     } else {
         k = *sp.nW;
-        for (int i = threadIdx.x; i < n; i += WS_NT) SMV(yc)[i] = sp.yc[i];
-        for (int i = threadIdx.x; i < k; i += WS_NT) { SMI(irow)[i] = sp.row[i]; SMI(iside)[i] = sp.side[i]; SMV(lam)[i] = sp.lam[i]; }
+        for (int i = WS_TID; i < n; i += WS_NT) SMV(yc)[i] = sp.yc[i];
+        for (int i = WS_TID; i < k; i += WS_NT) { SMI(irow)[i] = sp.row[i]; SMI(iside)[i] = sp.side[i]; SMV(lam)[i] = sp.lam[i]; }
     }
-    __syncthreads();
+    WS_SYNC();
 }
 
 __device__ inline void store_slot(const DevProblem &P, const Ctx &cx, const SlotPtrs &sp, int k) {
     const int n = P.n;
-    for (int i = threadIdx.x; i < n; i += WS_NT) sp.yc[i] = SMV(yc)[i];
-    for (int i = threadIdx.x; i < k; i += WS_NT) { sp.row[i] = SMI(irow)[i]; sp.side[i] = SMI(iside)[i]; sp.lam[i] = SMV(lam)[i]; }
-    if (threadIdx.x == 0) *sp.nW = k;
-    __syncthreads();
+    for (int i = WS_TID; i < n; i += WS_NT) sp.yc[i] = SMV(yc)[i];
+    for (int i = WS_TID; i < k; i += WS_NT) { sp.row[i] = SMI(irow)[i]; sp.side[i] = SMI(iside)[i]; sp.lam[i] = SMV(lam)[i]; }
+    if (WS_TID == 0) *sp.nW = k;
+    WS_SYNC();
 }
 
 // Working set from signed multipliers of the ORIGINAL rows (ysigned(r) > 0: upper side, < 0: lower side) and a
@@ -873,22 +971,22 @@ __device__ inline void store_slot(const DevProblem &P, const Ctx &cx, const Slot
 // natural order.  yc0 may be null (centre 0).
 template <class Y>
 __device__ __forceinline__ void load_ws_from_multipliers(const DevProblem &P, const Ctx &cx, Y ysigned, const double *yc0, int &k) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int lane = WS_TID & 31, w = WS_TID >> 5;
     int *wsum = SMI(ired);                       // WS_NW ints
     int *row = SMI(irow), *side = SMI(iside);
     double *lam = SMV(lam);
     const int d = SMI(idep)[0];
-    for (int i = threadIdx.x; i < P.n; i += WS_NT) SMV(yc)[i] = yc0 ? yc0[i] : 0.;
+    for (int i = WS_TID; i < P.n; i += WS_NT) SMV(yc)[i] = yc0 ? yc0[i] : 0.;
     int base = 0;
     for (int r0 = 0; r0 < P.m; r0 += WS_NT) {
-        const int r = r0 + threadIdx.x;
+        const int r = r0 + WS_TID;
         double yv = 0.;
         if (r < P.m) yv = ysigned(r);
         const int keep = yv != 0. && base < P.n && !(r >= P.mc && r - P.mc < d);   // eliminated rows carry no working-set entry
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
-        __syncthreads();
+        WS_SYNC();
         if (lane == 0) wsum[w] = __popc(bal);
-        __syncthreads();
+        WS_SYNC();
         int pre = base, tot = 0;
         for (int q = 0; q < WS_NW; ++q) { const int c = wsum[q]; if (q < w) pre += c; tot += c; }
         const int idx = pre + __popc(bal & ((1u << lane) - 1u));
@@ -896,25 +994,25 @@ __device__ __forceinline__ void load_ws_from_multipliers(const DevProblem &P, co
         base += tot;
     }
     k = base < P.n ? base : P.n;
-    __syncthreads();
+    WS_SYNC();
 #ifndef WS_NO_SORT
     // Order the start by DECREASING multiplier: the rows the ratio test drops first (small multipliers) sit at the end
     // of the factor, where a removal rotates few columns (position k - 1 costs nothing); rank by counting, ties by row.
     {
         int *scr = SMI(iscr); double *tmp = SMV(cw);
-        for (int i = threadIdx.x; i < k; i += WS_NT) {
+        for (int i = WS_TID; i < k; i += WS_NT) {
             const double li = lam[i];
             int rank = 0;
             for (int j = 0; j < k; ++j) { const double lj = lam[j]; rank += (lj > li || (lj == li && j < i)) ? 1 : 0; }
             scr[i] = rank | (row[i] << 10) | (side[i] > 0 ? (1 << 30) : 0);     // rank < 1024 (k <= n <= 2 WS_NT), row < 2^20
             tmp[i] = li;
         }
-        __syncthreads();
-        for (int i = threadIdx.x; i < k; i += WS_NT) {
+        WS_SYNC();
+        for (int i = WS_TID; i < k; i += WS_NT) {
             const int e = scr[i], rank = e & 0x3ff;
             row[rank] = (e >> 10) & 0xfffff; side[rank] = (e >> 30) & 1 ? 1 : -1; lam[rank] = tmp[i];
         }
-        __syncthreads();
+        WS_SYNC();
     }
 #endif
 }
@@ -923,30 +1021,31 @@ __device__ __forceinline__ void load_ws_from_multipliers(const DevProblem &P, co
 // their multipliers, dropping rows that have become dependent) and reset the anti-cycling bookkeeping.
 // Mirrors the warm start of oracle/qp_core.c qp_solve.
 __device__ __forceinline__ void rebuild_factor(const DevProblem &P, const Ctx &cx, int &k) {
+    const Geom gm = load_geom(P, cx);
     signed char *inW = reinterpret_cast<signed char *>(SMB(binW));
     unsigned char *ign = SMB(bign), *nadd = SMB(bnadd);
-    const int d = SMI(idep)[0];
-    for (int r = threadIdx.x; r < P.m; r += WS_NT) { inW[r] = 0; ign[r] = (r >= P.mc && r - P.mc < d) ? 3 : 0; nadd[r] = 0; }
+    const int d = gm.d;
+    for (int r = WS_TID; r < P.m; r += WS_NT) { inW[r] = 0; ign[r] = (r >= P.mc && r - P.mc < d) ? 3 : 0; nadd[r] = 0; }
     // the inherited rows are parked in scratch while the factor grows from the front
     const int k0 = k;
     double *lam0 = SMV(cw), *lam = SMV(lam);
     int *row = SMI(irow), *side = SMI(iside);
     int *row0 = SMI(iscr);                           // (row, side) packed, n + 1 ints
-    __syncthreads();
-    for (int i = threadIdx.x; i < k0; i += WS_NT) { row0[i] = row[i] * 2 + (side[i] > 0 ? 1 : 0); lam0[i] = lam[i]; }
-    __syncthreads();
+    WS_SYNC();
+    for (int i = WS_TID; i < k0; i += WS_NT) { row0[i] = row[i] * 2 + (side[i] > 0 ? 1 : 0); lam0[i] = lam[i]; }
+    WS_SYNC();
     k = 0;
-    double2 pre = k0 > 0 ? load_row_entries(P, row0[0] >> 1, d) : make_double2(0., 0.);
+    RowEnt pre = load_row_entries(P, k0 > 0 ? row0[0] >> 1 : 0, d, gm.d0);
     for (int i = 0; i < k0; ++i) {
         const int r = row0[i] >> 1, s = (row0[i] & 1) ? 1 : -1;
-        const double2 cur = pre;
-        if (i + 1 < k0) pre = load_row_entries(P, row0[i + 1] >> 1, d);      // in flight during this append
+        const RowEnt cur = pre;
+        if (i + 1 < k0) pre = load_row_entries(P, row0[i + 1] >> 1, d, gm.d0);      // in flight during this append
         if (r >= P.mc && r - P.mc < d) continue;          // eliminated in this node
         if (thin_append(P, cx, k, r, s, false, &cur) > 0) {
-            if (threadIdx.x == 0) { lam[k - 1] = lam0[i]; inW[r] = (signed char)s; }
+            if (WS_TID == 0) { lam[k - 1] = lam0[i]; inW[r] = (signed char)s; }
         }
     }
-    __syncthreads();
+    WS_SYNC();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -956,34 +1055,35 @@ __device__ __forceinline__ void rebuild_factor(const DevProblem &P, const Ctx &c
 // and read back by the sibling: 2 x 50 KB of L2 traffic instead of ~40 Gram-Schmidt appends.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void save_factor(const DevProblem &P, const Ctx &cx, const SlotPtrs &sp, int k) {
-    const int ldh = P.ld >> 1;
-    const double2 *s2 = reinterpret_cast<const double2 *>(SMV(Q));
-    double2 *g2 = reinterpret_cast<double2 *>(sp.Q);
-    for (int e = threadIdx.x; e < k * ldh; e += WS_NT) g2[e] = s2[e];
+    const Geom gm = load_geom(P, cx);
+    // the k columns are all in the pool (caller checks k <= ks): Ri image, then the Q1 columns at their pool stride
     const int nt = tri_off(k);
-    for (int e = threadIdx.x; e < nt; e += WS_NT) sp.Ri[e] = SMV(Ri)[e];
-    for (int i = threadIdx.x; i < k; i += WS_NT) { sp.row[i] = SMI(irow)[i]; sp.side[i] = SMI(iside)[i]; sp.lam[i] = SMV(lam)[i]; }
-    if (threadIdx.x == 0) *sp.nW = k;
-    __syncthreads();
+    for (int e = WS_TID; e < nt; e += WS_NT) sp.Ri[e] = SMV(pool)[e];
+    const double2 *s2 = reinterpret_cast<const double2 *>(SMV(pool) + gm.triR);
+    double2 *g2 = reinterpret_cast<double2 *>(sp.Q);
+    for (int e = WS_TID; e < k * (gm.ldc >> 1); e += WS_NT) g2[e] = s2[e];
+    for (int i = WS_TID; i < k; i += WS_NT) { sp.row[i] = SMI(irow)[i]; sp.side[i] = SMI(iside)[i]; sp.lam[i] = SMV(lam)[i]; }
+    if (WS_TID == 0) *sp.nW = k;
+    WS_SYNC();
 }
 
-// the state rebuild_factor leaves behind, from the memo.  Ends with a barrier.
+// the state rebuild_factor leaves behind, from the memo (same eliminated prefix, hence same geometry).  Ends with a barrier.
 __device__ __forceinline__ void restore_factor(const DevProblem &P, const Ctx &cx, const SlotPtrs &sp, int &k) {
+    const Geom gm = load_geom(P, cx);
     signed char *inW = reinterpret_cast<signed char *>(SMB(binW));
     unsigned char *ign = SMB(bign), *nadd = SMB(bnadd);
-    const int d = SMI(idep)[0];
+    const int d = gm.d;
     k = *sp.nW;
-    for (int r = threadIdx.x; r < P.m; r += WS_NT) { inW[r] = 0; ign[r] = (r >= P.mc && r - P.mc < d) ? 3 : 0; nadd[r] = 0; }
-    const int ldh = P.ld >> 1;
-    double2 *s2 = reinterpret_cast<double2 *>(SMV(Q));
-    const double2 *g2 = reinterpret_cast<const double2 *>(sp.Q);
-    for (int e = threadIdx.x; e < k * ldh; e += WS_NT) s2[e] = g2[e];
+    for (int r = WS_TID; r < P.m; r += WS_NT) { inW[r] = 0; ign[r] = (r >= P.mc && r - P.mc < d) ? 3 : 0; nadd[r] = 0; }
     const int nt = tri_off(k);
-    for (int e = threadIdx.x; e < nt; e += WS_NT) SMV(Ri)[e] = sp.Ri[e];
-    for (int i = threadIdx.x; i < k; i += WS_NT) { SMI(irow)[i] = sp.row[i]; SMI(iside)[i] = sp.side[i]; SMV(lam)[i] = sp.lam[i]; }
-    __syncthreads();
-    for (int i = threadIdx.x; i < k; i += WS_NT) inW[SMI(irow)[i]] = (signed char)SMI(iside)[i];
-    __syncthreads();
+    for (int e = WS_TID; e < nt; e += WS_NT) SMV(pool)[e] = sp.Ri[e];
+    double2 *s2 = reinterpret_cast<double2 *>(SMV(pool) + gm.triR);
+    const double2 *g2 = reinterpret_cast<const double2 *>(sp.Q);
+    for (int e = WS_TID; e < k * (gm.ldc >> 1); e += WS_NT) s2[e] = g2[e];
+    for (int i = WS_TID; i < k; i += WS_NT) { SMI(irow)[i] = sp.row[i]; SMI(iside)[i] = sp.side[i]; SMV(lam)[i] = sp.lam[i]; }
+    WS_SYNC();
+    for (int i = WS_TID; i < k; i += WS_NT) inW[SMI(irow)[i]] = (signed char)SMI(iside)[i];
+    WS_SYNC();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -994,18 +1094,18 @@ __device__ __forceinline__ void restore_factor(const DevProblem &P, const Ctx &c
 // the multipliers of the d eliminated rows follow from stationarity in the eliminated coordinates.
 // ---------------------------------------------------------------------------------------------
 
-// d from the bounds of the node.  Ends with a barrier.
+// d from the bounds of the node; fixes the geometry of the factor.  Ends with a barrier.
 __device__ inline void set_node_prefix(const DevProblem &P, const Ctx &cx, const double *lb, const double *ub) {
     double far = 0.;                                        // nb - (first binary that is not pinned)
-    for (int j = threadIdx.x; j < P.nb; j += WS_NT) if (lb[j] != ub[j]) far = fmax(far, (double)(P.nb - j));
+    for (int j = WS_TID; j < P.nb; j += WS_NT) if (lb[j] != ub[j]) far = fmax(far, (double)(P.nb - j));
     far = block_max(far, SMV(red));
-    if (threadIdx.x == 0) { const int d = P.nb - (int)far; SMI(idep)[0] = d < P.n_elim ? d : P.n_elim; }
-    __syncthreads();
+    if (WS_TID == 0) store_geom(P, cx, P.nb - (int)far);
+    WS_SYNC();
 }
 
 // d known by the caller (depth of a branch_in_time node).  The caller provides the barrier.
 __device__ inline void set_node_prefix_known(const DevProblem &P, const Ctx &cx, int d) {
-    if (threadIdx.x == 0) SMI(idep)[0] = d < P.n_elim ? d : P.n_elim;
+    if (WS_TID == 0) store_geom(P, cx, d);
 }
 
 // y_out of the eliminated rows:  L' eta = -( [v_f] + sum_i coef_i mh_{row_i}[:d] + pcoef mh_pend[:d] )
@@ -1014,7 +1114,7 @@ __device__ __forceinline__ void pinned_multipliers(const DevProblem &P, const Ct
     if (d == 0) return;
     double *g = SMV(c2);
     const int *row = SMI(irow);
-    for (int c = threadIdx.x; c < d; c += WS_NT) {
+    for (int c = WS_TID; c < d; c += WS_NT) {
         double s0 = with_v ? SMV(vf)[c] : 0., s1 = 0.;
         int i = 0;
         for (; i + 1 < k; i += 2) {
@@ -1025,15 +1125,15 @@ __device__ __forceinline__ void pinned_multipliers(const DevProblem &P, const Ct
         if (pend >= 0) s1 += pcoef * __ldg(P.Mh + (size_t)pend * P.n + c);
         g[c] = s0 + s1;
     }
-    __syncthreads();
-    for (int j = threadIdx.x; j < d; j += WS_NT) {
+    WS_SYNC();
+    for (int j = WS_TID; j < d; j += WS_NT) {
         double s0 = 0., s1 = 0.;
         int c = j;
         for (; c + 1 < d; c += 2) { s0 += __ldg(P.Linv + (size_t)c * P.nb + j) * g[c]; s1 += __ldg(P.Linv + (size_t)(c + 1) * P.nb + j) * g[c + 1]; }
         if (c < d) s0 += __ldg(P.Linv + (size_t)c * P.nb + j) * g[c];
-        y_out[P.mc + j] = -(s0 + s1) * SMV(inr)[P.mc + j];
+        y_out[P.mc + j] = -(s0 + s1) * TBV(inr)[P.mc + j];
     }
-    __syncthreads();
+    WS_SYNC();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1052,7 +1152,7 @@ __device__ __forceinline__ int qp_solve(const DevProblem &P, const Ctx &cx, int 
     const int n = P.n, m = P.m, mc = P.mc, nx = P.nx;
     signed char *inW = reinterpret_cast<signed char *>(SMB(binW));
     unsigned char *ign = SMB(bign), *nadd = SMB(bnadd);
-    double *lam = SMV(lam), *ls = SMV(ls), *t = SMV(t), *bu = SMV(bu), *blb = SMV(blb), *vsc = SMV(vsc);
+    double *lam = SMV(lam), *ls = SMV(ls), *t = SMV(t), *bu = SMV(bu), *blb = SMV(blb), *vsc = TBV(vsc);
     int *row = SMI(irow), *side = SMI(iside);
     double *red = SMV(red); int *ired = SMI(ired);
     int it = 0, status = WS_ITER_LIMIT, kmax = 0;
@@ -1062,17 +1162,17 @@ __device__ __forceinline__ int qp_solve(const DevProblem &P, const Ctx &cx, int 
 
     // eliminated coordinates: L v_f = b with b_j = ub_j / nrm_j + (Mh wv)_j  =>  v_f = vf0 + wv[:d], vf0 = L^-1 (ub / nrm)
     const int d = SMI(idep)[0];
-    for (int c = threadIdx.x; c < d; c += WS_NT) {
+    for (int c = WS_TID; c < d; c += WS_NT) {
         double s0 = 0., s1 = 0.;
         int j = 0;
         for (; j + 1 <= c; j += 2) {
-            s0 += __ldg(P.LinvT + (size_t)j * P.nb + c) * (ub[j] * SMV(inr)[mc + j]);
-            s1 += __ldg(P.LinvT + (size_t)(j + 1) * P.nb + c) * (ub[j + 1] * SMV(inr)[mc + j + 1]);
+            s0 += __ldg(P.LinvT + (size_t)j * P.nb + c) * (ub[j] * TBV(inr)[mc + j]);
+            s1 += __ldg(P.LinvT + (size_t)(j + 1) * P.nb + c) * (ub[j + 1] * TBV(inr)[mc + j + 1]);
         }
-        if (j <= c) s0 += __ldg(P.LinvT + (size_t)j * P.nb + c) * (ub[j] * SMV(inr)[mc + j]);
+        if (j <= c) s0 += __ldg(P.LinvT + (size_t)j * P.nb + c) * (ub[j] * TBV(inr)[mc + j]);
         SMV(vf0)[c] = s0 + s1;
     }
-    __syncthreads();
+    WS_SYNC();
     prof_mark(2);
 
 restart:
@@ -1080,7 +1180,7 @@ restart:
         restore_factor(P, cx, sp, k);
     } else {
         rebuild_factor(P, cx, k);
-        if (memo == 1 && k > 0 && k <= P.ks) { save_factor(P, cx, sp, k); memo_saved = 1; }
+        if (memo == 1 && k > 0 && k <= SMI(idep)[5]) { save_factor(P, cx, sp, k); memo_saved = 1; }
     }
     memo = 0;                                   // a restart from the empty working set rebuilds
     prof_mark(3);
@@ -1088,7 +1188,7 @@ restart:
     const int k_start = k; int n_prox = 0;
     int pending = -1, pside = 0, just_added = -1, n_verify = 0;
     bool prox_conv = false;
-    if (threadIdx.x == 0) SMI(idep)[1] = 0;
+    if (WS_TID == 0) SMI(idep)[1] = 0;
     double plam = 0.;
     for (int pk = 0; pk < P.max_prox; ++pk) {
         ++n_prox;
@@ -1109,12 +1209,12 @@ restart:
                 bu[r] = P.hh[r] - e + g;
             } else {
                 const int i = r - mc;
-                const double inr = SMV(inr)[r];
+                const double inr = TBV(inr)[r];
                 bu[r] = ub[i] * inr + g;
                 blb[i] = lb[i] * inr + g;
             }
         });
-        __syncthreads();
+        WS_SYNC();
         prof_mark(5);
         refresh_uv(P, cx, k);
         prof_mark(6);
@@ -1126,7 +1226,7 @@ restart:
                 // ratio test on the way to lam* = ls ; sum of the positive multipliers
                 // every warp runs the whole test (k / 32 entries per lane): no barrier, same bits in every thread
                 double amin = INFINITY, lpart = 0.; int kmin = -1;
-                for (int i = threadIdx.x & 31; i < k; i += 32) {
+                for (int i = WS_TID & 31; i < k; i += 32) {
                     const double l = ls[i];
                     if (l < -P.tol_d) {
                         const double a = lam[i] / (lam[i] - l);
@@ -1135,13 +1235,13 @@ restart:
                     lpart += l > 0. ? l : 0.;
                 }
                 warp_argmin_sum(amin, kmin, lpart);
-                __syncthreads();                                  // every warp has read lam, ls before they change
+                WS_SYNC();                                  // every warp has read lam, ls before they change
                 prof_mark(7);
                 if (hot && !(lpart < WS_LAM_MAX)) break;          // degenerate hot start: restart cold
                 if (kmin >= 0) {
-                    for (int i = threadIdx.x; i < k; i += WS_NT) lam[i] += amin * (ls[i] - lam[i]);
-                    __syncthreads();
-                    if (threadIdx.x == 0) {
+                    for (int i = WS_TID; i < k; i += WS_NT) lam[i] += amin * (ls[i] - lam[i]);
+                    WS_SYNC();
+                    if (WS_TID == 0) {
                         const int rr = row[kmin];
                         if (rr == just_added && lam[kmin] == 0.) { ign[rr] |= (side[kmin] > 0 ? 1 : 2); SMI(idep)[1] = 1; }
                         if (amin <= 1e-9 && nadd[rr] < 255) ++nadd[rr];
@@ -1151,7 +1251,7 @@ restart:
                     ws_remove(P, cx, k, kmin);
                     continue;
                 }
-                for (int i = threadIdx.x; i < k; i += WS_NT) lam[i] = ls[i] > 0. ? ls[i] : 0.;
+                for (int i = WS_TID; i < k; i += WS_NT) lam[i] = ls[i] > 0. ? ls[i] : 0.;
                 const double vnoise = 1e-14 * lpart, vcap = 100. * P.tol_p;
                 double vbest = 0.; int ibest = -1;                 // ibest = 2 r + (lower side)
                 price_rows(P, cx, SMV(v), d, 62, [&](int r) { return inW[r] != 0 || ign[r] == 3; }, [&](int r, double sv) {
@@ -1187,13 +1287,13 @@ restart:
                         });
                         block_argmax(wbest, wi, red, ired);
                         ++n_verify;
-                        if (threadIdx.x == 0) SMI(idep)[1] = 0;
+                        if (WS_TID == 0) SMI(idep)[1] = 0;
                         if (wi >= 0) {
-                            for (int r = threadIdx.x; r < m; r += WS_NT) if (ign[r] != 3) ign[r] = 0;
-                            __syncthreads();
+                            for (int r = WS_TID; r < m; r += WS_NT) if (ign[r] != 3) ign[r] = 0;
+                            WS_SYNC();
                             continue;
                         }
-                        __syncthreads();
+                        WS_SYNC();
                     }
                     status = WS_OPTIMAL; break;
                 }
@@ -1202,17 +1302,17 @@ restart:
                 if (ar < 0) break;                                  // capacity: reported as iteration limit
                 if (ar) {
                     kmax = max(kmax, k);
-                    if (threadIdx.x == 0) inW[jb] = (signed char)sb;
+                    if (WS_TID == 0) inW[jb] = (signed char)sb;
                     just_added = jb;
-                    __syncthreads();
+                    WS_SYNC();
                 } else { pending = jb; pside = sb; plam = 0.; }
             } else {
                 // dependent entering row: dual ray (p_W, 1), p_W = -t
                 double pm = 1.;
-                for (int i = threadIdx.x; i < k; i += WS_NT) pm = fmax(pm, fabs(t[i]));
+                for (int i = WS_TID; i < k; i += WS_NT) pm = fmax(pm, fabs(t[i]));
                 pm = block_max(pm, red);
                 double amin = INFINITY; int kmin = -1;
-                for (int i = threadIdx.x; i < k; i += WS_NT) if (t[i] > P.tol_ray * pm) {
+                for (int i = WS_TID; i < k; i += WS_NT) if (t[i] > P.tol_ray * pm) {
                     const double a = lam[i] / t[i];
                     if (a < amin || (a == amin && i < kmin)) { amin = a; kmin = i; }
                 }
@@ -1220,7 +1320,7 @@ restart:
                 prof_mark(13);
                 if (kmin < 0) {
                     double cpart = 0., wpart = 0.;
-                    for (int i = threadIdx.x; i < k; i += WS_NT) {
+                    for (int i = WS_TID; i < k; i += WS_NT) {
                         const double pi = t[i] < 0. ? -t[i] : 0.;
                         const int r = row[i];
                         cpart -= pi * (side[i] > 0 ? bu[r] : -blb[r - mc]);
@@ -1231,42 +1331,42 @@ restart:
                     cost -= (pside > 0 ? bu[pending] : -blb[pending - mc]);
                     wsum += 1. / vsc[pending];
                     if (cost > P.tol_p * wsum) {
-                        for (int r = threadIdx.x; r < m; r += WS_NT) y_out[r] = 0.;
-                        __syncthreads();
-                        for (int i = threadIdx.x; i < k; i += WS_NT) {
+                        for (int r = WS_TID; r < m; r += WS_NT) y_out[r] = 0.;
+                        WS_SYNC();
+                        for (int i = WS_TID; i < k; i += WS_NT) {
                             const double pi = t[i] < 0. ? -t[i] : 0.;
                             const int r = row[i];
-                            y_out[r] = (double)side[i] * pi * SMV(inr)[r];
+                            y_out[r] = (double)side[i] * pi * TBV(inr)[r];
                         }
-                        if (threadIdx.x == 0) y_out[pending] = (double)pside * SMV(inr)[pending];
-                        for (int i = threadIdx.x; i < k; i += WS_NT) SMV(cw)[i] = (double)side[i] * (t[i] < 0. ? -t[i] : 0.);
-                        __syncthreads();
+                        if (WS_TID == 0) y_out[pending] = (double)pside * TBV(inr)[pending];
+                        for (int i = WS_TID; i < k; i += WS_NT) SMV(cw)[i] = (double)side[i] * (t[i] < 0. ? -t[i] : 0.);
+                        WS_SYNC();
                         pinned_multipliers(P, cx, k, d, SMV(cw), pending, (double)pside, false, y_out);
                         status = WS_INFEASIBLE;
                         break;
                     }
-                    if (threadIdx.x == 0) { ign[pending] |= (pside > 0 ? 1 : 2); SMI(idep)[1] = 1; }
+                    if (WS_TID == 0) { ign[pending] |= (pside > 0 ? 1 : 2); SMI(idep)[1] = 1; }
                     pending = -1;
-                    __syncthreads();
+                    WS_SYNC();
                     continue;
                 }
-                for (int i = threadIdx.x; i < k; i += WS_NT) lam[i] -= amin * t[i];
+                for (int i = WS_TID; i < k; i += WS_NT) lam[i] -= amin * t[i];
                 plam += amin;
-                __syncthreads();
-                if (threadIdx.x == 0 && amin <= 1e-9 * (1. + plam) && nadd[row[kmin]] < 255) ++nadd[row[kmin]];
+                WS_SYNC();
+                if (WS_TID == 0 && amin <= 1e-9 * (1. + plam) && nadd[row[kmin]] < 255) ++nadd[row[kmin]];
                 ws_remove(P, cx, k, kmin);
                 if (thin_append(P, cx, k, pending, pside, true) > 0) {
-                    if (threadIdx.x == 0) { lam[k - 1] = plam; inW[pending] = (signed char)pside; }
+                    if (WS_TID == 0) { lam[k - 1] = plam; inW[pending] = (signed char)pside; }
                     pending = -1;
-                    __syncthreads();
+                    WS_SYNC();
                 }
             }
         }
         if (status != WS_OPTIMAL) break;
         // yc <- Rinv (v - wv) ; proximal convergence
-        __syncthreads();
-        for (int r = threadIdx.x; r < n; r += WS_NT) SMV(c1)[r] = SMV(v)[r] - SMV(wv)[r];
-        __syncthreads();
+        WS_SYNC();
+        for (int r = WS_TID; r < n; r += WS_NT) SMV(c1)[r] = SMV(v)[r] - SMV(wv)[r];
+        WS_SYNC();
         double dz = 0.;
         grouped_matvec(P.RinvT, n, n, 0, n, SMV(c1), SMV(part), [&](int r, double s) {
             dz = fmax(dz, fabs(s - SMV(yc)[r]));
@@ -1274,8 +1374,8 @@ restart:
         });
         dz = block_max(dz, red);
         prof_mark(15);
-        for (int r = threadIdx.x; r < n; r += WS_NT) SMV(yc)[r] = SMV(c2)[r];
-        __syncthreads();
+        for (int r = WS_TID; r < n; r += WS_NT) SMV(yc)[r] = SMV(c2)[r];
+        WS_SYNC();
         if (P.eps * dz <= P.prox_tol) { prox_conv = true; break; }
     }
     // max_prox passes without meeting the proximal tolerance: the iterate is not the optimum -- report it as an iteration limit
@@ -1283,26 +1383,26 @@ restart:
     if (status == WS_ITER_LIMIT && hot) {
         // a hot start from a stale, nearly dependent working set can degenerate: solve once more from scratch
         hot = false; cap = it + P.max_iter; k = 0;
-        for (int i = threadIdx.x; i < n; i += WS_NT) SMV(yc)[i] = 0.;
-        __syncthreads();
+        for (int i = WS_TID; i < n; i += WS_NT) SMV(yc)[i] = 0.;
+        WS_SYNC();
         goto restart;
     }
     if (status == WS_OPTIMAL) {
-        for (int r = threadIdx.x; r < m; r += WS_NT) y_out[r] = 0.;
-        __syncthreads();
-        for (int i = threadIdx.x; i < k; i += WS_NT) {
+        for (int r = WS_TID; r < m; r += WS_NT) y_out[r] = 0.;
+        WS_SYNC();
+        for (int i = WS_TID; i < k; i += WS_NT) {
             const int r = row[i];
 #ifdef WS_KEEPW
-            y_out[r] = (double)side[i] * fmax(lam[i], 1e-200) * SMV(inr)[r];
+            y_out[r] = (double)side[i] * fmax(lam[i], 1e-200) * TBV(inr)[r];
 #else
-            y_out[r] = (double)side[i] * lam[i] * SMV(inr)[r];
+            y_out[r] = (double)side[i] * lam[i] * TBV(inr)[r];
 #endif
             SMV(cw)[i] = (double)side[i] * lam[i];
         }
-        __syncthreads();
+        WS_SYNC();
         pinned_multipliers(P, cx, k, d, SMV(cw), -1, 0., true, y_out);
     }
     prof_mark(16);
-    if (threadIdx.x == 0) { *iters_out = it; if (kmax_out) { kmax_out[0] = kmax; kmax_out[1] = k_start | (n_prox << 16); } }
+    if (WS_TID == 0) { *iters_out = it; if (kmax_out) { kmax_out[0] = kmax; kmax_out[1] = k_start | (n_prox << 16); } }
     return status;
 }

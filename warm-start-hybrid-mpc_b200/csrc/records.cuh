@@ -23,55 +23,55 @@ __device__ inline void build_records(const DevProblem &P, int status, const doub
     if (opt) {
         // z = Zmap yc ; pinned binaries hold exactly (rows lb <= z_i <= ub with lb == ub)
         grouped_matvec(P.ZmapT, n, n, 0, n, yc, scratch, [&](int c, double s) { U[c] = s; });
-        for (int i = threadIdx.x; i < nb; i += WS_NT) if (lb[i] == ub[i]) U[P.bin_idx[i]] = lb[i];
-        for (int j = threadIdx.x; j < nx; j += WS_NT) X[j] = x0[j];
-        __syncthreads();
+        for (int i = WS_TID; i < nb; i += WS_NT) if (lb[i] == ub[i]) U[P.bin_idx[i]] = lb[i];
+        for (int j = WS_TID; j < nx; j += WS_NT) X[j] = x0[j];
+        WS_SYNC();
         if (nx <= 32) {
             // x_{t+1} = A x_t + B u_t: the input terms of all stages in parallel, then ONE warp runs the recursion with
             // the state in registers (lane j holds x_t[j]) -- no barrier per stage
-            for (int e = threadIdx.x; e < T * nx; e += WS_NT) {
+            for (int e = WS_TID; e < T * nx; e += WS_NT) {
                 const int t = e / nx, j = e - t * nx;
                 double s = 0.;
                 for (int c = 0; c < nu; ++c) s += P.B[j * nu + c] * U[(size_t)t * nu + c];
                 X[(size_t)(t + 1) * nx + j] = s;
             }
-            __syncthreads();
-            if (threadIdx.x < 32) {
-                const int j = threadIdx.x < nx ? threadIdx.x : 0;
+            WS_SYNC();
+            if (WS_TID < 32) {
+                const int j = WS_TID < nx ? WS_TID : 0;
                 double xj = X[j];
                 for (int t = 0; t < T; ++t) {
                     double s = X[(size_t)(t + 1) * nx + j];
                     for (int c = 0; c < nx; ++c) s += P.A[j * nx + c] * __shfl_sync(0xffffffffu, xj, c);
-                    if (threadIdx.x < nx) X[(size_t)(t + 1) * nx + j] = s;
+                    if (WS_TID < nx) X[(size_t)(t + 1) * nx + j] = s;
                     xj = s;
                 }
             }
-            __syncthreads();
+            WS_SYNC();
         } else {
             for (int t = 0; t < T; ++t) {
-                for (int j = threadIdx.x; j < nx; j += WS_NT) {
+                for (int j = WS_TID; j < nx; j += WS_NT) {
                     double s = 0.;
                     for (int c = 0; c < nx; ++c) s += P.A[j * nx + c] * X[(size_t)t * nx + c];
                     for (int c = 0; c < nu; ++c) s += P.B[j * nu + c] * U[(size_t)t * nu + c];
                     X[(size_t)(t + 1) * nx + j] = s;
                 }
-                __syncthreads();
+                WS_SYNC();
             }
         }
         // rho_t = 2 Q x_t, rho_T = 2 Q_T x_T, sigma_t = 2 R u_t ; cost = 1/4 (|rho|^2 + |sigma|^2)
         double part = 0.;
-        for (int e = threadIdx.x; e < T * P.nq; e += WS_NT) {
+        for (int e = WS_TID; e < T * P.nq; e += WS_NT) {
             const int t = e / P.nq, i = e % P.nq;
             double s = 0.;
             for (int c = 0; c < nx; ++c) s += P.Q[i * nx + c] * X[(size_t)t * nx + c];
             rho[e] = 2. * s; part += s * s;
         }
-        for (int i = threadIdx.x; i < P.nqT; i += WS_NT) {
+        for (int i = WS_TID; i < P.nqT; i += WS_NT) {
             double s = 0.;
             for (int c = 0; c < nx; ++c) s += P.QT[i * nx + c] * X[(size_t)T * nx + c];
             rho[T * P.nq + i] = 2. * s; part += s * s;
         }
-        for (int e = threadIdx.x; e < T * P.nr; e += WS_NT) {
+        for (int e = WS_TID; e < T * P.nr; e += WS_NT) {
             const int t = e / P.nr, i = e % P.nr;
             double s = 0.;
             for (int c = 0; c < nu; ++c) s += P.R[i * nu + c] * U[(size_t)t * nu + c];
@@ -79,29 +79,29 @@ __device__ inline void build_records(const DevProblem &P, int status, const doub
         }
         cost = block_sum(part, red);
     } else {
-        for (int e = threadIdx.x; e < T * P.nq + P.nqT; e += WS_NT) rho[e] = 0.;
-        for (int e = threadIdx.x; e < T * P.nr; e += WS_NT) sigma[e] = 0.;
+        for (int e = WS_TID; e < T * P.nq + P.nqT; e += WS_NT) rho[e] = 0.;
+        for (int e = WS_TID; e < T * P.nr; e += WS_NT) sigma[e] = 0.;
     }
     // multipliers of the inequality rows
-    for (int r = threadIdx.x; r < mc; r += WS_NT) mu[r] = y[r] > 0. ? y[r] : 0.;
-    for (int i = threadIdx.x; i < nb; i += WS_NT) {
+    for (int r = WS_TID; r < mc; r += WS_NT) mu[r] = y[r] > 0. ? y[r] : 0.;
+    for (int i = WS_TID; i < nb; i += WS_NT) {
         const double yy = y[mc + i];
         nuub[i] = yy > 0. ? yy : 0.;
         nulb[i] = yy < 0. ? -yy : 0.;
     }
-    __syncthreads();
+    WS_SYNC();
     // lam_T = -Q_T' rho_T ; lam_t = A' lam_{t+1} - Q' rho_t - F_t' mu_t
-    for (int j = threadIdx.x; j < nx; j += WS_NT) {
+    for (int j = WS_TID; j < nx; j += WS_NT) {
         double s = 0.;
         for (int i = 0; i < P.nqT; ++i) s += P.QT[i * nx + j] * rho[T * P.nq + i];
         lam[(size_t)T * nx + j] = -s;
     }
-    __syncthreads();
+    WS_SYNC();
     if (nx <= 32) {
         // lam_t = A' lam_{t+1} - g_t,  g_t = Q' rho_t + F_t' mu_t: one warp per stage forms g_t (lanes split the rows,
         // one shuffle reduction per state), then ONE warp runs the backward recursion in registers
-        const int lane = threadIdx.x & 31;
-        for (int t = threadIdx.x >> 5; t < T; t += WS_NW) {
+        const int lane = WS_TID & 31;
+        for (int t = WS_TID >> 5; t < T; t += WS_NW) {
             const double *Ft = t < T - 1 ? P.F : P.F1;
             const int k = t < T - 1 ? P.nh : P.nh1;
             const double *mut = mu + (size_t)t * P.nh;
@@ -113,47 +113,47 @@ __device__ inline void build_records(const DevProblem &P, int status, const doub
                 if (lane == 0) lam[(size_t)t * nx + j] = -s;
             }
         }
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            const int j = threadIdx.x < nx ? threadIdx.x : 0;
+        WS_SYNC();
+        if (WS_TID < 32) {
+            const int j = WS_TID < nx ? WS_TID : 0;
             double lj = lam[(size_t)T * nx + j];
             for (int t = T - 1; t >= 0; --t) {
                 double s = lam[(size_t)t * nx + j];
                 for (int c = 0; c < nx; ++c) s += P.A[c * nx + j] * __shfl_sync(0xffffffffu, lj, c);
-                if (threadIdx.x < nx) lam[(size_t)t * nx + j] = s;
+                if (WS_TID < nx) lam[(size_t)t * nx + j] = s;
                 lj = s;
             }
         }
-        __syncthreads();
+        WS_SYNC();
     } else {
         for (int t = T - 1; t >= 0; --t) {
             const double *Ft = t < T - 1 ? P.F : P.F1;
             const int k = t < T - 1 ? P.nh : P.nh1;
             const double *mut = mu + (size_t)t * P.nh;
-            for (int j = threadIdx.x; j < nx; j += WS_NT) {
+            for (int j = WS_TID; j < nx; j += WS_NT) {
                 double s = 0.;
                 for (int c = 0; c < nx; ++c) s += P.A[c * nx + j] * lam[(size_t)(t + 1) * nx + c];
                 for (int i = 0; i < P.nq; ++i) s -= P.Q[i * nx + j] * rho[(size_t)t * P.nq + i];
                 for (int i = 0; i < k; ++i) s -= Ft[i * nx + j] * mut[i];
                 lam[(size_t)t * nx + j] = s;
             }
-            __syncthreads();
+            WS_SYNC();
         }
     }
     double dobj = cost;
     if (!opt) {
         // cost of the Farkas proof: -(sum rhs_r y_r)  (bounded_qp.py:328-332)
         double part = 0.;
-        for (int j = threadIdx.x; j < nx; j += WS_NT) part -= lam[j] * x0[j];
-        for (int r = threadIdx.x; r < mc; r += WS_NT) {
+        for (int j = WS_TID; j < nx; j += WS_NT) part -= lam[j] * x0[j];
+        for (int r = WS_TID; r < mc; r += WS_NT) {
             const int t = r / P.nh < T - 1 ? r / P.nh : T - 1;
             const double hr = t < T - 1 ? P.h[r - t * P.nh] : P.h1[r - (T - 1) * P.nh];
             part -= hr * mu[r];
         }
-        for (int i = threadIdx.x; i < nb; i += WS_NT) part += lb[i] * nulb[i] - ub[i] * nuub[i];
+        for (int i = WS_TID; i < nb; i += WS_NT) part += lb[i] * nulb[i] - ub[i] * nuub[i];
         dobj = block_sum(part, red);
     }
-    if (threadIdx.x == 0) { *cost_out = cost; *dobj_out = dobj; }
-    __syncthreads();
+    if (WS_TID == 0) { *cost_out = cost; *dobj_out = dobj; }
+    WS_SYNC();
     (void)nub; (void)nuc; (void)scratch;
 }

@@ -30,7 +30,9 @@ struct wshmpc_handle {
 };
 
 extern "C" const char *wshmpc_last_error(void) { return g_err.c_str(); }
-extern "C" int wshmpc_ctas_per_sm(void) { return WS_MINB; }
+static int g_lanes_last = WS_MAXL;
+// solver states resident per SM: lanes per CTA of the most recently created handle (WS_MAXL before any handle exists)
+extern "C" int wshmpc_ctas_per_sm(void) { return g_lanes_last; }
 #ifdef WS_PROF
 // experiment builds only: [2 id] cycles, [2 id + 1] visits of phase id (see prof_mark)
 extern "C" int wshmpc_prof_read(unsigned long long *out, int reset) {
@@ -43,18 +45,19 @@ extern "C" int wshmpc_prof_read(unsigned long long *out, int reset) {
 // ---------------------------------------------------------------------------------------------
 // K1: one CTA per solver slot; the CTA solves, in index order, every node assigned to its slot
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(WS_NT, WS_MINB)
-solve_nodes_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, int n_nodes,
+__global__ void __launch_bounds__(WS_MAXL * WS_NT, 1)
+solve_nodes_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, int n_slots, int n_nodes,
                    const double *__restrict__ x0, const double *__restrict__ lb, const double *__restrict__ ub,
                    const int *__restrict__ slot_of, const int *__restrict__ hot,
                    const double *__restrict__ y0, const double *__restrict__ yc0,
                    int *status, double *cost, double *dobj, int *iters, double *primal, double *dual, double *yc_out)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int slot = blockIdx.x;
-    SlotPtrs sp = slot_ptrs(slot_d, slot_i, slot, P.n, P.ld);
+    const int slot = blockIdx.x * P.lanes + WS_LANE;
+    SlotPtrs sp = slot_ptrs(slot_d, slot_i, slot < n_slots ? slot : 0, P.n, P.ld);
     const Ctx cx = make_ctx(P, smem_raw, sp);
     init_shared_tables(P, cx);
+    if (slot >= n_slots) return;                       // a lane without a solver state (after the CTA-wide barrier)
     double *y = ybuf + (size_t)slot * P.m;
     int k = 0;
     bool loaded = false;
@@ -75,9 +78,9 @@ solve_nodes_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, int 
         const int st = qp_solve(P, cx, k, xi, lbi, ubi, y, iters + i, nullptr, 0, sp, memo_saved);
         build_records(P, st, SMV(yc), y, xi, lbi, ubi, primal + (size_t)i * P.n_primal,
                       dual + (size_t)i * P.n_dual, cost + i, dobj + i, SMV(part), SMV(red));
-        if (yc_out) for (int j = threadIdx.x; j < P.n; j += WS_NT) yc_out[(size_t)i * P.n + j] = st == WS_OPTIMAL ? SMV(yc)[j] : 0.;
-        if (threadIdx.x == 0) status[i] = st;
-        __syncthreads();
+        if (yc_out) for (int j = WS_TID; j < P.n; j += WS_NT) yc_out[(size_t)i * P.n + j] = st == WS_OPTIMAL ? SMV(yc)[j] : 0.;
+        if (WS_TID == 0) status[i] = st;
+        WS_SYNC();
     }
     if (loaded) store_slot(P, cx, sp, k);
 }
@@ -175,55 +178,71 @@ extern "C" int wshmpc_create(const wshmpc_problem *p, int device, int n_slots, v
     L.rec_stride = L.dual + n;
     P.n_primal = L.primal; P.n_dual = L.dual; P.n_rec = L.rec_stride; P.off_lam = L.off_lam; P.off_mu = L.off_mu; P.off_nulb = L.off_nu_lb;
     P.off_nuub = L.off_nu_ub; P.off_rho = L.off_rho; P.off_sigma = L.off_sigma;
-    // shared memory budget: one CTA per SM; the first ks columns of Q1 and of Ri live in shared memory
+    // shared memory budget: one CTA per SM holding `lanes` solver lanes; the lanes share the read-only tables, each lane has
+    // its vectors and a pool for the leading columns of its factor
     cudaDeviceProp prop;
     WS_CUDA(cudaGetDeviceProperties(&prop, device));
-    size_t optin = prop.sharedMemPerBlockOptin;
-    if (WS_MINB > 1) {
-        // WS_MINB CTAs per SM: each gets an equal share of the SM's shared memory (1 KB per CTA is reserved by the system)
-        const size_t share = prop.sharedMemPerMultiprocessor / WS_MINB - 1024;
-        if (share < optin) optin = share & ~(size_t)15;
-    }
-    if (n > 2 * WS_NT) { wshmpc_destroy(h); WS_FAIL(-4, "problem too large: n = %d condensed inputs, at most %d supported", n, 2 * WS_NT); }
+    const size_t optin = prop.sharedMemPerBlockOptin;
+    if (n > WS_RPT * WS_NT) { wshmpc_destroy(h); WS_FAIL(-4, "problem too large: n = %d condensed inputs, at most %d supported", n, WS_RPT * WS_NT); }
     if (p->T > 32767 || p->nh > 65535 || p->nh1 > 65535) { wshmpc_destroy(h); WS_FAIL(-4, "problem too large for the packed row map"); }
     P.np = (n + 1) & ~1;
     P.ns2 = (p->ns + 1) & ~1;
-    P.ld = P.np; while (((P.ld >> 1) & 1) == 0) P.ld += 2;     // even, ld / 2 odd
-    P.kp_ = P.np;
-    P.gb = WS_NT / (P.np >> 1);
+    P.ld = 2 * ((P.np >> 1) | 1);                               // >= the ldc of every node
     P.gp = WS_NT / (P.ns2 >> 1);
     P.hot_cap = 2 * n > 200 ? 2 * n : 200;
     {
         SmemOff &so = P.so;
+        memset(&so, 0, sizeof(so));
         const int nvl = P.np + 2;
         int part = 2 * WS_NT > P.np + 2 ? 2 * WS_NT : P.np + 2;
+        if (part < P.ns2 + 2) part = P.ns2 + 2;                             // partial sums of the pricing operator (one group)
         if (part < 2 * (p->T + 1) * nx) part = 2 * (p->T + 1) * nx;         // scratch of the record epilogue
         int o = 0;
         auto take = [&](int cnt) { const int at = o; o += (cnt + 1) & ~1; return at; };   // keep 16-byte alignment
-        // fixed part first, then Q and Ri take what is left
-        so.z = take(nvl); so.z2 = take(nvl); so.c1 = take(nvl); so.c2 = take(nvl); so.t = take(nvl); so.u = take(nvl); so.ls = take(nvl);
-        so.lam = take(nvl); so.cw = take(nvl); so.yc = take(nvl); so.wv = take(nvl); so.v = take(nvl); so.gc = take(nvl); so.gs = take(nvl);
+        // shared tables
+        so.t_inr = take(m); so.t_vsc = take(m);
+        so.t_sF = take(p->nh * nx); so.t_sG = take(p->nh * nu); so.t_sF1 = take(p->nh1 * nx); so.t_sG1 = take(p->nh1 * nu);
+        so.t_rinfo = take((m + 1) / 2);
+        so.tab_doubles = o;
+        // one lane
+        o = 0;
+        so.z = take(nvl); so.c1 = take(nvl); so.c2 = take(nvl); so.t = take(nvl); so.u = take(nvl); so.ls = take(nvl);
+        so.lam = take(nvl); so.cw = take(nvl); so.yc = take(nvl); so.wv = take(nvl); so.v = take(nvl);
         so.vf0 = take(nvl); so.vf = take(nvl);
-        so.bu = take(m); so.blb = take(p->nb); so.inr = take(m); so.vsc = take(m); so.xi = take(P.ns2); so.part = take(part);
+        so.bu = take(m); so.blb = take(p->nb); so.xi = take(P.ns2); so.part = take(part);
         so.red = take(112);
-        so.sF = take(p->nh * nx); so.sG = take(p->nh * nu); so.sF1 = take(p->nh1 * nx); so.sG1 = take(p->nh1 * nu);
         so.ints = o;
         int io = 0;
         so.irow = io; io += n + 1; so.iside = io; io += n + 1; so.ired = io; io += 40; so.iscr = io; io += n + 1;
-        so.rinfo = io; io += m;
-        so.idep = io; io += 2;
+        so.idep = io; io += 10;
         o += (io + 1) / 2; o = (o + 1) & ~1;
         so.bytes = o;
         so.binW = 0; so.bign = m; so.bnadd = 2 * m;
         o += (3 * m + 7) / 8; o = (o + 1) & ~1;
-        const size_t fixed = (size_t)o * 8;
-        if (fixed + 64 > optin) { wshmpc_destroy(h); WS_FAIL(-4, "problem too large: %zu bytes of shared memory needed, %zu available", fixed, optin); }
-        int ks = 0;
-        while (ks < n && fixed + ((size_t)(ks + 1) * P.ld + (size_t)tri_off(ks + 1) + 2) * 8 <= optin) ++ks;
-        P.ks = ks;
-        so.Q = o; o += ks * P.ld;
-        so.Ri = o; o += (tri_off(ks) + 1) & ~1;
-        so.total_bytes = o * 8;
+        const int fixed = o;                                                // doubles of a lane without its pool
+        // lanes: as many as leave every lane a pool that holds the factor of a typical deep node (half of the coordinates
+        // eliminated, working set of n / 3 rows); at least one
+        const size_t avail = optin / 8 - 8;
+        const int n_half = P.np / 2, k_typ = n / 3 + 8;
+        const size_t pool_want = (size_t)k_typ * (2 * ((n_half >> 1) | 1)) + tri_off(k_typ) + 2;
+        const size_t need_shift = shift_smem_doubles(P, WS_NT) + 2;
+        int lanes = WS_MAXL;
+        const char *env = getenv("WSHMPC_LANES");
+        if (env && atoi(env) >= 1 && atoi(env) <= WS_MAXL) lanes = atoi(env);
+        else while (lanes > 1 && (size_t)so.tab_doubles + (size_t)lanes * (fixed + (pool_want > need_shift ? pool_want : need_shift)) > avail) --lanes;
+        if ((size_t)so.tab_doubles + (size_t)lanes * (fixed + 64) > avail) {
+            wshmpc_destroy(h);
+            WS_FAIL(-4, "problem too large: %zu bytes of shared memory needed, %zu available", ((size_t)so.tab_doubles + (size_t)lanes * (fixed + 64)) * 8, optin);
+        }
+        P.lanes = lanes;
+        g_lanes_last = lanes;
+        size_t pool = (avail - so.tab_doubles) / lanes - fixed;
+        pool &= ~(size_t)1;
+        const size_t pool_max = (size_t)n * P.ld + tri_off(n) + 2;          // the whole factor of the largest node
+        if (pool > pool_max) pool = pool_max;
+        so.pool = fixed; so.pool_sz = (int)pool;
+        so.lane_doubles = fixed + (int)pool;
+        so.total_bytes = (so.tab_doubles + lanes * so.lane_doubles) * 8;
         h->smem = (size_t)so.total_bytes;
     }
     WS_CUDA(cudaFuncSetAttribute(solve_nodes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
@@ -277,8 +296,8 @@ extern "C" int wshmpc_solve_nodes(wshmpc_handle *h, int n_nodes, const double *d
     if (!h) WS_FAIL(-1, "null handle");
     if (n_nodes <= 0) return 0;
     WS_CUDA(cudaSetDevice(h->device));
-    solve_nodes_kernel<<<h->n_slots, WS_NT, h->smem, h->stream>>>(
-        h->P, h->slot_d, h->slot_i, h->ybuf, n_nodes, d_x0, d_lb, d_ub, d_slot, d_hot, d_y0, d_yc0,
+    solve_nodes_kernel<<<(h->n_slots + h->P.lanes - 1) / h->P.lanes, h->P.lanes * WS_NT, h->smem, h->stream>>>(
+        h->P, h->slot_d, h->slot_i, h->ybuf, h->n_slots, n_nodes, d_x0, d_lb, d_ub, d_slot, d_hot, d_y0, d_yc0,
         d_status, d_cost, d_dobj, d_iters, d_primal, d_dual, d_yc);
     WS_CUDA(cudaGetLastError());
     return 0;
@@ -323,9 +342,9 @@ extern "C" int wshmpc_bnb_solve(wshmpc_handle *h, int n_inst, const double *d_x0
     TreeView tv; int rc = tree_view(h, tree, &tv); if (rc) return rc;
     WS_CUDA(cudaSetDevice(h->device));
     WS_CUDA(cudaMemsetAsync(h->work_counter, 0, sizeof(int), h->stream));
-    const int grid = n_inst < h->n_slots ? n_inst : h->n_slots;
-    bnb_kernel<<<grid, WS_NT, h->smem, h->stream>>>(
-        h->P, h->slot_d, h->slot_i, h->ybuf, h->scratch, h->work_counter, n_inst, d_x0, d_active, tv, tol, max_solves,
+    const int slots = n_inst < h->n_slots ? n_inst : h->n_slots;
+    bnb_kernel<<<(slots + h->P.lanes - 1) / h->P.lanes, h->P.lanes * WS_NT, h->smem, h->stream>>>(
+        h->P, h->slot_d, h->slot_i, h->ybuf, h->scratch, h->work_counter, slots, n_inst, d_x0, d_active, tv, tol, max_solves,
         d_inc_cost, d_inc_node, d_inc_primal, d_n_solves, d_status, d_trace, d_totals);
     WS_CUDA(cudaGetLastError());
     return 0;
@@ -363,7 +382,7 @@ extern "C" int wshmpc_closed_loop(wshmpc_handle *h, int n_inst, const wshmpc_loo
         WS_FAIL(-1, "null argument");
     if (h->P.T < 2) WS_FAIL(-1, "tree shifting needs T >= 2");
     if (h->P.nub > 32) WS_FAIL(-1, "tree shifting supports nub <= 32");
-    if ((size_t)h->P.ks * h->P.ld < shift_smem_doubles(h->P, WS_NT)) WS_FAIL(-4, "shared memory too small for the fused warm start");
+    if ((size_t)h->P.so.pool_sz < shift_smem_doubles(h->P, WS_NT)) WS_FAIL(-4, "shared memory too small for the fused warm start");
     if ((long long)n_inst * (loop->n_steps + 1) > 0x7fffffffLL) WS_FAIL(-1, "too many tasks");
     TreeView v0, v1; int rc = tree_view(h, tree0, &v0); if (rc) return rc;
     rc = tree_view(h, tree1, &v1); if (rc) return rc;
@@ -376,9 +395,9 @@ extern "C" int wshmpc_closed_loop(wshmpc_handle *h, int n_inst, const wshmpc_loo
     const int n_items = n_inst * (loop->n_steps + 1);
     loop_init_kernel<<<(n_items + 255) / 256, 256, 0, h->stream>>>(n_inst, n_items, L);
     WS_CUDA(cudaGetLastError());
-    const int grid = n_inst < h->n_slots ? n_inst : h->n_slots;
-    closed_loop_kernel<<<grid, WS_NT, h->smem, h->stream>>>(
-        h->P, h->slot_d, h->slot_i, h->ybuf, h->scratch, L, n_inst, v0, v1, tol, max_solves,
+    const int slots = n_inst < h->n_slots ? n_inst : h->n_slots;
+    closed_loop_kernel<<<(slots + h->P.lanes - 1) / h->P.lanes, h->P.lanes * WS_NT, h->smem, h->stream>>>(
+        h->P, h->slot_d, h->slot_i, h->ybuf, h->scratch, L, slots, n_inst, v0, v1, tol, max_solves,
         d_inc_cost, d_inc_node, d_inc_primal, d_n_solves, d_status, d_totals);
     WS_CUDA(cudaGetLastError());
     return 0;
