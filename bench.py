@@ -1,21 +1,24 @@
 #!/usr/bin/env python
 """bench.py -- B&B QP relaxations/s (and ms per MPC step, warm vs cold) of the hybrid-MPC hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cp20|cp40|syn30]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
-Workload (BASELINE.json configs[1] per instance, configs[2] = 4096 instances over 8 GPUs as the batch):
-closed loop of the notebook two-wall cart-pole (T = 20), `--instances` independent initial states per GPU
-(warm-start-hybrid-mpc_b200/data/cp20_instances.npy), model error e_t = sigma * randn * x_max, warm-started branch and bound
-with tree shifting.  One bench "step" = ONE fused launch (wshmpc_closed_loop) that advances every instance of
-the batch by `--window` receding-horizon steps = K3 (device B&B, K1 inside) + K2/K4 (tree shift + plant
-update) per MPC step, with no barrier between instances.  Instances are independent: ranks own contiguous
-blocks of instances, there is no collective on the data path (weak scaling).
+Workloads (BASELINE.json configs):
+  cp20  (default; configs[1] per instance, batched as configs[2]): closed loop of the notebook two-wall cart-pole
+        (T = 20), `--instances` independent initial states per GPU (data/cp20_instances.npy), model error
+        e_t = sigma * randn * x_max, warm-started branch and bound with tree shifting;
+  cp40  (configs[3]): the same system with horizon 40, states around the nominal x0;
+  syn30 (configs[4]): synthetic MLD system nx = 20, 8 binaries / step, N = 30.
+One bench "step" = ONE fused launch (wshmpc_closed_loop) that advances every instance of the batch by `--window`
+receding-horizon steps = K3 (device B&B, K1 inside) + K2/K4 (tree shift + plant update) per MPC step, with no
+barrier between instances.  Instances are independent: ranks own contiguous blocks of instances, there is no
+collective on the data path (weak scaling; `--scaling strong` fixes the total instead).
 
 Prints ONE JSON line (rank 0).  `value` = QP relaxations solved by all ranks / max-over-ranks device time,
 states resident in HBM; `e2e` = the same loop driven from HOST buffers through the public Python API
-(pinned H2D of the measured state and model error, D2H of input, cost and next state, every step).
+(pinned H2D of the measured state and model error, D2H of input, cost and next state, every bench step).
 `--impl reference` times the CPU path (oracle/bnb_ref.py + oracle/qp_core.c, the restatement of the
 reference's Python B&B pinned bit-exactly against it -- Gurobi is not available offline) on the host cores.
 """
@@ -36,39 +39,75 @@ if ROOT not in sys.path:
 METRIC = 'bnb_qp_relaxations_per_s'
 UNIT = 'QP/s'
 
+WORKLOADS = {
+    'cp20': dict(model='cp20', instances=512, window=20, max_solves=1024, max_roots=512,
+                 text='cp20_closed_loop_warm_start (two-wall cart-pole, T=20, nx=4, nu=7, 4 binaries/step; '
+                      'BASELINE configs[1] per instance, batched as configs[2])'),
+    'cp40': dict(model='cp40', instances=296, window=4, max_solves=4096, max_roots=1024,
+                 text='cp40_closed_loop_warm_start (two-wall cart-pole, T=40: n=280 condensed inputs, 160 binaries, deep trees; '
+                      'BASELINE configs[3])'),
+    'syn30': dict(model='syn30', instances=148, window=2, max_solves=4096, max_roots=2048,
+                  text='syn30_closed_loop_warm_start (synthetic MLD, nx=20, nu=12 of which 8 binary, T=30: n=360, 240 binaries; '
+                       'BASELINE configs[4]; states 0.3 x0_nominal (1 + 0.1 randn): at x0_nominal the MIQP needs > 10^4 nodes)'),
+}
+
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=10)
-    ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--window', type=int, default=20, help='receding-horizon steps per bench step (one fused launch)')
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--workload', default='cp20', choices=sorted(WORKLOADS))
+    ap.add_argument('--window', type=int, default=None, help='receding-horizon steps per bench step (one fused launch)')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--instances', type=int, default=512, help='independent MPC instances per GPU')
+    ap.add_argument('--instances', type=int, default=None, help='independent MPC instances per GPU')
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                    help='weak: --instances per GPU; strong: --instances-total split over the GPUs')
+    ap.add_argument('--instances-total', type=int, default=4096, help='(strong scaling) instances of the whole job')
     ap.add_argument('--sigma', type=float, default=0.003, help='model error std (fraction of x_max)')
-    ap.add_argument('--max-solves', type=int, default=1024)
-    ap.add_argument('--max-roots', type=int, default=512)
-    ap.add_argument('--no-extras', action='store_true', help='skip cold / single-instance / cpu legs')
+    ap.add_argument('--max-solves', type=int, default=None)
+    ap.add_argument('--max-roots', type=int, default=None)
+    ap.add_argument('--no-extras', action='store_true', help='skip the legs outside the headline (cold / fresh start / per-step API / '
+                                                             'published protocol / K2+K4 roofline / cpu baseline)')
     ap.add_argument('--cpu-seconds', type=float, default=15., help='budget of the cpu_baseline sample')
-    return ap.parse_args()
+    a = ap.parse_args()
+    w = WORKLOADS[a.workload]
+    for k in ('instances', 'window', 'max_solves', 'max_roots'):
+        if getattr(a, k) is None:
+            setattr(a, k, w[k])
+    return a
 
 
 def workload_config(args, world):
-    return {'workload': 'cp20_closed_loop_warm_start (two-wall cart-pole, T=20, nx=4, nu=7, 4 binaries/step; '
-                        'BASELINE configs[1] per instance, batched as configs[2])',
-            'instances_per_gpu': args.instances, 'instances_total': args.instances * world,
-            'horizon': 20, 'sigma': args.sigma, 'tol': 0.,
+    n_total = args.instances_total if args.scaling == 'strong' else args.instances * world
+    return {'workload': WORKLOADS[args.workload]['text'],
+            'instances_per_gpu': n_total // world if args.scaling == 'strong' else args.instances, 'instances_total': n_total,
+            'horizon': {'cp20': 20, 'cp40': 40, 'syn30': 30}[args.workload], 'sigma': args.sigma, 'tol': 0.,
             'window': args.window,
             'step': 'one fused launch = %d receding-horizon steps of every instance: device B&B (K3+K1) + tree shift/plant '
                     'update (K2+K4) per MPC step, task queue over (instance, step), no barrier between instances' % args.window,
+            'timed_region': 'bench steps after `warmup` windows of the same loop (step 0 of every instance = cold solve, inside the '
+                            'warm-up); inputs larger than L2 (two device trees of several GB per rank, leaf records touched per step >> 126 MB)',
             'search': 'best_first / branch_in_time, reference order, no speculative solves',
             'parallelism': 'instances sharded over %d GPU(s), no data-path collective' % world}
 
 
-def load_instances(lo, hi):
-    x = np.load(os.path.join(ROOT, 'warm-start-hybrid-mpc_b200', 'data', 'cp20_instances.npy'))
-    idx = np.arange(lo, hi) % len(x)
-    return np.ascontiguousarray(x[idx])
+def initial_states(workload, model, lo, hi):
+    """Frozen / seeded initial states lo..hi-1 of a workload (identical bits for the CPU and the GPU arm)."""
+    if workload == 'cp20':
+        x = np.load(os.path.join(ROOT, 'warm-start-hybrid-mpc_b200', 'data', 'cp20_instances.npy'))
+        return np.ascontiguousarray(x[np.arange(lo, hi) % len(x)])
+    nx = model['A'].shape[0]
+    out = np.zeros((hi - lo, nx))
+    for k in range(lo, hi):
+        rng = np.random.default_rng(10_000 + k)
+        if workload == 'cp40':
+            # x0_nominal = [0, 0, 1, 0] sits at the edge of the set the horizon-40 MIQP is feasible on (a faster cart cannot be
+            # stopped before the wall): scale it DOWN by up to 15 % and add a small offset in the other coordinates
+            out[k - lo] = model['x0_nominal'] * rng.uniform(0.85, 1.0) + rng.uniform(-1, 1, nx) * np.array([0.005, 0.0025, 0., 0.0125])
+        else:
+            out[k - lo] = 0.3 * model['x0_nominal'] * (1. + 0.1 * rng.standard_normal(nx))
+    return out
 
 
 def noise(model, n_steps, n_inst, sigma, seed):
@@ -121,11 +160,11 @@ class ClockSampler(threading.Thread):
 # ---------------------------------------------------------------------------------------------------
 def _cpu_worker(job):
     """Closed loop of one instance on one host core.  Returns per-step (t_start, t_end, solves)."""
-    k, x0, e, n_steps, budget = job
+    name, x0, e, n_steps, budget = job
     from oracle.models import load_model
     from oracle.qp_c import CoreC
     from oracle.bnb_ref import OracleController
-    model = load_model('cp20')
+    model = load_model(name)
     ctl = OracleController(model, CoreC(model, variant=1), hot_start='record')
     x = x0.copy(); ws = None; rows = []
     t_begin = time.perf_counter()
@@ -146,17 +185,18 @@ def _cpu_worker(job):
     return rows, ctl.qp_time
 
 
-def cpu_baseline_sample(args, model, x0, e, seconds):
+def cpu_baseline_sample(args, x0, e, seconds):
     """rank 0, N = 1: instance 0 of the workload on ONE host core (the reference loop is single-threaded)."""
     from oracle import qp_c
     qp_c.build()
     t0 = time.perf_counter()
-    rows, qp_time = _cpu_worker((0, x0[0], e[:, 0], e.shape[0], seconds))
+    rows, qp_time = _cpu_worker((WORKLOADS[args.workload]['model'], x0[0], e[:, 0], e.shape[0], seconds))
     wall = time.perf_counter() - t0
     solves = sum(r[2] for r in rows)
     return {'value': solves / wall, 'unit': UNIT, 'cores': 1, 'kind': 'port',
             'sample': 'instance 0 of the workload, %d closed-loop steps (1 cold + %d warm), %d QPs in %.1f s; '
-                      'oracle/bnb_ref.py + oracle/qp_core.c variant 1 (dual active-set, thin QR, each node started from the dual solution it carries; no pinned-prefix elimination), Python overhead included'
+                      'oracle/bnb_ref.py + oracle/qp_core.c variant 1 (dual active-set, thin QR, each node started from the dual '
+                      'solution it carries; no pinned-prefix elimination), Python overhead included'
                       % (len(rows), len(rows) - 1, solves, wall),
             'qp_only_value': solves / max(qp_time, 1e-9), 'ms_per_qp': 1e3 * wall / max(solves, 1),
             'host_cores_available': os.cpu_count()}
@@ -171,18 +211,23 @@ def run_reference(args):
     from oracle import qp_c
     from oracle.models import load_model
     qp_c.build()
-    model = load_model('cp20')
+    name = WORKLOADS[args.workload]['model']
+    model = load_model(name)
     cores = max(1, os.cpu_count() or 1)
     S = args.window
     n_steps = (args.warmup + args.steps) * S
-    x0 = load_instances(0, cores)
+    if args.workload != 'cp20':
+        # the big systems cost ~35 ms per QP on a core: a bounded sample = a cold step + the timed warm steps
+        n_steps = min(n_steps, (1 + args.steps) * S)
+    warm_steps = n_steps - args.steps * S
+    x0 = initial_states(args.workload, model, 0, cores)
     e = noise(model, n_steps, cores, args.sigma, 1000)
-    jobs = [(k, x0[k], e[:, k], n_steps, None) for k in range(cores)]
+    jobs = [(name, x0[k], e[:, k], n_steps, None) for k in range(cores)]
     with mp.get_context('fork').Pool(cores) as pool:
         res = pool.map(_cpu_worker, jobs)
     solves, t_lo, t_hi = 0, [], []
     for rows, _ in res:
-        timed = rows[args.warmup * S:]
+        timed = rows[warm_steps:]
         if not timed:
             continue
         solves += sum(r[2] for r in timed)
@@ -192,9 +237,9 @@ def run_reference(args):
     value = solves / elapsed
     cfg = workload_config(args, world)
     sample = ('%d instances (one per host core, fork pool) x %d timed closed-loop MPC steps (= %d bench steps of %d) after %d '
-              'warm-up MPC steps (step 0 = cold solve); %d QPs' % (cores, args.steps * S, args.steps, S, args.warmup * S, solves))
+              'warm-up MPC steps (step 0 = cold solve); %d QPs' % (cores, args.steps * S, args.steps, S, warm_steps, solves))
     line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
-            'warmup': args.warmup, 'ms_per_step': 1e3 * elapsed / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'warmup': args.warmup, 'ms_per_step': 1e3 * elapsed / args.steps, 'higher_is_better': True, 'scaling': args.scaling,
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': cfg,
             'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample,
                              'note': 'Gurobi (the reference QP back end) is not installable offline; the reference B&B / '
@@ -247,6 +292,78 @@ def timed_loop(torch, dist, loop, steps, world, body):
     return ms_max, qps, iters, int(d[0])
 
 
+def published_protocol(torch, ctl, model, n_traj=100, n_steps=50):
+    """The reference's experiment (notebooks/cart_pole_with_walls/statistical_analysis.py:58-196): x0 = [0, 0, 1, 0],
+    sigma in {0, .001, .003, .01}, trajectory i drawn with np.random.seed(i), 50 closed-loop steps, cold-started and
+    warm-started B&B side by side; QPs per step of both and their ratio (steps >= 1, trajectories that stay feasible)
+    next to the published Gurobi-backed numbers (12.6 / 12.6 / 11.7 / 8.9)."""
+    from warm_start_hmpc_b200.closed_loop import ClosedLoop
+    published = {0.: 12.6, 0.001: 12.6, 0.003: 11.7, 0.01: 8.9}
+    out = {}
+    nx = model['A'].shape[0]
+    for sigma in (0., 0.001, 0.003, 0.01):
+        N = 1 if sigma == 0. else n_traj
+        e = np.zeros((n_steps, N, nx))
+        for i in range(N):
+            np.random.seed(i)                                       # statistical_analysis.py:73
+            for t in range(n_steps):
+                e[t, i] = sigma * np.multiply(np.random.randn(nx), model['x_max'])      # :176
+        ed = torch.as_tensor(e, device='cuda')
+        res = {}
+        for warm in (True, False):
+            L = ClosedLoop(ctl, N, warm=warm, max_solves=2048, max_roots=1024)
+            L.reset(np.repeat(model['x0_nominal'][None], N, 0))
+            t0 = time.perf_counter()
+            logs = L.run(n_steps, e=ed)
+            torch.cuda.synchronize()
+            res[warm] = (logs['n_solves'].cpu().numpy(), logs['status'].cpu().numpy(), logs['cost'].cpu().numpy(), time.perf_counter() - t0)
+            del L
+        ok = np.all(res[True][1] == 0, axis=0) & np.all(res[False][1] == 0, axis=0)
+        nw, nc = res[True][0][1:, ok], res[False][0][1:, ok]
+        cw, cc = res[True][2][:, ok], res[False][2][:, ok]
+        out['sigma_%g' % sigma] = {
+            'trajectories': int(N), 'feasible_for_50_steps': int(ok.sum()),
+            'cold_qp_per_step': float(nc.mean()) if ok.any() else None, 'warm_qp_per_step': float(nw.mean()) if ok.any() else None,
+            'cold_over_warm': float(nc.mean() / nw.mean()) if ok.any() else None, 'published_cold_over_warm': published[sigma],
+            'max_rel_cost_gap_warm_vs_cold': float(np.max(np.abs(cw - cc) / np.abs(cc))) if ok.any() else None,
+            'ms_per_mpc_step_warm': 1e3 * res[True][3] / n_steps, 'ms_per_mpc_step_cold': 1e3 * res[False][3] / n_steps}
+    out['published'] = 'BASELINE.md section 1 (Gurobi default method): cold 159.0 QPs/step, warm 12.6 QPs/step at sigma = 0'
+    return out
+
+
+def k2k4_roofline(torch, loop, pd, hbm_peak):
+    """shift_tree_kernel (K2+K4) alone on the trees the timed loop left behind: algorithmic bytes = one dual record read
+    and one written per retained leaf (+ the node arrays) / CUDA-event time, against the measured HBM copy bandwidth."""
+    h = loop.h
+    cur, nxt = loop.trees[loop.cur], loop.trees[1 - loop.cur]
+    n_inst = loop.n_inst
+    # one more search (K3) on the current trees gives the leaves a real step hands to the shift; K2+K4 is then timed on
+    # (cur -> nxt), which it does not modify
+    h.bnb_solve(loop.x, cur, tol=loop.tol, max_solves=loop.max_solves, active=loop.active, out=loop.out)
+    args = (loop.x, None, cur, loop.out['cost'], loop.out['primal'], nxt)
+    act = loop.active.clone()
+    h.shift_tree(*args, active=act)
+    torch.cuda.synchronize()
+    leaves = int(nxt.n_nodes.sum()); nodes_in = int(cur.n_nodes.sum())
+    reps = 5
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(reps):
+        act.copy_(loop.active)
+        h.shift_tree(*args, active=act)
+    e.record(); torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / reps
+    rec_bytes = 8 * h.layout.rec_stride
+    node_bytes = 4 * 3 + 8 + 4 * cur.words
+    algo = leaves * 2 * rec_bytes + nodes_in * node_bytes + leaves * node_bytes
+    gbs = algo / (ms * 1e-3) / 1e9
+    return {'bound': 'hbm', 'kernel': 'shift_tree_kernel', 'achieved': gbs, 'peak': hbm_peak, 'unit': 'GB/s',
+            'frac': gbs / hbm_peak if hbm_peak else None, 'ms': ms, 'instances': n_inst, 'retained_leaves': leaves,
+            'algorithmic_bytes': algo,
+            'note': 'K2+K4 alone, one CTA per instance, one warp per retained leaf: reads + writes one dual record (%d B) per leaf; '
+                    'inside the fused loop the same code runs on the solver lanes' % rec_bytes}
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -265,27 +382,35 @@ def run_b200(args):
             dist.barrier()
     from warm_start_hmpc_b200.instances import load_model, controller_from_model
     from warm_start_hmpc_b200.closed_loop import ClosedLoop, shard
-    model = load_model('cp20')
+    model = load_model(WORKLOADS[args.workload]['model'])
     ctl = controller_from_model(model, device=local)
     dev = torch.device('cuda', local)
-    n_inst, S = args.instances, args.window
-    lo, hi = shard(n_inst * world, rank, world)
-    x0 = load_instances(lo, hi)
+    S = args.window
+    n_total = args.instances_total if args.scaling == 'strong' else args.instances * world
+    lo, hi = shard(n_total, rank, world)
+    n_inst = hi - lo
+    x0 = initial_states(args.workload, model, lo, hi)
     n_win = args.warmup + args.steps
+    nx, nu = ctl.mld.nx, ctl.mld.nu
     e_host = noise(model, (2 * n_win + 4) * S, n_inst, args.sigma, 1000 + rank).reshape(2 * n_win + 4, S, n_inst, -1)
     e_dev = torch.as_tensor(e_host, device=dev)
 
+    tiny = ClosedLoop(ctl, 1, warm=True, max_solves=64, max_roots=64, n_slots=1)      # loads the module, creates the context
+    tiny.reset(x0[:1]); tiny.run(1); torch.cuda.synchronize()
+    del tiny
     loop = ClosedLoop(ctl, n_inst, warm=True, max_solves=args.max_solves, max_roots=args.max_roots)
     tree_bytes = loop.nbytes()
-    nx, nu = ctl.mld.nx, ctl.mld.nu
     f64 = dict(dtype=torch.float64, device=dev)
     logs = dict(cost=torch.empty((S, n_inst), **f64), u0=torch.empty((S, n_inst, nu), **f64),
                 n_solves=torch.empty((S, n_inst), dtype=torch.int32, device=dev),
                 status=torch.empty((S, n_inst), dtype=torch.int32, device=dev))
     loop.reset(x0)
+    # warm-up windows; their wall time (from fresh states, cold step 0 included) is reported as `from_fresh_states`
+    torch.cuda.synchronize(); t_fresh = time.perf_counter(); b_fresh = loop.totals.clone()
     for w in range(args.warmup):
         loop.run(S, e=e_dev[w], logs=logs)
-    torch.cuda.synchronize()
+    torch.cuda.synchronize(); t_fresh = time.perf_counter() - t_fresh
+    q_fresh = int((loop.totals - b_fresh)[0])
 
     # ---- device-resident timed region: args.steps fused launches
     sampler = ClockSampler(local); sampler.start(); time.sleep(0.3)
@@ -325,7 +450,9 @@ def run_b200(args):
     e2e = {'value': qps_e / (ms_e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': (S + 1) * n_inst * nx * 8,
            'd2h_bytes_per_step': n_inst * (S * (nu + 1) + nx) * 8, 'ms_per_step': ms_e / args.steps,
            'ms_per_mpc_step_of_the_batch': ms_e / args.steps / S,
-           'api': 'ClosedLoop.run(n_steps, e) of warm_start_hmpc_b200 (ctypes -> C ABI wshmpc_closed_loop)'}
+           'api': 'ClosedLoop.run(n_steps, e) of warm_start_hmpc_b200 (ctypes -> C ABI wshmpc_closed_loop): host I/O once per '
+                  'window of %d MPC steps, the plant (linear model + error) is advanced on the device; the per-MPC-step API with '
+                  'host I/O every step is timed in `per_mpc_step_api`' % S}
 
     # ---- roofline of the dominant kernel (closed_loop_kernel = K3 with K1 inside + K2/K4)
     pd = ctl.problem
@@ -343,42 +470,49 @@ def run_b200(args):
     ker_avg_ms = float(np.mean(ker_ms))
     achieved = F_qp * qp_per_launch / (ker_avg_ms * 1e-3) / 1e12
     peak = fp64_peak_probe(torch, dev)
-    roofline = {'bound': 'tensor', 'kernel': 'closed_loop_kernel', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
+    peaks_file = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    hbm_peak = json.load(open(peaks_file)).get('hbm_gbs') if os.path.exists(peaks_file) else 6650.
+    hbm_src = 'MEASURED_PEAKS.json (measured copy bandwidth)' if os.path.exists(peaks_file) else 'fallback of B200_PROFILING.md'
+    B_node = 8 * (2 * pd.nb + pd.nx + pd.n + 2 * pd.m) + 12
+    rec_bytes = 8 * loop.h.layout.rec_stride
+    algo_hbm = qp_per_launch * B_node + S * n_inst * leaves_mean * 2 * rec_bytes
+    roofline = {'bound': 'fp64-pipe (the kernel is LATENCY bound: neither the fp64 pipe nor HBM is near its roof)',
+                'kernel': 'closed_loop_kernel', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
                 'frac': achieved / peak, 'traffic': None,
                 'peak_source': 'measured in this run: cuBLAS DGEMM 4096^3 best of 5 (fp64 pipe; MEASURED_PEAKS.json has no fp64 entry)',
                 'algorithmic': 'flops per QP in the form the kernel executes: iterations x [2 ns n_eff (pricing operator) + 2 mc (nx+nu) '
                                '(stage rows) + 4 n_eff k + k^2 (Gram-Schmidt append, R^-1 column)] + re-factorisation of the k0 inherited '
                                'rows, with the measured means n_eff = n - d = %.1f, k = %.1f, k0 = %.1f, %.1f iterations/QP: %.0f flop/iteration, '
-                               '%.0f flop/QP (the dense shared-operator form of SURVEY 8d would be %.0f flop/iteration); %.0f QPs/launch; '
-                               'the kernel is latency bound (dependent phases of one small QP per CTA), see DESIGN.md'
+                               '%.0f flop/QP (the dense shared-operator form of SURVEY 8d would be %.0f flop/iteration); %.0f QPs/launch'
                                % (n_eff, kbar, k0bar, it_per_qp, F_iter, F_qp, F_dense, qp_per_launch),
                 'achieved_dense_form_tflops': F_dense * it_per_launch / (ker_avg_ms * 1e-3) / 1e12,
-                'kernel_ms_avg': ker_avg_ms, 'kernel_share_of_step': float(np.sum(ker_ms) / ms)}
-    peaks_file = os.path.join(ROOT, 'MEASURED_PEAKS.json')
-    if os.path.exists(peaks_file):
-        roofline['hbm_peak_gbs_measured'] = json.load(open(peaks_file)).get('hbm_gbs')
-    # algorithmic HBM bytes of one launch: K1 reads / writes B_node per QP, K2+K4 read and write one dual record
-    # per retained leaf and MPC step (the reference shifts every leaf's dual solution, controller.py:431-501)
-    B_node = 8 * (2 * pd.nb + pd.nx + pd.n + 2 * pd.m) + 12
-    rec_bytes = 8 * loop.h.layout.rec_stride
-    roofline['algorithmic_hbm_bytes_per_launch'] = qp_per_launch * B_node + S * n_inst * leaves_mean * 2 * rec_bytes
-    roofline['algorithmic_hbm_note'] = ('%.0f QPs x %d B (K1) + %d steps x %d instances x %.1f leaves x 2 x %d B (K2+K4 tree shift)'
-                                        % (qp_per_launch, B_node, S, n_inst, leaves_mean, rec_bytes))
+                'kernel_ms_avg': ker_avg_ms, 'kernel_share_of_step': float(np.sum(ker_ms) / ms),
+                'hbm': {'achieved_gbs': algo_hbm / (ker_avg_ms * 1e-3) / 1e9, 'peak_gbs': hbm_peak, 'peak_source': hbm_src,
+                        'frac': algo_hbm / (ker_avg_ms * 1e-3) / 1e9 / hbm_peak,
+                        'algorithmic_bytes_per_launch': algo_hbm,
+                        'note': '%.0f QPs x %d B (K1) + %d steps x %d instances x %.1f leaves x 2 x %d B (K2+K4 tree shift)'
+                                % (qp_per_launch, B_node, S, n_inst, leaves_mean, rec_bytes)},
+                'solver_lanes_per_sm': int(ctl.default_slots() // torch.cuda.get_device_properties(local).multi_processor_count)}
     traffic_file = os.path.join(ROOT, 'profiles', 'closed_loop_kernel_traffic.json')
-    if os.path.exists(traffic_file):
+    if os.path.exists(traffic_file) and args.workload == 'cp20':
         roofline['traffic'] = json.load(open(traffic_file)).get('dram_bytes_per_launch')
 
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None,
             'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(args, world),
             'roofline': roofline, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks,
             'ms_per_mpc_step_of_the_batch': ms / args.steps / S,
-            'qp_per_mpc_step_per_instance': qps / args.steps / S / (n_inst * world),
-            'active_instances_rank0': n_active, 'bnb_status_counts_rank0': {int(k): int((status == k).sum()) for k in np.unique(status)}}
-    line['config']['l2'] = 'inputs larger than L2: two device trees of %.1f GB per rank, leaf records touched per step >> 126 MB' % (tree_bytes / 2 / 1e9)
+            'qp_per_mpc_step_per_instance': qps / args.steps / S / max(n_total, 1),
+            'tree_bytes_per_rank': tree_bytes, 'active_instances_rank0': n_active, 'bnb_status_counts_rank0': {int(k): int((status == k).sum()) for k in np.unique(status)},
+            'from_fresh_states': {'mpc_steps': args.warmup * S, 'qp': q_fresh, 'value': q_fresh / max(t_fresh, 1e-9), 'unit': UNIT,
+                                  'ms_per_mpc_step_of_the_batch': 1e3 * t_fresh / max(args.warmup * S, 1),
+                                  'note': 'rank 0, wall clock of the warm-up windows: MPC steps 0..%d of every instance from its fresh '
+                                          'initial state, the cold solve of step 0 and the contact-mode transient included '
+                                          '(BASELINE configs[1] asks for 100 steps)' % (args.warmup * S - 1)}}
 
-    # ---- extras (outside the timed region): cold start, lock-step API, single instance latency, CPU baseline
+    # ---- extras (outside the timed region)
     if not args.no_extras:
+        line['roofline_k2k4'] = k2k4_roofline(torch, loop, pd, hbm_peak)
         del loop
         torch.cuda.empty_cache()
         cold = ClosedLoop(ctl, n_inst, warm=False, max_solves=args.max_solves, max_roots=args.max_roots)
@@ -386,25 +520,40 @@ def run_b200(args):
         cold.run(1, e=e_dev[0, :1])
         ms_c, qps_c, _, _ = timed_loop(torch, dist, cold, 1, world, lambda t: cold.run(2, e=e_dev[1, :2]))
         line['cold_start'] = {'value': qps_c / (ms_c * 1e-3), 'unit': UNIT, 'ms_per_mpc_step_of_the_batch': ms_c / 2,
-                              'qp_per_mpc_step_per_instance': qps_c / 2 / (n_inst * world)}
+                              'qp_per_mpc_step_per_instance': qps_c / 2 / max(n_total, 1)}
         line['warm_start'] = {'value': value, 'unit': UNIT, 'ms_per_mpc_step_of_the_batch': ms / args.steps / S,
                               'qp_per_mpc_step_per_instance': line['qp_per_mpc_step_per_instance']}
         del cold
         torch.cuda.empty_cache()
+        # per-MPC-step API with HOST I/O every step: H2D of the measured state and model error, K3, K2+K4, D2H of the applied
+        # input and cost; every instance waits for the slowest one of the step (lock step)
         lock = ClosedLoop(ctl, n_inst, warm=True, max_solves=args.max_solves, max_roots=args.max_roots)
         lock.reset(x0)
         for t in range(3):
-            lock.step(e=e_dev[0, t])
-        ms_l, qps_l, _, _ = timed_loop(torch, dist, lock, 5, world, lambda t: lock.step(e=e_dev[1, t]))
-        line['lock_step_api'] = {'value': qps_l / (ms_l * 1e-3), 'unit': UNIT, 'ms_per_mpc_step_of_the_batch': ms_l / 5,
-                                 'note': 'ClosedLoop.step(): one launch pair per MPC step, every instance waits for the slowest one'}
+            lock.step(e=e_dev[0, t % S])
+        xs_h, es_h, us_h, cs_h = pin(n_inst, nx), pin(n_inst, nx), pin(n_inst, nu), pin(n_inst)
+        es_d = torch.empty((n_inst, nx), **f64)
+        xs_h.copy_(lock.x); torch.cuda.synchronize()
+        n_lock = 5
+
+        def lock_step(t):
+            es_h.copy_(e_host_t[1, t % S])
+            es_d.copy_(es_h, non_blocking=True); lock.x.copy_(xs_h, non_blocking=True)
+            out = lock.step(e=es_d)
+            us_h.copy_(lock.u0, non_blocking=True); cs_h.copy_(out['cost'], non_blocking=True); xs_h.copy_(lock.x, non_blocking=True)
+            torch.cuda.synchronize()
+        ms_l, qps_l, _, _ = timed_loop(torch, dist, lock, n_lock, world, lock_step)
+        line['per_mpc_step_api'] = {'value': qps_l / (ms_l * 1e-3), 'unit': UNIT, 'ms_per_mpc_step_of_the_batch': ms_l / n_lock,
+                                    'h2d_bytes_per_mpc_step': 2 * n_inst * nx * 8, 'd2h_bytes_per_mpc_step': n_inst * (nu + 1 + nx) * 8,
+                                    'note': 'ClosedLoop.step(): host I/O every MPC step, one launch pair per step, every instance waits '
+                                            'for the slowest one of the step (10-30x the median number of QPs)'}
         del lock
         torch.cuda.empty_cache()
         if rank == 0:
             single = {}
             for warm in (True, False):
-                L = ClosedLoop(ctl, 1, warm=warm, max_solves=4096, max_roots=512, n_slots=1)
-                L.reset(model['x0_nominal'][None])
+                L = ClosedLoop(ctl, 1, warm=warm, max_solves=4096, max_roots=args.max_roots, n_slots=1)
+                L.reset(x0[:1] if args.workload != 'cp20' else model['x0_nominal'][None])
                 L.step(); torch.cuda.synchronize()
                 before = L.totals.clone()
                 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -416,46 +565,18 @@ def run_b200(args):
                 d = (L.totals - before).cpu().numpy()
                 single['warm' if warm else 'cold'] = {'ms_per_mpc_step': s.elapsed_time(e) / k, 'qp_per_step': float(d[0]) / k,
                                                       'qp_per_s': float(d[0]) / (s.elapsed_time(e) * 1e-3)}
-            single['reference_published'] = {'cold_ms_per_mpc_step': 530., 'warm_ms_per_mpc_step': 37.4, 'qp_per_s': 300.,
-                                             'source': 'BASELINE.md (Gurobi, unknown CPU)'}
+                del L
+            if args.workload == 'cp20':
+                single['reference_published'] = {'cold_ms_per_mpc_step': 530., 'warm_ms_per_mpc_step': 37.4, 'qp_per_s': 300.,
+                                                 'source': 'BASELINE.md (Gurobi, unknown CPU)'}
             line['single_instance_nominal'] = single
-    if rank == 0 and not args.no_extras:
-        # the other BASELINE configs, as information (they are parity-test cases, not the headline): cold batched B&B
-        # of the horizon-40 cart-pole (configs[3]) and the root relaxation + dive nodes of the synthetic system (configs[4])
-        other = {}
-        try:
-            m40 = load_model('cp40')
-            c40 = controller_from_model(m40, device=local)
-            rng = np.random.default_rng(40)
-            xs = m40['x0_nominal'][None] + rng.uniform(-1, 1, (148, 4)) * np.array([0.02, 0.01, 0.05, 0.05])
-            c40.handle(min(len(xs), c40.default_slots()))
-            c40.feedforward_batch(xs[:8], max_solves=2048)
-            torch.cuda.synchronize(); t0 = time.perf_counter()
-            res, _ = c40.feedforward_batch(xs, max_solves=2048)
-            torch.cuda.synchronize(); dt = time.perf_counter() - t0
-            ns = res['n_solves'].cpu().numpy(); st = res['status'].cpu().numpy()
-            other['cp40_cold_bnb'] = {'instances': int(len(xs)), 'qp': int(ns.sum()), 'qp_per_s': float(ns.sum() / dt),
-                                      'wall_ms': 1e3 * dt, 'ms_per_qp_of_the_longest_instance': float(1e3 * dt / max(ns.max(), 1)), 'status_counts': {int(k): int((st == k).sum()) for k in np.unique(st)},
-                                      'note': 'horizon 40: n = 280, factor columns beyond the shared-memory budget spill to L2'}
-            del c40
-            g30 = np.load(os.path.join(ROOT, 'tests', 'golden', 'syn30_nodes.npz'))
-            m30 = load_model('syn30')
-            c30 = controller_from_model(m30, device=local)
-            reps = 5
-            N30 = len(g30['status']) * reps
-            x30 = np.repeat(g30['x0'][None], N30, 0); lb30 = np.tile(g30['lb'], (reps, 1)); ub30 = np.tile(g30['ub'], (reps, 1))
-            h30 = c30.handle(n_slots=min(N30, c30.default_slots()))
-            h30.solve_nodes(x30[:8], lb30[:8], ub30[:8]); torch.cuda.synchronize(); t0 = time.perf_counter()
-            out = h30.solve_nodes(x30, lb30, ub30)
-            torch.cuda.synchronize(); dt = time.perf_counter() - t0
-            other['syn30_k1_dive_nodes'] = {'nodes': int(N30), 'qp_per_s': float(N30 / dt), 'iterations_mean': float(out['iters'].float().mean()),
-                                            'note': 'nx = 20, 8 binaries/step, N = 30: n = 360, m = 2640; cold solves of the golden dive nodes'}
-            del c30
-        except Exception as ex:                     # information only
-            other['error'] = repr(ex)
-        line['other_configs'] = other
+            if args.workload == 'cp20':
+                try:
+                    line['published_protocol'] = published_protocol(torch, ctl, model)
+                except Exception as ex:                     # information only
+                    line['published_protocol'] = {'error': repr(ex)}
     if rank == 0 and world == 1 and not args.no_extras:
-        line['cpu_baseline'] = cpu_baseline_sample(args, model, x0, e_host.reshape(-1, n_inst, nx), args.cpu_seconds)
+        line['cpu_baseline'] = cpu_baseline_sample(args, x0, e_host.reshape(-1, n_inst, nx), args.cpu_seconds)
     elif rank == 0:
         line['cpu_baseline'] = None
     if rank == 0:

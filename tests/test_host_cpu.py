@@ -270,3 +270,20 @@ def test_product_control_flow_equals_reference_on_the_golden_run():
         x = sr.variables['x'][1] + e
         asked['product'].clear(); asked['reference'].clear()
     assert n_p < 40
+
+
+def test_miqp_comparator_finds_the_same_optimum():
+    """the Gurobi-free stand-in of `feedforward_gurobi` (controller.py:723-776) -- a conventional MIQP
+    branch and bound through the QP seam that ignores the time structure -- must return the optimum the structured
+    search returns (the reference asserts exactly this, statistical_analysis.py:171-173), with far more nodes.
+    (Device call of the seam replaced by the CPU oracle core: no GPU here.)"""
+    from tests.util import oracle_launch
+    model = load_model('cp20')
+    ctl = make_controller(model)
+    ctl.qp._launch = oracle_launch(model, ctl.problem)
+    g = np.load(os.path.join(GOLDEN, 'cp20_nodes.npz'))
+    variables, objective, nodes, seconds = ctl.feedforward_gurobi(g['x0'], {'OutputFlag': 0, 'MIPGap': 0})
+    assert abs(objective - float(g['opt_cost'])) <= 1e-6 * float(g['opt_cost'])
+    assert np.array_equal(variables['ub'], g['opt_ub']) and variables['x'].shape == (ctl.T + 1, 4) and variables['uc'].shape == (ctl.T, 3)
+    assert nodes > 2 * len(g['status'])          # no dual-bound inheritance, no time structure: many more relaxations
+    assert np.allclose(variables['x'][0], g['x0'])

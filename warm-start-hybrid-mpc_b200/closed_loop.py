@@ -40,6 +40,7 @@ class ClosedLoop(object):
                         n_solves=torch.zeros(n_inst, dtype=torch.int32, device=dev),
                         status=torch.zeros(n_inst, dtype=torch.int32, device=dev))
         self.totals = torch.zeros(8, dtype=torch.int64, device=dev)     # wshmpc.h d_totals: QP solves, iterations, working-set statistics
+        self.gid = torch.arange(n_inst, dtype=torch.int64, device=dev)     # global identity of the instance in every slot (rebalance moves instances)
         self.fresh = True
         self.launches = 0
         self.events = None          # list -> (start, after K3, after K2+K4) CUDA events of every step
@@ -59,6 +60,13 @@ class ClosedLoop(object):
         self.active.fill_(1)
         self.totals.zero_()
         self.fresh = True
+
+    def rebalance(self, group=None, min_gap=2):
+        """Periodic load balancing between the ranks of a torch.distributed job (rebalance.py): live instances move from
+        the busiest ranks into the slots of dead instances of the idlest ones, with their warm-start trees.  Call it
+        between steps / windows.  Returns (sent, received, plan)."""
+        from .rebalance import rebalance
+        return rebalance(self.trees[self.cur], self.x, self.active, self.gid, group, min_gap)
 
     def step(self, e=None, x=None):
         """One receding-horizon step of every instance.  `x` (optional, [n_inst, nx] CUDA tensor)

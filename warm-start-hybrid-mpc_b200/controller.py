@@ -465,6 +465,63 @@ class HybridModelPredictiveController(object):
         primal = PrimalSolution.from_record(self.problem, res['primal'][0].cpu().numpy(), float(res['cost'][0]), True, True)
         return primal, leaves, n_qp, solver_time
 
+    # -- comparator: a conventional MIQP branch and bound ----------------------------------
+    def feedforward_miqp(self, x0, gurobi_params={}, ub_guess=None, tol=0.):
+        """Stand-in for `feedforward_gurobi` (controller.py:723-776; the paper's third curve, "Gurobi fair": no presolve, no
+        heuristics, one thread -- statistical_analysis.py:151-154) that needs no Gurobi: a textbook MIQP branch and bound
+        through the same QP seam (`self.qp`, one K1 launch per node) that knows NOTHING about the time structure --
+        best-bound node selection, branching on the MOST FRACTIONAL binary of the relaxation wherever it sits in the
+        horizon, a node is integral when its relaxation is (not when every binary is pinned), children start from their
+        parent's active set like a dual-simplex B&B, bounds are the relaxation values only (no dual-bound inheritance, no
+        warm start across time steps).  `ub_guess` [T, nub] is a MIP start (controller.py:798-818).
+        Returns (variables {'x', 'uc', 'ub'} stacked over time, objective, nodes, solver seconds) like the reference."""
+        self._set_gurobi_params(gurobi_params)
+        self.qp.reset()
+        T, nub = self.T, self.mld.nub
+        solver_time = 0.
+        nodes = 0
+        best, best_sol = np.inf, None
+
+        def relax(identifier, start):
+            nonlocal solver_time, nodes
+            sol, dt = self._solve_subproblem(identifier, x0, start)
+            solver_time += dt; nodes += 1
+            return sol
+
+        if ub_guess is not None:                 # MIP start: the guess, fully pinned
+            guess = {(t, i): float(round(ub_guess[t][i])) for t in range(T) for i in range(nub)}
+            sol = relax(guess, None)
+            if np.isfinite(sol.primal.objective):
+                best, best_sol = sol.primal.objective, sol
+        frontier = [({}, -np.inf, None)]         # (identifier, bound of the parent, parent's active set)
+        while frontier:
+            k = int(np.argmin([f[1] for f in frontier]))
+            identifier, bound, start = frontier.pop(k)
+            if bound >= best - tol:
+                continue
+            sol = relax(identifier, start)
+            cost = sol.primal.objective
+            if cost >= best - tol:
+                continue
+            ub = np.array(sol.primal.variables['ub'])
+            frac = np.abs(ub - np.round(ub))
+            for key in identifier:               # pinned binaries are integral by construction
+                frac[key] = 0.
+            if frac.max() <= 1e-9:
+                best, best_sol = cost, sol
+                continue
+            t, i = np.unravel_index(int(np.argmax(frac)), frac.shape)
+            for v in (0., 1.):
+                frontier.append(({**identifier, (int(t), int(i)): v}, cost, sol.active_set))
+        self.qp.reset()
+        if best_sol is None:
+            return None, np.inf, nodes, solver_time
+        variables = {k: np.vstack(best_sol.primal.variables[k]) for k in ('x', 'uc', 'ub')}
+        variables['ub'] = np.round(variables['ub'])
+        return variables, best, nodes, solver_time
+
+    feedforward_gurobi = feedforward_miqp       # the reference's name for the comparator leg (there is no Gurobi underneath)
+
     def shift_binary_solution(self, ub):
         """controller.py:811-812."""
         return np.vstack((ub[1:], np.zeros(self.mld.nub)))

@@ -21,7 +21,7 @@ struct TreeView {
 #define BNB_QP_LIMIT 3
 
 // per-slot scratch of the B&B kernel (doubles): lb | ub | primal record | cost | dobj
-__host__ __device__ inline size_t bnb_scratch_doubles(int nb, int n_primal) { return 2 * (size_t)nb + n_primal + 4; }
+__host__ __device__ __forceinline__ size_t bnb_scratch_doubles(int nb, int n_primal) { return 2 * (size_t)nb + n_primal + 4; }
 
 __global__ void init_root_kernel(int n_inst, TreeView tr)
 {
@@ -37,7 +37,7 @@ __global__ void init_root_kernel(int n_inst, TreeView tr)
 // K3
 // ---------------------------------------------------------------------------------------------
 // branch and bound of ONE instance by the calling CTA (all threads).  Returns the status.
-__device__ inline int bnb_instance(const DevProblem &P, const Ctx &cx, const SlotPtrs &sp, double *y, double *sc, int *iters_s,
+__device__ __forceinline__ int bnb_instance(const DevProblem &P, const Ctx &cx, const SlotPtrs &sp, double *y, double *sc, int *iters_s,
                                    int inst, const double *xi, const TreeView &tr, double tol, int max_solves,
                                    double *inc_cost, int *inc_node, double *inc_primal, int *n_solves, int *trace,
                                    unsigned long long *totals)
@@ -174,16 +174,17 @@ __device__ inline int bnb_instance(const DevProblem &P, const Ctx &cx, const Slo
     return st;
 }
 
-__global__ void __launch_bounds__(WS_MAXL * WS_NT, 1)
-bnb_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, double *scratch, int *work_counter, int n_slots,
-           int n_inst, const double *__restrict__ x0, const int *__restrict__ active, TreeView tr,
+template <int LANES>
+__device__ __forceinline__ void
+bnb_body(const DevProblem &P, double *slot_d, int *slot_i, double *ybuf, double *scratch, int *work_counter, int n_slots,
+           int n_inst, const double *__restrict__ x0, const int *__restrict__ active, const TreeView &tr,
            double tol, int max_solves,
            double *inc_cost, int *inc_node, double *inc_primal, int *n_solves, int *status_out, int *trace,
            unsigned long long *totals)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_inst[WS_MAXL];
-    const int slot = blockIdx.x * P.lanes + WS_LANE;
+    const int slot = blockIdx.x * LANES + WS_LANE;
     SlotPtrs sp = slot_ptrs(slot_d, slot_i, slot < n_slots ? slot : 0, P.n, P.ld);
     const Ctx cx = make_ctx(P, smem_raw, sp);
     init_shared_tables(P, cx);
@@ -207,6 +208,17 @@ bnb_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, double *scra
         if (WS_TID == 0) status_out[inst] = st;
     }
 }
+
+
+#define WS_BNB_ARGS DevProblem P, double *slot_d, int *slot_i, double *ybuf, double *scratch, int *work_counter, int n_slots, \
+    int n_inst, const double *__restrict__ x0, const int *__restrict__ active, TreeView tr, double tol, int max_solves, \
+    double *inc_cost, int *inc_node, double *inc_primal, int *n_solves, int *status_out, int *trace, unsigned long long *totals
+#define WS_BNB_PASS P, slot_d, slot_i, ybuf, scratch, work_counter, n_slots, n_inst, x0, active, tr, tol, max_solves, \
+    inc_cost, inc_node, inc_primal, n_solves, status_out, trace, totals
+// one lane per CTA: 255 registers per thread (launches that cannot fill two lanes per SM: latency mode, large systems)
+__global__ void __launch_bounds__(WS_NT, 1) bnb_kernel_1(WS_BNB_ARGS) { bnb_body<1>(WS_BNB_PASS); }
+// WS_MAXL lanes per CTA: 65536 / (WS_MAXL WS_NT) registers per thread (throughput mode)
+__global__ void __launch_bounds__(WS_MAXL * WS_NT, 1) bnb_kernel_m(WS_BNB_ARGS) { bnb_body<WS_MAXL>(WS_BNB_PASS); }
 
 // ---------------------------------------------------------------------------------------------
 // K2 + K4: retain / shift identifiers / shift duals / re-evaluate the bounds / plant update
@@ -238,7 +250,7 @@ __device__ __forceinline__ void warp_copy(double *__restrict__ dst, const double
 }
 
 // doubles of shared scratch the shift needs with NT threads
-__host__ __device__ inline size_t shift_smem_doubles(const DevProblem &P, int nt) {
+__host__ __device__ __forceinline__ size_t shift_smem_doubles(const DevProblem &P, int nt) {
     return (size_t)2 * P.nx + P.nu + P.nq + P.nr + P.nh + (size_t)(nt / 32) * (P.nh1 + P.nqT + P.nh + P.nq) + 8;
 }
 
@@ -250,7 +262,7 @@ __host__ __device__ inline size_t shift_smem_doubles(const DevProblem &P, int nt
 // LANE: the caller is a solver lane of WS_NT threads (fused loop): lane-local thread index and the lane's named barrier;
 // otherwise a whole CTA of NT threads.
 template <int NT, bool LANE>
-__device__ inline int shift_instance(const DevProblem &P, double *shm, int *s_wsum, int *s_base_p, int inst,
+__device__ __forceinline__ int shift_instance(const DevProblem &P, double *shm, int *s_wsum, int *s_base_p, int inst,
                                       const double *__restrict__ x0, const double *__restrict__ e0,
                                       const TreeView &ot, const double *__restrict__ inc_cost, const double *__restrict__ inc_primal,
                                       int *active, const TreeView &nt, double *x_next, double *u0_out)
@@ -497,7 +509,7 @@ __global__ void loop_init_kernel(int n_inst, int n_items, LoopView L)
     if (i < n_inst) L.step_of[i] = 0;
 }
 
-__device__ inline void init_root(const TreeView &tr, int k)
+__device__ __forceinline__ void init_root(const TreeView &tr, int k)
 {
     const size_t o = (size_t)k * tr.cap_nodes;
     tr.n_nodes[k] = 1; tr.n_recs[k] = 0;
@@ -505,15 +517,16 @@ __device__ inline void init_root(const TreeView &tr, int k)
     for (int w = 0; w < tr.words; ++w) tr.bits[o * tr.words + w] = 0u;
 }
 
-__global__ void __launch_bounds__(WS_MAXL * WS_NT, 1)
-closed_loop_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, double *scratch, LoopView L, int n_slots, int n_inst,
-                   TreeView t0, TreeView t1, double tol, int max_solves,
+template <int LANES>
+__device__ __forceinline__ void
+closed_loop_body(const DevProblem &P, double *slot_d, int *slot_i, double *ybuf, double *scratch, const LoopView &L, int n_slots, int n_inst,
+                   const TreeView &t0, const TreeView &t1, double tol, int max_solves,
                    double *inc_cost, int *inc_node, double *inc_primal, int *n_solves, int *status_out,
                    unsigned long long *totals)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_inst_[WS_MAXL];
-    const int slot = blockIdx.x * P.lanes + WS_LANE;
+    const int slot = blockIdx.x * LANES + WS_LANE;
     SlotPtrs sp = slot_ptrs(slot_d, slot_i, slot < n_slots ? slot : 0, P.n, P.ld);
     const Ctx cx = make_ctx(P, smem_raw, sp);
     init_shared_tables(P, cx);
@@ -604,3 +617,11 @@ closed_loop_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, doub
     }
 }
 #undef s_inst
+
+#define WS_LOOP_ARGS DevProblem P, double *slot_d, int *slot_i, double *ybuf, double *scratch, LoopView L, int n_slots, int n_inst, \
+    TreeView t0, TreeView t1, double tol, int max_solves, double *inc_cost, int *inc_node, double *inc_primal, int *n_solves, \
+    int *status_out, unsigned long long *totals
+#define WS_LOOP_PASS P, slot_d, slot_i, ybuf, scratch, L, n_slots, n_inst, t0, t1, tol, max_solves, inc_cost, inc_node, inc_primal, \
+    n_solves, status_out, totals
+__global__ void __launch_bounds__(WS_NT, 1) closed_loop_kernel_1(WS_LOOP_ARGS) { closed_loop_body<1>(WS_LOOP_PASS); }
+__global__ void __launch_bounds__(WS_MAXL * WS_NT, 1) closed_loop_kernel_m(WS_LOOP_ARGS) { closed_loop_body<WS_MAXL>(WS_LOOP_PASS); }

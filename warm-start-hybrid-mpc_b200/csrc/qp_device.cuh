@@ -60,7 +60,7 @@
 #define WS_RRT (256 / WS_NT)    // rows of Ri a thread sweeps in a removal: working sets of up to WS_RRT * WS_NT = 256 rows
 #endif
 #ifndef WS_NOINLINE
-#define WS_NOINLINE inline      // measured: out-of-line phases (__noinline__) shrink the code by a third and cost 25 % (call ABI spills)
+#define WS_NOINLINE __forceinline__      // measured: out-of-line phases (__noinline__) shrink the code by a third and cost 25 % (call ABI spills)
 #endif
 #ifndef WS_CH
 #define WS_CH 4                 // columns per chunk of the removal sweep (8 spills under the 128-register cap of two lanes)
@@ -147,10 +147,10 @@ struct SlotPtrs {
     int *nW;        // 1
 };
 
-__host__ __device__ inline size_t slot_doubles(int n, int ld) { return (((size_t)n * ld + (size_t)tri_off(n) + (n + 1) + n + 4) + 1) & ~(size_t)1; }   // even: 16-byte aligned slots
-__host__ __device__ inline size_t slot_ints(int n) { return 2 * (size_t)(n + 1) + 4; }
+__host__ __device__ __forceinline__ size_t slot_doubles(int n, int ld) { return (((size_t)n * ld + (size_t)tri_off(n) + (n + 1) + n + 4) + 1) & ~(size_t)1; }   // even: 16-byte aligned slots
+__host__ __device__ __forceinline__ size_t slot_ints(int n) { return 2 * (size_t)(n + 1) + 4; }
 
-__device__ inline SlotPtrs slot_ptrs(double *dbase, int *ibase, int slot, int n, int ld) {
+__device__ __forceinline__ SlotPtrs slot_ptrs(double *dbase, int *ibase, int slot, int n, int ld) {
     SlotPtrs s;
     double *d = dbase + (size_t)slot * slot_doubles(n, ld);
     int *i = ibase + (size_t)slot * slot_ints(n);
@@ -178,7 +178,7 @@ struct Ctx {
 #define TBV(name) (cx.tab + P.so.t_##name)
 #define TBI(name) (reinterpret_cast<const int *>(cx.tab + P.so.t_##name))
 
-__device__ inline Ctx make_ctx(const DevProblem &P, unsigned char *smem_raw, const SlotPtrs &sp) {
+__device__ __forceinline__ Ctx make_ctx(const DevProblem &P, unsigned char *smem_raw, const SlotPtrs &sp) {
     Ctx cx;
     cx.tab = reinterpret_cast<double *>(smem_raw);
     cx.smd = cx.tab + P.so.tab_doubles + (size_t)WS_LANE * P.so.lane_doubles;
@@ -207,7 +207,7 @@ __device__ __forceinline__ Geom load_geom(const DevProblem &P, const Ctx &cx) {
 }
 
 // thread 0 of the lane: geometry for d eliminated coordinates.  The caller provides the barrier.
-__device__ inline void store_geom(const DevProblem &P, const Ctx &cx, int d) {
+__device__ __forceinline__ void store_geom(const DevProblem &P, const Ctx &cx, int d) {
     int *g = SMI(idep);
     d = d < P.n_elim ? d : P.n_elim;
     const int d0 = d & ~1, he = (P.np - d0) >> 1, ldc = 2 * (he | 1);
@@ -230,7 +230,7 @@ __device__ __forceinline__ double warp_sum(double x) {
 static_assert(WS_NW == 16 || WS_NW == 8 || WS_NW == 4 || WS_NW == 2, "the two-level reductions assume 2, 4, 8 or 16 warps per CTA");
 
 // block-wide sum, result to all threads
-__device__ inline double block_sum(double x, double *red) {
+__device__ __forceinline__ double block_sum(double x, double *red) {
     const int lane = WS_TID & 31, w = WS_TID >> 5;
     x = warp_sum(x);
     WS_SYNC();
@@ -243,7 +243,7 @@ __device__ inline double block_sum(double x, double *red) {
 }
 
 // two block-wide sums at once
-__device__ inline void block_sum2(double &x, double &y, double *red) {
+__device__ __forceinline__ void block_sum2(double &x, double &y, double *red) {
     const int lane = WS_TID & 31, w = WS_TID >> 5;
     x = warp_sum(x); y = warp_sum(y);
     WS_SYNC();
@@ -261,7 +261,7 @@ __device__ __forceinline__ bool better_max(double ov, int oi, double val, int id
 }
 
 // block-wide arg-max of (val, idx): larger val wins, ties -> smaller idx.  idx < 0 = no candidate.
-__device__ inline void block_argmax(double &val, int &idx, double *red, int *ired) {
+__device__ __forceinline__ void block_argmax(double &val, int &idx, double *red, int *ired) {
     const int lane = WS_TID & 31, w = WS_TID >> 5;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -283,7 +283,7 @@ __device__ inline void block_argmax(double &val, int &idx, double *red, int *ire
 }
 
 // block-wide max of a non-negative value
-__device__ inline double block_max(double x, double *red) {
+__device__ __forceinline__ double block_max(double x, double *red) {
     const int lane = WS_TID & 31, w = WS_TID >> 5;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(WS_FULL, x, o));
@@ -297,14 +297,14 @@ __device__ inline double block_max(double x, double *red) {
 }
 
 // block-wide arg-min (ratio tests): smaller val wins, ties -> smaller idx
-__device__ inline void block_argmin(double &val, int &idx, double *red, int *ired) {
+__device__ __forceinline__ void block_argmin(double &val, int &idx, double *red, int *ired) {
     double nv = -val;
     block_argmax(nv, idx, red, ired);
     val = -nv;
 }
 
 // warp-wide arg-min (ties -> smaller idx) and sum, result in every lane
-__device__ inline void warp_argmin_sum(double &val, int &idx, double &sum) {
+__device__ __forceinline__ void warp_argmin_sum(double &val, int &idx, double &sum) {
     double nv = -val;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -317,7 +317,7 @@ __device__ inline void warp_argmin_sum(double &val, int &idx, double &sum) {
 }
 
 // arg-min and a sum in one pass (ratio test + sum of the positive multipliers)
-__device__ inline void block_argmin_sum(double &val, int &idx, double &sum, double *red, int *ired) {
+__device__ __forceinline__ void block_argmin_sum(double &val, int &idx, double &sum, double *red, int *ired) {
     const int lane = WS_TID & 31, w = WS_TID >> 5;
     double nv = -val;
 #pragma unroll
@@ -350,7 +350,7 @@ __device__ inline void block_argmin_sum(double &val, int &idx, double &sum, doub
 // (refresh / record paths only: once per proximal pass, not per iteration)
 // ---------------------------------------------------------------------------------------------
 template <class Out>
-__device__ inline void grouped_matvec(const double *__restrict__ M, int ld, int rows, int j0, int j1,
+__device__ __forceinline__ void grouped_matvec(const double *__restrict__ M, int ld, int rows, int j0, int j1,
                                       const double *x, double *part, Out out) {
     if (rows <= WS_NT) {
         const int G = WS_NT / rows;
@@ -437,7 +437,7 @@ __device__ __forceinline__ double team_sum(double s, int lg) {
 
 // out[j] = q_j . x  for j < k  (x indexed by coordinate, entries below d0 ignored).  Ends with a barrier.
 template <bool SM>
-__device__ inline void qt_dots_t(const DevProblem &P, const Ctx &cx, int k, const double *x, double *out) {
+__device__ __forceinline__ void qt_dots_t(const DevProblem &P, const Ctx &cx, int k, const double *x, double *out) {
     const Geom gm = load_geom(P, cx);
     const int lg = team_log2(k), ng = 1 << lg, C = 32 >> lg, jw = WS_NT >> lg;
     const int lane = WS_TID & 31, g = lane >> (5 - lg), jl = (WS_TID >> 5) * C + (lane & (C - 1));
@@ -460,7 +460,7 @@ __device__ inline void qt_dots_t(const DevProblem &P, const Ctx &cx, int k, cons
 // |zout|^2 and the lane-wide sum of `extra` (a second quantity the caller wants reduced: it rides on the barrier this
 // phase needs anyway) in every thread.  Ends with a barrier.
 template <bool SM>
-__device__ inline double q_apply_t(const DevProblem &P, const Ctx &cx, int k, const double *c, const double *zin, double *zout,
+__device__ __forceinline__ double q_apply_t(const DevProblem &P, const Ctx &cx, int k, const double *c, const double *zin, double *zout,
                                  double extra = 0., double *extra_sum = nullptr) {
     const Geom gm = load_geom(P, cx);
     double2 *part2 = reinterpret_cast<double2 *>(SMV(part));
@@ -507,7 +507,7 @@ __device__ inline double q_apply_t(const DevProblem &P, const Ctx &cx, int k, co
 // t_i = (Ri c[:k])_i = sum_{j >= i} Ri[tri_off(j) + i] c_j handed to out(i, t_i) by the leader of the team of row i
 // (columns j = i + g, i + g + ng, ...).  No barrier.
 template <bool SM, class Out>
-__device__ inline void ri_matvec_ep(const DevProblem &P, const Ctx &cx, int k, const double *c, Out out) {
+__device__ __forceinline__ void ri_matvec_ep(const DevProblem &P, const Ctx &cx, int k, const double *c, Out out) {
     const Geom gm = load_geom(P, cx);
     const int lg = team_log2(k), ng = 1 << lg, C = 32 >> lg, jw = WS_NT >> lg;
     const int lane = WS_TID & 31, g = lane >> (5 - lg), il = (WS_TID >> 5) * C + (lane & (C - 1));
@@ -526,14 +526,14 @@ __device__ inline void ri_matvec_ep(const DevProblem &P, const Ctx &cx, int k, c
 
 // t = Ri * c[:k].  Ends with a barrier.
 template <bool SM>
-__device__ inline void ri_matvec(const DevProblem &P, const Ctx &cx, int k, const double *c, double *t) {
+__device__ __forceinline__ void ri_matvec(const DevProblem &P, const Ctx &cx, int k, const double *c, double *t) {
     ri_matvec_ep<SM>(P, cx, k, c, [&](int i, double s) { t[i] = s; });
     WS_SYNC();
 }
 
 // u = Ri' * d[:k]  (u_j = sum_{i <= j} Ri[tri_off(j) + i] d_i).  Refresh path only.  Ends with a barrier.
 template <bool SM>
-__device__ inline void rit_matvec_t(const DevProblem &P, const Ctx &cx, int k, const double *d, double *u) {
+__device__ __forceinline__ void rit_matvec_t(const DevProblem &P, const Ctx &cx, int k, const double *d, double *u) {
     const Geom gm = load_geom(P, cx);
     const int lg = team_log2(k), ng = 1 << lg, C = 32 >> lg, jw = WS_NT >> lg;
     const int lane = WS_TID & 31, g = lane >> (5 - lg), jl = (WS_TID >> 5) * C + (lane & (C - 1));
@@ -583,7 +583,7 @@ __device__ __forceinline__ RowEnt load_row_entries(const DevProblem &P, int r, i
 // `pre`: the row's entries, already loaded by the caller (rebuild: the load of the next row overlaps the append of the
 // current one).
 template <bool SM>
-__device__ inline int thin_append_t(const DevProblem &P, const Ctx &cx, int &k, int r, int sgn, bool track, const RowEnt *pre = nullptr) {
+__device__ __forceinline__ int thin_append_t(const DevProblem &P, const Ctx &cx, int &k, int r, int sgn, bool track, const RowEnt *pre = nullptr) {
     const Geom gm = load_geom(P, cx);
     const int n = P.n, d = gm.d;
     if (k >= WS_RRT * WS_NT) return -1;
@@ -645,7 +645,7 @@ __device__ inline int thin_append_t(const DevProblem &P, const Ctx &cx, int &k, 
 // Remove position kp from the working set (u, ls, v follow).  Returns the smallest position >= kp whose
 // diagonal of R collapsed (|Ri_ii| >= 1 / tol_sing) after the removal, or -1.
 template <bool SM>
-__device__ inline int thin_remove_t(const DevProblem &P, const Ctx &cx, int &k, int kp) {
+__device__ __forceinline__ int thin_remove_t(const DevProblem &P, const Ctx &cx, int &k, int kp) {
     const Geom gm = load_geom(P, cx);
     auto QC = [&](int j) -> double * { return qcol_w<SM>(P, cx, gm, j); };
     auto RC = [&](int j) -> double * { return ricol_w<SM>(P, cx, gm, j); };
@@ -789,11 +789,11 @@ __device__ inline int thin_remove_t(const DevProblem &P, const Ctx &cx, int &k, 
     return bad == 0x7fffffff ? -1 : bad;
 }
 
-__device__ inline int thin_append(const DevProblem &P, const Ctx &cx, int &k, int r, int sgn, bool track, const RowEnt *pre = nullptr) {
+__device__ __forceinline__ int thin_append(const DevProblem &P, const Ctx &cx, int &k, int r, int sgn, bool track, const RowEnt *pre = nullptr) {
     const Geom gm = load_geom(P, cx);
     return k < gm.ks ? thin_append_t<true>(P, cx, k, r, sgn, track, pre) : thin_append_t<false>(P, cx, k, r, sgn, track, pre);
 }
-__device__ inline int thin_remove(const DevProblem &P, const Ctx &cx, int &k, int kp) {
+__device__ __forceinline__ int thin_remove(const DevProblem &P, const Ctx &cx, int &k, int kp) {
     const Geom gm = load_geom(P, cx);
     return k <= gm.ks ? thin_remove_t<true>(P, cx, k, kp) : thin_remove_t<false>(P, cx, k, kp);
 }
@@ -820,7 +820,7 @@ __device__ __forceinline__ void ws_remove(const DevProblem &P, const Ctx &cx, in
 // x[c] = 0 for c < c0 (the eliminated coordinates): those columns of the operator are skipped.
 // skip(r): rows whose value is not wanted (in the working set, eliminated) are dropped BEFORE their products.
 template <class Skip, class Fn>
-__device__ inline void price_rows(const DevProblem &P, const Ctx &cx, const double *x, int c0, int pid, Skip skip, Fn f) {
+__device__ __forceinline__ void price_rows(const DevProblem &P, const Ctx &cx, const double *x, int c0, int pid, Skip skip, Fn f) {
     const int n = P.n, m = P.m, mc = P.mc, nx = P.nx, nu = P.nu;
     const int hs = P.ns2 >> 1;
     double *xi = SMV(xi);
@@ -916,10 +916,44 @@ __device__ inline void price_rows(const DevProblem &P, const Ctx &cx, const doub
 // slot state
 // ---------------------------------------------------------------------------------------------
 
+// ---------------------------------------------------------------------------------------------
+// TMA bulk copies (cp.async.bulk, SASS UBLKCP): the copy engine moves a contiguous image between the lane's pool and
+// the slot's global home while the threads do something else; completion of a load is signalled on an mbarrier.
+// Sizes are multiples of 16 bytes, both addresses 16-byte aligned.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_g2s(void *sdst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *gdst, const void *ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_wait() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+// the lane's mbarrier (one 64-bit word of `red`) and its phase bit (idep[9])
+#define WS_MBAR (reinterpret_cast<uint64_t *>(SMV(red) + 100))
+
 // once per kernel launch, by ALL threads of the CTA: the shared copies of the stage rows, row scalings and the
 // row -> (stage, index) map (one copy for all lanes), then every lane clears its own vectors.  Contains __syncthreads:
 // call it before any lane leaves the kernel.
-__device__ inline void init_shared_tables(const DevProblem &P, const Ctx &cx) {
+__device__ __forceinline__ void init_shared_tables(const DevProblem &P, const Ctx &cx) {
     // stage rows TRANSPOSED (entry (row i, column c) at c * rows + i): adjacent threads price adjacent rows, so
     // their reads of one column are consecutive words (no bank conflicts)
     const int nt = blockDim.x, t0 = threadIdx.x;
@@ -938,13 +972,13 @@ __device__ inline void init_shared_tables(const DevProblem &P, const Ctx &cx) {
     }
     for (int i = WS_TID; i < P.np + 2; i += WS_NT) { SMV(z)[i] = 0.; SMV(v)[i] = 0.; SMV(wv)[i] = 0.; SMV(yc)[i] = 0.; }
     for (int i = WS_TID; i < P.ns2; i += WS_NT) SMV(xi)[i] = 0.;
-    if (WS_TID == 0) store_geom(P, cx, 0);
+    if (WS_TID == 0) { store_geom(P, cx, 0); SMI(idep)[9] = 0; mbar_init(WS_MBAR, 1); fence_async_smem(); }
     __syncthreads();
 }
 
 // working set of the slot: empty (reset) or the one stored by the previous launch.  The factor is NOT
 // loaded: every node rebuilds it (rebuild_factor).
-__device__ inline void load_slot(const DevProblem &P, const Ctx &cx, const SlotPtrs &sp, int &k, bool reset) {
+__device__ __forceinline__ void load_slot(const DevProblem &P, const Ctx &cx, const SlotPtrs &sp, int &k, bool reset) {
     const int n = P.n;
     if (reset) {
         for (int i = WS_TID; i < n; i += WS_NT) SMV(yc)[i] = 0.;
@@ -957,7 +991,7 @@ __device__ inline void load_slot(const DevProblem &P, const Ctx &cx, const SlotP
     WS_SYNC();
 }
 
-__device__ inline void store_slot(const DevProblem &P, const Ctx &cx, const SlotPtrs &sp, int k) {
+__device__ __forceinline__ void store_slot(const DevProblem &P, const Ctx &cx, const SlotPtrs &sp, int k) {
     const int n = P.n;
     for (int i = WS_TID; i < n; i += WS_NT) sp.yc[i] = SMV(yc)[i];
     for (int i = WS_TID; i < k; i += WS_NT) { sp.row[i] = SMI(irow)[i]; sp.side[i] = SMI(iside)[i]; sp.lam[i] = SMV(lam)[i]; }
@@ -1056,14 +1090,22 @@ __device__ __forceinline__ void rebuild_factor(const DevProblem &P, const Ctx &c
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void save_factor(const DevProblem &P, const Ctx &cx, const SlotPtrs &sp, int k) {
     const Geom gm = load_geom(P, cx);
-    // the k columns are all in the pool (caller checks k <= ks): Ri image, then the Q1 columns at their pool stride
-    const int nt = tri_off(k);
-    for (int e = WS_TID; e < nt; e += WS_NT) sp.Ri[e] = SMV(pool)[e];
-    const double2 *s2 = reinterpret_cast<const double2 *>(SMV(pool) + gm.triR);
-    double2 *g2 = reinterpret_cast<double2 *>(sp.Q);
-    for (int e = WS_TID; e < k * (gm.ldc >> 1); e += WS_NT) g2[e] = s2[e];
-    for (int i = WS_TID; i < k; i += WS_NT) { sp.row[i] = SMI(irow)[i]; sp.side[i] = SMI(iside)[i]; sp.lam[i] = SMV(lam)[i]; }
+    // the k columns are all in the pool (caller checks k <= ks): the Ri image, then the Q1 columns at their pool stride, go
+    // to the slot's home as two bulk copies issued by one thread while the others write the bookkeeping
+#ifdef WS_NO_TMA
+    for (int e = WS_TID; e < tri_off(k); e += WS_NT) sp.Ri[e] = SMV(pool)[e];
+    for (int e = WS_TID; e < k * gm.ldc; e += WS_NT) sp.Q[e] = (SMV(pool) + gm.triR)[e];
     if (WS_TID == 0) *sp.nW = k;
+#else
+    if (WS_TID == 0) {
+        fence_async_smem();                               // the factor was written through the generic proxy
+        bulk_s2g(sp.Ri, SMV(pool), (uint32_t)(((tri_off(k) + 1) & ~1) * 8));
+        bulk_s2g(sp.Q, SMV(pool) + gm.triR, (uint32_t)(k * gm.ldc * 8));
+        bulk_commit_wait();                               // the sibling reads the home much later, from this lane
+        *sp.nW = k;
+    }
+#endif
+    for (int i = WS_TID; i < k; i += WS_NT) { sp.row[i] = SMI(irow)[i]; sp.side[i] = SMI(iside)[i]; sp.lam[i] = SMV(lam)[i]; }
     WS_SYNC();
 }
 
@@ -1074,15 +1116,30 @@ __device__ __forceinline__ void restore_factor(const DevProblem &P, const Ctx &c
     unsigned char *ign = SMB(bign), *nadd = SMB(bnadd);
     const int d = gm.d;
     k = *sp.nW;
+    int *phase = SMI(idep) + 9;
+    const uint32_t par = (uint32_t)*phase;
+    WS_SYNC();                                            // nobody still reads the pool; everybody has read the phase bit
+#ifdef WS_NO_TMA
+    for (int e = WS_TID; e < tri_off(k); e += WS_NT) SMV(pool)[e] = sp.Ri[e];
+    for (int e = WS_TID; e < k * gm.ldc; e += WS_NT) (SMV(pool) + gm.triR)[e] = sp.Q[e];
+#else
+    if (WS_TID == 0) {
+        const uint32_t bR = (uint32_t)(((tri_off(k) + 1) & ~1) * 8), bQ = (uint32_t)(k * gm.ldc * 8);
+        fence_async_smem();
+        mbar_expect_tx(WS_MBAR, bR + bQ);
+        bulk_g2s(SMV(pool), sp.Ri, bR, WS_MBAR);
+        bulk_g2s(SMV(pool) + gm.triR, sp.Q, bQ, WS_MBAR);
+        *phase = (int)(par ^ 1u);
+    }
+#endif
+    // ... while the copy engine streams the factor in, the threads reset the row flags and fetch the bookkeeping
     for (int r = WS_TID; r < P.m; r += WS_NT) { inW[r] = 0; ign[r] = (r >= P.mc && r - P.mc < d) ? 3 : 0; nadd[r] = 0; }
-    const int nt = tri_off(k);
-    for (int e = WS_TID; e < nt; e += WS_NT) SMV(pool)[e] = sp.Ri[e];
-    double2 *s2 = reinterpret_cast<double2 *>(SMV(pool) + gm.triR);
-    const double2 *g2 = reinterpret_cast<const double2 *>(sp.Q);
-    for (int e = WS_TID; e < k * (gm.ldc >> 1); e += WS_NT) s2[e] = g2[e];
     for (int i = WS_TID; i < k; i += WS_NT) { SMI(irow)[i] = sp.row[i]; SMI(iside)[i] = sp.side[i]; SMV(lam)[i] = sp.lam[i]; }
     WS_SYNC();
     for (int i = WS_TID; i < k; i += WS_NT) inW[SMI(irow)[i]] = (signed char)SMI(iside)[i];
+#ifndef WS_NO_TMA
+    mbar_wait(WS_MBAR, par);
+#endif
     WS_SYNC();
 }
 
@@ -1095,7 +1152,7 @@ __device__ __forceinline__ void restore_factor(const DevProblem &P, const Ctx &c
 // ---------------------------------------------------------------------------------------------
 
 // d from the bounds of the node; fixes the geometry of the factor.  Ends with a barrier.
-__device__ inline void set_node_prefix(const DevProblem &P, const Ctx &cx, const double *lb, const double *ub) {
+__device__ __forceinline__ void set_node_prefix(const DevProblem &P, const Ctx &cx, const double *lb, const double *ub) {
     double far = 0.;                                        // nb - (first binary that is not pinned)
     for (int j = WS_TID; j < P.nb; j += WS_NT) if (lb[j] != ub[j]) far = fmax(far, (double)(P.nb - j));
     far = block_max(far, SMV(red));
@@ -1104,7 +1161,7 @@ __device__ inline void set_node_prefix(const DevProblem &P, const Ctx &cx, const
 }
 
 // d known by the caller (depth of a branch_in_time node).  The caller provides the barrier.
-__device__ inline void set_node_prefix_known(const DevProblem &P, const Ctx &cx, int d) {
+__device__ __forceinline__ void set_node_prefix_known(const DevProblem &P, const Ctx &cx, int d) {
     if (WS_TID == 0) store_geom(P, cx, d);
 }
 

@@ -9,7 +9,7 @@
 
 // yc: solution in orthonormal coordinates (shared memory), y: signed row multipliers (global, m).
 // scratch: >= max(WS_NT, n) doubles of shared memory (Smem::part).  Returns cost (inf if infeasible) and dual objective.
-__device__ inline void build_records(const DevProblem &P, int status, const double *yc, const double *y,
+__device__ __forceinline__ void build_records(const DevProblem &P, int status, const double *yc, const double *y,
                                      const double *x0, const double *lb, const double *ub,
                                      double *primal, double *dual, double *cost_out, double *dobj_out,
                                      double *scratch, double *red)

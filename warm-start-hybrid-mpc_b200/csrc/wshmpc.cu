@@ -15,7 +15,10 @@ static thread_local std::string g_err;
 #define WS_CUDA(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) WS_FAIL(-2, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(_e), __FILE__, __LINE__); } while (0)
 
 struct wshmpc_handle {
-    DevProblem P;
+    DevProblem P;            // shared-memory layout for P.lanes solver lanes per CTA (throughput launches)
+    DevProblem P1;           // the same problem laid out for ONE lane per CTA (launches that cannot fill two lanes per SM)
+    int n_sm;
+    void *hot_ptr; size_t hot_bytes; int l2_window;      // L2 persistence window over WfT | Mh (l2_window = 1 if it was accepted)
     int device, n_slots;
     cudaStream_t stream;
     std::vector<void *> allocs;
@@ -45,15 +48,19 @@ extern "C" int wshmpc_prof_read(unsigned long long *out, int reset) {
 // ---------------------------------------------------------------------------------------------
 // K1: one CTA per solver slot; the CTA solves, in index order, every node assigned to its slot
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(WS_MAXL * WS_NT, 1)
-solve_nodes_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, int n_slots, int n_nodes,
+// LANES: solver lanes per CTA the kernel is compiled for (its register budget is 65536 / (LANES WS_NT) per thread): the
+// one-lane instantiation keeps 255 registers per thread and serves launches that cannot fill two lanes per SM anyway
+// (single-instance latency, the large systems); results do not depend on the choice.
+template <int LANES>
+__device__ __forceinline__ void
+solve_nodes_body(const DevProblem &P, double *slot_d, int *slot_i, double *ybuf, int n_slots, int n_nodes,
                    const double *__restrict__ x0, const double *__restrict__ lb, const double *__restrict__ ub,
                    const int *__restrict__ slot_of, const int *__restrict__ hot,
                    const double *__restrict__ y0, const double *__restrict__ yc0,
                    int *status, double *cost, double *dobj, int *iters, double *primal, double *dual, double *yc_out)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int slot = blockIdx.x * P.lanes + WS_LANE;
+    const int slot = blockIdx.x * LANES + WS_LANE;
     SlotPtrs sp = slot_ptrs(slot_d, slot_i, slot < n_slots ? slot : 0, P.n, P.ld);
     const Ctx cx = make_ctx(P, smem_raw, sp);
     init_shared_tables(P, cx);
@@ -84,6 +91,14 @@ solve_nodes_kernel(DevProblem P, double *slot_d, int *slot_i, double *ybuf, int 
     }
     if (loaded) store_slot(P, cx, sp, k);
 }
+
+#define WS_K1_ARGS DevProblem P, double *slot_d, int *slot_i, double *ybuf, int n_slots, int n_nodes, \
+    const double *__restrict__ x0, const double *__restrict__ lb, const double *__restrict__ ub, const int *__restrict__ slot_of, \
+    const int *__restrict__ hot, const double *__restrict__ y0, const double *__restrict__ yc0, \
+    int *status, double *cost, double *dobj, int *iters, double *primal, double *dual, double *yc_out
+#define WS_K1_PASS P, slot_d, slot_i, ybuf, n_slots, n_nodes, x0, lb, ub, slot_of, hot, y0, yc0, status, cost, dobj, iters, primal, dual, yc_out
+__global__ void __launch_bounds__(WS_NT, 1) solve_nodes_kernel_1(WS_K1_ARGS) { solve_nodes_body<1>(WS_K1_PASS); }
+__global__ void __launch_bounds__(WS_MAXL * WS_NT, 1) solve_nodes_kernel_m(WS_K1_ARGS) { solve_nodes_body<WS_MAXL>(WS_K1_PASS); }
 
 // ---------------------------------------------------------------------------------------------
 // host side
@@ -131,7 +146,7 @@ extern "C" int wshmpc_create(const wshmpc_problem *p, int device, int n_slots, v
     UP(Q, p->Q, p->nq * nx) UP(R, p->R, p->nr * nu) UP(QT, p->Q_T, p->nqT * nx)
     UP(Mmu, p->M_mu, p->nh * p->nh1) UP(Mrho, p->M_rho, p->nq * p->nqT)
     { std::vector<double> mt = transpose(p->M_mu, p->nh, p->nh1); UP(MmuT, mt.data(), mt.size()) }
-    UP(Mh, p->Mh, (size_t)m * n) UP(nrm, p->nrm, m) UP(vscale, p->vscale, m) UP(Eh, p->Eh, (size_t)p->mc * nx)
+    UP(nrm, p->nrm, m) UP(vscale, p->vscale, m) UP(Eh, p->Eh, (size_t)p->mc * nx)
     UP(hh, p->hh, p->mc) UP(Rinv, p->Rinv, (size_t)n * n) UP(Kx, p->Kx, (size_t)n * nx)
     UP(bin_idx, p->bin_idx, p->nb)
     {
@@ -162,7 +177,14 @@ extern "C" int wshmpc_create(const wshmpc_problem *p, int device, int n_slots, v
         const int ns2 = (p->ns + 1) & ~1;
         std::vector<double> wt((size_t)n * ns2, 0.);
         for (int r2 = 0; r2 < p->ns; ++r2) for (int c = 0; c < n; ++c) wt[(size_t)c * ns2 + r2] = p->Wf[(size_t)r2 * n + c];
-        UP(WfT, wt.data(), (size_t)n * ns2)
+        // the two operators every iteration of every lane streams (pricing operator WfT, rows Mh) live in ONE allocation:
+        // a single L2 access-policy window keeps them resident while the dual records of the trees stream through L2
+        std::vector<double> hot(wt.size() + (size_t)m * n);
+        memcpy(hot.data(), wt.data(), wt.size() * sizeof(double));
+        memcpy(hot.data() + wt.size(), p->Mh, (size_t)m * n * sizeof(double));
+        UP(WfT, hot.data(), hot.size())
+        P.Mh = P.WfT + wt.size();
+        h->hot_ptr = (void *)P.WfT; h->hot_bytes = hot.size() * sizeof(double);
     }
 #undef UP
     // record layout (subproblem_solution.py:86-91, 137-166)
@@ -236,29 +258,57 @@ extern "C" int wshmpc_create(const wshmpc_problem *p, int device, int n_slots, v
         }
         P.lanes = lanes;
         g_lanes_last = lanes;
-        size_t pool = (avail - so.tab_doubles) / lanes - fixed;
-        pool &= ~(size_t)1;
+        h->n_sm = prop.multiProcessorCount;
         const size_t pool_max = (size_t)n * P.ld + tri_off(n) + 2;          // the whole factor of the largest node
-        if (pool > pool_max) pool = pool_max;
-        so.pool = fixed; so.pool_sz = (int)pool;
-        so.lane_doubles = fixed + (int)pool;
-        so.total_bytes = (so.tab_doubles + lanes * so.lane_doubles) * 8;
-        h->smem = (size_t)so.total_bytes;
+        auto lay = [&](DevProblem &D, int L) {
+            size_t pool = (avail - so.tab_doubles) / L - fixed;
+            pool &= ~(size_t)1;
+            if (pool > pool_max) pool = pool_max;
+            D.lanes = L;
+            D.so.pool = fixed; D.so.pool_sz = (int)pool;
+            D.so.lane_doubles = fixed + (int)pool;
+            D.so.total_bytes = (D.so.tab_doubles + L * D.so.lane_doubles) * 8;
+        };
+        lay(P, lanes);
+        h->P1 = P;
+        lay(h->P1, 1);
+        h->smem = (size_t)(P.so.total_bytes > h->P1.so.total_bytes ? P.so.total_bytes : h->P1.so.total_bytes);
     }
-    WS_CUDA(cudaFuncSetAttribute(solve_nodes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+    WS_CUDA(cudaFuncSetAttribute(solve_nodes_kernel_1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+    WS_CUDA(cudaFuncSetAttribute(solve_nodes_kernel_m, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
     // slot memory
     void *d = nullptr;
     WS_CUDA(cudaMalloc(&d, (size_t)n_slots * slot_doubles(n, P.ld) * sizeof(double))); h->allocs.push_back(d); h->slot_d = (double *)d;
     WS_CUDA(cudaMalloc(&d, (size_t)n_slots * slot_ints(n) * sizeof(int))); h->allocs.push_back(d); h->slot_i = (int *)d;
     WS_CUDA(cudaMemset(h->slot_i, 0, (size_t)n_slots * slot_ints(n) * sizeof(int)));
     WS_CUDA(cudaMalloc(&d, (size_t)n_slots * m * sizeof(double))); h->allocs.push_back(d); h->ybuf = (double *)d;
-    WS_CUDA(cudaFuncSetAttribute(bnb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
-    WS_CUDA(cudaFuncSetAttribute(closed_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+    WS_CUDA(cudaFuncSetAttribute(bnb_kernel_1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+    WS_CUDA(cudaFuncSetAttribute(bnb_kernel_m, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+    WS_CUDA(cudaFuncSetAttribute(closed_loop_kernel_1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+    WS_CUDA(cudaFuncSetAttribute(closed_loop_kernel_m, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
     WS_CUDA(cudaMalloc(&d, (size_t)n_slots * bnb_scratch_doubles(p->nb, L.primal) * sizeof(double))); h->allocs.push_back(d); h->scratch = (double *)d;
     WS_CUDA(cudaMalloc(&d, 64)); h->allocs.push_back(d); h->work_counter = (int *)d;
     h->shift_smem = shift_smem_bytes(P);
     if (h->shift_smem > 48 * 1024)
         WS_CUDA(cudaFuncSetAttribute(shift_tree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->shift_smem));
+    {
+        // best effort: persisting L2 lines for the shared operators (1.2 MB on the T = 20 cart-pole; the trees are GBs)
+        h->l2_window = 0;
+        cudaDeviceProp pr;
+        if (!getenv("WSHMPC_NO_L2_WINDOW") && cudaGetDeviceProperties(&pr, device) == cudaSuccess && pr.persistingL2CacheMaxSize > 0 && h->hot_bytes > 0) {
+            size_t want = h->hot_bytes < (size_t)pr.persistingL2CacheMaxSize ? h->hot_bytes : (size_t)pr.persistingL2CacheMaxSize;
+            cudaStreamAttrValue av;
+            memset(&av, 0, sizeof(av));
+            av.accessPolicyWindow.base_ptr = h->hot_ptr;
+            av.accessPolicyWindow.num_bytes = h->hot_bytes < (size_t)pr.accessPolicyMaxWindowSize ? h->hot_bytes : (size_t)pr.accessPolicyMaxWindowSize;
+            av.accessPolicyWindow.hitRatio = 1.f;
+            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess &&
+                cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &av) == cudaSuccess) h->l2_window = 1;
+            cudaGetLastError();                         // a refused window is not an error of the handle
+        }
+    }
     *out = h;
     return 0;
 }
@@ -276,7 +326,7 @@ extern "C" int wshmpc_set_search_rule(wshmpc_handle *h, int rule)
 {
     if (!h) WS_FAIL(-1, "null handle");
     if (rule < 0 || rule > 2) WS_FAIL(-1, "search rule %d: 0 best_first, 1 depth_first, 2 breadth_first", rule);
-    h->P.search_rule = rule;
+    h->P.search_rule = rule; h->P1.search_rule = rule;
     return 0;
 }
 
@@ -296,7 +346,12 @@ extern "C" int wshmpc_solve_nodes(wshmpc_handle *h, int n_nodes, const double *d
     if (!h) WS_FAIL(-1, "null handle");
     if (n_nodes <= 0) return 0;
     WS_CUDA(cudaSetDevice(h->device));
-    solve_nodes_kernel<<<(h->n_slots + h->P.lanes - 1) / h->P.lanes, h->P.lanes * WS_NT, h->smem, h->stream>>>(
+    if (h->n_slots <= h->n_sm || h->P.lanes == 1)
+        solve_nodes_kernel_1<<<h->n_slots, WS_NT, h->P1.so.total_bytes, h->stream>>>(
+            h->P1, h->slot_d, h->slot_i, h->ybuf, h->n_slots, n_nodes, d_x0, d_lb, d_ub, d_slot, d_hot, d_y0, d_yc0,
+            d_status, d_cost, d_dobj, d_iters, d_primal, d_dual, d_yc);
+    else
+    solve_nodes_kernel_m<<<(h->n_slots + h->P.lanes - 1) / h->P.lanes, h->P.lanes * WS_NT, h->P.so.total_bytes, h->stream>>>(
         h->P, h->slot_d, h->slot_i, h->ybuf, h->n_slots, n_nodes, d_x0, d_lb, d_ub, d_slot, d_hot, d_y0, d_yc0,
         d_status, d_cost, d_dobj, d_iters, d_primal, d_dual, d_yc);
     WS_CUDA(cudaGetLastError());
@@ -343,7 +398,12 @@ extern "C" int wshmpc_bnb_solve(wshmpc_handle *h, int n_inst, const double *d_x0
     WS_CUDA(cudaSetDevice(h->device));
     WS_CUDA(cudaMemsetAsync(h->work_counter, 0, sizeof(int), h->stream));
     const int slots = n_inst < h->n_slots ? n_inst : h->n_slots;
-    bnb_kernel<<<(slots + h->P.lanes - 1) / h->P.lanes, h->P.lanes * WS_NT, h->smem, h->stream>>>(
+    if (slots <= h->n_sm || h->P.lanes == 1)
+        bnb_kernel_1<<<slots, WS_NT, h->P1.so.total_bytes, h->stream>>>(
+            h->P1, h->slot_d, h->slot_i, h->ybuf, h->scratch, h->work_counter, slots, n_inst, d_x0, d_active, tv, tol, max_solves,
+            d_inc_cost, d_inc_node, d_inc_primal, d_n_solves, d_status, d_trace, d_totals);
+    else
+    bnb_kernel_m<<<(slots + h->P.lanes - 1) / h->P.lanes, h->P.lanes * WS_NT, h->P.so.total_bytes, h->stream>>>(
         h->P, h->slot_d, h->slot_i, h->ybuf, h->scratch, h->work_counter, slots, n_inst, d_x0, d_active, tv, tol, max_solves,
         d_inc_cost, d_inc_node, d_inc_primal, d_n_solves, d_status, d_trace, d_totals);
     WS_CUDA(cudaGetLastError());
@@ -396,7 +456,12 @@ extern "C" int wshmpc_closed_loop(wshmpc_handle *h, int n_inst, const wshmpc_loo
     loop_init_kernel<<<(n_items + 255) / 256, 256, 0, h->stream>>>(n_inst, n_items, L);
     WS_CUDA(cudaGetLastError());
     const int slots = n_inst < h->n_slots ? n_inst : h->n_slots;
-    closed_loop_kernel<<<(slots + h->P.lanes - 1) / h->P.lanes, h->P.lanes * WS_NT, h->smem, h->stream>>>(
+    if (slots <= h->n_sm || h->P.lanes == 1)
+        closed_loop_kernel_1<<<slots, WS_NT, h->P1.so.total_bytes, h->stream>>>(
+            h->P1, h->slot_d, h->slot_i, h->ybuf, h->scratch, L, slots, n_inst, v0, v1, tol, max_solves,
+            d_inc_cost, d_inc_node, d_inc_primal, d_n_solves, d_status, d_totals);
+    else
+    closed_loop_kernel_m<<<(slots + h->P.lanes - 1) / h->P.lanes, h->P.lanes * WS_NT, h->P.so.total_bytes, h->stream>>>(
         h->P, h->slot_d, h->slot_i, h->ybuf, h->scratch, L, slots, n_inst, v0, v1, tol, max_solves,
         d_inc_cost, d_inc_node, d_inc_primal, d_n_solves, d_status, d_totals);
     WS_CUDA(cudaGetLastError());
