@@ -1,0 +1,108 @@
+"""-m gpu: the round-2 execution model and the multi-GPU / comparator code paths on a real device.
+
+* one-lane (255 registers) and two-lane (128 registers) builds of the kernels, and any number of solver slots, give
+  bit-identical results (the factor's summation order does not depend on where a column lives);
+* capacity overflow of the warm start switches an instance off with status 2 instead of truncating its cover;
+* split-frontier search (single rank: no collective) and the MIQP comparator against the device-side search.
+"""
+import os
+import numpy as np
+import pytest
+import torch
+
+from oracle.models import load_model, MODELS
+from tests.util import make_controller
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def cp20():
+    model = load_model('cp20')
+    return model, make_controller(model)
+
+
+def test_one_lane_and_two_lane_builds_agree_bit_for_bit(cp20):
+    model, ctl = cp20
+    from warm_start_hmpc_b200.closed_loop import ClosedLoop
+    N, S = 300, 3
+    x0 = np.load(os.path.join(MODELS, 'cp20_instances.npy'))[200:200 + N]
+    e = torch.as_tensor(0.003 * np.random.default_rng(3).standard_normal((S, N, 4)) * model['x_max'], device='cuda')
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    runs = {}
+    for slots in (8, sms, ctl.default_slots()):       # <= SMs: one lane per CTA (255 registers); more: two lanes (128 registers)
+        L = ClosedLoop(ctl, N, warm=True, max_solves=1024, max_roots=512, n_slots=slots)
+        L.reset(x0)
+        logs = L.run(S, e=e)
+        torch.cuda.synchronize()
+        runs[slots] = (logs['cost'].clone(), logs['n_solves'].clone(), L.x.clone(), L.active.clone(), int(L.totals[1]))
+        del L
+    ref = runs[8]
+    for slots, r in runs.items():
+        assert torch.equal(r[0], ref[0]) and torch.equal(r[1], ref[1]) and torch.equal(r[2], ref[2]) and torch.equal(r[3], ref[3])
+        assert r[4] == ref[4]                           # the same number of active-set iterations, too
+    assert ctl.default_slots() >= 2 * sms               # CP20 runs two lanes per SM
+
+
+def test_warm_start_overflow_switches_the_instance_off(cp20):
+    """a cover that does not fit the new tree must not be truncated (a truncated cover can report a
+    suboptimal or 'infeasible' MIQP as solved): the instance gets status 2 and leaves the loop."""
+    model, ctl = cp20
+    from warm_start_hmpc_b200.closed_loop import ClosedLoop
+    L = ClosedLoop(ctl, 2, warm=True, max_solves=256, max_roots=8, n_slots=2)      # cap_recs = 265 >= 160 solves, cap for roots tiny
+    # new trees with room for fewer records than the 77 leaves the shift retains
+    small = [ctl.handle().new_tree(2, 600, 40) for _ in range(2)]
+    L.reset(np.repeat(model['x0_nominal'][None], 2, 0))
+    out = L.step()                                       # cold solve in the regular tree, shift into ... the regular other tree
+    assert int(out['status'][0]) == 0 and int(L.trees[L.cur].n_nodes[0]) == 77
+    # shift the same leaves into the small tree through the C ABI: overflow
+    h = L.h
+    L2 = ClosedLoop(ctl, 2, warm=True, max_solves=256, max_roots=8, n_slots=2)
+    L2.reset(np.repeat(model['x0_nominal'][None], 2, 0))
+    tree = L2.trees[0]
+    h.tree_init_root(tree)
+    h.bnb_solve(L2.x, tree, max_solves=256, active=L2.active, out=L2.out)
+    act = L2.active.clone()
+    h.shift_tree(L2.x, None, tree, L2.out['cost'], L2.out['primal'], small[0], active=act)
+    torch.cuda.synchronize()
+    assert act.tolist() == [0, 0] and small[0].n_nodes.tolist() == [0, 0]
+    # ... and in the fused loop the status says why
+    L3 = ClosedLoop(ctl, 2, warm=True, max_solves=256, max_roots=8, n_slots=2)
+    L3.trees = [ctl.handle().new_tree(2, 600, 200), ctl.handle().new_tree(2, 600, 40)]
+    L3.reset(np.repeat(model['x0_nominal'][None], 2, 0))
+    logs = L3.run(2)
+    torch.cuda.synchronize()
+    assert logs['status'][0].tolist() == [2, 2] and L3.active.tolist() == [0, 0]
+    assert np.isfinite(logs['cost'][0].cpu().numpy()).all()          # the step itself was solved; only its warm start did not fit
+
+
+def test_split_frontier_single_rank_equals_device_search(cp20):
+    model, ctl = cp20
+    from warm_start_hmpc_b200.split_frontier import split_frontier_bnb, GpuBatchSolver
+    x0 = model['x0_nominal']
+    sol_d, leaves_d, n_d, _ = ctl.feedforward(x0, printing_period=None)
+    solver = GpuBatchSolver(ctl, n_slots=4)
+    for npr in (1, 3):
+        sol, leaves, n, rounds = split_frontier_bnb(ctl, x0, solver, nodes_per_rank=npr)
+        assert abs(sol.objective - sol_d.objective) <= 1e-12 * sol_d.objective
+        assert np.array_equal(np.array(sol.variables['ub']), np.array(sol_d.variables['ub']))
+        assert n >= n_d and rounds <= n
+        if npr == 1:
+            # one node per round on one rank IS the reference's loop: same nodes, same leaves, same bounds
+            assert n == n_d and rounds == n
+            assert [sorted(l.identifier.items()) for l in leaves] == [sorted(l.identifier.items()) for l in leaves_d]
+            assert np.array_equal(np.array([l.lb for l in leaves]), np.array([l.lb for l in leaves_d]))
+    # the leaves of a multi-node round are a cover the device shifts
+    ws, _, _ = ctl.construct_warm_start(leaves, x0, sol.variables['uc'][0], sol.variables['ub'][0], np.zeros(4))
+    assert len(ws) >= 70
+
+
+def test_miqp_comparator_on_the_device(cp20):
+    """the conventional MIQP branch and bound through the QP seam returns the structured search's optimum."""
+    model, ctl = cp20
+    x0 = model['x0_nominal']
+    sol, _, n_qp, _ = ctl.feedforward(x0, printing_period=None)
+    variables, objective, nodes, seconds = ctl.feedforward_gurobi(x0, {'OutputFlag': 0, 'MIPGap': 0, 'Threads': 1})
+    assert abs(objective - sol.objective) <= 1e-9 * sol.objective
+    assert np.array_equal(variables['ub'], np.array(sol.variables['ub']))
+    assert nodes > n_qp and seconds > 0.
