@@ -106,3 +106,31 @@ def test_miqp_comparator_on_the_device(cp20):
     assert abs(objective - sol.objective) <= 1e-9 * sol.objective
     assert np.array_equal(variables['ub'], np.array(sol.variables['ub']))
     assert nodes > n_qp and seconds > 0.
+
+
+def test_closed_loop_against_the_nonlinear_plant(cp20):
+    """warm-started hybrid MPC driving the TRUE plant (cart-pole between soft walls, Euler sub-steps of
+    1 ms): the model error fed to the warm start is the measured one; the cart that starts moving towards the right wall
+    (x0 = [0, 0, 1, 0]) is stopped and brought back, every step stays feasible, warm-started steps stay cheap."""
+    model, ctl = cp20
+    from warm_start_hmpc_b200.closed_loop import ClosedLoop
+    from warm_start_hmpc_b200.plants import CartPoleWithWalls
+    plant = CartPoleWithWalls()
+    h = 0.05
+    sim = lambda x, u0: plant.simulate(x, h, u0[:, 0])
+    N = 3
+    x0 = np.repeat(model['x0_nominal'][None], N, 0) * np.array([1., 0.9, 0.8])[:, None]
+    L = ClosedLoop(ctl, N, warm=True, max_solves=2048, max_roots=1024, n_slots=N)
+    L.reset(x0)
+    costs, solves, errs = [], [], []
+    for t in range(40):
+        out, u0, e = L.step_with_plant(sim)
+        assert out['status'].tolist() == [0] * N, (t, out['status'].tolist())
+        costs.append(out['cost'].cpu().numpy().copy()); solves.append(out['n_solves'].cpu().numpy().copy()); errs.append(np.abs(e).max())
+        assert np.all(np.abs(u0[:, 0]) <= 1. + 1e-9)
+    costs, solves = np.array(costs), np.array(solves)
+    x_end = L.x.cpu().numpy()
+    assert np.all(np.abs(x_end[:, 2]) < 0.5 * np.abs(x0[:, 2]))              # the cart has been slowed down
+    assert np.all(costs[-1] < costs[0])
+    assert solves[1:].mean() * 3 < solves[0].mean()                            # warm start pays off against the true plant too
+    assert max(errs) < 0.05                                                    # linear model vs plant: small one-step errors

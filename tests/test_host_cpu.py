@@ -287,3 +287,84 @@ def test_miqp_comparator_finds_the_same_optimum():
     assert np.array_equal(variables['ub'], g['opt_ub']) and variables['x'].shape == (ctl.T + 1, 4) and variables['uc'].shape == (ctl.T, 3)
     assert nodes > 2 * len(g['status'])          # no dual-bound inheritance, no time structure: many more relaxations
     assert np.allclose(variables['x'][0], g['x0'])
+
+
+def test_mld_from_symbolic_and_from_pwa():
+    """the modelling builders of the reference's MLDSystem (mld_system.py:68-214).  from_symbolic as in
+    the reference's own test (test_mld_system.py:44-68); from_pwa against the reference's output where it is importable
+    and against the meaning of the convex-hull formulation everywhere."""
+    import sympy as sp
+    rng = np.random.default_rng(0)
+    nx, nu, nub, nc = 5, 7, 3, 9
+    A, B = rng.standard_normal((nx, nx)), rng.standard_normal((nx, nu))
+    F, G, h = rng.standard_normal((nc, nx)), rng.standard_normal((nc, nu)), rng.standard_normal(nc)
+    x = sp.Matrix(sp.symbols('x:%d' % nx)); u = sp.Matrix(sp.symbols('u:%d' % nu))
+    d = sp.Matrix(A) * x + sp.Matrix(B) * u
+    c = sp.Matrix(F) * x + sp.Matrix(G) * u - sp.Matrix(h.reshape(nc, 1))
+    mld = ws.MLDSystem.from_symbolic(d, c, x, u, nub)
+    for got, want in ((mld.A, A), (mld.B, B), (mld.F, F), (mld.G, G), (mld.h, h)):
+        np.testing.assert_array_almost_equal(got, want)
+    assert sum(sp.Matrix(mld.V) * u - u[-nub:, :]) == 0
+    with pytest.raises(ValueError):
+        ws.MLDSystem.from_symbolic(d + sp.ones(nx, 1), c, x, u, nub)                # affine dynamics
+    # a PWA system with two modes split at x_0 = 0
+    nx, nu = 2, 1
+    dyn = [[rng.standard_normal((nx, nx)), rng.standard_normal((nx, nu)), rng.standard_normal(nx)] for _ in range(2)]
+    box = np.vstack((np.eye(nx + nu), -np.eye(nx + nu)))
+    dom = []
+    for sgn in (1., -1.):                                  # mode 0: x_0 <= 0, mode 1: x_0 >= 0, both inside |x|, |u| <= 2
+        Fi = np.vstack((box[:, :nx], [[sgn, 0.]])); Gi = np.vstack((box[:, nx:], [[0.]])); hi = np.concatenate((2. * np.ones(6), [0.]))
+        dom.append([Fi, Gi, hi])
+    pwa = ws.MLDSystem.from_pwa([[M.copy() for M in d_] for d_ in dyn], [[M.copy() for M in d_] for d_ in dom])
+    assert pwa.nub == 2 and pwa.nu == nu + 2 * (nx + nu) + 2 and np.all(pwa.A == 0.)
+    for _ in range(20):
+        xk = rng.uniform(-1.5, 1.5, nx); uk = rng.uniform(-1.5, 1.5, nu)
+        mode = 0 if xk[0] <= 0 else 1
+        for guess in (0, 1):
+            v = np.zeros(pwa.nu)
+            v[:nu] = uk
+            v[nu + guess * nx:nu + (guess + 1) * nx] = xk
+            v[nu + 2 * nx + guess * nu:nu + 2 * nx + (guess + 1) * nu] = uk
+            v[nu + 2 * (nx + nu) + guess] = 1.
+            ok = np.all(pwa.F.dot(xk) + pwa.G.dot(v) <= pwa.h + 1e-12)
+            assert ok == (guess == mode)
+            if ok:
+                assert np.allclose(pwa.A.dot(xk) + pwa.B.dot(v), dyn[mode][0].dot(xk) + dyn[mode][1].dot(uk) + dyn[mode][2])
+    if reference_available():
+        from oracle.refload import import_reference
+        _, _, _, rm = import_reference()
+        ref = rm.MLDSystem.from_pwa([[M.copy() for M in d_] for d_ in dyn], [[M.copy() for M in d_] for d_ in dom])
+        for name in ('A', 'B', 'F', 'G', 'h'):
+            assert np.array_equal(getattr(ref, name), getattr(pwa, name)), name
+        xs = sp.Matrix(sp.symbols('x:2')); us = sp.Matrix(sp.symbols('u:1'))
+        dsym = [sp.Matrix(d_[0]) * xs + sp.Matrix(d_[1]) * us + sp.Matrix(d_[2].reshape(2, 1)) for d_ in dyn]
+        csym = [sp.Matrix(d_[0]) * xs + sp.Matrix(d_[1]) * us - sp.Matrix(d_[2].reshape(-1, 1)) for d_ in dom]
+        a, b = ws.MLDSystem.from_symbolic_pwa(dsym, csym, xs, us), rm.MLDSystem.from_symbolic_pwa(dsym, csym, xs, us)
+        for name in ('A', 'B', 'F', 'G', 'h'):
+            assert np.allclose(getattr(a, name), getattr(b, name)), name
+
+
+def test_nonlinear_plant():
+    """closed-form cart-pole between soft walls (nonlinear_dynamics.py): its linearisation IS the MLD
+    model's (A, B) (explicit Euler, h = 0.05), energy is conserved without forces, the walls push back."""
+    from warm_start_hmpc_b200.plants import CartPoleWithWalls
+    model = load_model('cp20')
+    p = CartPoleWithWalls()
+    Ac, Bc = p.linearization()
+    assert np.allclose(np.eye(4) + 0.05 * Ac, model['A'], atol=1e-14) and np.allclose(0.05 * Bc, model['B'][:, :3], atol=1e-14)
+    J = np.array([(p.x_dot(1e-6 * np.eye(4)[i], 0.) - p.x_dot(-1e-6 * np.eye(4)[i], 0.)) / 2e-6 for i in range(4)]).T
+    assert np.abs(J - Ac).max() < 1e-8
+    def energy(x):
+        c, s = np.cos(x[1]), np.sin(x[1])
+        return .5 * (p.mc + p.mp) * x[2] ** 2 - p.mp * p.l * c * x[2] * x[3] + .5 * p.mp * p.l ** 2 * x[3] ** 2 + p.mp * p.g * p.l * c
+    x0 = np.array([0., 0.05, 0.1, 0.])
+    x1 = p.simulate(x0, 0.2, 0., h_des=1e-5)
+    assert abs(energy(x1) - energy(x0)) < 1e-4 * abs(energy(x0))
+    # tip inside the right wall, moving in: the wall pushes the tip back (fr > 0, fl = 0); outside: no force
+    xin = np.array([0.55, 0., 0.5, 0.])
+    fl, fr = p.contact_forces(xin)
+    assert fl == 0. and fr > 0. and p.x_dot(xin, 0.)[3] > 0.       # the pole rotates away from the wall (tip x = qc - l sin qp)
+    assert p.contact_forces(np.zeros(4)) == (0., 0.)
+    # batched
+    xb = np.stack((x0, xin)); out = p.simulate(xb, 0.05, np.array([0., 1.]))
+    assert out.shape == (2, 4) and np.allclose(out[0], p.simulate(x0, 0.05, 0.))

@@ -99,6 +99,39 @@ class ClosedLoop(object):
         self.xpar = 1 - self.xpar
         return self.out
 
+    def step_with_plant(self, plant):
+        """One receding-horizon step against a TRUE plant instead of the linear model + noise: branch and bound (K3), the
+        applied input goes to `plant(x [n, nx], u0 [n, nu]) -> next measured state [n, nx]` (host numpy, e.g.
+        plants.CartPoleWithWalls.simulate), the model error e_t = x_measured - x_1|t is what the warm start of the next
+        step is corrected with (construct_warm_start's e0, controller.py:503-564), then K2 + K4.
+        Returns (out, u0 [n, nu] numpy, e [n, nx] numpy)."""
+        import torch
+        h = self.h
+        tree = self.trees[self.cur]
+        if self.fresh or not self.warm:
+            h.tree_init_root(tree); self.launches += 1
+            self.fresh = False
+        h.bnb_solve(self.x, tree, tol=self.tol, max_solves=self.max_solves, active=self.active, out=self.out, totals=self.totals)
+        self.launches += 1
+        nx, nu, T = self.ctl.mld.nx, self.ctl.mld.nu, self.ctl.T
+        prim = self.out['primal'].cpu().numpy()
+        x_now = self.x.cpu().numpy()
+        u0 = prim[:, (T + 1) * nx:(T + 1) * nx + nu]
+        x_pred = prim[:, nx:2 * nx]
+        live = (self.active.cpu().numpy() != 0) & np.isfinite(self.out['cost'].cpu().numpy())
+        x_meas = np.array(x_now)
+        if live.any():
+            x_meas[live] = plant(x_now[live], u0[live])
+        e = np.where(live[:, None], x_meas - x_pred, 0.)
+        ed = torch.as_tensor(e, device=self.x.device)
+        new = self.trees[1 - self.cur]
+        h.shift_tree(self.x, ed, tree, self.out['cost'], self.out['primal'], new, active=self.active,
+                     x_next=self.xbuf[1 - self.xpar], u0=self.u0)
+        self.cur = 1 - self.cur
+        self.xpar = 1 - self.xpar
+        self.launches += 1
+        return self.out, u0, e
+
     def run(self, n_steps, e=None, logs=None):
         """`n_steps` receding-horizon steps of every instance in ONE launch (wshmpc_closed_loop): the fused
         form of calling step() n_steps times, without a barrier between the steps of different instances.
