@@ -206,6 +206,18 @@ int wshmpc_closed_loop(wshmpc_handle *h, int n_inst, const wshmpc_loop *loop,
                        double *d_inc_cost, int *d_inc_node, double *d_inc_primal, int *d_n_solves,
                        int *d_status, unsigned long long *d_totals);
 
+/* Batched small LPs in standard form:   min c'y  s.t.  E y = r,  y >= 0   for n_lp problems at once,
+ * one CTA per LP (two-phase tableau simplex in shared memory).  Replaces the host LP loops the reference runs through
+ * BoundedQP / Gurobi while a controller is built: `_update_mu` (controller.py:186-227: h_Tm1.size LPs sharing [F G]' and h,
+ * one right-hand side each) and, through the dual, the `max c.x s.t. D x <= e` LPs of mcais.py:44-184.
+ *   d_E [n_lp or 1][m][n] row-major, stride_E = m*n or 0 (shared); d_c [n_lp or 1][n], stride_c = n or 0; d_r [n_lp][m]
+ *   d_status [n_lp]: 2 optimal, 3 infeasible, 5 unbounded, 9 iteration limit;  d_obj [n_lp];  d_y [n_lp][n];
+ *   d_dual [n_lp][m]: multipliers pi of the equality rows (c - E'pi >= 0, obj = r.pi);  d_iters [n_lp] pivots.
+ * m <= 64.  All pointers are device pointers. */
+int wshmpc_lp_batch(int device, void *stream, int n_lp, int m, int n, const double *d_E, long long stride_E,
+                    const double *d_c, long long stride_c, const double *d_r, double tol, int max_iter,
+                    int *d_status, double *d_obj, double *d_y, double *d_dual, int *d_iters);
+
 #ifdef __cplusplus
 }
 #endif

@@ -43,7 +43,7 @@ def load_library():
 
 
 EXPORTS = ('wshmpc_last_error', 'wshmpc_ctas_per_sm', 'wshmpc_set_search_rule', 'wshmpc_create', 'wshmpc_destroy', 'wshmpc_get_layout', 'wshmpc_solve_nodes',
-           'wshmpc_tree_init_root', 'wshmpc_bnb_solve', 'wshmpc_shift_tree', 'wshmpc_closed_loop')
+           'wshmpc_tree_init_root', 'wshmpc_bnb_solve', 'wshmpc_shift_tree', 'wshmpc_closed_loop', 'wshmpc_lp_batch')
 
 
 class _Loop(C.Structure):
@@ -234,3 +234,29 @@ class Handle(object):
                                            int(max_solves), V(out['cost']), V(out['node']), V(out['primal']), V(out['n_solves']),
                                            V(out['status']), V(totals)))
         return logs
+
+
+def lp_batch(E, c, r, device=0, tol=1e-9, max_iter=None):
+    """Batched standard-form LPs on the device (wshmpc_lp_batch):  min c'y s.t. E y = r_k, y >= 0.
+    E [m, n] (shared) or [K, m, n]; c [n] (shared) or [K, n]; r [K, m] (numpy or CUDA tensors).
+    Returns dict(status [K], obj [K], y [K, n], dual [K, m], iters [K]) of CUDA tensors."""
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError('no CUDA device: wshmpc_lp_batch runs on the GPU')
+    lib = load_library()
+    dev = torch.device('cuda', device)
+    t = lambda a: torch.as_tensor(np.asarray(a, dtype=float) if not torch.is_tensor(a) else a, dtype=torch.float64, device=dev).contiguous()
+    E, c, r = t(E), t(c), t(r)
+    K, m = r.shape
+    n = E.shape[-1]
+    assert E.shape[-2] == m and c.shape[-1] == n
+    sE = m * n if E.dim() == 3 else 0
+    sc = n if c.dim() == 2 else 0
+    out = dict(status=torch.zeros(K, dtype=torch.int32, device=dev), obj=torch.zeros(K, dtype=torch.float64, device=dev),
+               y=torch.zeros((K, n), dtype=torch.float64, device=dev), dual=torch.zeros((K, m), dtype=torch.float64, device=dev),
+               iters=torch.zeros(K, dtype=torch.int32, device=dev))
+    P = lambda a: C.c_void_p(a.data_ptr())
+    _check(lib.wshmpc_lp_batch(device, C.c_void_p(0), K, m, n, P(E), C.c_longlong(sE), P(c), C.c_longlong(sc), P(r), C.c_double(tol),
+                               int(max_iter if max_iter is not None else 50 * (m + n)), P(out['status']), P(out['obj']), P(out['y']),
+                               P(out['dual']), P(out['iters'])))
+    return out

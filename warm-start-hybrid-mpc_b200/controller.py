@@ -84,10 +84,24 @@ class HybridModelPredictiveController(object):
         if self.G_Tm1.shape[0] != self.h_Tm1.size:
             raise ValueError('Terminal-set matrices have wrong number of rows.')
 
+    def _update_mu_device(self):
+        """controller.py:186-227 as ONE batched launch (wshmpc_lp_batch): all h_Tm1.size LPs share the
+        matrix [F G]' and the cost h and differ in the right-hand side.  Returns M (same optimal values h.M[:, i] as
+        `_update_mu`; an LP with several optimal vertices may return another one of them)."""
+        from .capi import lp_batch
+        mld = self.mld
+        E = np.vstack((mld.F.T, mld.G.T))
+        R = np.hstack((self.F_Tm1, self.G_Tm1))
+        out = lp_batch(E, mld.h, R, device=self.device)
+        st = out['status'].cpu().numpy()
+        if np.any(st != 2):
+            raise ValueError('The conic hull of [F G] does not contain the one of [F_Tm1 G_Tm1].')
+        return out['y'].cpu().numpy().T.copy()
+
     def _update_mu(self):
         """controller.py:186-227: column i of M solves  min h.mu  s.t.  F'mu = F_Tm1[i], G'mu = G_Tm1[i],
         mu >= 0  (host precompute, once per controller; the reference routes these LPs through Gurobi,
-        here HiGHS via scipy)."""
+        here HiGHS via scipy; `_update_mu_device` is the batched device version)."""
         from scipy.optimize import linprog
         mld = self.mld
         n = mld.h.size

@@ -4,6 +4,7 @@
 #include "qp_device.cuh"
 #include "records.cuh"
 #include "bnb.cuh"
+#include "lp_batch.cuh"
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -464,6 +465,30 @@ extern "C" int wshmpc_closed_loop(wshmpc_handle *h, int n_inst, const wshmpc_loo
     closed_loop_kernel_m<<<(slots + h->P.lanes - 1) / h->P.lanes, h->P.lanes * WS_NT, h->P.so.total_bytes, h->stream>>>(
         h->P, h->slot_d, h->slot_i, h->ybuf, h->scratch, L, slots, n_inst, v0, v1, tol, max_solves,
         d_inc_cost, d_inc_node, d_inc_primal, d_n_solves, d_status, d_totals);
+    WS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// batched small LPs (controller.py:186-227 _update_mu, mcais.py:44-184)
+// ---------------------------------------------------------------------------------------------
+extern "C" int wshmpc_lp_batch(int device, void *stream, int n_lp, int m, int n, const double *d_E, long long stride_E,
+                               const double *d_c, long long stride_c, const double *d_r, double tol, int max_iter,
+                               int *d_status, double *d_obj, double *d_y, double *d_dual, int *d_iters)
+{
+    if (n_lp <= 0) return 0;
+    if (m <= 0 || n <= 0 || m > LP_MAX_M) WS_FAIL(-1, "wshmpc_lp_batch: need 0 < m <= %d equality rows and n > 0 columns (m = %d, n = %d)", LP_MAX_M, m, n);
+    if (!d_E || !d_c || !d_r || !d_status || !d_obj || !d_y || !d_dual || !d_iters) WS_FAIL(-1, "null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) WS_FAIL(-3, "no CUDA device");
+    WS_CUDA(cudaSetDevice(device));
+    const size_t smem = sizeof(double) * (size_t)(m + 1) * (n + m + 1);
+    cudaDeviceProp prop;
+    WS_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (smem > prop.sharedMemPerBlockOptin) WS_FAIL(-4, "wshmpc_lp_batch: tableau of %zu bytes does not fit shared memory", smem);
+    if (smem > 48 * 1024) WS_CUDA(cudaFuncSetAttribute(lp_std_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lp_std_kernel<<<n_lp, LP_NT, smem, (cudaStream_t)stream>>>(n_lp, m, n, d_E, stride_E, d_c, stride_c, d_r, tol, max_iter,
+                                                              d_status, d_obj, d_y, d_dual, d_iters);
     WS_CUDA(cudaGetLastError());
     return 0;
 }
