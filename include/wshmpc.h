@@ -76,6 +76,14 @@ int wshmpc_get_layout(const wshmpc_handle *h, wshmpc_layout *out);
  * 0 best_first (:541-563, default), 1 depth_first (:521-538), 2 breadth_first (:501-518).  Sticky per handle. */
 int wshmpc_set_search_rule(wshmpc_handle *h, int rule);
 
+/* branching order of the device-side branch and bound, the `branch_rule` argument of feedforward (controller.py:329,
+ * 395-429) restricted to rules that pick the next binary from a FIXED priority order: `order` (host, nb ints) is a
+ * permutation of the binaries j = t*nub+i; a node is branched on the first binary of the order its identifier does not
+ * assign, children [value 0, value 1].  NULL = chronological order = branch_in_time (controller.py:13-44, default).
+ * Identifiers are (assigned mask, values) pairs, so any order -- and any warm start a host-side rule produced -- is
+ * representable; only the leading run of assigned binaries is eliminated from the node's QP.  Sticky per handle. */
+int wshmpc_set_branch_order(wshmpc_handle *h, const int *order);
+
 /* K1 -- batched node QP relaxation.
  * Replaces, per node: controller._solve_subproblem (controller.py:229-271) = _set_bound_binaries
  * (:273-298) + BoundedQP.optimize (bounded_qp.py:200-228) + SubproblemSolution.from_controller
@@ -123,11 +131,13 @@ typedef struct {
     int cap_nodes, cap_recs, words;   /* words = ceil(T*nub / 32) uint32 per identifier */
     int *n_nodes;                     /* [n_inst] */
     int *n_recs;                      /* [n_inst] */
-    int *depth;                       /* [n_inst][cap_nodes]  number of pinned binaries */
+    int *depth;                       /* [n_inst][cap_nodes]  number of pinned binaries (= popcount of the node's mask) */
     int *alive;                       /* [n_inst][cap_nodes]  1 = leaf, 0 = branched (removed from `leaves`) */
     int *rec;                         /* [n_inst][cap_nodes]  dual record of the node, < 0 = None (-2 - r: None, but record r
                                          holds the shifted ray of a leaf whose proof lapsed: used to start its QP) */
-    unsigned int *bits;               /* [n_inst][cap_nodes][words]  bit j = value of binary j = t*nub+i, j < depth */
+    unsigned int *bits;               /* [n_inst][cap_nodes][words]  bit j = value of binary j = t*nub+i if it is assigned */
+    unsigned int *mask;               /* [n_inst][cap_nodes][words]  bit j = 1 iff binary j is assigned by the node's identifier (the low `depth` bits
+                                         for branch_in_time trees; any set for other branching orders / user-built warm starts) */
     double *lb;                       /* [n_inst][cap_nodes]  Node.lb */
     double *rec_dobj;                 /* [n_inst][cap_recs]   DualSolution.objective */
     double *rec_dual;                 /* [n_inst][cap_recs][layout.rec_stride]  DualSolution.variables | proximal centre */

@@ -59,10 +59,8 @@ def test_device_bnb_equals_host_bnb(cp20, rule):
     assert float(res['cost'][0]) == sol_h.objective                       # bit-identical
     # explored sequence
     tr = res['trace'][0].cpu().numpy().reshape(-1, 2)[:n_d]
-    depth = tree.depth[0].cpu().numpy(); bits = tree.bits[0].cpu().numpy().view(np.uint32)
-    nub = ctl.mld.nub
-    dev_order = [tuple(sorted({(q // nub, q % nub): float((bits[j, q >> 5] >> (q & 31)) & 1) for q in range(depth[j])}.items()))
-                 for j in tr[:, 0]]
+    bits = tree.bits[0].cpu().numpy().view(np.uint32); mask = tree.mask[0].cpu().numpy().view(np.uint32)
+    dev_order = [tuple(sorted(ctl._identifier(bits[j], mask[j]).items())) for j in tr[:, 0]]
     assert dev_order == order
     # leaves: same identifiers in the same order, same bounds
     leaves_d = ctl.tree_to_leaves(tree, 0)
@@ -116,6 +114,12 @@ def _upload_golden_tree(ctl, g):
     tree.depth[0, :n0] = torch.as_tensor(g['depth'], device=dev); tree.alive[0, :n0] = 1
     tree.rec[0, :n0] = torch.as_tensor(g['rec'], device=dev); tree.lb[0, :n0] = torch.as_tensor(g['lb'], device=dev)
     tree.bits[0, :n0] = torch.as_tensor(g['bits'].view(np.int32), device=dev)
+    # branch_in_time identifiers: the assigned binaries are the first `depth` ones
+    mask = np.zeros_like(g['bits'])
+    for j, d in enumerate(g['depth']):
+        for q in range(int(d)):
+            mask[j, q >> 5] |= np.uint32(1 << (q & 31))
+    tree.mask[0, :n0] = torch.as_tensor(mask.view(np.int32), device=dev)
     tree.rec_dual[0, :len(g['dobj'])] = 0.
     tree.rec_dual[0, :len(g['dobj']), :g['recs'].shape[1]] = torch.as_tensor(g['recs'], device=dev)
     tree.rec_dobj[0, :len(g['dobj'])] = torch.as_tensor(g['dobj'], device=dev)
@@ -143,6 +147,8 @@ def test_shift_tree_matches_reference_golden(cp20, tag):
     assert n == len(g['ws_%s_lb' % tag])                                 # cover size (77)
     assert np.array_equal(new.depth[0, :n].cpu().numpy(), g['ws_%s_depth' % tag])
     assert np.array_equal(new.bits[0, :n].cpu().numpy().view(np.uint32), g['ws_%s_bits' % tag])
+    pop = np.array([sum(bin(int(v)).count('1') for v in row) for row in new.mask[0, :n].cpu().numpy().view(np.uint32)])
+    assert np.array_equal(pop, g['ws_%s_depth' % tag])                 # branch_in_time trees: mask = the first `depth` binaries
     lb = new.lb[0, :n].cpu().numpy(); ref = g['ws_%s_lb' % tag]
     assert np.array_equal(np.isinf(lb), np.isinf(ref))
     fin = np.isfinite(ref)

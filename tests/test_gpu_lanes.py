@@ -135,3 +135,47 @@ def test_closed_loop_against_the_nonlinear_plant(cp20):
     assert solves[1:].mean() * 3 < solves[0].mean()                            # warm start pays off against the true plant too
     # linear model vs plant: a one-step error of 1e-3 in free flight, up to ~0.3 (velocity) on the steps the stiff wall acts
     assert errs[0] < 0.01 and max(errs) < 1.
+
+
+@pytest.mark.parametrize('order_name', ['branch_in_reverse_time', 'branch_by_index'])
+def test_static_branch_orders_on_the_device_equal_the_host_loop(cp20, order_name):
+    """a user branch_rule of the static-order family runs in the device-side search (identifiers are
+    (assigned mask, values) pairs, wshmpc_set_branch_order): same explored nodes, leaves, bounds and optimum as the
+    reference's host loop driven by the same rule through the QP seam; the non-prefix leaves are time-shifted by K2+K4
+    like the host formulation does, and the warm-started next step finds the optimum the default rule finds."""
+    import warm_start_hmpc_b200 as ws
+    model, ctl = cp20
+    rule = getattr(ws, order_name)(ctl.T, ctl.mld.nub)
+    x0 = model['x0_nominal'] * 0.5                       # a state whose tree stays small under any branching order
+    ctl.device_search = False
+    try:
+        sol_h, leaves_h, n_h, _ = ctl.feedforward(x0, branch_rule=rule, printing_period=None)
+        ws_h, _, _ = ctl.construct_warm_start(leaves_h, x0, sol_h.variables['uc'][0], sol_h.variables['ub'][0], np.zeros(4))
+    finally:
+        ctl.device_search = True
+    sol_d, leaves_d, n_d, _ = ctl.feedforward(x0, branch_rule=rule, printing_period=None)
+    sol_0, _, n_0, _ = ctl.feedforward(x0, printing_period=None)                      # branch_in_time
+    assert n_d == n_h and sol_d.objective == sol_h.objective
+    assert abs(sol_d.objective - sol_0.objective) <= 1e-9 * sol_0.objective
+    key = lambda ls: [sorted(l.identifier.items()) for l in ls]
+    assert key(leaves_d) == key(leaves_h)
+    assert np.array_equal(np.array([l.lb for l in leaves_d]), np.array([l.lb for l in leaves_h]))
+    assert any(not all((q // ctl.mld.nub, q % ctl.mld.nub) in l.identifier for q in range(len(l.identifier))) for l in leaves_d)   # non-prefix identifiers
+    # warm start of the non-prefix leaves: K2+K4 against the host formulation
+    e0 = 0.003 * np.random.default_rng(0).standard_normal(4) * model['x_max']
+    ws_d, _, _ = ctl.construct_warm_start(leaves_d, x0, sol_d.variables['uc'][0], sol_d.variables['ub'][0], e0)
+    ctl.device_search = False
+    try:
+        ws_h, _, _ = ctl.construct_warm_start(leaves_h, x0, sol_h.variables['uc'][0], sol_h.variables['ub'][0], e0)
+    finally:
+        ctl.device_search = True
+    assert key(ws_d) == key(ws_h)
+    a, b = np.array([l.lb for l in ws_d]), np.array([l.lb for l in ws_h])
+    assert np.array_equal(np.isinf(a), np.isinf(b)) and np.all(np.abs(a[np.isfinite(a)] - b[np.isfinite(b)]) <= 1e-11)
+    assert [l.extra.dual is None for l in ws_d] == [l.extra.dual is None for l in ws_h]
+    # next step, warm-started with the same rule on the device, against a cold default-rule solve
+    x1 = sol_d.variables['x'][1] + e0
+    sol_w, _, n_w, _ = ctl.feedforward(x1, branch_rule=rule, warm_start=ws_d, printing_period=None)
+    sol_c, _, n_c, _ = ctl.feedforward(x1, printing_period=None)
+    assert abs(sol_w.objective - sol_c.objective) <= 1e-9 * sol_c.objective
+    assert np.array_equal(np.array(sol_w.variables['ub']), np.array(sol_c.variables['ub']))

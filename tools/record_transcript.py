@@ -62,8 +62,8 @@ def main():
         assert int(res['status'][0]) == 0
         n_d = int(res['n_solves'][0])
         tr = res['trace'][0].cpu().numpy().reshape(-1, 2)[:n_d]
-        depth = tree.depth[0].cpu().numpy(); bits = tree.bits[0].cpu().numpy().view(np.uint32)
-        order = [{(q // nub, q % nub): float((bits[j, q >> 5] >> (q & 31)) & 1) for q in range(depth[j])} for j in tr[:, 0]]
+        bits = tree.bits[0].cpu().numpy().view(np.uint32); mask = tree.mask[0].cpu().numpy().view(np.uint32)
+        order = [ctl._identifier(bits[j], mask[j]) for j in tr[:, 0]]
         dev_leaves = ctl.tree_to_leaves(tree, 0)
         assert n_d == n_qp == len(calls) - c0, (n_d, n_qp, len(calls) - c0)
         assert float(res['cost'][0]) == sol.objective

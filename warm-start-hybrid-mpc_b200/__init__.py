@@ -10,5 +10,6 @@ csrc/); there is no CPU fallback: importing is fine anywhere, solving needs the 
 from .mld_system import MLDSystem                                               # noqa: F401
 from .subproblem_solution import SubproblemSolution, PrimalSolution, DualSolution  # noqa: F401
 from .branch_and_bound import Node, branch_and_bound, best_first, depth_first, breadth_first  # noqa: F401
-from .controller import HybridModelPredictiveController, branch_in_time          # noqa: F401
+from .controller import (HybridModelPredictiveController, branch_in_time, StaticBranchOrder,   # noqa: F401
+                         branch_in_reverse_time, branch_by_index)
 from .bounded_qp import BoundedQP                                                # noqa: F401

@@ -42,7 +42,7 @@ def load_library():
     return _lib
 
 
-EXPORTS = ('wshmpc_last_error', 'wshmpc_ctas_per_sm', 'wshmpc_set_search_rule', 'wshmpc_create', 'wshmpc_destroy', 'wshmpc_get_layout', 'wshmpc_solve_nodes',
+EXPORTS = ('wshmpc_last_error', 'wshmpc_ctas_per_sm', 'wshmpc_set_search_rule', 'wshmpc_set_branch_order', 'wshmpc_create', 'wshmpc_destroy', 'wshmpc_get_layout', 'wshmpc_solve_nodes',
            'wshmpc_tree_init_root', 'wshmpc_bnb_solve', 'wshmpc_shift_tree', 'wshmpc_closed_loop', 'wshmpc_lp_batch')
 
 
@@ -54,7 +54,7 @@ class _Loop(C.Structure):
 
 class _Tree(C.Structure):
     _fields_ = ([(k, C.c_int) for k in ('cap_nodes', 'cap_recs', 'words')]
-                + [(k, C.c_void_p) for k in ('n_nodes', 'n_recs', 'depth', 'alive', 'rec', 'bits', 'lb', 'rec_dobj',
+                + [(k, C.c_void_p) for k in ('n_nodes', 'n_recs', 'depth', 'alive', 'rec', 'bits', 'mask', 'lb', 'rec_dobj',
                                              'rec_dual')])
 
 
@@ -74,19 +74,20 @@ class Tree(object):
         self.depth = torch.zeros((n_inst, cap_nodes), **i32)
         self.alive = torch.zeros((n_inst, cap_nodes), **i32)
         self.rec = torch.zeros((n_inst, cap_nodes), **i32)
-        self.bits = torch.zeros((n_inst, cap_nodes, self.words), **i32)     # uint32 payload
+        self.bits = torch.zeros((n_inst, cap_nodes, self.words), **i32)     # uint32 payload: values of the assigned binaries
+        self.mask = torch.zeros((n_inst, cap_nodes, self.words), **i32)     # uint32 payload: which binaries are assigned
         self.lb = torch.zeros((n_inst, cap_nodes), **f64)
         self.rec_dobj = torch.zeros((n_inst, cap_recs), **f64)
         self.rec_dual = torch.empty((n_inst, cap_recs, n_dual), **f64)
         c = _Tree()
         c.cap_nodes, c.cap_recs, c.words = cap_nodes, cap_recs, self.words
-        for k in ('n_nodes', 'n_recs', 'depth', 'alive', 'rec', 'bits', 'lb', 'rec_dobj', 'rec_dual'):
+        for k in ('n_nodes', 'n_recs', 'depth', 'alive', 'rec', 'bits', 'mask', 'lb', 'rec_dobj', 'rec_dual'):
             setattr(c, k, getattr(self, k).data_ptr())
         self.c = c
 
     def nbytes(self):
         return sum(getattr(self, k).numel() * getattr(self, k).element_size()
-                   for k in ('n_nodes', 'n_recs', 'depth', 'alive', 'rec', 'bits', 'lb', 'rec_dobj', 'rec_dual'))
+                   for k in ('n_nodes', 'n_recs', 'depth', 'alive', 'rec', 'bits', 'mask', 'lb', 'rec_dobj', 'rec_dual'))
 
 
 def _check(rc):
@@ -125,6 +126,15 @@ class Handle(object):
     def set_search_rule(self, rule):
         """0 best_first, 1 depth_first, 2 breadth_first (branch_and_bound.py:501-563) for the device-side B&B."""
         _check(self.lib.wshmpc_set_search_rule(self._h, int(rule)))
+
+    def set_branch_order(self, order):
+        """Static branching order of the device-side B&B: permutation of the binaries j = t * nub + i, or None for the
+        chronological order of branch_in_time (wshmpc_set_branch_order)."""
+        if order is None:
+            _check(self.lib.wshmpc_set_branch_order(self._h, None))
+        else:
+            a = np.ascontiguousarray(order, dtype=np.int32)
+            _check(self.lib.wshmpc_set_branch_order(self._h, a.ctypes.data_as(C.c_void_p)))
 
     def close(self):
         if self._h:

@@ -36,6 +36,39 @@ def branch_in_time(identifier, nub):
     return [{(t + 1, 0): 0.}, {(t + 1, 0): 1.}]
 
 
+class StaticBranchOrder(object):
+    """A `branch_rule` (controller.py:329, 395-429: callable (identifier, nub) -> list of branch dicts) that picks the next
+    binary from a FIXED priority order: the first (t, i) of `order` the identifier does not assign, children
+    [value 0, value 1].  `branch_in_time` is the chronological order.  Rules of this family run in the device-side
+    search (wshmpc_set_branch_order); any other callable runs the host loop."""
+
+    def __init__(self, order):
+        self.order = [tuple(k) for k in order]
+        if len(set(self.order)) != len(self.order):
+            raise ValueError('a branching order lists every binary once')
+
+    def __call__(self, identifier, nub):
+        for k in self.order:
+            if k not in identifier:
+                return [{k: 0.}, {k: 1.}]
+        raise ValueError('every binary of the order is assigned')
+
+    def permutation(self, T, nub):
+        if sorted(self.order) != [(t, i) for t in range(T) for i in range(nub)]:
+            raise ValueError('the branching order must list every binary (t, i), t < T, i < nub, once')
+        return np.array([t * nub + i for t, i in self.order], dtype=np.int32)
+
+
+def branch_in_reverse_time(T, nub):
+    """binaries of the LAST time step first"""
+    return StaticBranchOrder([(t, i) for t in range(T - 1, -1, -1) for i in range(nub)])
+
+
+def branch_by_index(T, nub):
+    """all time steps of binary 0, then all of binary 1, ..."""
+    return StaticBranchOrder([(t, i) for i in range(nub) for t in range(T)])
+
+
 class HybridModelPredictiveController(object):
 
     def __init__(self, mld, T, objective, terminal_set, device=0, qp_options=None):
@@ -191,10 +224,10 @@ class HybridModelPredictiveController(object):
         self._set_gurobi_params(gurobi_params)
         self.qp.reset()
         rules = {best_first: 0, depth_first: 1, breadth_first: 2}
-        if self.device_search and self.qp.Params.Method == 1 and search_rule in rules and branch_rule is branch_in_time:
-            ws = kwargs.get('warm_start')
-            if ws is None or all(_is_prefix(l.identifier, self.mld.nub) for l in ws):
-                return self._feedforward_device(x0, kwargs.get('tol', 0.), ws, rules[search_rule])
+        static = branch_rule is branch_in_time or isinstance(branch_rule, StaticBranchOrder)
+        if self.device_search and self.qp.Params.Method == 1 and search_rule in rules and static:
+            order = None if branch_rule is branch_in_time else branch_rule.permutation(self.T, self.mld.nub)
+            return self._feedforward_device(x0, kwargs.get('tol', 0.), kwargs.get('warm_start'), rules[search_rule], order)
 
         def solver(identifier, cutoff, extra):
             start = extra.active_set if extra is not None else None
@@ -223,11 +256,11 @@ class HybridModelPredictiveController(object):
         of the next step's.  Returns (nodes, runtime seconds, inter-step seconds) like the reference; the device kernel
         does both parts at once, so all its time is reported as run time.
 
-        Leaves with chronological-prefix identifiers (everything branch_in_time produces) are shifted by kernel K2+K4
-        (wshmpc_shift_tree): uploaded as a one-instance device tree, shifted, read back.  Other identifiers (user
-        branch rules) take the batched host formulation `_shift_records_host`."""
+        The leaves (any identifiers: device trees hold (assigned mask, values) pairs) are shifted by kernel K2+K4
+        (wshmpc_shift_tree): uploaded as a one-instance device tree, shifted, read back.  With `device_search = False`
+        the batched host formulation `_shift_records_host` runs instead."""
         leaves = list(leaves)
-        if self.device_search and all(_is_prefix(l.identifier, self.mld.nub) for l in leaves):
+        if self.device_search:
             return self._construct_warm_start_device(leaves, x0, uc0, ub0, e0)
         tic = time()
         nodes = self._shift_records_host(leaves, np.asarray(x0, float), np.concatenate((uc0, ub0)), np.asarray(e0, float))
@@ -375,6 +408,7 @@ class HybridModelPredictiveController(object):
         depth = tree.depth[inst, :nn].cpu().numpy(); alive = tree.alive[inst, :nn].cpu().numpy()
         rec = tree.rec[inst, :nn].cpu().numpy(); lb = tree.lb[inst, :nn].cpu().numpy()
         bits = tree.bits[inst, :nn].cpu().numpy().view(np.uint32)
+        mask = tree.mask[inst, :nn].cpu().numpy().view(np.uint32)
         nr = int(tree.n_recs[inst])
         duals = tree.rec_dual[inst, :nr].cpu().numpy(); dobj = tree.rec_dobj[inst, :nr].cpu().numpy()
         cache = {}
@@ -388,7 +422,7 @@ class HybridModelPredictiveController(object):
         for j in range(nn):
             if not alive[j]:
                 continue
-            ident = {(q // nub, q % nub): float((bits[j, q >> 5] >> (q & 31)) & 1) for q in range(depth[j])}
+            ident = self._identifier(bits[j], mask[j])
             r = int(rec[j])
             if r >= 0:
                 extra = SubproblemSolution(None, record(r)[0], record(r)[1])
@@ -401,6 +435,15 @@ class HybridModelPredictiveController(object):
             leaves.append(node)
         return leaves
 
+    def _identifier(self, bits_j, mask_j):
+        """(assigned mask, values) words of a device node -> the reference's identifier dict {(t, i): 0. | 1.}"""
+        nub = self.mld.nub
+        out = {}
+        for q in range(self.problem.nb):
+            if (int(mask_j[q >> 5]) >> (q & 31)) & 1:
+                out[(q // nub, q % nub)] = float((int(bits_j[q >> 5]) >> (q & 31)) & 1)
+        return out
+
     def leaves_to_tree(self, leaves, max_solves=None):
         """Uploads a reference-style warm start (list of Node with prefix identifiers) as a device tree."""
         import torch
@@ -410,14 +453,15 @@ class HybridModelPredictiveController(object):
         tree = self.new_tree(1, n0, ms)
         nub = self.mld.nub
         depth = np.zeros(n0, np.int32); rec = np.full(n0, -1, np.int32); lb = np.zeros(n0)
-        bits = np.zeros((n0, tree.words), np.uint32)
+        bits = np.zeros((n0, tree.words), np.uint32); mask = np.zeros((n0, tree.words), np.uint32)
         recs, dobj, seen = [], [], {}
         L, n = h.layout, self.problem.n
         for j, l in enumerate(leaves):
             depth[j] = len(l.identifier)
             for (t, i), v in l.identifier.items():
+                q = t * nub + i
+                mask[j, q >> 5] |= np.uint32(1 << (q & 31))
                 if v:
-                    q = t * nub + i
                     bits[j, q >> 5] |= np.uint32(1 << (q & 31))
             lb[j] = l.lb
             dual = None if l.extra is None else l.extra.dual
@@ -446,22 +490,25 @@ class HybridModelPredictiveController(object):
         tree.depth[0, :n0] = torch.as_tensor(depth, device=dev); tree.alive[0, :n0] = 1
         tree.rec[0, :n0] = torch.as_tensor(rec, device=dev); tree.lb[0, :n0] = torch.as_tensor(lb, device=dev)
         tree.bits[0, :n0] = torch.as_tensor(bits.view(np.int32), device=dev)
+        tree.mask[0, :n0] = torch.as_tensor(mask.view(np.int32), device=dev)
         if recs:
             tree.rec_dual[0, :len(recs)] = torch.as_tensor(np.vstack(recs), device=dev)
             tree.rec_dobj[0, :len(recs)] = torch.as_tensor(np.array(dobj), device=dev)
         return tree
 
-    def _feedforward_device(self, x0, tol, warm_start, rule=0):
+    def _feedforward_device(self, x0, tol, warm_start, rule=0, order=None):
         import torch
         self._require_gpu()
         tree = None if warm_start is None else self.leaves_to_tree(warm_start)
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         start.record()
         self.handle().set_search_rule(rule)
+        self.handle().set_branch_order(order)
         try:
             res, tree = self.feedforward_batch(np.asarray(x0, dtype=float)[None], warm_start=tree, tol=tol, n_slots=1)
         finally:
             self.handle().set_search_rule(0)
+            self.handle().set_branch_order(None)
         end.record()
         end.synchronize()
         solver_time = start.elapsed_time(end) * 1e-3

@@ -11,7 +11,8 @@
 struct TreeView {
     int cap_nodes, cap_recs, words;
     int *n_nodes, *n_recs, *depth, *alive, *rec;
-    unsigned int *bits;
+    unsigned int *bits;      // values of the assigned binaries
+    unsigned int *mask;      // which binaries are assigned (a chronological prefix for branch_in_time trees; any set otherwise)
     double *lb, *rec_dobj, *rec_dual;
 };
 
@@ -30,7 +31,7 @@ __global__ void init_root_kernel(int n_inst, TreeView tr)
     const size_t o = (size_t)k * tr.cap_nodes;
     tr.n_nodes[k] = 1; tr.n_recs[k] = 0;
     tr.depth[o] = 0; tr.alive[o] = 1; tr.rec[o] = -1; tr.lb[o] = -INFINITY;
-    for (int w = 0; w < tr.words; ++w) tr.bits[o * tr.words + w] = 0u;
+    for (int w = 0; w < tr.words; ++w) { tr.bits[o * tr.words + w] = 0u; tr.mask[o * tr.words + w] = 0u; }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -46,7 +47,7 @@ __device__ __forceinline__ int bnb_instance(const DevProblem &P, const Ctx &cx, 
     double *lbv = sc, *ubv = sc + nb, *prim = sc + 2 * nb, *cost_s = prim + P.n_primal, *dobj_s = cost_s + 1;
     const size_t no = (size_t)inst * tr.cap_nodes;
     int *depth = tr.depth + no, *alive = tr.alive + no, *rec = tr.rec + no;
-    unsigned int *bits = tr.bits + no * tr.words;
+    unsigned int *bits = tr.bits + no * tr.words, *mask = tr.mask + no * tr.words;
     double *lb = tr.lb + no;
     double *rdobj = tr.rec_dobj + (size_t)inst * tr.cap_recs;
     double *rdual = tr.rec_dual + (size_t)inst * tr.cap_recs * P.n_rec;
@@ -76,15 +77,31 @@ __device__ __forceinline__ int bnb_instance(const DevProblem &P, const Ctx &cx, 
         block_argmin(best, bi, SMV(red), SMI(ired));
         if (bi < 0) { st = inc >= 0 ? BNB_OK : BNB_INFEASIBLE; break; }
         if (solves >= max_solves || nn + 2 > tr.cap_nodes || nr + 1 > tr.cap_recs) { st = BNB_CAPACITY; break; }
-        // ---- bounds of the node (controller.py:273-298)
+        // ---- bounds of the node (controller.py:273-298); the binary it would be branched on: the first unassigned one in the
+        //      branching order (chronological = branch_in_time, controller.py:13-44, or the handle's static order); the
+        //      eliminated prefix = the leading run of assigned binaries
         const int d = depth[bi];
-        const unsigned int *bw = bits + (size_t)bi * tr.words;
+        const unsigned int *bw = bits + (size_t)bi * tr.words, *mw = mask + (size_t)bi * tr.words;
+        double first_free = (double)nb, first_in_order = (double)nb; int ff = -1, fo = -1;
         for (int j = WS_TID; j < nb; j += WS_NT) {
+            const bool as = (mw[j >> 5] >> (j & 31)) & 1u;
             const double v = (double)((bw[j >> 5] >> (j & 31)) & 1u);
-            lbv[j] = j < d ? v : 0.;
-            ubv[j] = j < d ? v : 1.;
+            lbv[j] = as ? v : 0.;
+            ubv[j] = as ? v : 1.;
+            if (!as && ff < 0) { ff = j; first_free = (double)j; }
         }
-        set_node_prefix_known(P, cx, d);
+        block_argmin(first_free, ff, SMV(red), SMI(ired));
+        const int d_elim = ff < 0 ? nb : ff;
+        int jb = d_elim;
+        if (P.border) {
+            for (int p = WS_TID; p < nb; p += WS_NT) {
+                const int j = P.border[p];
+                if (!((mw[j >> 5] >> (j & 31)) & 1u) && fo < 0) { fo = p; first_in_order = (double)p; }
+            }
+            block_argmin(first_in_order, fo, SMV(red), SMI(ired));
+            jb = fo < 0 ? nb : P.border[fo];
+        }
+        set_node_prefix_known(P, cx, d_elim);
         WS_SYNC();
         prof_mark(0);
         // ---- solve (K1), started from the node's OWN dual record: the multipliers (and proximal centre) of its
@@ -98,7 +115,7 @@ __device__ __forceinline__ int bnb_instance(const DevProblem &P, const Ctx &cx, 
             const int r00 = rec[bi];
             const int r0 = r00 <= -2 ? -2 - r00 : r00;
             // children of this search share their parent's record: the second sibling takes the factor the first one built
-            memo = (r0 >= 0 && bi >= nn0) ? ((r0 == memo_rec && min(d, P.n_elim) == memo_d) ? 2 : 1) : 0;
+            memo = (r0 >= 0 && bi >= nn0) ? ((r0 == memo_rec && min(d_elim, P.n_elim) == memo_d) ? 2 : 1) : 0;
             memo_r0 = r0;
             if (memo == 2) {
                 const double *D = rdual + (size_t)r0 * P.n_rec;
@@ -116,7 +133,7 @@ __device__ __forceinline__ int bnb_instance(const DevProblem &P, const Ctx &cx, 
         prof_mark(1);
         int memo_saved = 0;
         const int qs = qp_solve(P, cx, k, xi, lbv, ubv, y, iters_s, iters_s + 1, memo, sp, memo_saved);
-        if (memo == 1) { memo_rec = memo_saved ? memo_r0 : -1; memo_d = min(d, P.n_elim); }
+        if (memo == 1) { memo_rec = memo_saved ? memo_r0 : -1; memo_d = min(d_elim, P.n_elim); }
         if (qs == WS_ITER_LIMIT) { st = BNB_QP_LIMIT; break; }
         double *dual = rdual + (size_t)nr * P.n_rec;
         build_records(P, qs, SMV(yc), y, xi, lbv, ubv, prim, dual, cost_s, dobj_s, SMV(part), SMV(red));
@@ -133,7 +150,7 @@ __device__ __forceinline__ int bnb_instance(const DevProblem &P, const Ctx &cx, 
 #endif
         }
         const int myrec = nr;
-        iters += *iters_s; ksum += k; kmx = max(kmx, iters_s[1]); dsum += min(d, P.n_elim); k0sum += iters_s[2] & 0xffff;
+        iters += *iters_s; ksum += k; kmx = max(kmx, iters_s[1]); dsum += min(d_elim, P.n_elim); k0sum += iters_s[2] & 0xffff;
         ++nr; ++solves;
         // ---- prune / incumbent / branch (branch_and_bound.py:476-489)
         if (cost >= cutoff) {
@@ -143,13 +160,15 @@ __device__ __forceinline__ int bnb_instance(const DevProblem &P, const Ctx &cx, 
             double *ip = inc_primal + (size_t)inst * P.n_primal;
             for (int j = WS_TID; j < P.n_primal; j += WS_NT) ip[j] = prim[j];
         } else {
-            // children [value 0, value 1] of binary d = (t, i); bound += multiplier of the bound that moves
-            const double l0 = cost + dual[P.off_nuub + d], l1 = cost + dual[P.off_nulb + d];
+            // children [value 0, value 1] of binary jb = (t, i); bound += multiplier of the bound that moves
+            const double l0 = cost + dual[P.off_nuub + jb], l1 = cost + dual[P.off_nulb + jb];
             unsigned int *c0 = bits + (size_t)nn * tr.words, *c1 = c0 + tr.words;
+            unsigned int *m0 = mask + (size_t)nn * tr.words, *m1 = m0 + tr.words;
             for (int w = WS_TID; w < tr.words; w += WS_NT) {
-                const unsigned int b = bw[w];
-                c0[w] = b & ~((w == (d >> 5)) ? (1u << (d & 31)) : 0u);
-                c1[w] = b | ((w == (d >> 5)) ? (1u << (d & 31)) : 0u);
+                const unsigned int b = bw[w], bit = (w == (jb >> 5)) ? (1u << (jb & 31)) : 0u;
+                c0[w] = b & ~bit;
+                c1[w] = b | bit;
+                m0[w] = m1[w] = mw[w] | bit;
             }
             if (WS_TID == 0) {
                 alive[bi] = 0;
@@ -314,11 +333,9 @@ __device__ __forceinline__ int shift_instance(const DevProblem &P, double *shm, 
         int keep = 0;
         if (j < nn && ot.alive[oo + j]) {
             keep = 1;
-            const int d = ot.depth[oo + j];
-            const unsigned int b0 = ot.bits[(oo + j) * ot.words];
-            const int lim = d < nub ? d : nub;
-            for (int i = 0; i < lim; ++i)
-                if ((double)((b0 >> i) & 1u) != us[nuc + i]) keep = 0;
+            const unsigned int b0 = ot.bits[(oo + j) * ot.words], m0 = ot.mask[(oo + j) * ot.words];
+            for (int i = 0; i < nub; ++i)
+                if (((m0 >> i) & 1u) && (double)((b0 >> i) & 1u) != us[nuc + i]) keep = 0;
         }
         const unsigned int bal = __ballot_sync(0xffffffffu, keep);
         if (lane == 0) s_wsum[w] = __popc(bal);
@@ -327,20 +344,21 @@ __device__ __forceinline__ int shift_instance(const DevProblem &P, double *shm, 
         for (int q = 0; q < w; ++q) pre += s_wsum[q];
         const int idx = pre + __popc(bal & ((1u << lane) - 1u));
         if (keep && idx < cap_new) {
-            const int d = ot.depth[oo + j];
-            const int dn = d > nub ? d - nub : 0;
+            const unsigned int first = ot.mask[(oo + j) * ot.words] & (nub >= 32 ? 0xffffffffu : ((1u << nub) - 1u));
+            const int dn = ot.depth[oo + j] - __popc(first);                       // assigned binaries that survive the shift
             nt.depth[on_ + idx] = dn; nt.alive[on_ + idx] = 1; nt.rec[on_ + idx] = j;   // rec = source node (pass 2 rewrites it)
-            const unsigned int *src = ot.bits + (oo + j) * ot.words;
-            unsigned int *dst = nt.bits + (on_ + idx) * nt.words;
+            const unsigned int *srcb = ot.bits + (oo + j) * ot.words, *srcm = ot.mask + (oo + j) * ot.words;
+            unsigned int *dstb = nt.bits + (on_ + idx) * nt.words, *dstm = nt.mask + (on_ + idx) * nt.words;
             for (int q = 0; q < nt.words; ++q) {
-                // shift the bit string right by nub bits
+                // shift both bit strings right by nub bits (identifier shift, controller.py:476)
                 const int sb = q * 32 + nub;
                 const int wq = sb >> 5, sh = sb & 31;
-                unsigned int lo = wq < ot.words ? src[wq] : 0u, hi = wq + 1 < ot.words ? src[wq + 1] : 0u;
-                unsigned int v = sh ? ((lo >> sh) | (hi << (32 - sh))) : lo;
-                const int valid = dn - q * 32;      // keep only bits < dn
-                if (valid <= 0) v = 0u; else if (valid < 32) v &= (1u << valid) - 1u;
-                dst[q] = v;
+                const unsigned int lob = wq < ot.words ? srcb[wq] : 0u, hib = wq + 1 < ot.words ? srcb[wq + 1] : 0u;
+                const unsigned int lom = wq < ot.words ? srcm[wq] : 0u, him = wq + 1 < ot.words ? srcm[wq + 1] : 0u;
+                const unsigned int vm = sh ? ((lom >> sh) | (him << (32 - sh))) : lom;
+                const unsigned int vb = sh ? ((lob >> sh) | (hib << (32 - sh))) : lob;
+                dstm[q] = vm;
+                dstb[q] = vb & vm;
             }
         }
         sync();
@@ -376,8 +394,7 @@ __device__ __forceinline__ int shift_instance(const DevProblem &P, double *shm, 
             }
         }
         for (int e = P.n_dual + lane; e < P.n_rec; e += 32) E[e] = 0.;          // a shifted root starts from the centre 0
-        const int d_old = ot.depth[oo + j];
-        const unsigned int b0 = ot.bits[(oo + j) * ot.words];
+        const unsigned int b0 = ot.bits[(oo + j) * ot.words], m0 = ot.mask[(oo + j) * ot.words];
         double acc = 0.;                     // pi_sum + pi3, lane-partial
         // lam: drop t = 0, append zero ; pi3 = -lam'_0 . e0 (controller.py:544)
         {
@@ -393,7 +410,8 @@ __device__ __forceinline__ int shift_instance(const DevProblem &P, double *shm, 
             for (int e = lane; e < nub; e += 32) {
                 tl[(T - 1) * nub + e] = 0.; tu[(T - 1) * nub + e] = 0.;
                 const double bit = (double)((b0 >> e) & 1u);
-                const double l0 = e < d_old ? bit : 0., u0b = e < d_old ? bit : 1.;
+                const bool as = (m0 >> e) & 1u;
+                const double l0 = as ? bit : 0., u0b = as ? bit : 1.;
                 const double vu = us[nuc + e];
                 acc -= (l0 - vu) * sl[e] + (vu - u0b) * su[e];
             }
@@ -514,7 +532,7 @@ __device__ __forceinline__ void init_root(const TreeView &tr, int k)
     const size_t o = (size_t)k * tr.cap_nodes;
     tr.n_nodes[k] = 1; tr.n_recs[k] = 0;
     tr.depth[o] = 0; tr.alive[o] = 1; tr.rec[o] = -1; tr.lb[o] = -INFINITY;
-    for (int w = 0; w < tr.words; ++w) tr.bits[o * tr.words + w] = 0u;
+    for (int w = 0; w < tr.words; ++w) { tr.bits[o * tr.words + w] = 0u; tr.mask[o * tr.words + w] = 0u; }
 }
 
 template <int LANES>

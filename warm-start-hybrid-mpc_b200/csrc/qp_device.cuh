@@ -100,6 +100,7 @@ struct DevProblem {
     const int *bin_idx;
     int n_elim;              // leading binaries that may be eliminated when pinned (0 = never)
     int search_rule;         // candidate selection of the device B&B: 0 best_first, 1 depth_first, 2 breadth_first
+    const int *border;       // branching order of the device B&B: permutation of the nb binaries, or null = chronological (branch_in_time)
     double eps, tol_p, tol_d, tol_sing, tol_ray, prox_tol;
     int max_iter, max_prox;
     int lanes;               // solver lanes per CTA of this handle (<= WS_MAXL)

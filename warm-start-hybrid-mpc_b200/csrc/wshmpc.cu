@@ -19,6 +19,7 @@ struct wshmpc_handle {
     DevProblem P;            // shared-memory layout for P.lanes solver lanes per CTA (throughput launches)
     DevProblem P1;           // the same problem laid out for ONE lane per CTA (launches that cannot fill two lanes per SM)
     int n_sm;
+    int *d_border;           // device copy of the branching order (wshmpc_set_branch_order)
     void *hot_ptr; size_t hot_bytes; int l2_window;      // L2 persistence window over WfT | Mh (l2_window = 1 if it was accepted)
     int device, n_slots;
     cudaStream_t stream;
@@ -331,6 +332,23 @@ extern "C" int wshmpc_set_search_rule(wshmpc_handle *h, int rule)
     return 0;
 }
 
+extern "C" int wshmpc_set_branch_order(wshmpc_handle *h, const int *order)
+{
+    if (!h) WS_FAIL(-1, "null handle");
+    if (!order) { h->P.border = nullptr; h->P1.border = nullptr; return 0; }
+    const int nb = h->P.nb;
+    std::vector<char> seen(nb, 0);
+    for (int p = 0; p < nb; ++p) {
+        if (order[p] < 0 || order[p] >= nb || seen[order[p]]) WS_FAIL(-1, "branch order is not a permutation of 0..%d", nb - 1);
+        seen[order[p]] = 1;
+    }
+    WS_CUDA(cudaSetDevice(h->device));
+    if (!h->d_border) { void *d = nullptr; WS_CUDA(cudaMalloc(&d, nb * sizeof(int))); h->allocs.push_back(d); h->d_border = (int *)d; }
+    WS_CUDA(cudaMemcpy(h->d_border, order, nb * sizeof(int), cudaMemcpyHostToDevice));
+    h->P.border = h->d_border; h->P1.border = h->d_border;
+    return 0;
+}
+
 extern "C" int wshmpc_get_layout(const wshmpc_handle *h, wshmpc_layout *out)
 {
     if (!h || !out) WS_FAIL(-1, "null argument");
@@ -367,11 +385,11 @@ static int tree_view(const wshmpc_handle *h, const wshmpc_tree *t, TreeView *v)
     if (!t) WS_FAIL(-1, "null tree");
     if (t->words != (h->P.nb + 31) / 32) WS_FAIL(-1, "tree.words = %d, expected %d", t->words, (h->P.nb + 31) / 32);
     if (t->cap_nodes < 3 || t->cap_recs < 1) WS_FAIL(-1, "tree capacity too small");
-    if (!t->n_nodes || !t->n_recs || !t->depth || !t->alive || !t->rec || !t->bits || !t->lb || !t->rec_dobj || !t->rec_dual)
+    if (!t->n_nodes || !t->n_recs || !t->depth || !t->alive || !t->rec || !t->bits || !t->mask || !t->lb || !t->rec_dobj || !t->rec_dual)
         WS_FAIL(-1, "null pointer in tree");
     v->cap_nodes = t->cap_nodes; v->cap_recs = t->cap_recs; v->words = t->words;
     v->n_nodes = t->n_nodes; v->n_recs = t->n_recs; v->depth = t->depth; v->alive = t->alive; v->rec = t->rec;
-    v->bits = t->bits; v->lb = t->lb; v->rec_dobj = t->rec_dobj; v->rec_dual = t->rec_dual;
+    v->bits = t->bits; v->mask = t->mask; v->lb = t->lb; v->rec_dobj = t->rec_dobj; v->rec_dual = t->rec_dual;
     return 0;
 }
 
@@ -423,6 +441,7 @@ extern "C" int wshmpc_shift_tree(wshmpc_handle *h, int n_inst, const double *d_x
     TreeView ov, nv; int rc = tree_view(h, old_tree, &ov); if (rc) return rc;
     rc = tree_view(h, new_tree, &nv); if (rc) return rc;
     if (ov.rec_dual == nv.rec_dual || ov.lb == nv.lb) WS_FAIL(-1, "old and new tree must be distinct buffers");
+    if (ov.words != nv.words) WS_FAIL(-1, "old and new tree differ in words");
     WS_CUDA(cudaSetDevice(h->device));
     shift_tree_kernel<<<n_inst, SH_NT, h->shift_smem, h->stream>>>(
         h->P, n_inst, d_x0, d_e0, ov, d_inc_cost, d_inc_primal, d_active, nv, d_x_next, d_u0);

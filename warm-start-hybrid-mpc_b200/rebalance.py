@@ -46,12 +46,13 @@ def pack(tree, x, gid, idx):
     nn = int(tree.n_nodes[idx].max()) if m else 0
     nr = int(tree.n_recs[idx].max()) if m else 0
     W = tree.words
-    ints = torch.zeros((m, 2 + nn * (3 + W)), dtype=torch.int32, device=x.device)
+    ints = torch.zeros((m, 2 + nn * (3 + 2 * W)), dtype=torch.int32, device=x.device)
     ints[:, 0] = tree.n_nodes[idx]; ints[:, 1] = tree.n_recs[idx]
     o = 2
     for name in ('depth', 'alive', 'rec'):
         ints[:, o:o + nn] = getattr(tree, name)[idx, :nn]; o += nn
-    ints[:, o:o + nn * W] = tree.bits[idx, :nn].reshape(m, nn * W)
+    ints[:, o:o + nn * W] = tree.bits[idx, :nn].reshape(m, nn * W); o += nn * W
+    ints[:, o:o + nn * W] = tree.mask[idx, :nn].reshape(m, nn * W)
     nx = x.shape[1]
     S = tree.rec_dual.shape[2]
     dbl = torch.zeros((m, 1 + nx + nn + nr * (1 + S)), dtype=torch.float64, device=x.device)
@@ -76,7 +77,8 @@ def unpack(tree, x, gid, slots, hdr, ints, dbl):
     o = 2
     for name in ('depth', 'alive', 'rec'):
         getattr(tree, name)[slots, :nn] = ints[:, o:o + nn]; o += nn
-    tree.bits[slots, :nn] = ints[:, o:o + nn * W].reshape(m, nn, W)
+    tree.bits[slots, :nn] = ints[:, o:o + nn * W].reshape(m, nn, W); o += nn * W
+    tree.mask[slots, :nn] = ints[:, o:o + nn * W].reshape(m, nn, W)
     nx = x.shape[1]
     S = tree.rec_dual.shape[2]
     gid[slots] = dbl[:, 0].to(gid.dtype)
@@ -117,7 +119,7 @@ def rebalance(tree, x, active, gid, group=None, min_gap=2):
             hdr = torch.zeros(3, dtype=torch.int64, device=dev)
             dist.recv(hdr, src, group=group)
             m, nn, nr = [int(v) for v in hdr]
-            ints = torch.zeros((m, 2 + nn * (3 + tree.words)), dtype=torch.int32, device=dev)
+            ints = torch.zeros((m, 2 + nn * (3 + 2 * tree.words)), dtype=torch.int32, device=dev)
             dbl = torch.zeros((m, 1 + x.shape[1] + nn + nr * (1 + tree.rec_dual.shape[2])), dtype=torch.float64, device=dev)
             dist.recv(ints, src, group=group); dist.recv(dbl, src, group=group)
             slots = torch.nonzero(active == 0)[:, 0][:m]
