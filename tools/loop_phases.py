@@ -16,7 +16,8 @@ NAMES = {0: 'bnb select + bounds', 1: 'load working set', 2: 'vf0', 3: 'rebuild 
 lib = load_library()
 model = load_model('cp20')
 ctl = controller_from_model(model)
-x0 = np.load('tests/golden/cp20_instances.npy'); x0 = x0[np.arange(N) % len(x0)]
+from warm_start_hmpc_b200.instances import load_initial_states
+x0 = load_initial_states(0, N)
 rng = np.random.default_rng(1)
 e = torch.as_tensor(0.003 * rng.standard_normal((6, S, N, 4)) * model['x_max'], device='cuda')
 L = ClosedLoop(ctl, N, warm=True, max_solves=1024, max_roots=512)

@@ -8,7 +8,7 @@ N = int(sys.argv[1]) if len(sys.argv) > 1 else 148
 S = int(sys.argv[2]) if len(sys.argv) > 2 else 4
 model = load_model('cp20')
 ctl = controller_from_model(model)
-x0 = np.load('tests/golden/cp20_instances.npy')[:N]
+x0 = np.load('warm-start-hybrid-mpc_b200/data/cp20_instances.npy')[:N]
 rng = np.random.default_rng(1)
 e = torch.as_tensor(0.003 * rng.standard_normal((4, S, N, 4)) * model['x_max'], device='cuda')
 L = ClosedLoop(ctl, N, warm=True, max_solves=512, max_roots=256)

@@ -9,7 +9,7 @@ S = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 W = int(sys.argv[3]) if len(sys.argv) > 3 else 6
 model = load_model('cp20')
 ctl = controller_from_model(model)
-x0 = np.load('tests/golden/cp20_instances.npy')
+x0 = np.load('warm-start-hybrid-mpc_b200/data/cp20_instances.npy')
 x0 = x0[np.arange(N) % len(x0)]
 rng = np.random.default_rng(1)
 e = torch.as_tensor(0.003 * rng.standard_normal((W, S, N, 4)) * model['x_max'], device='cuda')

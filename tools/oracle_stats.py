@@ -17,7 +17,7 @@ def solve(x0, lb, ub, warm=None):
     return out
 core.solve = solve
 ctl = OracleController(model, core, hot_start=True)
-x = np.load('tests/golden/cp20_instances.npy')[0] if name == 'cp20' else model['x0_nominal']
+x = np.load('warm-start-hybrid-mpc_b200/data/cp20_instances.npy')[0] if name == 'cp20' else model['x0_nominal']
 rng = np.random.default_rng(0)
 ws = None
 for t in range(int(sys.argv[2]) if len(sys.argv) > 2 else 6):

@@ -43,7 +43,7 @@ core.solve = solve
 ctl = Ctl(model, core, hot_start=True)
 tot = []
 for inst in range(3):
-    x = np.load('tests/golden/cp20_instances.npy')[inst]
+    x = np.load('warm-start-hybrid-mpc_b200/data/cp20_instances.npy')[inst]
     rng = np.random.default_rng(inst)
     ws = None
     for t in range(nsteps):

@@ -29,7 +29,7 @@ from warm_start_hmpc_b200.closed_loop import ClosedLoop
 model = load_model('cp20')
 ctl = controller_from_model(model)
 N, S = 512, 100
-x0 = np.load('tests/golden/cp20_instances.npy')[:N]
+x0 = np.load('warm-start-hybrid-mpc_b200/data/cp20_instances.npy')[:N]
 rng = np.random.default_rng(3)
 e = torch.as_tensor(0.003 * rng.standard_normal((S, N, 4)) * model['x_max'], device='cuda')
 L = ClosedLoop(ctl, N, warm=True, max_solves=1024, max_roots=512)

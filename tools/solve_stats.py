@@ -7,7 +7,7 @@ N = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 STEPS = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 model = load_model('cp20')
 ctl = controller_from_model(model)
-x = np.load('tests/golden/cp20_instances.npy')[:N]
+x = np.load('warm-start-hybrid-mpc_b200/data/cp20_instances.npy')[:N]
 rng = np.random.default_rng(1)
 tree = None
 rows = []
