@@ -62,7 +62,7 @@ typedef struct {
 
 const char *wshmpc_last_error(void);
 
-/* solver CTAs the library keeps resident per SM (a build constant): n_slots = SMs x this fills the GPU */
+/* solver lanes (independent solver states) resident per SM for the handle created last: n_slots = SMs x this fills the GPU */
 int wshmpc_ctas_per_sm(void);
 
 /* create / destroy.  `n_slots` = number of independent solver states (one per concurrently solved
@@ -143,7 +143,8 @@ typedef struct {
     double *rec_dual;                 /* [n_inst][cap_recs][layout.rec_stride]  DualSolution.variables | proximal centre */
 } wshmpc_tree;
 
-/* K3 -- device-side branch and bound, one CTA per instance, no host round trip per node.
+/* K3 -- device-side branch and bound, one solver lane (256 threads; up to two lanes per CTA / SM) per instance at a time, no
+ * host round trip per node.
  * Replaces branch_and_bound(solver, best_first, brancher, tol, warm_start) (branch_and_bound.py:408-499)
  * with the controller's closures (controller.py:365-380): select = best_first (first minimum wins,
  * branch_and_bound.py:541-563), solve = K1 (hot-started from the node solved before it), prune /
