@@ -24,6 +24,7 @@ struct TreeView {
 // per-slot scratch of the B&B kernel (doubles): lb | ub | primal record | cost | dobj
 __host__ __device__ __forceinline__ size_t bnb_scratch_doubles(int nb, int n_primal) { return 2 * (size_t)nb + n_primal + 4; }
 
+#if WS_TU_HAS(0)
 __global__ void init_root_kernel(int n_inst, TreeView tr)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -33,6 +34,7 @@ __global__ void init_root_kernel(int n_inst, TreeView tr)
     tr.depth[o] = 0; tr.alive[o] = 1; tr.rec[o] = -1; tr.lb[o] = -INFINITY;
     for (int w = 0; w < tr.words; ++w) { tr.bits[o * tr.words + w] = 0u; tr.mask[o * tr.words + w] = 0u; }
 }
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // K3
@@ -235,9 +237,19 @@ bnb_body(const DevProblem &P, double *slot_d, int *slot_i, double *ybuf, double 
 #define WS_BNB_PASS P, slot_d, slot_i, ybuf, scratch, work_counter, n_slots, n_inst, x0, active, tr, tol, max_solves, \
     inc_cost, inc_node, inc_primal, n_solves, status_out, trace, totals
 // one lane per CTA: 255 registers per thread (launches that cannot fill two lanes per SM: latency mode, large systems)
-__global__ void __launch_bounds__(WS_NT, 1) bnb_kernel_1(WS_BNB_ARGS) { bnb_body<1>(WS_BNB_PASS); }
+__global__ void __launch_bounds__(WS_NT, 1) bnb_kernel_1(WS_BNB_ARGS)
+#if WS_TU_HAS(3)
+{ bnb_body<1>(WS_BNB_PASS); }
+#else
+;
+#endif
 // WS_MAXL lanes per CTA: 65536 / (WS_MAXL WS_NT) registers per thread (throughput mode)
-__global__ void __launch_bounds__(WS_MAXL * WS_NT, 1) bnb_kernel_m(WS_BNB_ARGS) { bnb_body<WS_MAXL>(WS_BNB_PASS); }
+__global__ void __launch_bounds__(WS_MAXL * WS_NT, 1) bnb_kernel_m(WS_BNB_ARGS)
+#if WS_TU_HAS(4)
+{ bnb_body<WS_MAXL>(WS_BNB_PASS); }
+#else
+;
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // K2 + K4: retain / shift identifiers / shift duals / re-evaluate the bounds / plant update
@@ -476,6 +488,7 @@ __device__ __forceinline__ int shift_instance(const DevProblem &P, double *shm, 
 #undef s_base
 }
 
+#if WS_TU_HAS(0)
 __global__ void __launch_bounds__(SH_NT)
 shift_tree_kernel(DevProblem P, int n_inst, const double *__restrict__ x0, const double *__restrict__ e0,
                   TreeView ot, const double *__restrict__ inc_cost, const double *__restrict__ inc_primal,
@@ -489,6 +502,7 @@ shift_tree_kernel(DevProblem P, int n_inst, const double *__restrict__ x0, const
         shift_instance<SH_NT, false>(P, shm, s_wsum, &s_base_v, inst, x0, e0, ot, inc_cost, inc_primal, active, nt, x_next, u0_out);
     }
 }
+#endif
 
 __host__ inline size_t shift_smem_bytes(const DevProblem &P) { return sizeof(double) * shift_smem_doubles(P, SH_NT); }
 
@@ -515,6 +529,7 @@ struct LoopView {
     int *log_status;        // [n_steps][n_inst]
 };
 
+#if WS_TU_HAS(0)
 __global__ void loop_init_kernel(int n_inst, int n_items, LoopView L)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -526,6 +541,7 @@ __global__ void loop_init_kernel(int n_inst, int n_items, LoopView L)
     if (i < n_items) L.q[4 + 2 * S + i] = i < n_inst ? i : -1;
     if (i < n_inst) L.step_of[i] = 0;
 }
+#endif
 
 __device__ __forceinline__ void init_root(const TreeView &tr, int k)
 {
@@ -641,5 +657,15 @@ closed_loop_body(const DevProblem &P, double *slot_d, int *slot_i, double *ybuf,
     int *status_out, unsigned long long *totals
 #define WS_LOOP_PASS P, slot_d, slot_i, ybuf, scratch, L, n_slots, n_inst, t0, t1, tol, max_solves, inc_cost, inc_node, inc_primal, \
     n_solves, status_out, totals
-__global__ void __launch_bounds__(WS_NT, 1) closed_loop_kernel_1(WS_LOOP_ARGS) { closed_loop_body<1>(WS_LOOP_PASS); }
-__global__ void __launch_bounds__(WS_MAXL * WS_NT, 1) closed_loop_kernel_m(WS_LOOP_ARGS) { closed_loop_body<WS_MAXL>(WS_LOOP_PASS); }
+__global__ void __launch_bounds__(WS_NT, 1) closed_loop_kernel_1(WS_LOOP_ARGS)
+#if WS_TU_HAS(5)
+{ closed_loop_body<1>(WS_LOOP_PASS); }
+#else
+;
+#endif
+__global__ void __launch_bounds__(WS_MAXL * WS_NT, 1) closed_loop_kernel_m(WS_LOOP_ARGS)
+#if WS_TU_HAS(6)
+{ closed_loop_body<WS_MAXL>(WS_LOOP_PASS); }
+#else
+;
+#endif

@@ -41,6 +41,16 @@
 #include <math.h>
 #include <stdint.h>
 
+// Translation units.  The six large kernels (K1 / K3 / fused loop, one- and multi-lane build each) take about a minute of
+// ptxas each; wshmpc.cu can be compiled as ONE unit (WS_TU undefined: everything) or as seven units in parallel
+// (-DWS_TU=0: C ABI + the small kernels, -DWS_TU=1..6: one large kernel each; __graft_entry__.build()).  A unit that does
+// not define a kernel only declares it.
+#ifndef WS_TU
+#define WS_TU_HAS(id) 1
+#else
+#define WS_TU_HAS(id) (WS_TU == (id))
+#endif
+
 // Measured on the 512-instance warm-started cart-pole loop (B200, round 2, tools/loop_timing.py; QP/s):
 //   1 lane  x 256 threads, 255 registers  257 k   (the round-1 configuration: 250 k with the round-1 code)
 //   1 lane  x 256 threads, 128 registers  195 k   (what the register cap of two lanes costs one lane)
@@ -710,6 +720,22 @@ __device__ __forceinline__ int thin_remove_t(const DevProblem &P, const Ctx &cx,
         rr[q] = r < k - 1 ? r : -1;
         ro[q] = r < kp ? r : r + 1;
     }
+#ifndef WS_NO_FAST_SWEEP
+    // FAST sweep (the common case: at most 32 rows move up, they fit one warp).  The only hazard of the in-place update of Ri
+    // is between NEIGHBOURING rows that move up (row a is written where row a - 1 reads one column later); rows below kp
+    // and the rows of Q1 are updated by their owner alone.  With the rows kp .. k - 2 on the lanes of the LAST warp, a
+    // __syncwarp between the reads and the writes of a chunk orders them and the sweep needs no lane-wide barrier at all.
+    // Same operations on every element as the chunked sweep below: the result does not depend on which one runs.
+    const bool fast = WS_RRT == 1 && k - 1 - kp <= 32 && kp <= WS_NT - 32;
+    if (fast) {
+        const bool up = w == WS_NW - 1;
+        const int r = up ? kp + lane : WS_NT - 33 - tid;
+        rr[0] = (up ? r < k - 1 : r < kp) ? r : -1;
+        ro[0] = up ? r + 1 : r;
+    }
+#else
+    const bool fast = false;
+#endif
     const int nq1 = (2 * gm.he + 31) & ~31;
     const bool uth = tid == (nq1 < WS_NT ? nq1 : 0);
     const double big = 1. / P.tol_sing;
@@ -723,6 +749,67 @@ __device__ __forceinline__ int thin_remove_t(const DevProblem &P, const Ctx &cx,
         ls_old[q] = rr[q] >= 0 ? SMV(ls)[ro[q]] : 0.;                       // read before any thread writes its new entry
     }
     double ucarry = uth ? u[kp] : 0.;
+    if (fast) {
+#pragma unroll
+        for (int q = 0; q < WS_RRT; ++q) {
+            const int ts = kp + 1 + tid + q * WS_NT;
+            if (ts < k) { row[ts - 1] = rw[q]; side[ts - 1] = sd[q]; SMV(lam)[ts - 1] = lm[q]; }
+        }
+        {
+            const int rr0 = rr[0], ro0 = ro[0];
+            double rc = rcarry[0];
+            for (int i0 = kp; i0 < k - 1; i0 += 4) {
+                double b[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { const int i = i0 + c; b[c] = (rr0 >= 0 && i < k - 1 && ro0 <= i + 1) ? RC(i + 1)[ro0] : 0.; }
+                __syncwarp();
+                if (rr0 >= 0 && ro0 <= i0 + 4) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int i = i0 + c;
+                        if (i < k - 1) {
+                            const double cs = gc[i], sn = gs[i];
+                            const double o = cs * rc + sn * b[c];
+                            rc = -sn * rc + cs * b[c];
+                            if (rr0 <= i) {
+                                RC(i)[rr0] = o;
+                                if (rr0 == i && fabs(o) >= big) atomicMin(flag, rr0);
+                            }
+                        }
+                    }
+                }
+            }
+            rcarry[0] = rc;
+        }
+#pragma unroll
+        for (int q = 0; q < WS_RPT; ++q) if (qr[q] >= 0) {
+            const int ri = qr[q];
+            double qc = qcarry[q];
+            for (int i0 = kp; i0 < k - 1; i0 += 4) {
+                double bq[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { const int i = i0 + c; bq[c] = i < k - 1 ? QC(i + 1)[ri] : 0.; }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int i = i0 + c;
+                    if (i < k - 1) {
+                        const double cs = gc[i], sn = gs[i];
+                        QC(i)[ri] = cs * qc + sn * bq[c];
+                        qc = -sn * qc + cs * bq[c];
+                    }
+                }
+            }
+            qcarry[q] = qc;
+        }
+        if (uth) {
+            for (int i = kp; i < k - 1; ++i) {
+                const double bu_ = u[i + 1];
+                const double cs = gc[i], sn = gs[i];
+                u[i] = cs * ucarry + sn * bu_;
+                ucarry = -sn * ucarry + cs * bu_;
+            }
+        }
+    } else
     for (int i0 = kp; i0 < k - 1; i0 += WS_CH) {
         double b[WS_RRT][WS_CH];
 #pragma unroll

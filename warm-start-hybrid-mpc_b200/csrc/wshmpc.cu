@@ -4,7 +4,9 @@
 #include "qp_device.cuh"
 #include "records.cuh"
 #include "bnb.cuh"
+#if WS_TU_HAS(0)
 #include "lp_batch.cuh"
+#endif
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -15,6 +17,7 @@ static thread_local std::string g_err;
 #define WS_FAIL(code, ...) do { char _b[512]; snprintf(_b, sizeof(_b), __VA_ARGS__); g_err = _b; return code; } while (0)
 #define WS_CUDA(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) WS_FAIL(-2, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(_e), __FILE__, __LINE__); } while (0)
 
+#if WS_TU_HAS(0)
 struct wshmpc_handle {
     DevProblem P;            // shared-memory layout for P.lanes solver lanes per CTA (throughput launches)
     DevProblem P1;           // the same problem laid out for ONE lane per CTA (launches that cannot fill two lanes per SM)
@@ -45,6 +48,8 @@ extern "C" int wshmpc_prof_read(unsigned long long *out, int reset) {
     if (reset) { static unsigned long long z[256]; cudaMemcpyToSymbol(g_prof, z, sizeof(z)); }
     return 0;
 }
+#endif
+
 #endif
 
 // ---------------------------------------------------------------------------------------------
@@ -99,8 +104,20 @@ solve_nodes_body(const DevProblem &P, double *slot_d, int *slot_i, double *ybuf,
     const int *__restrict__ hot, const double *__restrict__ y0, const double *__restrict__ yc0, \
     int *status, double *cost, double *dobj, int *iters, double *primal, double *dual, double *yc_out
 #define WS_K1_PASS P, slot_d, slot_i, ybuf, n_slots, n_nodes, x0, lb, ub, slot_of, hot, y0, yc0, status, cost, dobj, iters, primal, dual, yc_out
-__global__ void __launch_bounds__(WS_NT, 1) solve_nodes_kernel_1(WS_K1_ARGS) { solve_nodes_body<1>(WS_K1_PASS); }
-__global__ void __launch_bounds__(WS_MAXL * WS_NT, 1) solve_nodes_kernel_m(WS_K1_ARGS) { solve_nodes_body<WS_MAXL>(WS_K1_PASS); }
+__global__ void __launch_bounds__(WS_NT, 1) solve_nodes_kernel_1(WS_K1_ARGS)
+#if WS_TU_HAS(1)
+{ solve_nodes_body<1>(WS_K1_PASS); }
+#else
+;
+#endif
+__global__ void __launch_bounds__(WS_MAXL * WS_NT, 1) solve_nodes_kernel_m(WS_K1_ARGS)
+#if WS_TU_HAS(2)
+{ solve_nodes_body<WS_MAXL>(WS_K1_PASS); }
+#else
+;
+#endif
+
+#if WS_TU_HAS(0)          // the C ABI (host code) lives in unit 0
 
 // ---------------------------------------------------------------------------------------------
 // host side
@@ -511,3 +528,4 @@ extern "C" int wshmpc_lp_batch(int device, void *stream, int n_lp, int m, int n,
     WS_CUDA(cudaGetLastError());
     return 0;
 }
+#endif  // WS_TU_HAS(0)
