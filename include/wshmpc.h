@@ -196,12 +196,42 @@ int wshmpc_shift_tree(wshmpc_handle *h, int n_inst, const double *d_x0, const do
  * construct_warm_start, x <- x_1|t + e_t on the linear plant) for the whole batch; results are identical to
  * calling wshmpc_bnb_solve + wshmpc_shift_tree once per step.
  */
+/* Host mailbox of the fused closed loop: the host is in the loop EVERY receding-horizon step of every instance (a true
+ * plant, measured states) and there is still no barrier between instances -- what a per-step call of
+ * `feedforward` + `construct_warm_start` (statistical_analysis.py:120-196) costs the reference once per instance, without
+ * the lock step a batched per-step call would impose.  All arrays are pinned, mapped HOST memory owned by the library; the
+ * kernel of wshmpc_closed_loop runs while the host polls them:
+ *   kernel, after the B&B of step s of instance i:  writes out_u0 / out_x1 / out_cost / out_status [i], then out_step[i] = s + 1
+ *   host, when it sees out_step[i] == s + 1:        applies out_u0[i] to its plant, writes the measured state in_x[i] and the
+ *                                                   model error in_e[i] = in_x[i] - out_x1[i] (construct_warm_start's e0,
+ *                                                   controller.py:503-564), then in_step[i] = s + 1
+ *   kernel, when a lane next picks instance i:      waits for in_step[i] >= s + 1, builds the warm start (K2 + K4), solves step s + 1
+ * The host answers EVERY published step, also the last one of the launch and those of instances that report no incumbent.
+ * `stop` != 0 (or 20 s without an answer) makes the kernel abandon the instances it waits for (status 4) and drain.
+ * Counters are per launch: zero in_step / out_step / stop before each wshmpc_closed_loop. */
+typedef struct {
+    int n_inst, nx, nu;
+    volatile int *out_step;           /* [n_inst] steps of the instance published in this launch */
+    double *out_u0;                   /* [n_inst][nu] input to apply (NaN: the step has no incumbent) */
+    double *out_x1;                   /* [n_inst][nx] predicted next state x_1|t */
+    double *out_cost;                 /* [n_inst] optimal cost (+inf: none) */
+    int *out_status;                  /* [n_inst] status of the step's branch and bound (wshmpc_bnb_solve) */
+    volatile int *in_step;            /* [n_inst] steps of the instance answered in this launch */
+    double *in_x;                     /* [n_inst][nx] measured state the next step starts from */
+    double *in_e;                     /* [n_inst][nx] model error */
+    volatile int *stop;               /* [1] */
+    void *priv;                       /* library-owned (device scratch) */
+} wshmpc_mailbox;
+
+int wshmpc_mailbox_create(wshmpc_handle *h, int n_inst, wshmpc_mailbox *mb);
+int wshmpc_mailbox_destroy(wshmpc_handle *h, wshmpc_mailbox *mb);
+
 typedef struct {
     int n_steps;                      /* receding-horizon steps to run per instance */
     int warm;                         /* 1: warm start by tree shifting, 0: every step from the root node */
     int fresh;                        /* 1: step 0 starts from the root node (no tree yet) */
     int par;                          /* which tree / state buffer (0 or 1) holds the data of step 0 */
-    int *d_queue;                     /* [4 + 2 * n_steps + n_inst * (n_steps + 1)] scratch (per-step task queues) */
+    int *d_queue;                     /* [4 + (n_inst + 2) * (n_steps + 1)] scratch (per-step task queues) */
     int *d_step_of;                   /* [n_inst] scratch */
     double *d_x;                      /* [2][n_inst][nx] states, buffer `par` holds the current ones */
     const double *d_e;                /* [n_steps][n_inst][nx] model errors, or NULL */
@@ -210,6 +240,8 @@ typedef struct {
     double *d_log_u0;                 /* [n_steps][n_inst][nu] applied input (NaN once an instance is off) */
     int *d_log_solves;                /* [n_steps][n_inst] QP relaxations solved */
     int *d_log_status;                /* [n_steps][n_inst] status of wshmpc_bnb_solve */
+    const wshmpc_mailbox *mailbox;    /* NULL: the plant x <- x_1|t + e_t is advanced on the device (d_e); else the host is
+                                       * in the loop every step (d_e unused) and the call returns while the kernel runs */
 } wshmpc_loop;
 
 int wshmpc_closed_loop(wshmpc_handle *h, int n_inst, const wshmpc_loop *loop,

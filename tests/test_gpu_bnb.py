@@ -287,3 +287,68 @@ def test_noisy_closed_loop_warm_equals_cold():
     assert torch.equal(W.active, Cd.active)
     nw, nc = lw['n_solves'].cpu().numpy()[1:].sum(), lc['n_solves'].cpu().numpy()[1:].sum()
     assert nw * 4 < nc
+
+
+def test_mailbox_loop_equals_the_device_resident_loop():
+    """Host in the loop EVERY step (wshmpc_mailbox, persistent launch, no barrier between instances): when the host's
+    plant answers with the same x_1|t + e_t and e_t the device-resident loop uses, costs, inputs, solve counts, statuses,
+    final states and the warm-start trees are bit-identical to wshmpc_closed_loop without a mailbox -- also across two
+    consecutive launches (the second one resumes from the trees of the first)."""
+    from warm_start_hmpc_b200.closed_loop import ClosedLoop
+    from warm_start_hmpc_b200.instances import load_initial_states
+    model = load_model('cp20')
+    ctl = make_controller(model)
+    N, S = 24, 5
+    xs = load_initial_states(0, N)
+    rng = np.random.default_rng(7)
+    e = 0.003 * rng.standard_normal((2, S, N, 4)) * model['x_max']
+    ref = ClosedLoop(ctl, N, warm=True, max_solves=1024, max_roots=512)
+    ref.reset(xs)
+    mbx = ClosedLoop(ctl, N, warm=True, max_solves=1024, max_roots=512)
+    mbx.reset(xs)
+    calls = []
+    for w in range(2):
+        lr = ref.run(S, e=torch.as_tensor(e[w], device='cuda'))
+        torch.cuda.synchronize()
+
+        def plant(idx, step, u0, x1, w=w):
+            calls.append(len(idx))
+            return x1 + e[w][step, idx], e[w][step, idx]
+        lm = mbx.run_mailbox(S, plant, timeout_s=60.)
+        torch.cuda.synchronize()
+        for k in ('cost', 'n_solves', 'status'):
+            assert torch.equal(lr[k], lm[k]), (w, k)
+        assert torch.equal(torch.nan_to_num(lr['u0'], nan=-7.), torch.nan_to_num(lm['u0'], nan=-7.))
+        assert torch.equal(ref.x, mbx.x)
+        assert torch.equal(ref.active, mbx.active)
+        # what the host saw is what the device logged
+        assert np.array_equal(lm['host']['cost'], lm['cost'].cpu().numpy())
+        live = np.isfinite(lm['host']['cost'])
+        assert np.array_equal(lm['host']['u0'][live], lm['u0'].cpu().numpy()[live])
+        ta, tb = ref.trees[ref.cur], mbx.trees[mbx.cur]
+        assert torch.equal(ta.n_nodes, tb.n_nodes)
+        for i in range(N):
+            n = int(ta.n_nodes[i])
+            assert torch.equal(ta.lb[i, :n], tb.lb[i, :n]) and torch.equal(ta.bits[i, :n], tb.bits[i, :n])
+    assert sum(calls) == 2 * S * N and len(calls) > 2 * S        # answered per instance, not per batch step
+
+
+def test_mailbox_loop_drains_when_the_host_stops():
+    """A host that stops answering (exception in the plant) sets the stop flag: the launch abandons the instances it waits
+    for (status 4) and ends -- the GPU is never left spinning."""
+    from warm_start_hmpc_b200.closed_loop import ClosedLoop
+    from warm_start_hmpc_b200.instances import load_initial_states
+    model = load_model('cp20')
+    ctl = make_controller(model)
+    N = 8
+    loop = ClosedLoop(ctl, N, warm=True, max_solves=1024, max_roots=512)
+    loop.reset(load_initial_states(0, N))
+
+    def plant(idx, step, u0, x1):
+        if (step >= 1).any():
+            raise KeyError('plant died')
+        return x1
+    with pytest.raises(KeyError):
+        loop.run_mailbox(4, plant, timeout_s=30.)
+    torch.cuda.synchronize()
+    assert int(loop.active.sum()) < N

@@ -43,13 +43,50 @@ def load_library():
 
 
 EXPORTS = ('wshmpc_last_error', 'wshmpc_ctas_per_sm', 'wshmpc_set_search_rule', 'wshmpc_set_branch_order', 'wshmpc_create', 'wshmpc_destroy', 'wshmpc_get_layout', 'wshmpc_solve_nodes',
-           'wshmpc_tree_init_root', 'wshmpc_bnb_solve', 'wshmpc_shift_tree', 'wshmpc_closed_loop', 'wshmpc_lp_batch')
+           'wshmpc_tree_init_root', 'wshmpc_bnb_solve', 'wshmpc_shift_tree', 'wshmpc_closed_loop', 'wshmpc_mailbox_create', 'wshmpc_mailbox_destroy', 'wshmpc_lp_batch')
+
+
+class _Mailbox(C.Structure):
+    _fields_ = ([(k, C.c_int) for k in ('n_inst', 'nx', 'nu')]
+                + [(k, C.c_void_p) for k in ('out_step', 'out_u0', 'out_x1', 'out_cost', 'out_status', 'in_step', 'in_x', 'in_e', 'stop', 'priv')])
+
+
+class Mailbox(object):
+    """Host mailbox of the fused closed loop (wshmpc_mailbox in include/wshmpc.h): numpy views of the pinned, mapped host
+    arrays the running kernel publishes steps to and reads the host's answers from."""
+
+    def __init__(self, handle, n_inst):
+        self._handle, self.c = handle, _Mailbox()
+        _check(handle.lib.wshmpc_mailbox_create(handle._h, int(n_inst), C.byref(self.c)))
+        nx, nu = self.c.nx, self.c.nu
+
+        def view(ptr, ctype, shape):
+            n = int(np.prod(shape))
+            return np.ctypeslib.as_array((ctype * n).from_address(ptr)).reshape(shape)
+        self.out_step = view(self.c.out_step, C.c_int, (n_inst,))
+        self.out_u0 = view(self.c.out_u0, C.c_double, (n_inst, nu))
+        self.out_x1 = view(self.c.out_x1, C.c_double, (n_inst, nx))
+        self.out_cost = view(self.c.out_cost, C.c_double, (n_inst,))
+        self.out_status = view(self.c.out_status, C.c_int, (n_inst,))
+        self.in_step = view(self.c.in_step, C.c_int, (n_inst,))
+        self.in_x = view(self.c.in_x, C.c_double, (n_inst, nx))
+        self.in_e = view(self.c.in_e, C.c_double, (n_inst, nx))
+        self.stop = view(self.c.stop, C.c_int, (1,))
+
+    def clear(self):
+        self.out_step[:] = 0; self.in_step[:] = 0; self.stop[0] = 0
+
+    def close(self):
+        if self.c.priv:
+            for k in ('out_step', 'out_u0', 'out_x1', 'out_cost', 'out_status', 'in_step', 'in_x', 'in_e', 'stop'):
+                setattr(self, k, None)
+            self._handle.lib.wshmpc_mailbox_destroy(self._handle._h, C.byref(self.c))
 
 
 class _Loop(C.Structure):
     _fields_ = ([(k, C.c_int) for k in ('n_steps', 'warm', 'fresh', 'par')]
                 + [(k, C.c_void_p) for k in ('d_queue', 'd_step_of', 'd_x', 'd_e', 'd_active', 'd_log_cost', 'd_log_u0',
-                                             'd_log_solves', 'd_log_status')])
+                                             'd_log_solves', 'd_log_status', 'mailbox')])
 
 
 class _Tree(C.Structure):
@@ -213,9 +250,11 @@ class Handle(object):
         _check(self.lib.wshmpc_shift_tree(self._h, old_tree.n_inst, P(x0), P(e0), C.byref(old_tree.c), P(inc_cost),
                                           P(inc_primal), P(active), C.byref(new_tree.c), P(x_next), P(u0)))
 
-    def closed_loop(self, n_steps, warm, fresh, par, xbuf, e, active, trees, out, tol=0., max_solves=1024, totals=None, logs=None):
+    def closed_loop(self, n_steps, warm, fresh, par, xbuf, e, active, trees, out, tol=0., max_solves=1024, totals=None, logs=None,
+                    mailbox=None):
         """Fused closed loop (wshmpc_closed_loop): `n_steps` receding-horizon steps of every instance in one
         launch.  xbuf [2, n_inst, nx]; e [n_steps, n_inst, nx] or None; trees = (tree0, tree1).  Asynchronous.
+        mailbox: a Mailbox -- the host is in the loop every step (the caller must answer it while the kernel runs).
         Returns the dict of per-step logs (CUDA tensors)."""
         import torch
         dev = self.torch_device
@@ -229,7 +268,7 @@ class Handle(object):
                         u0=torch.empty((n_steps, N, nu), dtype=torch.float64, device=dev),
                         n_solves=torch.empty((n_steps, N), dtype=torch.int32, device=dev),
                         status=torch.empty((n_steps, N), dtype=torch.int32, device=dev))
-        need = 4 + 2 * n_steps + N * (n_steps + 1)
+        need = 4 + (N + 2) * (n_steps + 1)
         if getattr(self, '_queue', None) is None or self._queue.numel() < need:
             self._queue = torch.empty(need, dtype=torch.int32, device=dev)
         if getattr(self, '_step_of', None) is None or self._step_of.numel() < N:
@@ -239,6 +278,7 @@ class Handle(object):
         L.n_steps, L.warm, L.fresh, L.par = int(n_steps), int(bool(warm)), int(bool(fresh)), int(par) & 1
         L.d_queue, L.d_step_of, L.d_x, L.d_e, L.d_active = P(self._queue), P(self._step_of), P(xbuf), P(e), P(active)
         L.d_log_cost, L.d_log_u0, L.d_log_solves, L.d_log_status = P(logs['cost']), P(logs['u0']), P(logs['n_solves']), P(logs['status'])
+        L.mailbox = C.addressof(mailbox.c) if mailbox is not None else None
         V = lambda a: C.c_void_p(a.data_ptr()) if a is not None else None
         _check(self.lib.wshmpc_closed_loop(self._h, N, C.byref(L), C.byref(trees[0].c), C.byref(trees[1].c), C.c_double(tol),
                                            int(max_solves), V(out['cost']), V(out['node']), V(out['primal']), V(out['n_solves']),

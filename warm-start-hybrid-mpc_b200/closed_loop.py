@@ -154,6 +154,72 @@ class ClosedLoop(object):
         return logs
 
 
+    def run_mailbox(self, n_steps, plant, timeout_s=120., logs=None):
+        """`n_steps` receding-horizon steps of every instance with the HOST in the loop every step and no barrier between
+        instances (wshmpc_closed_loop with a wshmpc_mailbox): one persistent launch solves; this thread polls the pinned
+        mailbox, and whenever instances have published a step it calls
+            plant(idx [k] instance indices, step [k], u0 [k, nu], x_pred [k, nx]) -> x_measured [k, nx]  or  (x_measured, e)
+        (host numpy; u0 is NaN where a step has no incumbent) and hands the measured states and the model errors
+        e = x_measured - x_pred back -- the per-step use of `feedforward` + `construct_warm_start`
+        (statistical_analysis.py:120-196) for a batch of independent plants.  Returns the device logs of run() plus
+        'host' = dict(u0, x1, cost, status) numpy arrays [n_steps, n_inst, ...] as the host saw them."""
+        import time
+        import torch
+        from .capi import Mailbox
+        h, N = self.h, self.n_inst
+        if getattr(self, '_mailbox', None) is None:
+            self._mailbox = Mailbox(h, N)
+        mb = self._mailbox
+        mb.clear()
+        if self.warm:
+            par, fresh = self.cur, self.fresh
+        else:
+            par, fresh = self.cur, True
+        if self.xpar != par:
+            self.xbuf[par].copy_(self.xbuf[self.xpar]); self.xpar = par
+        nx, nu = self.ctl.mld.nx, self.ctl.mld.nu
+        host = dict(u0=np.full((n_steps, N, nu), np.nan), x1=np.zeros((n_steps, N, nx)), cost=np.full((n_steps, N), np.inf),
+                    status=np.zeros((n_steps, N), dtype=np.int32))
+        logs = h.closed_loop(n_steps, self.warm, fresh, par, self.xbuf, None, self.active, self.trees, self.out,
+                             tol=self.tol, max_solves=self.max_solves, totals=self.totals, logs=logs, mailbox=mb)
+        self.launches += 2
+        seen = np.zeros(N, dtype=np.int32)
+        t_end = time.time() + timeout_s
+        n_left = N * n_steps
+        try:
+            while n_left > 0:
+                idx = np.nonzero(mb.out_step > seen)[0]
+                if idx.size == 0:
+                    if time.time() > t_end:
+                        raise RuntimeError('run_mailbox: the kernel published nothing for %.0f s' % timeout_s)
+                    continue
+                s = seen[idx]
+                u0 = mb.out_u0[idx].copy(); x1 = mb.out_x1[idx].copy()
+                host['u0'][s, idx] = u0; host['x1'][s, idx] = x1
+                host['cost'][s, idx] = mb.out_cost[idx]; host['status'][s, idx] = mb.out_status[idx]
+                ans = plant(idx, s, u0, x1)
+                if isinstance(ans, tuple):
+                    xm, e = ans
+                else:
+                    xm = np.asarray(ans, dtype=float); e = xm - x1
+                live = np.isfinite(u0).all(axis=1)
+                mb.in_x[idx] = np.where(live[:, None], xm, x1)
+                mb.in_e[idx] = np.where(live[:, None], e, 0.)
+                mb.in_step[idx] = s + 1            # after the data (x86 stores are not reordered)
+                seen[idx] = s + 1
+                n_left -= idx.size
+                t_end = time.time() + timeout_s
+        except BaseException:
+            mb.stop[0] = 1                          # never leave the kernel waiting for an answer
+            torch.cuda.synchronize(h.torch_device)
+            raise
+        self.fresh = False
+        self.cur = (self.cur + n_steps) & 1
+        self.xpar = (self.xpar + n_steps) & 1
+        logs['host'] = host
+        return logs
+
+
 def reduce_stats(n_units, elapsed_ms, device=None):
     """Whole-job aggregate under torch.distributed (one process per GPU, no data-path collective):
     units are summed over ranks, time is the MAX over ranks.  Works with NCCL (CUDA tensors) and gloo

@@ -527,7 +527,16 @@ struct LoopView {
     double *log_u0;         // [n_steps][n_inst][nu]
     int *log_solves;        // [n_steps][n_inst]
     int *log_status;        // [n_steps][n_inst]
+    // host mailbox (wshmpc_mailbox; all null = the plant is advanced on the device).  mb_* point into pinned, mapped HOST
+    // memory and are read / written with system-scope ordering; mb_stage is device scratch [n_inst][nx].
+    volatile int *mb_in_step, *mb_out_step, *mb_stop;
+    const volatile double *mb_in_x, *mb_in_e;
+    double *mb_out_u0, *mb_out_x1, *mb_out_cost;
+    int *mb_out_status;
+    double *mb_stage;
 };
+#define BNB_HOST_ABORT 4          // mailbox mode: the host stopped answering (stop flag or time-out)
+#define WS_MB_TIMEOUT_NS 20000000000ull     // a lane gives up on a silent host after 20 s (the launch then drains)
 
 #if WS_TU_HAS(0)
 __global__ void loop_init_kernel(int n_inst, int n_items, LoopView L)
@@ -535,7 +544,7 @@ __global__ void loop_init_kernel(int n_inst, int n_items, LoopView L)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     // q: [0] tasks completed, [1] lowest step with unclaimed tasks (hint), [4 + s] head of step s, [4 + S + s] tail of
     // step s, [4 + 2 S + s n_inst + pos] instances ready for step s in the order they became ready
-    const int S = L.n_steps;
+    const int S = L.n_steps + (L.mb_in_step ? 1 : 0);       // mailbox mode: one more level (the warm start after the last answer)
     if (i == 0) { L.q[0] = 0; L.q[1] = 0; L.q[2] = 0; L.q[3] = 0; }
     if (i < S) { L.q[4 + i] = 0; L.q[4 + S + i] = i == 0 ? n_inst : 0; }
     if (i < n_items) L.q[4 + 2 * S + i] = i < n_inst ? i : -1;
@@ -569,7 +578,14 @@ closed_loop_body(const DevProblem &P, double *slot_d, int *slot_i, double *ybuf,
     double *y = ybuf + (size_t)slot * P.m;
     double *sc = scratch + (size_t)slot * bnb_scratch_doubles(P.nb, P.n_primal);
     int *iters_s = slot_i + (size_t)slot * slot_ints(P.n) + 2 * (P.n + 1) + 1;
-    const int total = n_inst * L.n_steps;
+    // Mailbox mode (L.mb_in_step != null): the host is in the loop EVERY step of every instance, still without a barrier
+    // between instances.  Level t of an instance = [wait for the host's answer to step t - 1, then its warm start
+    // (K2 + K4) with the measured state and model error the host sent] + [B&B of step t, published to the host]; there is
+    // one level more than steps (the warm start after the last answer), so a launch ends in the same state as the
+    // device-resident loop.
+    const bool mbx = L.mb_in_step != nullptr;
+    const int S = L.n_steps + (mbx ? 1 : 0);
+    const int total = n_inst * S;
     const size_t xs = (size_t)n_inst * P.nx;
     prof_mark(127);
 
@@ -578,7 +594,6 @@ closed_loop_body(const DevProblem &P, double *slot_d, int *slot_i, double *ybuf,
         if (WS_TID == 0) {
             // pop a ready task of the LOWEST step: the instance that lags behind never waits in a queue, so the launch
             // ends with the longest chain of solves of one instance, not with that chain plus its queueing delays
-            const int S = L.n_steps;
             volatile int *q = L.q;
             int *head = L.q + 4, *items = L.q + 4 + 2 * S;
             volatile int *tail = L.q + 4 + S;
@@ -611,39 +626,95 @@ closed_loop_body(const DevProblem &P, double *slot_d, int *slot_i, double *ybuf,
         if (inst < 0) break;
         __threadfence();                                   // acquire: drop stale L1 lines of the instance's data
         const int t = L.step_of[inst];
-        const int par = (L.par + t) & 1;
-        const TreeView &cur = par ? t1 : t0;
-        const TreeView &nxt = par ? t0 : t1;
-        const double *xc = L.x + (size_t)par * xs;
-        double *xn = L.x + (size_t)(par ^ 1) * xs;
-        if (!L.warm || (t == 0 && L.fresh)) {
-            if (WS_TID == 0) init_root(cur, inst);
+        if (mbx && t > 0) {
+            // the warm start of step t - 1, once the host has answered it
+            const int ts = t - 1, ps = (L.par + ts) & 1;
+            const TreeView &cur = ps ? t1 : t0;
+            const TreeView &nxt = ps ? t0 : t1;
+            const double *xc = L.x + (size_t)ps * xs;
+            double *xn = L.x + (size_t)(ps ^ 1) * xs;
+            const bool live = L.active[inst] != 0;
+            if (live) {
+                if (WS_TID == 0) {
+                    unsigned long long t_begin = 0, now = 0;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
+                    int ok = 1;
+                    while (L.mb_in_step[inst] < t) {
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                        if (*L.mb_stop != 0 || now - t_begin > WS_MB_TIMEOUT_NS) { ok = 0; break; }
+                        __nanosleep(1000);
+                    }
+                    __threadfence_system();
+                    s_inst = ok;
+                }
+                WS_SYNC();
+                const int ok = s_inst;
+                WS_SYNC();
+                if (ok) {
+                    for (int j = WS_TID; j < P.nx; j += WS_NT) {
+                        xn[(size_t)inst * P.nx + j] = L.mb_in_x[(size_t)inst * P.nx + j];
+                        L.mb_stage[(size_t)inst * P.nx + j] = L.mb_in_e[(size_t)inst * P.nx + j];
+                    }
+                } else {
+                    for (int j = WS_TID; j < P.nx; j += WS_NT) { xn[(size_t)inst * P.nx + j] = xc[(size_t)inst * P.nx + j]; L.mb_stage[(size_t)inst * P.nx + j] = 0.; }
+                    if (WS_TID == 0) { inc_cost[inst] = INFINITY; status_out[inst] = BNB_HOST_ABORT; L.log_status[(size_t)ts * n_inst + inst] = BNB_HOST_ABORT; }
+                }
+            } else {
+                for (int j = WS_TID; j < P.nx; j += WS_NT) xn[(size_t)inst * P.nx + j] = xc[(size_t)inst * P.nx + j];
+            }
+            WS_SYNC();
+            const int ovf = shift_instance<WS_NT, true>(P, SMV(pool), SMI(ired), SMI(ired) + 16, inst, xc, L.mb_stage, cur, inc_cost, inc_primal,
+                                                  L.active, nxt, nullptr, L.log_u0 + (size_t)ts * n_inst * P.nu);
+            if (ovf && WS_TID == 0) { status_out[inst] = BNB_CAPACITY; L.log_status[(size_t)ts * n_inst + inst] = BNB_CAPACITY; }
+            prof_mark(19);
             WS_SYNC();
         }
-        int st;
-        if (!L.active[inst]) {
-            if (WS_TID == 0) { inc_cost[inst] = INFINITY; inc_node[inst] = -1; n_solves[inst] = 0; }
-            st = BNB_INFEASIBLE;
+        if (t < L.n_steps) {
+            const int par = (L.par + t) & 1;
+            const TreeView &cur = par ? t1 : t0;
+            const TreeView &nxt = par ? t0 : t1;
+            const double *xc = L.x + (size_t)par * xs;
+            double *xn = L.x + (size_t)(par ^ 1) * xs;
+            if (!L.warm || (t == 0 && L.fresh)) {
+                if (WS_TID == 0) init_root(cur, inst);
+                WS_SYNC();
+            }
+            int st;
+            if (!L.active[inst]) {
+                if (WS_TID == 0) { inc_cost[inst] = INFINITY; inc_node[inst] = -1; n_solves[inst] = 0; }
+                st = BNB_INFEASIBLE;
+                WS_SYNC();
+            } else {
+                st = bnb_instance(P, cx, sp, y, sc, iters_s, inst, xc + (size_t)inst * P.nx, cur, tol, max_solves,
+                                  inc_cost, inc_node, inc_primal, n_solves, nullptr, totals);
+            }
+            if (WS_TID == 0) {
+                status_out[inst] = st;
+                const size_t lo = (size_t)t * n_inst + inst;
+                L.log_cost[lo] = inc_cost[inst]; L.log_solves[lo] = n_solves[inst]; L.log_status[lo] = st;
+            }
             WS_SYNC();
-        } else {
-            st = bnb_instance(P, cx, sp, y, sc, iters_s, inst, xc + (size_t)inst * P.nx, cur, tol, max_solves,
-                              inc_cost, inc_node, inc_primal, n_solves, nullptr, totals);
+            if (!mbx) {
+                const int ovf = shift_instance<WS_NT, true>(P, SMV(pool), SMI(ired), SMI(ired) + 16, inst, xc, L.e ? L.e + (size_t)t * xs : nullptr,
+                                                      cur, inc_cost, inc_primal, L.active, nxt, xn, L.log_u0 + (size_t)t * n_inst * P.nu);
+                if (ovf && WS_TID == 0) { status_out[inst] = BNB_CAPACITY; L.log_status[(size_t)t * n_inst + inst] = BNB_CAPACITY; }
+                prof_mark(19);
+            } else {
+                // publish step t: applied input, predicted next state, cost, status -- then the step counter
+                const bool has = L.active[inst] != 0 && inc_cost[inst] < INFINITY;
+                const double *ip = inc_primal + (size_t)inst * P.n_primal;
+                for (int j = WS_TID; j < P.nu; j += WS_NT) L.mb_out_u0[(size_t)inst * P.nu + j] = has ? ip[(size_t)(P.T + 1) * P.nx + j] : nan("");
+                for (int j = WS_TID; j < P.nx; j += WS_NT) L.mb_out_x1[(size_t)inst * P.nx + j] = has ? ip[P.nx + j] : xc[(size_t)inst * P.nx + j];
+                if (WS_TID == 0) { L.mb_out_cost[inst] = has ? inc_cost[inst] : INFINITY; L.mb_out_status[inst] = st; }
+                __threadfence_system();
+                WS_SYNC();
+                if (WS_TID == 0) L.mb_out_step[inst] = t + 1;
+            }
         }
-        if (WS_TID == 0) {
-            status_out[inst] = st;
-            const size_t lo = (size_t)t * n_inst + inst;
-            L.log_cost[lo] = inc_cost[inst]; L.log_solves[lo] = n_solves[inst]; L.log_status[lo] = st;
-        }
-        WS_SYNC();
-        const int ovf = shift_instance<WS_NT, true>(P, SMV(pool), SMI(ired), SMI(ired) + 16, inst, xc, L.e ? L.e + (size_t)t * xs : nullptr,
-                                              cur, inc_cost, inc_primal, L.active, nxt, xn, L.log_u0 + (size_t)t * n_inst * P.nu);
-        if (ovf && WS_TID == 0) { status_out[inst] = BNB_CAPACITY; L.log_status[(size_t)t * n_inst + inst] = BNB_CAPACITY; }
-        prof_mark(19);
         if (WS_TID == 0) L.step_of[inst] = t + 1;
         __threadfence();                                   // release: the instance's data before the token
         WS_SYNC();
-        if (WS_TID == 0 && t + 1 < L.n_steps) {
-            const int S = L.n_steps;
+        if (WS_TID == 0 && t + 1 < S) {
             const int p = atomicAdd(L.q + 4 + S + (t + 1), 1);
             atomicExch(L.q + 4 + 2 * S + (size_t)(t + 1) * n_inst + p, inst);
         }

@@ -489,6 +489,21 @@ extern "C" int wshmpc_closed_loop(wshmpc_handle *h, int n_inst, const wshmpc_loo
     L.q = loop->d_queue; L.step_of = loop->d_step_of; L.x = loop->d_x; L.e = loop->d_e; L.active = loop->d_active;
     L.log_cost = loop->d_log_cost; L.log_u0 = loop->d_log_u0; L.log_solves = loop->d_log_solves; L.log_status = loop->d_log_status;
     WS_CUDA(cudaSetDevice(h->device));
+    L.mb_in_step = L.mb_out_step = L.mb_stop = nullptr; L.mb_in_x = L.mb_in_e = nullptr;
+    L.mb_out_u0 = L.mb_out_x1 = L.mb_out_cost = nullptr; L.mb_out_status = nullptr; L.mb_stage = nullptr;
+    if (loop->mailbox) {
+        const wshmpc_mailbox *mb = loop->mailbox;
+        if (mb->n_inst < n_inst || mb->nx != h->P.nx || mb->nu != h->P.nu || !mb->priv) WS_FAIL(-1, "mailbox does not match the problem / batch");
+        void *dp;
+#define MB_DEV(dst, type, src) WS_CUDA(cudaHostGetDevicePointer(&dp, (void *)(src), 0)); dst = (type)dp
+        MB_DEV(L.mb_in_step, volatile int *, mb->in_step); MB_DEV(L.mb_out_step, volatile int *, mb->out_step);
+        MB_DEV(L.mb_stop, volatile int *, mb->stop);
+        MB_DEV(L.mb_in_x, const volatile double *, mb->in_x); MB_DEV(L.mb_in_e, const volatile double *, mb->in_e);
+        MB_DEV(L.mb_out_u0, double *, mb->out_u0); MB_DEV(L.mb_out_x1, double *, mb->out_x1); MB_DEV(L.mb_out_cost, double *, mb->out_cost);
+        MB_DEV(L.mb_out_status, int *, mb->out_status);
+#undef MB_DEV
+        L.mb_stage = (double *)mb->priv;
+    }
     const int n_items = n_inst * (loop->n_steps + 1);
     loop_init_kernel<<<(n_items + 255) / 256, 256, 0, h->stream>>>(n_inst, n_items, L);
     WS_CUDA(cudaGetLastError());
@@ -502,6 +517,41 @@ extern "C" int wshmpc_closed_loop(wshmpc_handle *h, int n_inst, const wshmpc_loo
         h->P, h->slot_d, h->slot_i, h->ybuf, h->scratch, L, slots, n_inst, v0, v1, tol, max_solves,
         d_inc_cost, d_inc_node, d_inc_primal, d_n_solves, d_status, d_totals);
     WS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// host mailbox: pinned, mapped host memory the running kernel and the host both see
+extern "C" int wshmpc_mailbox_create(wshmpc_handle *h, int n_inst, wshmpc_mailbox *mb)
+{
+    if (!h || !mb || n_inst <= 0) WS_FAIL(-1, "null argument");
+    memset(mb, 0, sizeof(*mb));
+    WS_CUDA(cudaSetDevice(h->device));
+    const int nx = h->P.nx, nu = h->P.nu;
+    const size_t n_d = (size_t)n_inst * (nu + nx + 1 + nx + nx), n_i = (size_t)n_inst * 3 + 16;
+    double *hd = nullptr; int *hi = nullptr; double *stage = nullptr;
+    WS_CUDA(cudaHostAlloc((void **)&hd, n_d * sizeof(double), cudaHostAllocMapped | cudaHostAllocPortable));
+    if (cudaHostAlloc((void **)&hi, n_i * sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) { cudaFreeHost(hd); WS_FAIL(-2, "cudaHostAlloc failed"); }
+    if (cudaMalloc((void **)&stage, (size_t)n_inst * nx * sizeof(double)) != cudaSuccess) { cudaFreeHost(hd); cudaFreeHost(hi); WS_FAIL(-2, "cudaMalloc failed"); }
+    memset(hd, 0, n_d * sizeof(double)); memset(hi, 0, n_i * sizeof(int));
+    mb->n_inst = n_inst; mb->nx = nx; mb->nu = nu;
+    mb->out_u0 = hd; hd += (size_t)n_inst * nu;
+    mb->out_x1 = hd; hd += (size_t)n_inst * nx;
+    mb->out_cost = hd; hd += n_inst;
+    mb->in_x = hd; hd += (size_t)n_inst * nx;
+    mb->in_e = hd;
+    mb->out_step = hi; mb->in_step = hi + n_inst; mb->out_status = hi + 2 * (size_t)n_inst; mb->stop = hi + 3 * (size_t)n_inst;
+    mb->priv = stage;
+    return 0;
+}
+
+extern "C" int wshmpc_mailbox_destroy(wshmpc_handle *h, wshmpc_mailbox *mb)
+{
+    if (!mb) return 0;
+    if (h) cudaSetDevice(h->device);
+    if (mb->out_u0) cudaFreeHost(mb->out_u0);
+    if (mb->out_step) cudaFreeHost((void *)mb->out_step);
+    if (mb->priv) cudaFree(mb->priv);
+    memset(mb, 0, sizeof(*mb));
     return 0;
 }
 
