@@ -17,8 +17,9 @@ barrier between instances.  Instances are independent: ranks own contiguous bloc
 collective on the data path (weak scaling; `--scaling strong` fixes the total instead).
 
 Prints ONE JSON line (rank 0).  `value` = QP relaxations solved by all ranks / max-over-ranks device time,
-states resident in HBM; `e2e` = the same loop driven from HOST buffers through the public Python API
-(pinned H2D of the measured state and model error, D2H of input, cost and next state, every bench step).
+states resident in HBM; `e2e` = the same loop with the HOST in it every MPC step of every instance through the public
+Python API (ClosedLoop.run_mailbox: the kernel publishes each step's input to pinned mapped memory, a host plant answers
+with the measured state and model error; `e2e.per_window_io` = host I/O once per window instead).
 `--impl reference` times the CPU path (oracle/bnb_ref.py + oracle/qp_core.c, the restatement of the
 reference's Python B&B pinned bit-exactly against it -- Gurobi is not available offline) on the host cores.
 """
@@ -392,7 +393,7 @@ def run_b200(args):
     x0 = initial_states(args.workload, model, lo, hi)
     n_win = args.warmup + args.steps
     nx, nu = ctl.mld.nx, ctl.mld.nu
-    e_host = noise(model, (2 * n_win + 4) * S, n_inst, args.sigma, 1000 + rank).reshape(2 * n_win + 4, S, n_inst, -1)
+    e_host = noise(model, (3 * n_win + 4) * S, n_inst, args.sigma, 1000 + rank).reshape(3 * n_win + 4, S, n_inst, -1)
     e_dev = torch.as_tensor(e_host, device=dev)
 
     tiny = ClosedLoop(ctl, 1, warm=True, max_solves=64, max_roots=64, n_slots=1)      # loads the module, creates the context
@@ -447,12 +448,37 @@ def run_b200(args):
         torch.cuda.synchronize()                                                    # the host needs the inputs now
         xh.copy_(xnh)
     ms_e, qps_e, _, _ = timed_loop(torch, dist, loop, args.steps, world, e2e_step)
-    e2e = {'value': qps_e / (ms_e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': (S + 1) * n_inst * nx * 8,
-           'd2h_bytes_per_step': n_inst * (S * (nu + 1) + nx) * 8, 'ms_per_step': ms_e / args.steps,
-           'ms_per_mpc_step_of_the_batch': ms_e / args.steps / S,
-           'api': 'ClosedLoop.run(n_steps, e) of warm_start_hmpc_b200 (ctypes -> C ABI wshmpc_closed_loop): host I/O once per '
-                  'window of %d MPC steps, the plant (linear model + error) is advanced on the device; the per-MPC-step API with '
-                  'host I/O every step is timed in `per_mpc_step_api`' % S}
+    e2e_window = {'value': qps_e / (ms_e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': (S + 1) * n_inst * nx * 8,
+                  'd2h_bytes_per_step': n_inst * (S * (nu + 1) + nx) * 8, 'ms_per_step': ms_e / args.steps,
+                  'ms_per_mpc_step_of_the_batch': ms_e / args.steps / S,
+                  'api': 'ClosedLoop.run(n_steps, e): host I/O once per window of %d MPC steps, the plant (linear model + error) '
+                         'is advanced on the device' % S}
+
+    # ---- end to end with the HOST IN THE LOOP EVERY MPC STEP of every instance (the headline e2e): one persistent launch
+    # per bench step; after each B&B the kernel publishes the applied input / predicted state of that instance to a pinned
+    # mailbox, the host plant (numpy) answers with the measured state and the model error, and the instance's next step
+    # starts as soon as a lane picks it up -- no barrier between instances (wshmpc_mailbox, ClosedLoop.run_mailbox)
+    plant_calls = [0]
+
+    def mailbox_step(t):
+        ew = e_host[n_win + args.steps + t]
+
+        def plant(idx, step, u0, x1):
+            plant_calls[0] += 1
+            return x1 + ew[step, idx], ew[step, idx]
+        loop.run_mailbox(S, plant, logs=logs)
+    mailbox_step(-1)                                                            # allocates the mailbox (untimed)
+    plant_calls[0] = 0
+    ms_m, qps_m, _, _ = timed_loop(torch, dist, loop, args.steps, world, mailbox_step)
+    e2e = {'value': qps_m / (ms_m * 1e-3), 'unit': UNIT,
+           'h2d_bytes_per_step': S * n_inst * (2 * nx * 8 + 4), 'd2h_bytes_per_step': S * n_inst * ((nu + nx + 1) * 8 + 8),
+           'ms_per_step': ms_m / args.steps, 'ms_per_mpc_step_of_the_batch': ms_m / args.steps / S,
+           'host_plant_calls_per_step': plant_calls[0] / max(args.steps, 1),
+           'api': 'ClosedLoop.run_mailbox(n_steps, plant) of warm_start_hmpc_b200 (ctypes -> C ABI wshmpc_closed_loop with a '
+                  'wshmpc_mailbox): host I/O EVERY MPC step of EVERY instance through pinned mapped memory -- D2H applied input, '
+                  'predicted state, cost, status; H2D measured state and model error (host numpy plant x_1|t + e_t) -- with no barrier '
+                  'between instances; results bit-identical to the device-resident loop (tests/test_gpu_bnb.py)',
+           'per_window_io': e2e_window}
 
     # ---- roofline of the dominant kernel (closed_loop_kernel = K3 with K1 inside + K2/K4)
     pd = ctl.problem
@@ -545,8 +571,9 @@ def run_b200(args):
         ms_l, qps_l, _, _ = timed_loop(torch, dist, lock, n_lock, world, lock_step)
         line['per_mpc_step_api'] = {'value': qps_l / (ms_l * 1e-3), 'unit': UNIT, 'ms_per_mpc_step_of_the_batch': ms_l / n_lock,
                                     'h2d_bytes_per_mpc_step': 2 * n_inst * nx * 8, 'd2h_bytes_per_mpc_step': n_inst * (nu + 1 + nx) * 8,
-                                    'note': 'ClosedLoop.step(): host I/O every MPC step, one launch pair per step, every instance waits '
-                                            'for the slowest one of the step (10-30x the median number of QPs)'}
+                                    'note': 'ClosedLoop.step(): host I/O every MPC step IN LOCK STEP, one launch pair per step, every '
+                                            'instance waits for the slowest one of the step (10-30x the median number of QPs); the '
+                                            'mailbox loop timed in `e2e` has the same host I/O without that barrier'}
         del lock
         torch.cuda.empty_cache()
         if rank == 0:
