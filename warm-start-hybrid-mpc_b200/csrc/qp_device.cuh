@@ -720,22 +720,6 @@ __device__ __forceinline__ int thin_remove_t(const DevProblem &P, const Ctx &cx,
         rr[q] = r < k - 1 ? r : -1;
         ro[q] = r < kp ? r : r + 1;
     }
-#ifdef WS_FAST_SWEEP     // measured: bit-identical, 3 % SLOWER on the 512-instance loop (16 % more code); kept for experiments
-    // FAST sweep (the common case: at most 32 rows move up, they fit one warp).  The only hazard of the in-place update of Ri
-    // is between NEIGHBOURING rows that move up (row a is written where row a - 1 reads one column later); rows below kp
-    // and the rows of Q1 are updated by their owner alone.  With the rows kp .. k - 2 on the lanes of the LAST warp, a
-    // __syncwarp between the reads and the writes of a chunk orders them and the sweep needs no lane-wide barrier at all.
-    // Same operations on every element as the chunked sweep below: the result does not depend on which one runs.
-    const bool fast = WS_RRT == 1 && k - 1 - kp <= 32 && kp <= WS_NT - 32;
-    if (fast) {
-        const bool up = w == WS_NW - 1;
-        const int r = up ? kp + lane : WS_NT - 33 - tid;
-        rr[0] = (up ? r < k - 1 : r < kp) ? r : -1;
-        ro[0] = up ? r + 1 : r;
-    }
-#else
-    const bool fast = false;
-#endif
     const int nq1 = (2 * gm.he + 31) & ~31;
     const bool uth = tid == (nq1 < WS_NT ? nq1 : 0);
     const double big = 1. / P.tol_sing;
@@ -749,67 +733,6 @@ __device__ __forceinline__ int thin_remove_t(const DevProblem &P, const Ctx &cx,
         ls_old[q] = rr[q] >= 0 ? SMV(ls)[ro[q]] : 0.;                       // read before any thread writes its new entry
     }
     double ucarry = uth ? u[kp] : 0.;
-    if (fast) {
-#pragma unroll
-        for (int q = 0; q < WS_RRT; ++q) {
-            const int ts = kp + 1 + tid + q * WS_NT;
-            if (ts < k) { row[ts - 1] = rw[q]; side[ts - 1] = sd[q]; SMV(lam)[ts - 1] = lm[q]; }
-        }
-        {
-            const int rr0 = rr[0], ro0 = ro[0];
-            double rc = rcarry[0];
-            for (int i0 = kp; i0 < k - 1; i0 += 4) {
-                double b[4];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) { const int i = i0 + c; b[c] = (rr0 >= 0 && i < k - 1 && ro0 <= i + 1) ? RC(i + 1)[ro0] : 0.; }
-                __syncwarp();
-                if (rr0 >= 0 && ro0 <= i0 + 4) {
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const int i = i0 + c;
-                        if (i < k - 1) {
-                            const double cs = gc[i], sn = gs[i];
-                            const double o = cs * rc + sn * b[c];
-                            rc = -sn * rc + cs * b[c];
-                            if (rr0 <= i) {
-                                RC(i)[rr0] = o;
-                                if (rr0 == i && fabs(o) >= big) atomicMin(flag, rr0);
-                            }
-                        }
-                    }
-                }
-            }
-            rcarry[0] = rc;
-        }
-#pragma unroll
-        for (int q = 0; q < WS_RPT; ++q) if (qr[q] >= 0) {
-            const int ri = qr[q];
-            double qc = qcarry[q];
-            for (int i0 = kp; i0 < k - 1; i0 += 4) {
-                double bq[4];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) { const int i = i0 + c; bq[c] = i < k - 1 ? QC(i + 1)[ri] : 0.; }
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const int i = i0 + c;
-                    if (i < k - 1) {
-                        const double cs = gc[i], sn = gs[i];
-                        QC(i)[ri] = cs * qc + sn * bq[c];
-                        qc = -sn * qc + cs * bq[c];
-                    }
-                }
-            }
-            qcarry[q] = qc;
-        }
-        if (uth) {
-            for (int i = kp; i < k - 1; ++i) {
-                const double bu_ = u[i + 1];
-                const double cs = gc[i], sn = gs[i];
-                u[i] = cs * ucarry + sn * bu_;
-                ucarry = -sn * ucarry + cs * bu_;
-            }
-        }
-    } else
     for (int i0 = kp; i0 < k - 1; i0 += WS_CH) {
         double b[WS_RRT][WS_CH];
 #pragma unroll
@@ -889,14 +812,12 @@ __device__ __forceinline__ int thin_remove(const DevProblem &P, const Ctx &cx, i
 // remove position kp, then every row whose diagonal of R collapsed (see oracle/qp_core.c thin_ws_remove)
 __device__ __forceinline__ void ws_remove(const DevProblem &P, const Ctx &cx, int &k, int kp) {
     signed char *inW = reinterpret_cast<signed char *>(SMB(binW));
-    if (WS_TID == 0) inW[SMI(irow)[kp]] = 0;
-    WS_SYNC();
-    int bad = thin_remove(P, cx, k, kp);
-    while (bad >= 0) {
-        if (WS_TID == 0) inW[SMI(irow)[bad]] = 0;
+    int pos = kp;
+    do {                                   // ONE inlined copy of the removal (code size: the kernel's hot loop must stay in the instruction cache)
+        if (WS_TID == 0) inW[SMI(irow)[pos]] = 0;
         WS_SYNC();
-        bad = thin_remove(P, cx, k, bad);
-    }
+        pos = thin_remove(P, cx, k, pos);
+    } while (pos >= 0);
 }
 
 // sv_r = mh_r . x for all rows in factored form; calls f(r, sv) once per row.
@@ -1367,6 +1288,9 @@ restart:
         status = WS_ITER_LIMIT;
         while (it < cap) {
             ++it;
+            // an iteration decides on at most one removal (position `rem`) and one append (row `app`, side `apps`); both are
+            // carried out at the END of the iteration, by the only inlined copies of the removal and of the tracked append
+            int rem = -1, app = -1, apps = 0;
             if (pending < 0) {
                 // ratio test on the way to lam* = ls ; sum of the positive multipliers
                 // every warp runs the whole test (k / 32 entries per lane): no barrier, same bits in every thread
@@ -1393,9 +1317,8 @@ restart:
                     }
                     just_added = -1;
                     prof_mark(8);
-                    ws_remove(P, cx, k, kmin);
-                    continue;
-                }
+                    rem = kmin;
+                } else {
                 for (int i = WS_TID; i < k; i += WS_NT) lam[i] = ls[i] > 0. ? ls[i] : 0.;
                 const double vnoise = 1e-14 * lpart, vcap = 100. * P.tol_p;
                 double vbest = 0.; int ibest = -1;                 // ibest = 2 r + (lower side)
@@ -1442,15 +1365,8 @@ restart:
                     }
                     status = WS_OPTIMAL; break;
                 }
-                const int jb = ibest >> 1, sb = (ibest & 1) ? -1 : 1;
-                const int ar = thin_append(P, cx, k, jb, sb, true);
-                if (ar < 0) break;                                  // capacity: reported as iteration limit
-                if (ar) {
-                    kmax = max(kmax, k);
-                    if (WS_TID == 0) inW[jb] = (signed char)sb;
-                    just_added = jb;
-                    WS_SYNC();
-                } else { pending = jb; pside = sb; plam = 0.; }
+                app = ibest >> 1; apps = (ibest & 1) ? -1 : 1;
+                }
             } else {
                 // dependent entering row: dual ray (p_W, 1), p_W = -t
                 double pm = 1.;
@@ -1499,8 +1415,20 @@ restart:
                 plam += amin;
                 WS_SYNC();
                 if (WS_TID == 0 && amin <= 1e-9 * (1. + plam) && nadd[row[kmin]] < 255) ++nadd[row[kmin]];
-                ws_remove(P, cx, k, kmin);
-                if (thin_append(P, cx, k, pending, pside, true) > 0) {
+                rem = kmin; app = pending; apps = pside;
+            }
+            if (rem >= 0) ws_remove(P, cx, k, rem);
+            if (app >= 0) {
+                const int ar = thin_append(P, cx, k, app, apps, true);
+                if (pending < 0) {
+                    if (ar < 0) break;                                  // capacity: reported as iteration limit
+                    if (ar) {
+                        kmax = max(kmax, k);
+                        if (WS_TID == 0) inW[app] = (signed char)apps;
+                        just_added = app;
+                        WS_SYNC();
+                    } else { pending = app; pside = apps; plam = 0.; }
+                } else if (ar > 0) {
                     if (WS_TID == 0) { lam[k - 1] = plam; inW[pending] = (signed char)pside; }
                     pending = -1;
                     WS_SYNC();
