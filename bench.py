@@ -68,6 +68,8 @@ def parse_args():
     ap.add_argument('--sigma', type=float, default=0.003, help='model error std (fraction of x_max)')
     ap.add_argument('--max-solves', type=int, default=None)
     ap.add_argument('--max-roots', type=int, default=None)
+    ap.add_argument('--no-mailbox', action='store_true', help='e2e with host I/O once per window instead of the per-step mailbox (for runs '
+                    'under ncu: it serialises launches, and a mailbox launch would wait for a host that cannot answer)')
     ap.add_argument('--no-extras', action='store_true', help='skip the legs outside the headline (cold / fresh start / per-step API / '
                                                              'published protocol / K2+K4 roofline / cpu baseline)')
     ap.add_argument('--cpu-seconds', type=float, default=15., help='budget of the cpu_baseline sample')
@@ -467,18 +469,21 @@ def run_b200(args):
             plant_calls[0] += 1
             return x1 + ew[step, idx], ew[step, idx]
         loop.run_mailbox(S, plant, logs=logs)
-    mailbox_step(-1)                                                            # allocates the mailbox (untimed)
-    plant_calls[0] = 0
-    ms_m, qps_m, _, _ = timed_loop(torch, dist, loop, args.steps, world, mailbox_step)
-    e2e = {'value': qps_m / (ms_m * 1e-3), 'unit': UNIT,
-           'h2d_bytes_per_step': S * n_inst * (2 * nx * 8 + 4), 'd2h_bytes_per_step': S * n_inst * ((nu + nx + 1) * 8 + 8),
-           'ms_per_step': ms_m / args.steps, 'ms_per_mpc_step_of_the_batch': ms_m / args.steps / S,
-           'host_plant_calls_per_step': plant_calls[0] / max(args.steps, 1),
-           'api': 'ClosedLoop.run_mailbox(n_steps, plant) of warm_start_hmpc_b200 (ctypes -> C ABI wshmpc_closed_loop with a '
-                  'wshmpc_mailbox): host I/O EVERY MPC step of EVERY instance through pinned mapped memory -- D2H applied input, '
-                  'predicted state, cost, status; H2D measured state and model error (host numpy plant x_1|t + e_t) -- with no barrier '
-                  'between instances; results bit-identical to the device-resident loop (tests/test_gpu_bnb.py)',
-           'per_window_io': e2e_window}
+    if args.no_mailbox:
+        e2e = e2e_window
+    else:
+        mailbox_step(-1)                                                        # allocates the mailbox (untimed)
+        plant_calls[0] = 0
+        ms_m, qps_m, _, _ = timed_loop(torch, dist, loop, args.steps, world, mailbox_step)
+        e2e = {'value': qps_m / (ms_m * 1e-3), 'unit': UNIT,
+               'h2d_bytes_per_step': S * n_inst * (2 * nx * 8 + 4), 'd2h_bytes_per_step': S * n_inst * ((nu + nx + 1) * 8 + 8),
+               'ms_per_step': ms_m / args.steps, 'ms_per_mpc_step_of_the_batch': ms_m / args.steps / S,
+               'host_plant_calls_per_step': plant_calls[0] / max(args.steps, 1),
+               'api': 'ClosedLoop.run_mailbox(n_steps, plant) of warm_start_hmpc_b200 (ctypes -> C ABI wshmpc_closed_loop with a '
+                      'wshmpc_mailbox): host I/O EVERY MPC step of EVERY instance through pinned mapped memory -- D2H applied input, '
+                      'predicted state, cost, status; H2D measured state and model error (host numpy plant x_1|t + e_t) -- with no '
+                      'barrier between instances; results bit-identical to the device-resident loop (tests/test_gpu_bnb.py)',
+               'per_window_io': e2e_window}
 
     # ---- roofline of the dominant kernel (closed_loop_kernel = K3 with K1 inside + K2/K4)
     pd = ctl.problem

@@ -207,7 +207,8 @@ int wshmpc_shift_tree(wshmpc_handle *h, int n_inst, const double *d_x0, const do
  *                                                   controller.py:503-564), then in_step[i] = s + 1
  *   kernel, when a lane next picks instance i:      waits for in_step[i] >= s + 1, builds the warm start (K2 + K4), solves step s + 1
  * The host answers EVERY published step, also the last one of the launch and those of instances that report no incumbent.
- * `stop` != 0 (or 20 s without an answer) makes the kernel abandon the instances it waits for (status 4) and drain.
+ * `stop` != 0 (or `timeout_ms` without an answer; 0 = 5000 ms) makes the kernel abandon the instances it waits for
+ * (status 4) and drain -- a dead host, or a profiler that serialises launches, can never leave the GPU spinning.
  * Counters are per launch: zero in_step / out_step / stop before each wshmpc_closed_loop. */
 typedef struct {
     int n_inst, nx, nu;
@@ -220,6 +221,7 @@ typedef struct {
     double *in_x;                     /* [n_inst][nx] measured state the next step starts from */
     double *in_e;                     /* [n_inst][nx] model error */
     volatile int *stop;               /* [1] */
+    int timeout_ms;                   /* how long a lane waits for one answer before it gives the instance up (0: 5000 ms) */
     void *priv;                       /* library-owned (device scratch) */
 } wshmpc_mailbox;
 

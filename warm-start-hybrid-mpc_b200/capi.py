@@ -48,7 +48,8 @@ EXPORTS = ('wshmpc_last_error', 'wshmpc_ctas_per_sm', 'wshmpc_set_search_rule', 
 
 class _Mailbox(C.Structure):
     _fields_ = ([(k, C.c_int) for k in ('n_inst', 'nx', 'nu')]
-                + [(k, C.c_void_p) for k in ('out_step', 'out_u0', 'out_x1', 'out_cost', 'out_status', 'in_step', 'in_x', 'in_e', 'stop', 'priv')])
+                + [(k, C.c_void_p) for k in ('out_step', 'out_u0', 'out_x1', 'out_cost', 'out_status', 'in_step', 'in_x', 'in_e', 'stop')]
+                + [('timeout_ms', C.c_int), ('priv', C.c_void_p)])
 
 
 class Mailbox(object):

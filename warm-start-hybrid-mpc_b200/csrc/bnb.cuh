@@ -534,9 +534,9 @@ struct LoopView {
     double *mb_out_u0, *mb_out_x1, *mb_out_cost;
     int *mb_out_status;
     double *mb_stage;
+    unsigned long long mb_timeout_ns;   // a lane gives up on a silent host after this long (the launch then drains)
 };
 #define BNB_HOST_ABORT 4          // mailbox mode: the host stopped answering (stop flag or time-out)
-#define WS_MB_TIMEOUT_NS 20000000000ull     // a lane gives up on a silent host after 20 s (the launch then drains)
 
 #if WS_TU_HAS(0)
 __global__ void loop_init_kernel(int n_inst, int n_items, LoopView L)
@@ -641,7 +641,7 @@ closed_loop_body(const DevProblem &P, double *slot_d, int *slot_i, double *ybuf,
                     int ok = 1;
                     while (L.mb_in_step[inst] < t) {
                         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-                        if (*L.mb_stop != 0 || now - t_begin > WS_MB_TIMEOUT_NS) { ok = 0; break; }
+                        if (*L.mb_stop != 0 || now - t_begin > L.mb_timeout_ns) { ok = 0; break; }
                         __nanosleep(1000);
                     }
                     __threadfence_system();

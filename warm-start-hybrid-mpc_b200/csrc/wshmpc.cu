@@ -490,7 +490,7 @@ extern "C" int wshmpc_closed_loop(wshmpc_handle *h, int n_inst, const wshmpc_loo
     L.log_cost = loop->d_log_cost; L.log_u0 = loop->d_log_u0; L.log_solves = loop->d_log_solves; L.log_status = loop->d_log_status;
     WS_CUDA(cudaSetDevice(h->device));
     L.mb_in_step = L.mb_out_step = L.mb_stop = nullptr; L.mb_in_x = L.mb_in_e = nullptr;
-    L.mb_out_u0 = L.mb_out_x1 = L.mb_out_cost = nullptr; L.mb_out_status = nullptr; L.mb_stage = nullptr;
+    L.mb_out_u0 = L.mb_out_x1 = L.mb_out_cost = nullptr; L.mb_out_status = nullptr; L.mb_stage = nullptr; L.mb_timeout_ns = 0;
     if (loop->mailbox) {
         const wshmpc_mailbox *mb = loop->mailbox;
         if (mb->n_inst < n_inst || mb->nx != h->P.nx || mb->nu != h->P.nu || !mb->priv) WS_FAIL(-1, "mailbox does not match the problem / batch");
@@ -503,6 +503,7 @@ extern "C" int wshmpc_closed_loop(wshmpc_handle *h, int n_inst, const wshmpc_loo
         MB_DEV(L.mb_out_status, int *, mb->out_status);
 #undef MB_DEV
         L.mb_stage = (double *)mb->priv;
+        L.mb_timeout_ns = (unsigned long long)(mb->timeout_ms > 0 ? mb->timeout_ms : 5000) * 1000000ull;
     }
     const int n_items = n_inst * (loop->n_steps + 1);
     loop_init_kernel<<<(n_items + 255) / 256, 256, 0, h->stream>>>(n_inst, n_items, L);
