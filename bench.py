@@ -44,7 +44,7 @@ WORKLOADS = {
     'cp20': dict(model='cp20', instances=512, window=20, max_solves=1024, max_roots=512, steps=10, warmup=5,
                  text='cp20_closed_loop_warm_start (two-wall cart-pole, T=20, nx=4, nu=7, 4 binaries/step; '
                       'BASELINE configs[1] per instance, batched as configs[2])'),
-    'cp40': dict(model='cp40', instances=296, window=4, max_solves=4096, max_roots=1024, steps=4, warmup=3,
+    'cp40': dict(model='cp40', instances=592, window=4, max_solves=2048, max_roots=1024, steps=4, warmup=3,
                  text='cp40_closed_loop_warm_start (two-wall cart-pole, T=40: n=280 condensed inputs, 160 binaries, deep trees; '
                       'BASELINE configs[3])'),
     'syn30': dict(model='syn30', instances=148, window=2, max_solves=4096, max_roots=2048, steps=2, warmup=3,

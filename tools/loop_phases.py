@@ -12,15 +12,20 @@ NAMES = {0: 'bnb select + bounds', 1: 'load working set', 2: 'vf0', 3: 'rebuild 
          16: 'y_out + pinned', 17: 'build_records', 18: 'bnb post', 19: 'shift_instance', 20: 'queue pop',
          30: 'append: row load', 31: 'append: qt_dots', 32: 'append: q_apply', 33: 'append: sums', 34: 'append: reorth', 35: 'append: ri_matvec', 36: 'append: write',
          40: 'rebuild: row load', 41: 'rebuild: qt_dots', 42: 'rebuild: q_apply', 43: 'rebuild: sums', 44: 'rebuild: reorth', 45: 'rebuild: ri_matvec', 46: 'rebuild: write',
-         50: 'remove last', 51: 'remove: rotations', 52: 'remove: sweep', 53: 'remove: ri_matvec', 60: 'prox: bounds (xi)', 62: 'pricing xi', 127: 'start'}
+         50: 'remove last', 51: 'remove: rotations', 52: 'remove: sweep', 53: 'remove: ri_matvec', 54: 'sweep: loads + barrier', 55: 'sweep: Ri rows', 56: 'sweep: Q1 rows + u', 60: 'prox: bounds (xi)', 62: 'pricing xi', 127: 'start'}
 lib = load_library()
-model = load_model('cp20')
+MODEL = os.environ.get('WS_MODEL', 'cp20')
+model = load_model(MODEL)
 ctl = controller_from_model(model)
 from warm_start_hmpc_b200.instances import load_initial_states
-x0 = load_initial_states(0, N)
+if MODEL == 'cp20':
+    x0 = load_initial_states(0, N)
+else:
+    import bench
+    x0 = bench.initial_states(MODEL, model, 0, N)
 rng = np.random.default_rng(1)
-e = torch.as_tensor(0.003 * rng.standard_normal((6, S, N, 4)) * model['x_max'], device='cuda')
-L = ClosedLoop(ctl, N, warm=True, max_solves=1024, max_roots=512)
+e = torch.as_tensor(0.003 * rng.standard_normal((6, S, N, model['A'].shape[0])) * model['x_max'], device='cuda')
+L = ClosedLoop(ctl, N, warm=True, max_solves=1024 if MODEL == 'cp20' else 4096, max_roots=512 if MODEL == 'cp20' else 1024)
 L.reset(x0)
 buf = (C.c_ulonglong * 256)()
 for w in range(6):

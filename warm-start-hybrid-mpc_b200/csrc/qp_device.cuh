@@ -741,6 +741,7 @@ __device__ __forceinline__ int thin_remove_t(const DevProblem &P, const Ctx &cx,
             for (int c = 0; c < WS_CH; ++c) { const int i = i0 + c; b[q][c] = (i < k - 1 && ro[q] <= i + 1) ? RC(i + 1)[ro[q]] : 0.; }
         }
         WS_SYNC();                                                          // every old entry of the chunk has been read
+        prof_mark(54);
         if (i0 == kp) {
 #pragma unroll
             for (int q = 0; q < WS_RRT; ++q) {
@@ -765,6 +766,7 @@ __device__ __forceinline__ int thin_remove_t(const DevProblem &P, const Ctx &cx,
             }
         }
         const int iend = (i0 + WS_CH < k - 1) ? i0 + WS_CH : k - 1;
+        prof_mark(55);
 #pragma unroll
         for (int q = 0; q < WS_RPT; ++q) if (qr[q] >= 0) {
             for (int i = i0; i < iend; ++i) {
@@ -782,6 +784,7 @@ __device__ __forceinline__ int thin_remove_t(const DevProblem &P, const Ctx &cx,
                 ucarry = -sn * ucarry + cs * bu_;
             }
         }
+        prof_mark(56);
     }
     if (uth) SMV(red)[40] = ucarry;                                  // (G u)_last
     k -= 1;
