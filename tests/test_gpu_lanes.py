@@ -179,3 +179,37 @@ def test_static_branch_orders_on_the_device_equal_the_host_loop(cp20, order_name
     sol_c, _, n_c, _ = ctl.feedforward(x1, printing_period=None)
     assert abs(sol_w.objective - sol_c.objective) <= 1e-9 * sol_c.objective
     assert np.array_equal(np.array(sol_w.variables['ub']), np.array(sol_c.variables['ub']))
+
+
+def test_nonlinear_plant_through_the_mailbox_equals_lock_step(cp20):
+    """The TRUE plant in the loop every step of every instance WITHOUT lock step (ClosedLoop.run_mailbox, one persistent
+    launch, plant called per ready instance) gives bit for bit what ClosedLoop.step_with_plant gives step by step: the
+    plant is a deterministic function of (measured state, applied input), and the kernel's answers do not depend on
+    which lane solves what when."""
+    model, ctl = cp20
+    from warm_start_hmpc_b200.closed_loop import ClosedLoop
+    from warm_start_hmpc_b200.plants import CartPoleWithWalls
+    plant = CartPoleWithWalls()
+    h = 0.05
+    N, S = 6, 12
+    x0 = np.repeat(model['x0_nominal'][None], N, 0) * np.linspace(1., 0.8, N)[:, None]
+    lock = ClosedLoop(ctl, N, warm=True, max_solves=2048, max_roots=1024, n_slots=N)
+    lock.reset(x0)
+    costs, inputs = [], []
+    for t in range(S):
+        out, u0, e = lock.step_with_plant(lambda x, u: plant.simulate(x, h, u[:, 0]))
+        costs.append(out['cost'].cpu().numpy().copy()); inputs.append(u0.copy())
+    mbx = ClosedLoop(ctl, N, warm=True, max_solves=2048, max_roots=1024, n_slots=N)
+    mbx.reset(x0)
+    x_meas = np.array(x0)                                      # the host keeps the measured state of every plant
+
+    def host_plant(idx, step, u0, x_pred):
+        x_meas[idx] = plant.simulate(x_meas[idx], h, u0[:, 0])
+        return x_meas[idx]
+    logs = mbx.run_mailbox(S, host_plant, timeout_s=60.)
+    torch.cuda.synchronize()
+    costs = np.array(costs)
+    assert np.isfinite(costs).all()
+    assert np.array_equal(logs['cost'].cpu().numpy(), costs)
+    assert np.array_equal(logs['host']['u0'], np.array(inputs))
+    assert torch.equal(mbx.x, lock.x)

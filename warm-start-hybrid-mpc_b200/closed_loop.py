@@ -127,6 +127,10 @@ class ClosedLoop(object):
         new = self.trees[1 - self.cur]
         h.shift_tree(self.x, ed, tree, self.out['cost'], self.out['primal'], new, active=self.active,
                      x_next=self.xbuf[1 - self.xpar], u0=self.u0)
+        if live.any():
+            # the next step starts from the MEASURED state itself (x_1|t + (x_measured - x_1|t) is one rounding away from it)
+            lv = torch.as_tensor(live, device=self.x.device)
+            self.xbuf[1 - self.xpar][lv] = torch.as_tensor(x_meas[live], device=self.x.device)
         self.cur = 1 - self.cur
         self.xpar = 1 - self.xpar
         self.launches += 1
