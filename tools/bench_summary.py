@@ -12,7 +12,7 @@ for f in sys.argv[1:]:
         r = d['roofline']
         print('  roofline frac %.4f achieved %.3f TF hbm frac %.5f lanes %s' % (r['frac'], r['achieved'], r['hbm']['frac'], r['solver_lanes_per_sm']))
     if 'from_fresh_states' in d:
-        print('  fresh', {k: (round(v, 2) if isinstance(v, float) else v) for k, v in d['from_fresh_states'].items() if k != 'note'})
+        print('  fresh', {k: (round(v, 2) if isinstance(v, float) else v) for k, v in d['from_fresh_states'].items() if k not in ('note', 'one_launch')}, 'one launch: %.0f' % d['from_fresh_states'].get('one_launch', {}).get('value', 0))
     for k in ('roofline_k2k4', 'cold_start', 'per_mpc_step_api', 'single_instance_nominal', 'cpu_baseline'):
         if d.get(k):
             print('  ', k, {kk: (round(v, 4) if isinstance(v, float) else v) for kk, v in d[k].items() if kk not in ('note', 'sample')})
