@@ -282,8 +282,11 @@ __device__ __forceinline__ void warp_copy(double *__restrict__ dst, const double
 
 // doubles of shared scratch the shift needs with NT threads
 __host__ __device__ __forceinline__ size_t shift_smem_doubles(const DevProblem &P, int nt) {
-    return (size_t)2 * P.nx + P.nu + P.nq + P.nr + P.nh + (size_t)(nt / 32) * (P.nh1 + P.nqT + P.nh + P.nq) + 8;
+    // ... + one mbarrier per warp (TMA staging of the dual records), kept even so that what follows is 16-byte aligned
+    return ((size_t)2 * P.nx + P.nu + P.nq + P.nr + P.nh + (size_t)(nt / 32) * (P.nh1 + P.nqT + P.nh + P.nq) + 8 + nt / 32 + 1) & ~(size_t)1;
 }
+// doubles of one staging buffer: the dual part of a record (the proximal centre behind it is not read by the shift)
+__host__ __device__ __forceinline__ size_t shift_stage_doubles(const DevProblem &P) { return ((size_t)P.n_dual + 1) & ~(size_t)1; }
 
 // warm start of ONE instance by the calling CTA (NT threads): shm = shared scratch (shift_smem_doubles),
 // s_wsum (NT / 32 ints) and s_base (1 int) shared as well.
@@ -292,8 +295,13 @@ __host__ __device__ __forceinline__ size_t shift_smem_doubles(const DevProblem &
 // with an incomplete cover -- a truncated cover could report a suboptimal or "infeasible" MIQP as solved.
 // LANE: the caller is a solver lane of WS_NT threads (fused loop): lane-local thread index and the lane's named barrier;
 // otherwise a whole CTA of NT threads.
+// stage_avail: doubles of shared memory behind the scratch (shm + shift_smem_doubles) that may hold staging buffers.  A warp
+// with a buffer pulls the WHOLE dual record of its leaf into shared memory with one TMA bulk copy (cp.async.bulk,
+// completion on the warp's mbarrier) and runs every loop of the shift on that copy: one DRAM / L2 latency per leaf instead
+// of one per field of the record (HBM-bound stream).  Warps without a buffer read the record in place; the
+// arithmetic is the same either way.
 template <int NT, bool LANE>
-__device__ __forceinline__ int shift_instance(const DevProblem &P, double *shm, int *s_wsum, int *s_base_p, int inst,
+__device__ __forceinline__ int shift_instance(const DevProblem &P, double *shm, int stage_avail, int *s_wsum, int *s_base_p, int inst,
                                       const double *__restrict__ x0, const double *__restrict__ e0,
                                       const TreeView &ot, const double *__restrict__ inc_cost, const double *__restrict__ inc_primal,
                                       int *active, const TreeView &nt, double *x_next, double *u0_out)
@@ -385,6 +393,18 @@ __device__ __forceinline__ int shift_instance(const DevProblem &P, double *shm, 
     }
     const int nnew = s_base;
     // ---- pass 2: one warp per retained leaf
+    const size_t scr = shift_smem_doubles(P, NT), sbuf = shift_stage_doubles(P);
+#if defined(WS_NO_STAGE)
+    stage_avail = 0;
+#endif
+    const bool staged = (P.n_dual & 1) == 0 && stage_avail > 0 && (size_t)stage_avail >= (size_t)(w + 1) * sbuf;
+    double *stage = shm + scr + (size_t)w * sbuf;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(shm + scr - (NT / 32 + 1)) + w;
+    uint32_t par = 0;
+    if (staged) {
+        if (lane == 0) { mbar_init(bar, 1); fence_async_smem(); }
+        __syncwarp();
+    }
     for (int idx = w; idx < nnew; idx += (NT / 32)) {
         const int j = nt.rec[on_ + idx];
         const int ro = ot.rec[oo + j];
@@ -396,8 +416,17 @@ __device__ __forceinline__ int shift_instance(const DevProblem &P, double *shm, 
             if (lane == 0) { nt.lb[on_ + idx] = 0.; nt.rec[on_ + idx] = -1; nt.rec_dobj[(size_t)inst * nt.cap_recs + idx] = 0.; }
             continue;
         }
-        const double *D = ot.rec_dual + ((size_t)inst * ot.cap_recs + ro) * P.n_rec;
-        warp_prefetch_l2(D, P.n_dual, lane);
+        const double *Dg = ot.rec_dual + ((size_t)inst * ot.cap_recs + ro) * P.n_rec;
+        if (staged) {
+            __syncwarp();                                  // every lane is done with the previous leaf's copy
+            if (lane == 0) {
+                fence_async_smem();
+                mbar_expect_tx(bar, (uint32_t)(P.n_dual * 8));
+                bulk_g2s(stage, Dg, (uint32_t)(P.n_dual * 8), bar);
+            }
+        } else {
+            warp_prefetch_l2(Dg, P.n_dual, lane);
+        }
         {   // ... and the record of the leaf this warp takes next
             const int nx_idx = idx + (NT / 32);
             if (nx_idx < nnew) {
@@ -406,6 +435,8 @@ __device__ __forceinline__ int shift_instance(const DevProblem &P, double *shm, 
             }
         }
         for (int e = P.n_dual + lane; e < P.n_rec; e += 32) E[e] = 0.;          // a shifted root starts from the centre 0
+        const double *D = Dg;
+        if (staged) { mbar_wait(bar, par); par ^= 1u; D = stage; }
         const unsigned int b0 = ot.bits[(oo + j) * ot.words], m0 = ot.mask[(oo + j) * ot.words];
         double acc = 0.;                     // pi_sum + pi3, lane-partial
         // lam: drop t = 0, append zero ; pi3 = -lam'_0 . e0 (controller.py:544)
@@ -454,18 +485,25 @@ __device__ __forceinline__ int shift_instance(const DevProblem &P, double *shm, 
             warp_copy(t, s + nh, (T - 2) * nh, lane);
             for (int e = lane; e < nh; e += 32) acc -= rmu[e] * s[e];
             double *mT = wscr + nqT;
-            for (int e = lane; e < nh1; e += 32) { const double v = s[(T - 1) * nh + e]; mT[e] = v; acc += P.h1[e] * v; t[(T - 1) * nh + e] = 0.; }
+            int nz = 0;
+            for (int e = lane; e < nh1; e += 32) { const double v = s[(T - 1) * nh + e]; mT[e] = v; nz |= (v != 0.) ? 1 : 0; acc += P.h1[e] * v; t[(T - 1) * nh + e] = 0.; }
             __syncwarp();
+            // A leaf that has been shifted before has mu_{T-1} = 0 (written just above, one step ago): M_mu mu_{T-1} is then
+            // +0 in every entry whatever the order of the sums, and the nh1 x nh operator -- 29 KB streamed from L2 by every
+            // leaf, 43 % of the stall samples of this kernel (profiles/r02b_shift_tree_kernel_ncu_summary.txt) -- is not read.
+            const bool any_mu = __any_sync(0xffffffffu, nz) != 0;
             // M_mu stored transposed: the lanes of a warp read consecutive words, four independent chains per lane
             for (int i = lane; i < nh; i += 32) {
                 double v0 = 0., v1 = 0., v2 = 0., v3 = 0.;
                 const double *mc_ = P.MmuT + i;
                 int c = 0;
-                for (; c + 3 < nh1; c += 4) {
-                    v0 += __ldg(mc_ + (size_t)c * nh) * mT[c]; v1 += __ldg(mc_ + (size_t)(c + 1) * nh) * mT[c + 1];
-                    v2 += __ldg(mc_ + (size_t)(c + 2) * nh) * mT[c + 2]; v3 += __ldg(mc_ + (size_t)(c + 3) * nh) * mT[c + 3];
+                if (any_mu) {
+                    for (; c + 3 < nh1; c += 4) {
+                        v0 += __ldg(mc_ + (size_t)c * nh) * mT[c]; v1 += __ldg(mc_ + (size_t)(c + 1) * nh) * mT[c + 1];
+                        v2 += __ldg(mc_ + (size_t)(c + 2) * nh) * mT[c + 2]; v3 += __ldg(mc_ + (size_t)(c + 3) * nh) * mT[c + 3];
+                    }
+                    for (; c < nh1; ++c) v0 += __ldg(mc_ + (size_t)c * nh) * mT[c];
                 }
-                for (; c < nh1; ++c) v0 += __ldg(mc_ + (size_t)c * nh) * mT[c];
                 const double v = (v0 + v1) + (v2 + v3);
                 t[(T - 2) * nh + i] = v; acc -= P.h[i] * v;
             }
@@ -482,6 +520,11 @@ __device__ __forceinline__ int shift_instance(const DevProblem &P, double *shm, 
             nt.lb[on_ + idx] = lbn; nt.rec[on_ + idx] = rn; nt.rec_dobj[(size_t)inst * nt.cap_recs + idx] = obj;
         }
     }
+    if (staged) {
+        // the barrier's memory goes back to the solver (LANE) / is initialised again for the next instance: invalidate it
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+    }
     sync();
     if (tid_ == 0) { nt.n_nodes[inst] = nnew; nt.n_recs[inst] = nnew; }
     return 0;
@@ -492,19 +535,29 @@ __device__ __forceinline__ int shift_instance(const DevProblem &P, double *shm, 
 __global__ void __launch_bounds__(SH_NT)
 shift_tree_kernel(DevProblem P, int n_inst, const double *__restrict__ x0, const double *__restrict__ e0,
                   TreeView ot, const double *__restrict__ inc_cost, const double *__restrict__ inc_primal,
-                  int *active, TreeView nt, double *x_next, double *u0_out)
+                  int *active, TreeView nt, double *x_next, double *u0_out, int stage_avail)
 {
     extern __shared__ __align__(16) double shm[];
     __shared__ int s_wsum[SH_NW];
     __shared__ int s_base_v;
     for (int inst = blockIdx.x; inst < n_inst; inst += gridDim.x) {
         __syncthreads();
-        shift_instance<SH_NT, false>(P, shm, s_wsum, &s_base_v, inst, x0, e0, ot, inc_cost, inc_primal, active, nt, x_next, u0_out);
+        shift_instance<SH_NT, false>(P, shm, stage_avail, s_wsum, &s_base_v, inst, x0, e0, ot, inc_cost, inc_primal, active, nt, x_next, u0_out);
     }
 }
 #endif
 
-__host__ inline size_t shift_smem_bytes(const DevProblem &P) { return sizeof(double) * shift_smem_doubles(P, SH_NT); }
+// scratch + as many staging buffers as warps, if the device's shared memory holds them (else fewer; 0 = none)
+__host__ inline size_t shift_smem_bytes(const DevProblem &P, size_t optin, int *stage_avail) {
+    const size_t scr = shift_smem_doubles(P, SH_NT), sbuf = shift_stage_doubles(P);
+    size_t nb = SH_NT / 32;
+#if defined(WS_NO_STAGE)
+    nb = 0;
+#endif
+    while (nb > 0 && (scr + nb * sbuf) * sizeof(double) > optin) --nb;
+    *stage_avail = (int)(nb * sbuf);
+    return sizeof(double) * (scr + nb * sbuf);
+}
 
 
 // ---------------------------------------------------------------------------------------------
@@ -663,7 +716,7 @@ closed_loop_body(const DevProblem &P, double *slot_d, int *slot_i, double *ybuf,
                 for (int j = WS_TID; j < P.nx; j += WS_NT) xn[(size_t)inst * P.nx + j] = xc[(size_t)inst * P.nx + j];
             }
             WS_SYNC();
-            const int ovf = shift_instance<WS_NT, true>(P, SMV(pool), SMI(ired), SMI(ired) + 16, inst, xc, L.mb_stage, cur, inc_cost, inc_primal,
+            const int ovf = shift_instance<WS_NT, true>(P, SMV(pool), P.so.pool_sz - (int)shift_smem_doubles(P, WS_NT), SMI(ired), SMI(ired) + 16, inst, xc, L.mb_stage, cur, inc_cost, inc_primal,
                                                   L.active, nxt, nullptr, L.log_u0 + (size_t)ts * n_inst * P.nu);
             if (ovf && WS_TID == 0) { status_out[inst] = BNB_CAPACITY; L.log_status[(size_t)ts * n_inst + inst] = BNB_CAPACITY; }
             prof_mark(19);
@@ -695,7 +748,7 @@ closed_loop_body(const DevProblem &P, double *slot_d, int *slot_i, double *ybuf,
             }
             WS_SYNC();
             if (!mbx) {
-                const int ovf = shift_instance<WS_NT, true>(P, SMV(pool), SMI(ired), SMI(ired) + 16, inst, xc, L.e ? L.e + (size_t)t * xs : nullptr,
+                const int ovf = shift_instance<WS_NT, true>(P, SMV(pool), P.so.pool_sz - (int)shift_smem_doubles(P, WS_NT), SMI(ired), SMI(ired) + 16, inst, xc, L.e ? L.e + (size_t)t * xs : nullptr,
                                                       cur, inc_cost, inc_primal, L.active, nxt, xn, L.log_u0 + (size_t)t * n_inst * P.nu);
                 if (ovf && WS_TID == 0) { status_out[inst] = BNB_CAPACITY; L.log_status[(size_t)t * n_inst + inst] = BNB_CAPACITY; }
                 prof_mark(19);

@@ -32,7 +32,7 @@ struct wshmpc_handle {
     double *ybuf;            // n_slots x m : signed row multipliers of the node being solved
     double *scratch;         // n_slots x bnb_scratch_doubles : node bounds, primal record of the node being solved
     int *work_counter;       // instance hand-out of the B&B kernel
-    size_t shift_smem;
+    size_t shift_smem; int shift_stage;      // dynamic shared memory of shift_tree_kernel, of which staging buffers (doubles)
     size_t smem;
     wshmpc_layout layout;
 };
@@ -307,7 +307,7 @@ extern "C" int wshmpc_create(const wshmpc_problem *p, int device, int n_slots, v
     WS_CUDA(cudaFuncSetAttribute(closed_loop_kernel_m, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
     WS_CUDA(cudaMalloc(&d, (size_t)n_slots * bnb_scratch_doubles(p->nb, L.primal) * sizeof(double))); h->allocs.push_back(d); h->scratch = (double *)d;
     WS_CUDA(cudaMalloc(&d, 64)); h->allocs.push_back(d); h->work_counter = (int *)d;
-    h->shift_smem = shift_smem_bytes(P);
+    h->shift_smem = shift_smem_bytes(P, optin, &h->shift_stage);
     if (h->shift_smem > 48 * 1024)
         WS_CUDA(cudaFuncSetAttribute(shift_tree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->shift_smem));
     {
@@ -461,7 +461,7 @@ extern "C" int wshmpc_shift_tree(wshmpc_handle *h, int n_inst, const double *d_x
     if (ov.words != nv.words) WS_FAIL(-1, "old and new tree differ in words");
     WS_CUDA(cudaSetDevice(h->device));
     shift_tree_kernel<<<n_inst, SH_NT, h->shift_smem, h->stream>>>(
-        h->P, n_inst, d_x0, d_e0, ov, d_inc_cost, d_inc_primal, d_active, nv, d_x_next, d_u0);
+        h->P, n_inst, d_x0, d_e0, ov, d_inc_cost, d_inc_primal, d_active, nv, d_x_next, d_u0, h->shift_stage);
     WS_CUDA(cudaGetLastError());
     return 0;
 }
