@@ -8,7 +8,7 @@
 #include "qp_device.cuh"
 
 // yc: solution in orthonormal coordinates (shared memory), y: signed row multipliers (global, m).
-// scratch: >= max(WS_NT, n) doubles of shared memory (Smem::part).  Returns cost (inf if infeasible) and dual objective.
+// scratch: >= max(WS_NT, n, 2 (T + 1) nx) doubles of shared memory (Smem::part).  Returns cost (inf if infeasible) and dual objective.
 __device__ __forceinline__ void build_records(const DevProblem &P, int status, const double *yc, const double *y,
                                      const double *x0, const double *lb, const double *ub,
                                      double *primal, double *dual, double *cost_out, double *dobj_out,
@@ -29,18 +29,21 @@ __device__ __forceinline__ void build_records(const DevProblem &P, int status, c
         if (nx <= 32) {
             // x_{t+1} = A x_t + B u_t: the input terms of all stages in parallel, then ONE warp runs the recursion with
             // the state in registers (lane j holds x_t[j]) -- no barrier per stage
+            // (the input terms wait in SHARED memory: read back from the global record inside the recursion, every stage
+            // would expose an L2 round trip -- the stores of the loop keep the compiler from hoisting the loads)
+            double *bx = scratch + (size_t)(T + 1) * nx;
             for (int e = WS_TID; e < T * nx; e += WS_NT) {
                 const int t = e / nx, j = e - t * nx;
                 double s = 0.;
                 for (int c = 0; c < nu; ++c) s += P.B[j * nu + c] * U[(size_t)t * nu + c];
-                X[(size_t)(t + 1) * nx + j] = s;
+                bx[e] = s;
             }
             WS_SYNC();
             if (WS_TID < 32) {
                 const int j = WS_TID < nx ? WS_TID : 0;
                 double xj = X[j];
                 for (int t = 0; t < T; ++t) {
-                    double s = X[(size_t)(t + 1) * nx + j];
+                    double s = bx[(size_t)t * nx + j];
                     for (int c = 0; c < nx; ++c) s += P.A[j * nx + c] * __shfl_sync(0xffffffffu, xj, c);
                     if (WS_TID < nx) X[(size_t)(t + 1) * nx + j] = s;
                     xj = s;
@@ -91,10 +94,12 @@ __device__ __forceinline__ void build_records(const DevProblem &P, int status, c
     }
     WS_SYNC();
     // lam_T = -Q_T' rho_T ; lam_t = A' lam_{t+1} - Q' rho_t - F_t' mu_t
+    double *g = scratch;                       // (T + 1) nx: lam_T and the g_t in shared memory for the backward recursion
     for (int j = WS_TID; j < nx; j += WS_NT) {
         double s = 0.;
         for (int i = 0; i < P.nqT; ++i) s += P.QT[i * nx + j] * rho[T * P.nq + i];
         lam[(size_t)T * nx + j] = -s;
+        g[(size_t)T * nx + j] = -s;
     }
     WS_SYNC();
     if (nx <= 32) {
@@ -110,15 +115,15 @@ __device__ __forceinline__ void build_records(const DevProblem &P, int status, c
                 for (int i = lane; i < k; i += 32) s += Ft[i * nx + j] * mut[i];
                 for (int i = lane; i < P.nq; i += 32) s += P.Q[i * nx + j] * rho[(size_t)t * P.nq + i];
                 s = warp_sum(s);
-                if (lane == 0) lam[(size_t)t * nx + j] = -s;
+                if (lane == 0) g[(size_t)t * nx + j] = -s;
             }
         }
         WS_SYNC();
         if (WS_TID < 32) {
             const int j = WS_TID < nx ? WS_TID : 0;
-            double lj = lam[(size_t)T * nx + j];
+            double lj = g[(size_t)T * nx + j];
             for (int t = T - 1; t >= 0; --t) {
-                double s = lam[(size_t)t * nx + j];
+                double s = g[(size_t)t * nx + j];
                 for (int c = 0; c < nx; ++c) s += P.A[c * nx + j] * __shfl_sync(0xffffffffu, lj, c);
                 if (WS_TID < nx) lam[(size_t)t * nx + j] = s;
                 lj = s;
