@@ -564,15 +564,16 @@ def run_b200(args):
         torch.cuda.empty_cache()
         # the same MPC steps 0 .. warmup x window - 1 from fresh states as ONE launch (BASELINE configs[1]: 100 receding-horizon
         # steps on CP20): no launch boundary every `window` steps, so no instance waits for the slowest one of a window
-        fr = ClosedLoop(ctl, n_inst, warm=True, max_solves=args.max_solves, max_roots=args.max_roots)
-        fr.reset(x0)
         n_fr = args.warmup * S
-        ms_f, qps_f, _, _ = timed_loop(torch, dist, fr, 1, world, lambda t: fr.run(n_fr, e=e_dev[:args.warmup].reshape(n_fr, n_inst, nx)))
-        line['from_fresh_states']['one_launch'] = {
-            'value': qps_f / (ms_f * 1e-3), 'unit': UNIT, 'mpc_steps': n_fr, 'qp': qps_f, 'ms_per_mpc_step_of_the_batch': ms_f / n_fr,
-            'note': 'all ranks, CUDA events: the same steps and model errors in ONE fused launch'}
-        del fr
-        torch.cuda.empty_cache()
+        if n_fr > 0:
+            fr = ClosedLoop(ctl, n_inst, warm=True, max_solves=args.max_solves, max_roots=args.max_roots)
+            fr.reset(x0)
+            ms_f, qps_f, _, _ = timed_loop(torch, dist, fr, 1, world, lambda t: fr.run(n_fr, e=e_dev[:args.warmup].reshape(n_fr, n_inst, nx)))
+            line['from_fresh_states']['one_launch'] = {
+                'value': qps_f / max(ms_f * 1e-3, 1e-9), 'unit': UNIT, 'mpc_steps': n_fr, 'qp': qps_f, 'ms_per_mpc_step_of_the_batch': ms_f / n_fr,
+                'note': 'all ranks, CUDA events: the same steps and model errors in ONE fused launch'}
+            del fr
+            torch.cuda.empty_cache()
         cold = ClosedLoop(ctl, n_inst, warm=False, max_solves=args.max_solves, max_roots=args.max_roots)
         cold.reset(x0)
         cold.run(1, e=e_dev[0, :1])
