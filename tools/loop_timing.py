@@ -8,12 +8,17 @@ from warm_start_hmpc_b200.closed_loop import ClosedLoop
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 NW = int(sys.argv[2]) if len(sys.argv) > 2 else 6
 S = int(sys.argv[3]) if len(sys.argv) > 3 else 10
-model = load_model('cp20')
+MODEL = os.environ.get('WS_MODEL', 'cp20')
+model = load_model(MODEL)
 ctl = controller_from_model(model)
-x0 = load_initial_states(0, N)
+if MODEL == 'cp20':
+    x0 = load_initial_states(0, N)
+else:
+    import bench
+    x0 = bench.initial_states(MODEL, model, 0, N)
 rng = np.random.default_rng(1)
-e = torch.as_tensor(0.003 * rng.standard_normal((NW, S, N, 4)) * model['x_max'], device='cuda')
-L = ClosedLoop(ctl, N, warm=True, max_solves=1024, max_roots=512)
+e = torch.as_tensor(0.003 * rng.standard_normal((NW, S, N, model['A'].shape[0])) * model['x_max'], device='cuda')
+L = ClosedLoop(ctl, N, warm=True, max_solves=1024 if MODEL == 'cp20' else 2048, max_roots=512 if MODEL == 'cp20' else 1024)
 print('lanes per CTA', ctl.default_slots() // 148, 'slots', L.h.n_slots, flush=True)
 L.reset(x0)
 for w in range(NW):

@@ -72,8 +72,26 @@
 #ifndef WS_NOINLINE
 #define WS_NOINLINE __forceinline__      // measured: out-of-line phases (__noinline__) shrink the code by a third and cost 25 % (call ABI spills)
 #endif
+// Register-budget knobs of a translation unit: the one-lane kernels (units 1, 3, 5) have 255 registers per thread, the two-lane
+// kernels (2, 4, 6; also single-unit builds) 128.  None of them changes a result.
+#if defined(WS_TU) && (WS_TU == 1 || WS_TU == 3 || WS_TU == 5)
+#define WS_WIDE_REGS 1
+#else
+#define WS_WIDE_REGS 0
+#endif
 #ifndef WS_CH
-#define WS_CH 4                 // columns per chunk of the removal sweep (8 spills under the 128-register cap of two lanes)
+// columns per chunk of the removal sweep (results do not depend on it).  Measured on the 512-instance loop, two-lane build
+// (128 registers): 1: 407 k, 2: 417 k, 3: 412 k, 4: 403 k, 8: 370 k QP/s; one-lane build (255 registers, CP40): 4 and 2 within 1 %
+#if WS_WIDE_REGS
+#define WS_CH 4                 // the one-lane kernels
+#else
+#define WS_CH 2                 // the two-lane kernels (and single-unit builds)
+#endif
+#endif
+// loads of the pricing operator a thread keeps in flight: 8 with 255 registers; 4 under the 128-register cap (the same
+// accumulators take the same columns in the same order either way; measured +0.7 % on the 512-instance loop)
+#if !WS_WIDE_REGS && !defined(WS_PRICE8)
+#define WS_PRICE4 1
 #endif
 #define WS_OPTIMAL 2
 #define WS_INFEASIBLE 3
@@ -844,6 +862,7 @@ __device__ __forceinline__ void price_rows(const DevProblem &P, const Ctx &cx, c
             int c = c0 + cx.pg;
             const int G = P.gp;
             // 8 independent 16-byte loads in flight per thread: the operator comes from L2 (~700 cycles a round trip)
+#ifndef WS_PRICE4
             for (; c + 7 * G < n; c += 8 * G) {
                 double2 w[8];
 #pragma unroll
@@ -855,6 +874,7 @@ __device__ __forceinline__ void price_rows(const DevProblem &P, const Ctx &cx, c
                     ex += w[q + 2].x * xe; ey += w[q + 2].y * xe; dx += w[q + 3].x * xd; dy += w[q + 3].y * xd;
                 }
             }
+#endif
             for (; c + 3 * G < n; c += 4 * G) {
                 const double2 a = __ldg(w2 + (size_t)c * hs), b = __ldg(w2 + (size_t)(c + G) * hs),
                               e = __ldg(w2 + (size_t)(c + 2 * G) * hs), d = __ldg(w2 + (size_t)(c + 3 * G) * hs);
