@@ -405,13 +405,27 @@ __device__ __forceinline__ int shift_instance(const DevProblem &P, double *shm, 
         if (lane == 0) { mbar_init(bar, 1); fence_async_smem(); }
         __syncwarp();
     }
+    // the bookkeeping of a leaf (source node -> record, bound, running objective, first-stage bits) is a chain of dependent
+    // loads: it is fetched one leaf AHEAD, while the current leaf's record is in flight / being processed
+    int j_n = 0, ro_n = -1; double lb_n = 0., dobj_n = 0.; unsigned int b0_n = 0u, m0_n = 0u;
+    auto fetch_leaf = [&](int ix) {
+        j_n = nt.rec[on_ + ix];
+        ro_n = ot.rec[oo + j_n];
+        lb_n = ot.lb[oo + j_n];
+        b0_n = ot.bits[(oo + j_n) * ot.words]; m0_n = ot.mask[(oo + j_n) * ot.words];
+        dobj_n = ro_n >= 0 ? ot.rec_dobj[(size_t)inst * ot.cap_recs + ro_n] : 0.;
+    };
+    if (w < nnew) fetch_leaf(w);
     for (int idx = w; idx < nnew; idx += (NT / 32)) {
-        const int j = nt.rec[on_ + idx];
-        const int ro = ot.rec[oo + j];
-        const double lbo = ot.lb[oo + j];
+        const int j = j_n, ro = ro_n;
+        const double lbo = lb_n, dobj_o = dobj_n;
+        const unsigned int b0 = b0_n, m0 = m0_n;
+        const int nx_idx = idx + (NT / 32);
+        (void)j;
         double *E = nt.rec_dual + ((size_t)inst * nt.cap_recs + idx) * P.n_rec;
         if (ro < 0) {
             // dual = None (controller.py:556-558 on the previous step, never solved since): trivial bound
+            if (nx_idx < nnew) fetch_leaf(nx_idx);
             for (int e = lane; e < P.n_rec; e += 32) E[e] = 0.;
             if (lane == 0) { nt.lb[on_ + idx] = 0.; nt.rec[on_ + idx] = -1; nt.rec_dobj[(size_t)inst * nt.cap_recs + idx] = 0.; }
             continue;
@@ -427,17 +441,13 @@ __device__ __forceinline__ int shift_instance(const DevProblem &P, double *shm, 
         } else {
             warp_prefetch_l2(Dg, P.n_dual, lane);
         }
-        {   // ... and the record of the leaf this warp takes next
-            const int nx_idx = idx + (NT / 32);
-            if (nx_idx < nnew) {
-                const int rn_ = ot.rec[oo + nt.rec[on_ + nx_idx]];
-                if (rn_ >= 0) warp_prefetch_l2(ot.rec_dual + ((size_t)inst * ot.cap_recs + rn_) * P.n_rec, P.n_dual, lane);
-            }
+        if (nx_idx < nnew) {   // ... the bookkeeping of the leaf this warp takes next, and its record on the way to L2
+            fetch_leaf(nx_idx);
+            if (ro_n >= 0) warp_prefetch_l2(ot.rec_dual + ((size_t)inst * ot.cap_recs + ro_n) * P.n_rec, P.n_dual, lane);
         }
         for (int e = P.n_dual + lane; e < P.n_rec; e += 32) E[e] = 0.;          // a shifted root starts from the centre 0
         const double *D = Dg;
         if (staged) { mbar_wait(bar, par); par ^= 1u; D = stage; }
-        const unsigned int b0 = ot.bits[(oo + j) * ot.words], m0 = ot.mask[(oo + j) * ot.words];
         double acc = 0.;                     // pi_sum + pi3, lane-partial
         // lam: drop t = 0, append zero ; pi3 = -lam'_0 . e0 (controller.py:544)
         {
@@ -511,7 +521,7 @@ __device__ __forceinline__ int shift_instance(const DevProblem &P, double *shm, 
         }
         acc = warp_sum(acc);
         if (lane == 0) {
-            double obj = ot.rec_dobj[(size_t)inst * ot.cap_recs + ro] + acc;
+            double obj = dobj_o + acc;
             obj = obj > 0. ? obj : 0.;                     // controller.py:546
             double lbn; int rn = idx;
             if (!isinf(lbo)) lbn = obj;                    // :550-551
