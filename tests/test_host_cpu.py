@@ -368,3 +368,23 @@ def test_nonlinear_plant():
     # batched
     xb = np.stack((x0, xin)); out = p.simulate(xb, 0.05, np.array([0., 1.]))
     assert out.shape == (2, 4) and np.allclose(out[0], p.simulate(x0, 0.05, 0.))
+
+
+def test_bench_arguments_follow_the_driver_contract(monkeypatch):
+    """`python bench.py --gpus N --steps K --warmup W` is what the driver runs; without flags every workload has its own
+    defaults (W >= 3 warm-up steps) and both arms describe the same configuration."""
+    import sys
+    import bench
+    monkeypatch.setattr(sys, 'argv', ['bench.py'])
+    a = bench.parse_args()
+    assert (a.gpus, a.steps, a.warmup, a.workload, a.impl) == (1, 10, 5, 'cp20', 'b200')
+    monkeypatch.setattr(sys, 'argv', ['bench.py', '--gpus', '8', '--steps', '7', '--warmup', '4'])
+    a = bench.parse_args()
+    assert (a.gpus, a.steps, a.warmup) == (8, 7, 4)
+    for w in bench.WORKLOADS:
+        monkeypatch.setattr(sys, 'argv', ['bench.py', '--workload', w])
+        b = bench.parse_args()
+        assert b.warmup >= 3 and b.steps >= 1 and b.instances > 0 and b.window > 0
+        monkeypatch.setattr(sys, 'argv', ['bench.py', '--workload', w, '--impl', 'reference'])
+        r = bench.parse_args()
+        assert bench.workload_config(b, 1) == bench.workload_config(r, 1)
