@@ -718,7 +718,7 @@ __device__ __forceinline__ int thin_remove_t(const DevProblem &P, const Ctx &cx,
             run = __shfl_sync(0xffffffffu, s, 31);
         }
     }
-    // bookkeeping shift: read now, write after the first barrier of the sweep
+    // bookkeeping shift: read now, write after the barrier that publishes the rotations
     int rw[WS_RRT], sd[WS_RRT]; double lm[WS_RRT];
 #pragma unroll
     for (int q = 0; q < WS_RRT; ++q) {
@@ -741,14 +741,18 @@ __device__ __forceinline__ int thin_remove_t(const DevProblem &P, const Ctx &cx,
     const int nq1 = (2 * gm.he + 31) & ~31;
     const bool uth = tid == (nq1 < WS_NT ? nq1 : 0);
     const double big = 1. / P.tol_sing;
-    WS_SYNC();                                                              // gc, gs visible
+    WS_SYNC();                                                              // gc, gs visible; row / side / lam have been read
     prof_mark(51);
+#pragma unroll
+    for (int q = 0; q < WS_RRT; ++q) {
+        const int ts = kp + 1 + tid + q * WS_NT;
+        if (ts < k) { row[ts - 1] = rw[q]; side[ts - 1] = sd[q]; SMV(lam)[ts - 1] = lm[q]; }
+    }
 #pragma unroll
     for (int q = 0; q < WS_RPT; ++q) qcarry[q] = qr[q] >= 0 ? QC(kp)[qr[q]] : 0.;
 #pragma unroll
     for (int q = 0; q < WS_RRT; ++q) {
         rcarry[q] = (rr[q] >= 0 && ro[q] <= kp) ? RC(kp)[ro[q]] : 0.;
-        ls_old[q] = rr[q] >= 0 ? SMV(ls)[ro[q]] : 0.;                       // read before any thread writes its new entry
     }
     double ucarry = uth ? u[kp] : 0.;
     for (int i0 = kp; i0 < k - 1; i0 += WS_CH) {
@@ -760,13 +764,6 @@ __device__ __forceinline__ int thin_remove_t(const DevProblem &P, const Ctx &cx,
         }
         WS_SYNC();                                                          // every old entry of the chunk has been read
         prof_mark(54);
-        if (i0 == kp) {
-#pragma unroll
-            for (int q = 0; q < WS_RRT; ++q) {
-                const int ts = kp + 1 + tid + q * WS_NT;
-                if (ts < k) { row[ts - 1] = rw[q]; side[ts - 1] = sd[q]; SMV(lam)[ts - 1] = lm[q]; }
-            }
-        }
 #pragma unroll
         for (int q = 0; q < WS_RRT; ++q) if (rr[q] >= 0 && ro[q] <= i0 + WS_CH) {
 #pragma unroll
@@ -805,6 +802,8 @@ __device__ __forceinline__ int thin_remove_t(const DevProblem &P, const Ctx &cx,
         prof_mark(56);
     }
     if (uth) SMV(red)[40] = ucarry;                                  // (G u)_last
+#pragma unroll
+    for (int q = 0; q < WS_RRT; ++q) ls_old[q] = rr[q] >= 0 ? SMV(ls)[ro[q]] : 0.;   // read before any thread writes its new entry (after the barrier)
     k -= 1;
     WS_SYNC();
     prof_mark(52);
